@@ -1,0 +1,8 @@
+"""Import shim: the package directory is `da-detect_b200/` (the name the build contract
+fixes), which is not a valid Python identifier; `import dadetect_b200` resolves to it."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "da-detect_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
