@@ -1,0 +1,283 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.pt in the BUILD container by running
+the REAL reference (imported from /root/reference through oracle/ref_harness.py).
+The GPU box has no /root/reference, so the fixtures are committed together with this script.
+
+  python oracle/make_golden.py            # (re)writes tests/golden/
+
+Fixtures
+  ref_kats.pt            the reference's own known-answer vectors, lifted by parsing its test
+                         sources: tests/test_nms.py:11-58 and :60-217, tests/test_box_coder.py:11-105,
+                         and the anchor table comment in modeling/rpn/anchor_generator.py:209-219.
+  ref_ops.pt             outputs of reference sub-modules on seeded inputs: generate_anchors for the
+                         DA anchor set, BoxCoder.encode/decode, boxlist_iou, Matcher (both modes),
+                         compiled csrc/cpu ROIAlign forward and nms (>=), smooth_l1, consistency_loss,
+                         TripletMarginLoss (4-D and 2-D), Adv_GRL weights.
+  scenario_<name>.pt     one full GeneralizedRCNN.forward (training) + backward of the reference
+                         model on a small synthetic batch: loss dict, recorded random draws
+                         (randperm / dropout masks, bit-packed), proposal counts, sampled indices,
+                         and gradient probes (norm + leading values) of selected parameters.
+"""
+import ast
+import os
+import re
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+import ref_harness as rh          # noqa: E402
+import da_frcnn_ref as orc        # noqa: E402
+from dadetect_b200.utils.synthetic import make_batch, make_state_dict  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+SCENARIOS = {
+    # name: (yaml, opts, n_images, H, W, boxes_per_image)
+    "da_img_ins_cst": ("da_faster_rcnn/e2e_da_faster_rcnn_R_50_C4_cityscapes_to_foggy_cityscapes.yaml",
+                       [], 2, 192, 320, 6),
+    "da_img_only": ("da_faster_rcnn/e2e_da_faster_rcnn_R_50_C4_cityscapes_to_foggy_cityscapes.yaml",
+                    ["MODEL.DA_HEADS.DA_INS_LOSS_WEIGHT", 0.0, "MODEL.DA_HEADS.DA_CST_LOSS_WEIGHT", 0.0],
+                    2, 160, 256, 5),
+    "triplet_aligned_advgrl": ("da_faster_rcnn/e2e_triplet_da_faster_rcnn_R_50_C4_cityscapes_to_foggy_cityscapes.yaml",
+                               ["MODEL.DA_HEADS.ALIGNMENT", True, "MODEL.DA_HEADS.DA_TRIPLET_INS_WEIGHT", 1.0,
+                                "MODEL.DA_HEADS.DA_CST_LOSS_WEIGHT", 1.0],
+                               3, 160, 256, 5),
+    "triplet_yaml_default": ("da_faster_rcnn/e2e_triplet_da_faster_rcnn_R_50_C4_cityscapes_to_foggy_cityscapes.yaml",
+                             [], 3, 160, 256, 5),
+}
+
+GRAD_PROBES = [
+    "backbone.body.layer2.0.conv1.weight", "backbone.body.layer2.3.conv2.weight",
+    "backbone.body.layer3.0.downsample.0.weight", "backbone.body.layer3.5.conv3.weight",
+    "rpn.head.conv.weight", "rpn.head.conv.bias", "rpn.head.cls_logits.weight", "rpn.head.bbox_pred.bias",
+    "roi_heads.box.feature_extractor.head.layer4.0.conv1.weight",
+    "roi_heads.box.feature_extractor.head.layer4.0.downsample.0.weight",
+    "roi_heads.box.feature_extractor.head.layer4.2.conv2.weight",
+    "roi_heads.box.predictor.cls_score.weight", "roi_heads.box.predictor.bbox_pred.weight",
+    "{da}.imghead.conv1_da.weight", "{da}.imghead.conv2_da.bias",
+    "{da}.inshead.fc1_da.weight", "{da}.inshead.fc3_da.weight",
+]
+
+
+# ----------------------------------------------------------------------------- KATs
+def _literal_arrays(path, func_name):
+    """Evaluate the `name = <np.array/list literal>` assignments inside one test function."""
+    tree = ast.parse(open(path).read())
+    env = {"np": np, "torch": torch}
+    out = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == func_name:
+            for st in node.body:
+                if isinstance(st, ast.Assign) and len(st.targets) == 1 and isinstance(st.targets[0], ast.Name):
+                    name = st.targets[0].id
+                    src = ast.get_source_segment(open(path).read(), st.value)
+                    if "box_nms" in src or "box_coder" in src or "BoxCoder" in src or "np.sort" in src:
+                        continue
+                    try:
+                        val = eval(compile(ast.Expression(st.value), path, "eval"), dict(env, **out))
+                    except Exception:
+                        continue
+                    out[name] = val
+    return out
+
+
+def make_kats():
+    t = os.path.join(rh.REF, "tests")
+    a = _literal_arrays(os.path.join(t, "test_nms.py"), "test_nms_cpu")
+    b = _literal_arrays(os.path.join(t, "test_nms.py"), "test_nms1_cpu")
+    c = _literal_arrays(os.path.join(t, "test_box_coder.py"), "test_box_decoder")
+    src = open(os.path.join(rh.REF, "maskrcnn_benchmark/modeling/rpn/anchor_generator.py")).read()
+    m = re.search(r"# array\(\[\[(.*?)\]\]\)", src, re.S)
+    nums = [float(x) for x in re.findall(r"-?\d+\.", m.group(1))]
+    kats = dict(
+        nms5_boxes=torch.as_tensor(a["inputs"][:, :4]), nms5_scores=torch.as_tensor(a["inputs"][:, 4]),
+        nms5_thresh=list(a["test_thresh"]), nms5_keep=[list(x) for x in a["gt_indices"]],
+        nms53_boxes=torch.as_tensor(b["boxes"]), nms53_scores=torch.as_tensor(b["scores"]),
+        nms53_keep=torch.as_tensor(b["gt_indices"]),
+        coder_boxes=torch.as_tensor(c["bbox"]), coder_deltas=torch.as_tensor(c["deltas"]),
+        coder_decoded=torch.as_tensor(c["gt_bbox"]),
+        anchors_stride16_128_256_512=torch.tensor(nums).view(9, 4),
+    )
+    assert kats["nms53_boxes"].shape == (53, 4) and kats["nms53_keep"].numel() == 26
+    torch.save(kats, os.path.join(OUT, "ref_kats.pt"))
+    return kats
+
+
+# ----------------------------------------------------------------------------- op-level goldens
+def make_ops():
+    rh.install()
+    from maskrcnn_benchmark import _C
+    from maskrcnn_benchmark.layers import consistency_loss, smooth_l1_loss
+    from maskrcnn_benchmark.modeling.box_coder import BoxCoder
+    from maskrcnn_benchmark.modeling.matcher import Matcher
+    from maskrcnn_benchmark.modeling.rpn.anchor_generator import generate_anchors
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.boxlist_ops import boxlist_iou
+    g = torch.Generator().manual_seed(4242)
+    o = {}
+    o["cell_anchors_da"] = generate_anchors(16, (32, 64, 128, 256, 512), (0.5, 1.0, 2.0)).float()
+
+    def rand_boxes(n, w, h):
+        x1 = torch.rand(n, generator=g) * w * 0.8
+        y1 = torch.rand(n, generator=g) * h * 0.8
+        bw = 4 + torch.rand(n, generator=g) * w * 0.4
+        bh = 4 + torch.rand(n, generator=g) * h * 0.4
+        return torch.stack([x1, y1, (x1 + bw).clamp(max=w - 1), (y1 + bh).clamp(max=h - 1)], 1)
+
+    W, H = 320, 192
+    gt, pr = rand_boxes(7, W, H), rand_boxes(300, W, H)
+    pr[:7] = gt + 0.25                                    # a few high-IoU pairs
+    o["iou_gt"], o["iou_pr"] = gt, pr
+    iou = boxlist_iou(BoxList(gt, (W, H)), BoxList(pr, (W, H)))
+    o["iou"] = iou
+    o["match_rpn"] = Matcher(0.7, 0.3, allow_low_quality_matches=True)(iou.clone())
+    o["match_box"] = Matcher(0.5, 0.5, allow_low_quality_matches=False)(iou.clone())
+    for wts, tag in (((1.0, 1.0, 1.0, 1.0), "rpn"), ((10.0, 10.0, 5.0, 5.0), "box")):
+        coder = BoxCoder(weights=wts)
+        enc = coder.encode(gt[torch.arange(300) % 7], pr)
+        o["encode_" + tag] = enc
+        o["decode_" + tag] = coder.decode(enc * 0.7 + 0.05, pr)
+    deltas_big = torch.randn(300, 4, generator=g) * 3.0    # exercises the log(1000/16) clamp
+    o["decode_clamp_in"] = deltas_big
+    o["decode_clamp"] = BoxCoder(weights=(1.0, 1.0, 1.0, 1.0)).decode(deltas_big, pr)
+
+    feat = torch.randn(2, 8, 12, 20, generator=g)
+    rois = torch.cat([torch.randint(0, 2, (40, 1), generator=g).float(), rand_boxes(40, W, H)], 1)
+    rois[0, 1:] = torch.tensor([-40.0, -30.0, 500.0, 400.0])   # spills outside the map
+    rois[1, 1:] = torch.tensor([50.0, 60.0, 50.2, 60.1])       # degenerate -> min size 1
+    o["ra_feat"], o["ra_rois"] = feat, rois
+    o["ra_out_s0"] = _C.roi_align_forward(feat, rois, 1.0 / 16, 14, 14, 0)
+    o["ra_out_s2"] = _C.roi_align_forward(feat, rois, 1.0 / 16, 7, 7, 2)
+    sc = torch.rand(300, generator=g)
+    o["nms_scores"] = sc
+    for thr in (0.3, 0.5, 0.7):
+        o["nms_ge_%.1f" % thr] = _C.nms(pr, sc, thr)
+
+    x, t = torch.randn(50, 4, generator=g), torch.randn(50, 4, generator=g) * 0.2
+    o["sl1_x"], o["sl1_t"] = x, t
+    o["sl1_b9_sum"] = smooth_l1_loss(x, t, beta=1.0 / 9, size_average=False)
+    o["sl1_b1_sum"] = smooth_l1_loss(x, t, beta=1.0, size_average=False)
+
+    img_sig = torch.rand(2, 1, 12, 20, generator=g)
+    ins_sig = torch.rand(37, 1, generator=g)
+    dom = torch.cat([torch.ones(21, dtype=torch.bool), torch.zeros(16, dtype=torch.bool)])
+    o["cst_img"], o["cst_ins"], o["cst_dom"] = img_sig, ins_sig, dom
+    o["cst"] = consistency_loss([img_sig], ins_sig, dom, size_average=True)
+
+    a4, p4, n4 = (torch.randn(1, 6, 5, 8, generator=g) for _ in range(3))
+    a2, p2, n2 = (torch.randn(9, 16, generator=g) for _ in range(3))
+    o["trip4"] = (a4, p4, n4, torch.nn.TripletMarginLoss(margin=1.0, p=2)(a4, p4, n4))
+    o["trip2"] = (a2, p2, n2, torch.nn.TripletMarginLoss(margin=0.7, p=2)(a2, p2, n2))
+
+    # Adv_GRL weights straight from the reference method (da_heads.py:173-195)
+    from maskrcnn_benchmark.modeling.da_heads.da_heads import DomainAdaptationModule_triplet
+    cfg = rh.reference_cfg(SCENARIOS["triplet_yaml_default"][0])
+    mod = DomainAdaptationModule_triplet(cfg)
+    adv = []
+    for L in (0.70, 0.62877, 0.5, 0.2, 0.05):
+        mod.Adv_GRL(torch.tensor(L), [torch.zeros(1, 1, 1, 1)], list_option=True)
+        w = mod.advGRL_optimized.weight if L <= float(mod.bce) else mod.grl_img.weight
+        adv.append((L, float(w)))
+    o["adv_grl"] = adv
+    o["adv_bce"] = float(mod.bce)
+    torch.save(o, os.path.join(OUT, "ref_ops.pt"))
+    return o
+
+
+# ----------------------------------------------------------------------------- scenarios
+class _Recorder(object):
+    """Captures the reference's own torch.randperm / F.dropout draws while it runs."""
+
+    def __init__(self):
+        self.perms, self.masks = [], []
+        self._randperm, self._dropout = torch.randperm, torch.nn.functional.dropout
+
+    def __enter__(self):
+        rec = self
+
+        def randperm(n, *a, **k):
+            p = rec._randperm(n, *a, **k)
+            rec.perms.append(p.clone())
+            return p
+
+        def dropout(x, p=0.5, training=True, inplace=False):
+            if not training:
+                return x
+            keep = torch.empty_like(x).bernoulli_(1 - p)      # same generator consumption as F.dropout
+            rec.masks.append(keep.clone())
+            return x * keep / (1 - p)
+
+        torch.randperm = randperm
+        torch.nn.functional.dropout = dropout
+        return self
+
+    def __exit__(self, *exc):
+        torch.randperm, torch.nn.functional.dropout = self._randperm, self._dropout
+
+
+def pack_masks(masks):
+    return [(tuple(m.shape), torch.from_numpy(np.packbits(m.numpy().astype(np.uint8).reshape(-1)))) for m in masks]
+
+
+def unpack_masks(packed):
+    out = []
+    for shape, bits in packed:
+        n = int(np.prod(shape))
+        out.append(torch.from_numpy(np.unpackbits(bits.numpy())[:n].astype(np.float32)).view(shape))
+    return out
+
+
+def grad_probe(g):
+    g = g.detach().double().reshape(-1)
+    return dict(norm=float(g.norm()), head=g[:16].float().clone(), sum=float(g.sum()))
+
+
+def make_scenario(name):
+    yaml_name, opts, n, H, W, m = SCENARIOS[name]
+    cfg = rh.reference_cfg(yaml_name, opts)
+    sd = make_state_dict(orc.param_shapes(cfg))
+    model = rh.build_reference_model(cfg, sd)
+    model.train()
+    images, targets = make_batch(n, H, W, num_classes=cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES, boxes_per_image=m)
+    torch.manual_seed(20231017)
+    with _Recorder() as rec:
+        losses = model(images, rh.to_reference_targets(targets, (H, W)))
+        total = sum(losses.values())
+        total.backward()
+    named = dict(model.named_parameters())
+    da = "da_heads_triplet" if cfg.MODEL.DA_HEADS.TRIPLET_USE else "da_heads"
+    grads = {}
+    for k in GRAD_PROBES:
+        k = k.format(da=da)
+        if named[k].grad is not None:
+            grads[k] = grad_probe(named[k].grad)
+    none_grad = sorted(k for k, p in named.items() if p.requires_grad and p.grad is None)
+    fx = dict(
+        name=name, yaml=yaml_name, opts=list(opts), n_images=n, height=H, width=W, boxes_per_image=m,
+        losses={k: float(v) for k, v in losses.items()}, loss_order=list(losses.keys()),
+        perms=rec.perms, masks=pack_masks(rec.masks), grads=grads, params_without_grad=none_grad,
+        nms="cpu_ge",
+    )
+    torch.save(fx, os.path.join(OUT, "scenario_{}.pt".format(name)))
+    return fx
+
+
+def main():
+    assert rh.available(), "reference not mounted"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    make_kats()
+    make_ops()
+    for name in SCENARIOS:
+        fx = make_scenario(name)
+        print(name, {k: round(v, 6) for k, v in fx["losses"].items()}, "perms", len(fx["perms"]),
+              "masks", len(fx["masks"]), "no-grad params", len(fx["params_without_grad"]))
+    print("fixture bytes:", sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()
