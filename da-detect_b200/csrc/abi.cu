@@ -1,0 +1,10 @@
+#include "common.cuh"
+
+namespace dd {
+thread_local char g_err[512] = "";
+long long g_launches = 0;
+}  // namespace dd
+
+extern "C" const char* dd_last_error(void) { return dd::g_err; }
+extern "C" int dd_abi_version(void) { return 1; }
+extern "C" long long dd_launch_count(void) { return dd::g_launches; }

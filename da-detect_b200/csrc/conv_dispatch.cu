@@ -1,0 +1,57 @@
+// C-ABI entry points of the dense tier; selects the fp32 SIMT arm (conv_simt.cu) or the tcgen05 arm
+// (conv_tc.cu).  There is no CPU or library fallback: an unsupported (impl, shape) pair is an error.
+#include "common.cuh"
+
+int dd_simt_conv2d_forward(const float*, const float*, const float*, const float*, const float*, float*, int, int,
+                           int, int, int, int, int, int, int, int, cudaStream_t);
+int dd_simt_conv2d_dgrad(const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
+                         int, int, int, int, int, int, cudaStream_t);
+size_t dd_simt_wgrad_workspace_bytes(int, int, int, int, int, int, int, int, int);
+int dd_simt_conv2d_wgrad(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int,
+                         int, void*, cudaStream_t);
+
+int dd_tc_conv2d_forward(const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
+                         int, int, int, int, int, int, int, cudaStream_t);
+int dd_tc_conv2d_dgrad(const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
+                       int, int, int, int, int, int, cudaStream_t);
+int dd_tc_conv2d_wgrad(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int,
+                       int, void*, cudaStream_t);
+bool dd_tc_supports(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
+
+extern "C" int dd_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias,
+                                 const float* residual, float* y, int N, int H, int W, int Cin, int Cout, int KH,
+                                 int KW, int stride, int pad, int act, int impl, void* stream) {
+  DD_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0);
+  if (impl == DD_IMPL_TCGEN05 && dd_tc_supports(0, N, H, W, Cin, Cout, KH, KW, stride, pad))
+    return dd_tc_conv2d_forward(x, w, scale, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad, act,
+                                dd::S(stream));
+  return dd_simt_conv2d_forward(x, w, scale, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad, act,
+                                dd::S(stream));
+}
+
+extern "C" int dd_conv2d_dgrad(const float* gy, const float* w, const float* scale, const float* addend,
+                               const float* mask_act, float* gx, int N, int H, int W, int Cin, int Cout, int KH,
+                               int KW, int stride, int pad, int impl, void* stream) {
+  DD_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0);
+  if (impl == DD_IMPL_TCGEN05 && dd_tc_supports(1, N, H, W, Cin, Cout, KH, KW, stride, pad))
+    return dd_tc_conv2d_dgrad(gy, w, scale, addend, mask_act, gx, N, H, W, Cin, Cout, KH, KW, stride, pad,
+                              dd::S(stream));
+  return dd_simt_conv2d_dgrad(gy, w, scale, addend, mask_act, gx, N, H, W, Cin, Cout, KH, KW, stride, pad,
+                              dd::S(stream));
+}
+
+extern "C" size_t dd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
+                                                  int pad) {
+  return dd_simt_wgrad_workspace_bytes(N, H, W, Cin, Cout, KH, KW, stride, pad);
+}
+
+extern "C" int dd_conv2d_wgrad(const float* gy, const float* x, const float* scale, float* gw, int N, int H, int W,
+                               int Cin, int Cout, int KH, int KW, int stride, int pad, int accumulate, int impl,
+                               void* workspace, void* stream) {
+  DD_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0);
+  if (impl == DD_IMPL_TCGEN05 && dd_tc_supports(2, N, H, W, Cin, Cout, KH, KW, stride, pad))
+    return dd_tc_conv2d_wgrad(gy, x, scale, gw, N, H, W, Cin, Cout, KH, KW, stride, pad, accumulate, workspace,
+                              dd::S(stream));
+  return dd_simt_conv2d_wgrad(gy, x, scale, gw, N, H, W, Cin, Cout, KH, KW, stride, pad, accumulate, workspace,
+                              dd::S(stream));
+}

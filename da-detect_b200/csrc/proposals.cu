@@ -1,0 +1,432 @@
+// RPN proposal generation on device: anchor grid, sigmoid/top-k/decode/clip, and NMS with an
+// on-device scan (no D2H mask copy, no host loop — the reference's nms.cu:99-123 does both).
+//
+// Reference semantics: rpn/anchor_generator.py:73-111, rpn/inference.py:87-115, box_coder.py:52-95,
+// structures/bounding_box.py:214-225, structures/boxlist_ops.py:37-51, csrc/cuda/nms.cu:13-131.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSortCap = 16384;     // max elements of the in-shared-memory bitonic sort (128 KB of u64)
+constexpr int kTopkThreads = 1024;
+
+// ----------------------------------------------------------------------------- anchors
+__global__ void anchor_grid_kernel(const float* __restrict__ cell, int A, int FH, int FW, int stride, int img_w,
+                                   int img_h, int straddle, float* __restrict__ anchors,
+                                   uint8_t* __restrict__ vis) {
+  const int total = FH * FW * A;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int a = i % A, x = (i / A) % FW, y = i / (A * FW);
+    const float sx = (float)(x * stride), sy = (float)(y * stride);
+    float4 b;
+    b.x = sx + cell[a * 4 + 0];
+    b.y = sy + cell[a * 4 + 1];
+    b.z = sx + cell[a * 4 + 2];
+    b.w = sy + cell[a * 4 + 3];
+    reinterpret_cast<float4*>(anchors)[i] = b;
+    bool inside = true;
+    if (straddle >= 0)
+      inside = b.x >= (float)(-straddle) && b.y >= (float)(-straddle) && b.z < (float)(img_w + straddle) &&
+               b.w < (float)(img_h + straddle);
+    vis[i] = inside ? 1 : 0;
+  }
+}
+
+// ----------------------------------------------------------------------------- sort helpers
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// In-place bitonic sort, DESCENDING, of n_pow2 u64 keys in shared memory by the whole CTA.
+__device__ void bitonic_sort_desc(unsigned long long* s, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // index with bit j cleared
+        const int p = i | j;
+        const bool up = (i & k) == 0;                          // "up" block => descending here
+        const unsigned long long a = s[i], b = s[p];
+        if ((a < b) == up) { s[i] = b; s[p] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Exclusive block scan of 0/1 flags in index order; returns this thread's rank and the block total.
+__device__ __forceinline__ int block_rank(bool flag, int* warp_tot, int& total) {
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int within = __popc(bal & ((1u << lane) - 1u));
+  __syncthreads();
+  if (lane == 0) warp_tot[wid] = __popc(bal);
+  __syncthreads();
+  int base = 0, tot = 0;
+  const int nw = blockDim.x >> 5;
+  for (int w = 0; w < nw; ++w) {
+    const int c = warp_tot[w];
+    if (w < wid) base += c;
+    tot += c;
+  }
+  total = tot;
+  return base + within;
+}
+
+// ----------------------------------------------------------------------------- top-k + decode
+// One CTA per image.  dynamic smem: n_pow2 * 8 bytes.
+__global__ void __launch_bounds__(kTopkThreads) rpn_topk_decode_kernel(
+    const float* __restrict__ logits, const float* __restrict__ deltas, const float* __restrict__ anchors,
+    int num_anchors, int k, int img_w, int img_h, float min_size, float* __restrict__ boxes,
+    float* __restrict__ scores, int32_t* __restrict__ topk_idx, int32_t* __restrict__ valid) {
+  extern __shared__ unsigned long long skeys[];
+  __shared__ int hist[256];
+  __shared__ int warp_tot[32];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_need, s_count;
+
+  const int img = blockIdx.x;
+  const float* lg = logits + (size_t)img * num_anchors;
+  const int n_pow2 = next_pow2(k);
+
+  // ---- radix select: exact k-th largest ordered key -------------------------------------------
+  uint32_t prefix = 0, prefix_mask = 0;
+  int need = k;   // how many more elements we must take from the "== prefix so far" population
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < num_anchors; i += blockDim.x) {
+      const uint32_t key = float_to_ordered(lg[i]);
+      if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0, b = 255;
+      for (; b > 0; --b) {
+        if (acc + hist[b] >= need) break;
+        acc += hist[b];
+      }
+      s_prefix = prefix | ((uint32_t)b << shift);
+      s_need = need - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    need = s_need;
+    prefix_mask |= 0xFFu << shift;
+    __syncthreads();
+  }
+  const uint32_t kth = prefix;   // exact key of the k-th largest; `need` of the ties at kth are taken
+
+  // ---- compaction: everything > kth, plus the `need` lowest-index elements == kth ---------------
+  if (threadIdx.x == 0) s_count = 0;
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) skeys[i] = 0ull;
+  __syncthreads();
+  int ties_taken = 0;
+  for (int base = 0; base < num_anchors; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    uint32_t key = 0;
+    bool gt = false, eq = false;
+    if (i < num_anchors) {
+      key = float_to_ordered(lg[i]);
+      gt = key > kth;
+      eq = key == kth;
+    }
+    int tot;
+    const int r = block_rank(eq, warp_tot, tot);
+    const bool take_eq = eq && (ties_taken + r) < need;
+    ties_taken += tot;
+    if (gt || take_eq) {
+      const int slot = atomicAdd(&s_count, 1);
+      skeys[slot] = ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+    }
+  }
+  __syncthreads();
+  bitonic_sort_desc(skeys, n_pow2);
+
+  // ---- decode, clip, min-size filter, ordered compaction ------------------------------------------
+  const float clip = 4.135166556742356f;   // log(1000/16)
+  const float xmax = (float)(img_w - 1), ymax = (float)(img_h - 1);
+  int out_base = 0;
+  for (int base = 0; base < k; base += blockDim.x) {
+    const int r = base + threadIdx.x;
+    bool ok = false;
+    float4 b = make_float4(0, 0, 0, 0);
+    float sc = 0.f;
+    int idx = 0;
+    if (r < k) {
+      idx = (int)(0xFFFFFFFFu - (uint32_t)(skeys[r] & 0xFFFFFFFFull));
+      const float x = lg[idx];
+      sc = 1.0f / (1.0f + expf(-x));
+      const float4 d = dd::ldg4(deltas + ((size_t)img * num_anchors + idx) * 4);
+      const float4 a = dd::ldg4(anchors + (size_t)idx * 4);
+      const float w = __fadd_rn(__fsub_rn(a.z, a.x), 1.0f), h = __fadd_rn(__fsub_rn(a.w, a.y), 1.0f);
+      const float cx = __fadd_rn(a.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(a.y, __fmul_rn(0.5f, h));
+      const float dw = fminf(d.z, clip), dh = fminf(d.w, clip);
+      const float pcx = __fadd_rn(__fmul_rn(d.x, w), cx), pcy = __fadd_rn(__fmul_rn(d.y, h), cy);
+      const float pw = __fmul_rn(expf(dw), w), phh = __fmul_rn(expf(dh), h);
+      b.x = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+      b.y = __fsub_rn(pcy, __fmul_rn(0.5f, phh));
+      b.z = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.0f);
+      b.w = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, phh)), 1.0f);
+      b.x = fminf(fmaxf(b.x, 0.f), xmax);
+      b.y = fminf(fmaxf(b.y, 0.f), ymax);
+      b.z = fminf(fmaxf(b.z, 0.f), xmax);
+      b.w = fminf(fmaxf(b.w, 0.f), ymax);
+      const float ws = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f), hs = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
+      ok = ws >= min_size && hs >= min_size;
+    }
+    int tot;
+    const int rank = block_rank(ok, warp_tot, tot);
+    if (ok) {
+      const size_t o = (size_t)img * k + out_base + rank;
+      reinterpret_cast<float4*>(boxes)[o] = b;
+      scores[o] = sc;
+      topk_idx[o] = idx;
+    }
+    out_base += tot;
+  }
+  if (threadIdx.x == 0) valid[img] = out_base;
+}
+
+// ----------------------------------------------------------------------------- NMS
+__device__ __forceinline__ float iou_plus1(const float4 a, const float4 b) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+  const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+  const float inter = __fmul_rn(width, height);
+  const float sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
+  const float sb = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
+}
+
+// mask[i][cb] bit j: box (cb*64+j) is suppressed by box i (j > i only).  Upper triangle only.
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ boxes, int n, float thresh,
+                                                      unsigned long long* __restrict__ mask, int col_blocks) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;
+  __shared__ float4 cols[64];
+  const int col_size = min(n - cb * 64, 64);
+  if ((int)threadIdx.x < col_size) cols[threadIdx.x] = boxes[cb * 64 + threadIdx.x];
+  __syncthreads();
+  const int i = rb * 64 + threadIdx.x;
+  if (i < n) {
+    const float4 me = boxes[i];
+    unsigned long long bits = 0ull;
+    const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+    for (int j = start; j < col_size; ++j)
+      if (iou_plus1(me, cols[j]) > thresh) bits |= 1ull << j;
+    mask[(size_t)i * col_blocks + cb] = bits;
+  }
+}
+
+// Single-CTA greedy scan over the bitmask.  keep_pos receives kept positions (ascending = score order).
+__global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long* __restrict__ mask, int n,
+                                                       int col_blocks, int max_keep, int64_t* __restrict__ keep_pos,
+                                                       int* __restrict__ keep_count) {
+  extern __shared__ unsigned long long remv[];   // col_blocks words
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_kept_bits;
+  __shared__ int s_nkeep;
+  for (int j = threadIdx.x; j < col_blocks; j += blockDim.x) remv[j] = 0ull;
+  if (threadIdx.x == 0) s_nkeep = 0;
+  __syncthreads();
+  for (int b = 0; b < col_blocks; ++b) {
+    const int size = min(n - b * 64, 64);
+    if ((int)threadIdx.x < size) diag[threadIdx.x] = mask[(size_t)(b * 64 + threadIdx.x) * col_blocks + b];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long cur = remv[b], kept = 0ull;
+      int nk = s_nkeep;
+      for (int i = 0; i < size; ++i) {
+        if (!((cur >> i) & 1ull)) {
+          if (max_keep > 0 && nk >= max_keep) break;
+          kept |= 1ull << i;
+          keep_pos[nk++] = (int64_t)(b * 64 + i);
+          cur |= diag[i];
+        }
+      }
+      s_kept_bits = kept;
+      s_nkeep = nk;
+    }
+    __syncthreads();
+    const unsigned long long kept = s_kept_bits;
+    if (max_keep > 0 && s_nkeep >= max_keep) break;
+    if (kept) {
+      for (int j = b + 1 + threadIdx.x; j < col_blocks; j += blockDim.x) {
+        unsigned long long acc = remv[j];
+        unsigned long long kb = kept;
+        while (kb) {
+          const int i = __ffsll((long long)kb) - 1;
+          kb &= kb - 1;
+          acc |= mask[(size_t)(b * 64 + i) * col_blocks + j];
+        }
+        remv[j] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *keep_count = s_nkeep;
+}
+
+// Sort (score desc, index asc) -> order; gather boxes.  Single CTA, n <= kSortCap.
+__global__ void __launch_bounds__(1024) sort_scores_gather_kernel(const float* __restrict__ scores,
+                                                                  const float4* __restrict__ boxes, int n,
+                                                                  int32_t* __restrict__ order,
+                                                                  float4* __restrict__ boxes_sorted) {
+  extern __shared__ unsigned long long skeys[];
+  const int n_pow2 = next_pow2(n);
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x)
+    skeys[i] = i < n ? (((unsigned long long)float_to_ordered(scores[i]) << 32) |
+                        (unsigned long long)(0xFFFFFFFFu - (uint32_t)i))
+                     : 0ull;
+  __syncthreads();
+  bitonic_sort_desc(skeys, n_pow2);
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    const int idx = (int)(0xFFFFFFFFu - (uint32_t)(skeys[r] & 0xFFFFFFFFull));
+    order[r] = idx;
+    boxes_sorted[r] = boxes[idx];
+  }
+}
+
+// keep positions -> original indices, ascending.  Single CTA.
+__global__ void __launch_bounds__(1024) keep_to_sorted_indices_kernel(const int32_t* __restrict__ order,
+                                                                      const int* __restrict__ keep_count,
+                                                                      int64_t* __restrict__ keep, int cap_pow2) {
+  extern __shared__ unsigned long long skeys[];
+  const int m = *keep_count;
+  const int n_pow2 = next_pow2(m > 1 ? m : 1);
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x)
+    skeys[i] = i < m ? (0xFFFFFFFFFFFFFFFFull - (unsigned long long)order[keep[i]]) : 0ull;
+  __syncthreads();
+  bitonic_sort_desc(skeys, n_pow2);   // descending in (MAX - idx) == ascending in idx
+  for (int i = threadIdx.x; i < m; i += blockDim.x) keep[i] = (int64_t)(0xFFFFFFFFFFFFFFFFull - skeys[i]);
+  (void)cap_pow2;
+}
+
+int host_next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct NmsWs {
+  unsigned long long* mask;
+  float4* boxes_sorted;
+  int32_t* order;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+NmsWs carve(void* ws, int n) {
+  const int cb = (n + 63) / 64;
+  char* p = (char*)ws;
+  NmsWs w;
+  w.mask = (unsigned long long*)p;
+  p += align_up((size_t)n * cb * 8, 256);
+  w.boxes_sorted = (float4*)p;
+  p += align_up((size_t)n * 16, 256);
+  w.order = (int32_t*)p;
+  return w;
+}
+
+int nms_sorted_impl(const float* boxes_sorted, int n, float thresh, int max_keep, int64_t* keep, int* keep_count,
+                    unsigned long long* mask, cudaStream_t s) {
+  const int cb = (n + 63) / 64;
+  dim3 grid(cb, cb);
+  nms_mask_kernel<<<grid, 64, 0, s>>>(reinterpret_cast<const float4*>(boxes_sorted), n, thresh, mask, cb);
+  DD_LAUNCHED();
+  nms_scan_kernel<<<1, 256, cb * sizeof(unsigned long long), s>>>(mask, n, cb, max_keep, keep, keep_count);
+  DD_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int dd_anchor_grid(const float* cell_anchors, int A, int FH, int FW, int stride, int img_w, int img_h,
+                              int straddle_thresh, float* anchors, uint8_t* visibility, void* stream) {
+  DD_CHECK_ARG(A > 0 && FH > 0 && FW > 0 && stride > 0);
+  const int total = FH * FW * A;
+  anchor_grid_kernel<<<dd::grid_for(total, 256), 256, 0, dd::S(stream)>>>(cell_anchors, A, FH, FW, stride, img_w,
+                                                                          img_h, straddle_thresh, anchors, visibility);
+  DD_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t dd_rpn_topk_workspace_bytes(int N, int num_anchors) {
+  (void)N;
+  (void)num_anchors;
+  return 256;   // everything lives in shared memory; kept for ABI stability
+}
+
+extern "C" int dd_rpn_topk_decode(const float* logits, const float* deltas, const float* anchors, int N, int FH,
+                                  int FW, int A, int k, int img_w, int img_h, float min_size, float* boxes,
+                                  float* scores, int32_t* topk_idx, int32_t* valid, void* workspace, void* stream) {
+  (void)workspace;
+  const int num_anchors = FH * FW * A;
+  DD_CHECK_ARG(N > 0 && num_anchors > 0 && k > 0 && k <= num_anchors && k <= kSortCap);
+  const size_t smem = (size_t)host_next_pow2(k) * sizeof(unsigned long long);
+  static bool configured = false;
+  if (!configured) {
+    DD_CUDA(cudaFuncSetAttribute(rpn_topk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSortCap * (int)sizeof(unsigned long long)));
+    configured = true;
+  }
+  rpn_topk_decode_kernel<<<N, kTopkThreads, smem, dd::S(stream)>>>(logits, deltas, anchors, num_anchors, k, img_w,
+                                                                   img_h, min_size, boxes, scores, topk_idx, valid);
+  DD_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t dd_nms_workspace_bytes(int n) {
+  if (n <= 0) return 256;
+  const int cb = (n + 63) / 64;
+  return align_up((size_t)n * cb * 8, 256) + align_up((size_t)n * 16, 256) + align_up((size_t)n * 4, 256) + 256;
+}
+
+extern "C" int dd_nms_sorted(const float* boxes_sorted, int n, float thresh, int max_keep, int64_t* keep_out,
+                             int* keep_count, void* workspace, void* stream) {
+  DD_CHECK_ARG(n >= 0 && workspace != nullptr);
+  if (n == 0) {
+    DD_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(int), dd::S(stream)));
+    return 0;
+  }
+  NmsWs w = carve(workspace, n);
+  return nms_sorted_impl(boxes_sorted, n, thresh, max_keep, keep_out, keep_count, w.mask, dd::S(stream));
+}
+
+extern "C" int dd_nms(const float* boxes, const float* scores, int n, float thresh, int64_t* keep_out,
+                      int* keep_count, void* workspace, void* stream) {
+  DD_CHECK_ARG(n >= 0 && n <= kSortCap && workspace != nullptr);
+  cudaStream_t s = dd::S(stream);
+  if (n == 0) {
+    DD_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(int), s));
+    return 0;
+  }
+  static bool configured = false;
+  if (!configured) {
+    DD_CUDA(cudaFuncSetAttribute(sort_scores_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSortCap * (int)sizeof(unsigned long long)));
+    DD_CUDA(cudaFuncSetAttribute(keep_to_sorted_indices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kSortCap * (int)sizeof(unsigned long long)));
+    configured = true;
+  }
+  NmsWs w = carve(workspace, n);
+  const int p2 = host_next_pow2(n);
+  sort_scores_gather_kernel<<<1, 1024, (size_t)p2 * 8, s>>>(scores, reinterpret_cast<const float4*>(boxes), n,
+                                                            w.order, w.boxes_sorted);
+  DD_LAUNCHED();
+  int rc = nms_sorted_impl(reinterpret_cast<const float*>(w.boxes_sorted), n, thresh, 0, keep_out, keep_count,
+                           w.mask, s);
+  if (rc) return rc;
+  keep_to_sorted_indices_kernel<<<1, 1024, (size_t)p2 * 8, s>>>(w.order, keep_count, keep_out, p2);
+  DD_LAUNCHED();
+  return 0;
+}

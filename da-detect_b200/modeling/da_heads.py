@@ -1,0 +1,208 @@
+"""Domain-adaptation heads and losses.
+
+Mirrors maskrcnn_benchmark/modeling/da_heads/{da_heads.py,loss.py}, layers/gradient_scalar_layer.py and
+layers/consistency_loss.py.  State-dict names: ``da_heads.{imghead.conv1_da,imghead.conv2_da,
+inshead.fc1_da,inshead.fc2_da,inshead.fc3_da}.{weight,bias}`` and the same under ``da_heads_triplet``.
+
+Fusions relative to the reference: BCE/consistency/triplet are single fused forward+gradient kernels;
+the sigmoid of the consistency branch is folded into the loss kernel; the AdvGRL weight is computed and
+consumed on the device (no `.numpy()` / `.cpu()` sync); the AdvGRL "probe" pass of the image
+head is not recomputed because it has the same forward values as the GRL pass.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from .backbone import Conv2dParams
+
+
+class DAImgHead(nn.Module):
+    """Two 1x1 convs on the C4 map (da_heads.py:12-37); output NHWC [N,h,w,1]."""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        self.conv1_da = Conv2dParams(in_channels, 512, 1, bias=True)
+        self.conv2_da = Conv2dParams(512, 1, 1, bias=True)
+        for l in (self.conv1_da, self.conv2_da):
+            nn.init.normal_(l.weight, std=0.001)
+            nn.init.constant_(l.bias, 0)
+
+    def forward(self, feat):
+        t = ops.conv_bn_act(feat, self.conv1_da.weight, None, self.conv1_da.bias, relu=True)
+        return ops.conv_bn_act(t, self.conv2_da.weight, None, self.conv2_da.bias)
+
+
+class DAInsHead(nn.Module):
+    """FC 2048-1024-1024-1 with ReLU + dropout(0.5) (da_heads.py:40-68)."""
+
+    def __init__(self, in_channels, rng):
+        super().__init__()
+        self.fc1_da = nn.Linear(in_channels, 1024)
+        self.fc2_da = nn.Linear(1024, 1024)
+        self.fc3_da = nn.Linear(1024, 1)
+        for l in (self.fc1_da, self.fc2_da):
+            nn.init.normal_(l.weight, std=0.01)
+            nn.init.constant_(l.bias, 0)
+        nn.init.normal_(self.fc3_da.weight, std=0.05)
+        nn.init.constant_(self.fc3_da.bias, 0)
+        self.rng = rng
+
+    def forward(self, x):
+        x = ops.linear(x, self.fc1_da.weight, self.fc1_da.bias, relu=True)
+        if self.training:
+            x = ops.dropout_with_mask(x, self.rng.dropout_keep(tuple(x.shape), x.device))
+        x = ops.linear(x, self.fc2_da.weight, self.fc2_da.bias, relu=True)
+        if self.training:
+            x = ops.dropout_with_mask(x, self.rng.dropout_keep(tuple(x.shape), x.device))
+        return ops.linear(x, self.fc3_da.weight, self.fc3_da.bias)
+
+
+def _image_domain_labels(targets, device):
+    """prepare_masks (da_heads/loss.py:45-53): one bit per image, is_source.any()."""
+    return torch.tensor([1 if bool(t.get_field("is_source").any()) else 0 for t in targets],
+                        dtype=torch.uint8, device=device)
+
+
+def da_img_loss(img_logits, targets):
+    """Per-pixel BCE against the image's domain label, mean over N*h*w (loss.py:140-168)."""
+    n = img_logits.shape[0]
+    seg = _image_domain_labels(targets, img_logits.device)
+    return ops.bce_with_logits_mean(img_logits, None, seg, img_logits.numel() // n)
+
+
+def da_ins_loss(ins_logits, dom):
+    """Per-ROI BCE against the ROI's domain (loss.py:170-174)."""
+    return ops.bce_with_logits_mean(ins_logits.reshape(-1), dom.to(torch.float32))
+
+
+def _num_source(dom_sizes):
+    return int(dom_sizes)
+
+
+class _Base(nn.Module):
+    def __init__(self, cfg, rng):
+        super().__init__()
+        self.cfg = cfg.clone()
+        D = cfg.MODEL.DA_HEADS
+        if not cfg.MODEL.BACKBONE.CONV_BODY.startswith("R"):
+            raise NotImplementedError("only ResNet bodies are on the DA path")
+        self.img_weight, self.ins_weight, self.cst_weight = D.DA_IMG_LOSS_WEIGHT, D.DA_INS_LOSS_WEIGHT, D.DA_CST_LOSS_WEIGHT
+        self.imghead = DAImgHead(cfg.MODEL.BACKBONE.OUT_CHANNELS)
+        self.inshead = DAInsHead(cfg.MODEL.RESNETS.RES2_OUT_CHANNELS * 8, rng)
+
+
+class DomainAdaptationModule(_Base):
+    """The original DA module (da_heads.py:354-440 + DALossComputation loss.py:28-104)."""
+
+    def forward(self, img_features, pooled_ins, dom, n_src, targets):
+        if not self.training:
+            return {}
+        D = self.cfg.MODEL.DA_HEADS
+        feat = img_features[0]
+        img_g = ops.gradient_scalar(feat, -1.0 * D.DA_IMG_GRL_WEIGHT)
+        ins_g = ops.gradient_scalar(pooled_ins, -1.0 * D.DA_INS_GRL_WEIGHT)
+        img_c = ops.gradient_scalar(feat, 1.0 * D.DA_IMG_GRL_WEIGHT)
+        ins_c = ops.gradient_scalar(pooled_ins, 1.0 * D.DA_INS_GRL_WEIGHT)
+        da_img = self.imghead(img_g)
+        da_ins = self.inshead(ins_g)
+        da_img_c = self.imghead(img_c)
+        da_ins_c = self.inshead(ins_c)
+        l_img = da_img_loss(da_img, targets)
+        l_ins = da_ins_loss(da_ins, dom)
+        l_cst = ops.consistency_loss(da_img_c.reshape(da_img_c.shape[0], -1), da_ins_c.reshape(-1), n_src)
+        losses = {}
+        if self.img_weight > 0:
+            losses["loss_da_image"] = self.img_weight * l_img
+        if self.ins_weight > 0:
+            losses["loss_da_instance"] = self.ins_weight * l_ins
+        if self.cst_weight > 0:
+            losses["loss_da_consistency"] = self.cst_weight * l_cst
+        return losses
+
+
+ADV_BCE = float(F.binary_cross_entropy_with_logits(torch.tensor([[0.7, 0.3]]), torch.tensor([[1.0, 0.0]])))
+
+
+class DomainAdaptationModule_triplet(_Base):
+    """DA module with AdvGRL and the auxiliary-domain triplet losses (da_heads.py:72-344 +
+    DALossComputation_Component loss.py:108-222)."""
+
+    def __init__(self, cfg, rng):
+        super().__init__(cfg, rng)
+        D = cfg.MODEL.DA_HEADS
+        self.triplet_img_weight, self.triplet_ins_weight = D.DA_TRIPLET_IMG_WEIGHT, D.DA_TRIPLET_INS_WEIGHT
+        # host-side state of the reference (da_heads.py:107-110, loss.py:128-130); the previous triplet
+        # losses stay on the device and are only read when the adaptive margin can actually move.
+        self.prev_img, self.prev_ins = None, None
+        self.margin_img, self.margin_ins = 0.0, 0.0
+
+    def _margin(self, current, prev_loss, adaptive, lr, max_margin, margin):
+        if current == 0.0:
+            current = margin
+        if adaptive:
+            if int(current) != int(max_margin):             # only then is the previous loss consulted
+                prev = 1.0 if prev_loss is None else float(prev_loss)
+                if prev == 0.0:
+                    current = current + lr
+        else:
+            current = margin
+        return current
+
+    def _grl_weight(self, loss, lam, lam_adv):
+        D = self.cfg.MODEL.DA_HEADS
+        if D.DA_ADV_GRL:
+            return ops.adv_grl_weight(loss, ADV_BCE, lam, lam_adv, D.DA_ADV_GRL_THRESHOLD)
+        return torch.full((1,), -1.0 * lam, dtype=torch.float32, device=loss.device)
+
+    def forward(self, img_features, pooled_ins, dom, n_src, pooled_set, img_fea_set, targets):
+        if not self.training:
+            return {}
+        D = self.cfg.MODEL.DA_HEADS
+        feat = img_features[0]
+        losses = {}
+        if self.triplet_ins_weight > 0:                       # Domainlevel_Ins_component
+            s, p, n = pooled_set
+            self.margin_ins = self._margin(self.margin_ins, self.prev_ins, False, 0.001, D.TRIPLET_MAX_MARGIN,
+                                           D.TRIPLET_MARGIN_INS)
+            l = ops.triplet_margin_loss(s, p, n, self.margin_ins, s.shape[0], s.shape[1], 1)
+            losses["triplet_loss_instance"] = self.triplet_ins_weight * l
+            self.prev_ins = l.detach()
+        if self.triplet_img_weight > 0:                       # Domainlevel_Img_component
+            s, p, n = img_fea_set
+            self.margin_img = self._margin(self.margin_img, self.prev_img, True, 0.001, D.TRIPLET_MAX_MARGIN,
+                                           D.TRIPLET_MARGIN_IMG)
+            _, h, w, c = s.shape                              # NHWC [1,h,w,C]: distance over w per (c,h)
+            l = ops.triplet_margin_loss(s, p, n, self.margin_img, h * c, w, c)
+            losses["triplet_loss_image"] = self.triplet_img_weight * l
+            self.prev_img = l.detach()
+        if self.img_weight > 0:                               # DA_Img_component
+            wdev = torch.empty(1, dtype=torch.float32, device=feat.device)
+            da_img = self.imghead(ops.gradient_scalar_dev(feat, wdev))
+            l_img = da_img_loss(da_img, targets)
+            wdev.copy_(self._grl_weight(l_img, D.DA_IMG_GRL_WEIGHT, D.DA_IMG_advGRL_WEIGHT))
+            losses["loss_da_image"] = self.img_weight * l_img
+        if self.ins_weight > 0:                               # DA_Ins_component
+            with torch.no_grad():
+                cur = da_ins_loss(self.inshead(pooled_ins.detach()), dom)
+            w_ins = self._grl_weight(cur, D.DA_INS_GRL_WEIGHT, D.DA_INS_advGRL_WEIGHT)
+            da_ins = self.inshead(ops.gradient_scalar_dev(pooled_ins, w_ins))
+            losses["loss_da_instance"] = self.ins_weight * da_ins_loss(da_ins, dom)
+        if self.cst_weight > 0:                               # Consistency_component
+            img_c = self.imghead(ops.gradient_scalar(feat, 1.0 * D.DA_IMG_GRL_WEIGHT))
+            ins_c = self.inshead(ops.gradient_scalar(pooled_ins, 1.0 * D.DA_INS_GRL_WEIGHT))
+            l_cst = ops.consistency_loss(img_c.reshape(img_c.shape[0], -1), ins_c.reshape(-1), n_src)
+            losses["loss_da_consistency"] = self.cst_weight * l_cst
+        return losses
+
+
+def build_da_heads(cfg, rng):
+    if cfg.MODEL.DOMAIN_ADAPTATION_ON:
+        return DomainAdaptationModule(cfg, rng)
+    return []
+
+
+def build_da_heads_triplet(cfg, rng):
+    if cfg.MODEL.DOMAIN_ADAPTATION_ON:
+        return DomainAdaptationModule_triplet(cfg, rng)
+    return []

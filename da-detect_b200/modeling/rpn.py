@@ -1,0 +1,192 @@
+"""Region proposal network: head convs, on-device proposal generation, RPN losses.
+
+Mirrors maskrcnn_benchmark/modeling/rpn/{rpn,anchor_generator,inference,loss}.py for the
+single-level (C4) case; state-dict names ``rpn.head.{conv,cls_logits,bbox_pred}.{weight,bias}``
+and the buffer ``rpn.anchor_generator.cell_anchors.0`` are preserved.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from .. import ops
+from ..structures import BoxList
+from .backbone import Conv2dParams
+from .sampling import BELOW_LOW_THRESHOLD, BETWEEN_THRESHOLDS, balanced_sample
+
+
+def generate_cell_anchors(stride, sizes, aspect_ratios):
+    """The classic ratio-then-scale enumeration around the (0,0,stride-1,stride-1) window, float64 with
+    np.round, cast to float32 (rpn/anchor_generator.py:222-291)."""
+    scales = np.asarray(sizes, dtype=np.float64) / stride
+    ratios = np.asarray(aspect_ratios, dtype=np.float64)
+
+    def centre(box):
+        w, h = box[2] - box[0] + 1, box[3] - box[1] + 1
+        return w, h, box[0] + 0.5 * (w - 1), box[1] + 0.5 * (h - 1)
+
+    def windows(ws, hs, cx, cy):
+        ws, hs = ws.reshape(-1, 1), hs.reshape(-1, 1)
+        return np.hstack([cx - 0.5 * (ws - 1), cy - 0.5 * (hs - 1), cx + 0.5 * (ws - 1), cy + 0.5 * (hs - 1)])
+
+    w, h, cx, cy = centre(np.array([0, 0, stride - 1, stride - 1], dtype=np.float64))
+    ws = np.round(np.sqrt(w * h / ratios))
+    hs = np.round(ws * ratios)
+    out = []
+    for box in windows(ws, hs, cx, cy):
+        w, h, cx, cy = centre(box)
+        out.append(windows(w * scales, h * scales, cx, cy))
+    return torch.from_numpy(np.vstack(out)).float()
+
+
+class BufferList(nn.Module):
+    def __init__(self, buffers):
+        super().__init__()
+        for i, b in enumerate(buffers):
+            self.register_buffer(str(i), b)
+
+    def __iter__(self):
+        return iter(self._buffers.values())
+
+    def __len__(self):
+        return len(self._buffers)
+
+
+class AnchorGenerator(nn.Module):
+    """Single-level AnchorGenerator (anchor_generator.py:34-125).  The grid and its visibility mask are
+    produced by one kernel and cached per (feature size, image size) instead of being rebuilt from
+    arange/meshgrid/stack every iteration."""
+
+    def __init__(self, sizes, aspect_ratios, stride, straddle_thresh):
+        super().__init__()
+        self.stride = int(stride)
+        self.straddle_thresh = int(straddle_thresh)
+        self.cell_anchors = BufferList([generate_cell_anchors(self.stride, sizes, aspect_ratios)])
+        self._cache = {}
+
+    def num_anchors_per_location(self):
+        return [len(c) for c in self.cell_anchors]
+
+    def grid(self, fh, fw, img_w, img_h):
+        cell = next(iter(self.cell_anchors))
+        key = (fh, fw, img_w, img_h, cell.device, cell._version)
+        if key not in self._cache:
+            self._cache = {key: ops.anchor_grid(cell, fh, fw, self.stride, img_w, img_h, self.straddle_thresh)}
+        return self._cache[key]
+
+
+class RPNHead(nn.Module):
+    """3x3 conv + ReLU, then the two 1x1 predictors (rpn/rpn.py:13-46); outputs stay NHWC, which is
+    already the (h, w, anchor) order permute_and_flatten (rpn/utils.py:10-14) produces."""
+
+    def __init__(self, in_channels, num_anchors):
+        super().__init__()
+        self.conv = Conv2dParams(in_channels, in_channels, 3, 1, 1, bias=True)
+        self.cls_logits = Conv2dParams(in_channels, num_anchors, 1, bias=True)
+        self.bbox_pred = Conv2dParams(in_channels, num_anchors * 4, 1, bias=True)
+        for l in (self.conv, self.cls_logits, self.bbox_pred):
+            nn.init.normal_(l.weight, std=0.01)
+            nn.init.constant_(l.bias, 0)
+
+    def forward(self, feat):
+        t = ops.conv_bn_act(feat, self.conv.weight, None, self.conv.bias, pad=1, relu=True)
+        logits = ops.conv_bn_act(t, self.cls_logits.weight, None, self.cls_logits.bias)
+        deltas = ops.conv_bn_act(t, self.bbox_pred.weight, None, self.bbox_pred.bias)
+        return logits, deltas
+
+
+class RPNModule(nn.Module):
+    def __init__(self, cfg, rng):
+        super().__init__()
+        self.cfg = cfg.clone()
+        R = cfg.MODEL.RPN
+        if R.USE_FPN or len(R.ANCHOR_STRIDE) != 1:
+            raise NotImplementedError("multi-level RPN (FPN) is a 'next' row (SURVEY §8f)")
+        self.anchor_generator = AnchorGenerator(R.ANCHOR_SIZES, R.ASPECT_RATIOS, R.ANCHOR_STRIDE[0], R.STRADDLE_THRESH)
+        self.head = RPNHead(cfg.MODEL.BACKBONE.OUT_CHANNELS, self.anchor_generator.num_anchors_per_location()[0])
+        self.rng = rng
+
+    # ---- proposals (RPNPostProcessor, rpn/inference.py:76-152) -------------------------------------
+    @torch.no_grad()
+    def proposals(self, anchors, logits, deltas, image_sizes, targets):
+        R = self.cfg.MODEL.RPN
+        train = self.training
+        pre = R.PRE_NMS_TOP_N_TRAIN if train else R.PRE_NMS_TOP_N_TEST
+        post = R.POST_NMS_TOP_N_TRAIN if train else R.POST_NMS_TOP_N_TEST
+        n, fh, fw, a = logits.shape
+        k = min(pre, fh * fw * a)
+        sizes = set((int(h), int(w)) for h, w in image_sizes)
+        if len(sizes) != 1:
+            raise NotImplementedError("images of different un-padded sizes in one batch")
+        ih, iw = sizes.pop()
+        boxes, scores, _, valid = ops.rpn_topk_decode(logits, deltas, anchors, k, iw, ih, R.MIN_SIZE)
+        valid_h = valid.tolist()
+        pending = []
+        for i in range(n):
+            b = boxes[i, : valid_h[i]]
+            keep, cnt = ops.nms_sorted(b, R.NMS_THRESH, post) if R.NMS_THRESH > 0 else (None, None)
+            pending.append((b, scores[i, : valid_h[i]], keep.clone() if keep is not None else None, cnt))
+        counts = torch.cat([c for _, _, _, c in pending if c is not None]).tolist() if R.NMS_THRESH > 0 else []
+        out = []
+        for i, (b, s, keep, cnt) in enumerate(pending):
+            if keep is not None:
+                sel = keep[: counts[i]]
+                b, s = b[sel], s[sel]
+            bl = BoxList(b, (iw, ih), mode="xyxy")
+            bl.add_field("objectness", s)
+            out.append(bl)
+        if train and targets is not None:       # add_gt_proposals: source images only (:51-74)
+            for i, t in enumerate(targets):
+                if bool(t.get_field("is_source").any()):
+                    gt = t.bbox.to(out[i].bbox.dtype)
+                    bl = BoxList(torch.cat([out[i].bbox, gt]), out[i].size, mode="xyxy")
+                    bl.add_field("objectness", torch.cat([out[i].get_field("objectness"),
+                                                          torch.ones(len(gt), device=gt.device)]))
+                    out[i] = bl
+        return out
+
+    # ---- losses (RPNLossComputation, rpn/loss.py:57-143) -------------------------------------------
+    def losses(self, anchors, visibility, logits, deltas, targets):
+        R = self.cfg.MODEL.RPN
+        labels, reg_targets = [], []
+        vis = visibility.bool()
+        for t in targets:                                   # labels exist for source images only (:66-67)
+            if not bool(t.get_field("is_source").any()):
+                continue
+            gt = t.convert("xyxy").bbox
+            m, _ = ops.match(gt, anchors, R.FG_IOU_THRESHOLD, R.BG_IOU_THRESHOLD, True)
+            lab = (m >= 0).to(torch.float32)
+            lab[m == BELOW_LOW_THRESHOLD] = 0
+            lab[~vis] = -1
+            lab[m == BETWEEN_THRESHOLDS] = -1
+            labels.append(lab)
+            reg_targets.append(ops.box_encode(gt, anchors, m, (1.0, 1.0, 1.0, 1.0)))
+        pos_m, neg_m = balanced_sample(labels, R.BATCH_SIZE_PER_IMAGE, R.POSITIVE_FRACTION, self.rng)
+        pos = torch.nonzero(torch.cat(pos_m, dim=0)).squeeze(1)
+        neg = torch.nonzero(torch.cat(neg_m, dim=0)).squeeze(1)
+        sampled = torch.cat([pos, neg], dim=0)
+        obj = logits.reshape(-1)                             # (n, h, w, a) order == permute_and_flatten
+        reg = deltas.reshape(-1, 4)
+        labels = torch.cat(labels, dim=0)
+        reg_targets = torch.cat(reg_targets, dim=0)
+        box_loss = ops.smooth_l1_sum(reg[pos], reg_targets[pos], 1.0 / 9, float(sampled.numel()))
+        obj_loss = ops.bce_with_logits_mean(obj[sampled], labels[sampled])
+        self.last = dict(labels=labels, pos=pos, neg=neg, reg_targets=reg_targets)
+        return obj_loss, box_loss
+
+    def forward(self, images, features, targets=None):
+        feat = features[0]
+        logits, deltas = self.head(feat)
+        n, fh, fw, _ = feat.shape
+        ih, iw = images.image_sizes[0]
+        anchors, vis = self.anchor_generator.grid(fh, fw, int(iw), int(ih))
+        boxes = self.proposals(anchors, logits.detach(), deltas.detach(), images.image_sizes, targets)
+        if not self.training:
+            return boxes, {}
+        obj_loss, box_loss = self.losses(anchors, vis, logits, deltas, targets)
+        return boxes, {"loss_objectness": obj_loss, "loss_rpn_box_reg": box_loss}
+
+
+def build_rpn(cfg, rng):
+    if cfg.MODEL.RETINANET_ON:
+        raise NotImplementedError("RetinaNet is outside the accelerated path")
+    return RPNModule(cfg, rng)

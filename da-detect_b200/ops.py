@@ -1,0 +1,520 @@
+"""Operator layer: torch tensors in, C-ABI kernel launches on the current CUDA stream, torch tensors out.
+
+torch is plumbing here (device memory, streams, autograd bookkeeping); every arithmetic kernel is one
+of ours from libdadetect_b200.so.  Activations are NHWC (``[N, H, W, C]`` contiguous); convolution
+weights keep the reference's logical ``[Cout, Cin, KH, KW]`` shape (state-dict compatible) but are
+stored channels_last, i.e. physically OHWI, which is the layout the kernels consume.
+
+Each autograd Function fuses what the reference runs as several ATen kernels:
+  ConvBnAct       Conv2d + FrozenBatchNorm2d (+ residual add) (+ ReLU)   resnet.py:294-314, batch_norm.py:19-24
+  RoIAlign        layers/roi_align.py:11-44 -> _C.roi_align_forward/backward
+  GradientScalar  layers/gradient_scalar_layer.py:4-24
+  *Loss           rpn/loss.py:132-141, box_head/loss.py:200-219, da_heads/loss.py:140-222, consistency_loss.py
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+IMPL_SIMT = 0
+IMPL_TCGEN05 = 1
+_default_impl = IMPL_SIMT
+
+
+def set_default_impl(impl):
+    """Select the dense-tier arm used by conv2d/linear: IMPL_SIMT (fp32) or IMPL_TCGEN05 (TF32)."""
+    global _default_impl
+    _default_impl = int(impl)
+
+
+def get_default_impl():
+    return _default_impl
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype=torch.float32, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("dadetect_b200: {} must be a CUDA tensor — there is no CPU path".format(name))
+    if t.dtype != dtype:
+        raise RuntimeError("dadetect_b200: {} must be {}, got {}".format(name, dtype, t.dtype))
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16 != 0 and t.numel() > 0:
+        t = t.clone()
+    return t
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes, device, tag="ws"):
+    """Grow-only scratch buffer per (device, tag); reused across calls on the same stream."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def weight_ohwi(w):
+    """[Cout,Cin,KH,KW] (any strides) or [Cout,Cin] -> contiguous physical OHWI view (no copy when the
+    parameter is already channels_last)."""
+    if w.dim() == 2:
+        return w if w.is_contiguous() else w.contiguous()
+    return w.permute(0, 2, 3, 1).contiguous()
+
+
+def grad_like_weight(g_ohwi, w):
+    """physical OHWI gradient -> tensor with w's logical shape (channels_last strides for 4-D)."""
+    if w.dim() == 2:
+        return g_ohwi.view_as(w)
+    co, ci, kh, kw = w.shape
+    return g_ohwi.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+
+
+# ----------------------------------------------------------------------------------------- raw kernels
+def conv2d_forward_raw(x, w_ohwi, scale, bias, residual, kh, kw, stride, pad, relu, impl=None):
+    n, h, wd, cin = x.shape
+    cout = w_ohwi.shape[0]
+    oh = (h + 2 * pad - kh) // stride + 1
+    ow = (wd + 2 * pad - kw) // stride + 1
+    y = torch.empty((n, oh, ow, cout), dtype=torch.float32, device=x.device)
+    _lib.call("dd_conv2d_forward", _ptr(x), _ptr(w_ohwi), _ptr(scale), _ptr(bias), _ptr(residual), _ptr(y),
+              n, h, wd, cin, cout, kh, kw, stride, pad, 1 if relu else 0,
+              _default_impl if impl is None else impl, _stream())
+    return y
+
+
+def conv2d_dgrad_raw(gy, w_ohwi, scale, x_shape, kh, kw, stride, pad, addend=None, mask_act=None, impl=None):
+    n, h, wd, cin = x_shape
+    cout = w_ohwi.shape[0]
+    gx = torch.empty(x_shape, dtype=torch.float32, device=gy.device)
+    _lib.call("dd_conv2d_dgrad", _ptr(gy), _ptr(w_ohwi), _ptr(scale), _ptr(addend), _ptr(mask_act), _ptr(gx),
+              n, h, wd, cin, cout, kh, kw, stride, pad, _default_impl if impl is None else impl, _stream())
+    return gx
+
+
+def conv2d_wgrad_raw(gy, x, scale, cout, kh, kw, stride, pad, out=None, accumulate=False, impl=None):
+    n, h, wd, cin = x.shape
+    if out is None:
+        out = torch.empty((cout, kh, kw, cin), dtype=torch.float32, device=x.device)
+    nbytes = _lib.load().dd_conv2d_wgrad_workspace_bytes(n, h, wd, cin, cout, kh, kw, stride, pad)
+    ws = _workspace(nbytes, x.device, "wgrad")
+    _lib.call("dd_conv2d_wgrad", _ptr(gy), _ptr(x), _ptr(scale), _ptr(out), n, h, wd, cin, cout, kh, kw, stride, pad,
+              1 if accumulate else 0, _default_impl if impl is None else impl, _ptr(ws), _stream())
+    return out
+
+
+def bias_grad_raw(gy2d, c):
+    rows = gy2d.numel() // c
+    gb = torch.empty((c,), dtype=torch.float32, device=gy2d.device)
+    _lib.call("dd_bias_grad", _ptr(gy2d), _ptr(gb), rows, c, 0, _stream())
+    return gb
+
+
+def relu_backward_raw(g, act):
+    out = torch.empty_like(g)
+    _lib.call("dd_relu_backward", _ptr(g), _ptr(act), _ptr(out), g.numel(), _stream())
+    return out
+
+
+def nchw_to_nhwc(x):
+    x = _chk(x, name="input")
+    n, c, h, w = x.shape
+    y = torch.empty((n, h, w, c), dtype=torch.float32, device=x.device)
+    _lib.call("dd_nchw_to_nhwc", _ptr(x), _ptr(y), n, c, h, w, _stream())
+    return y
+
+
+def nhwc_to_nchw(x):
+    x = _chk(x, name="input")
+    n, h, w, c = x.shape
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    _lib.call("dd_nhwc_to_nchw", _ptr(x), _ptr(y), n, c, h, w, _stream())
+    return y
+
+
+def maxpool3x3s2(x):
+    n, h, w, c = x.shape
+    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.empty((n, oh, ow, c), dtype=torch.float32, device=x.device)
+    _lib.call("dd_maxpool3x3s2", _ptr(x), _ptr(y), n, h, w, c, _stream())
+    return y
+
+
+# ----------------------------------------------------------------------------------------- dense layers
+class _ConvBnAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, scale, bias, residual, stride, pad, relu):
+        x = _chk(x, name="x")
+        w = weight_ohwi(weight)
+        if weight.dim() == 4:
+            kh, kw = weight.shape[2], weight.shape[3]
+        else:
+            kh = kw = 1
+        residual = _chk(residual, name="residual")
+        y = conv2d_forward_raw(x, w, scale, bias, residual, kh, kw, stride, pad, relu)
+        ctx.save_for_backward(x, weight, scale, y if relu else None)
+        ctx.cfg = (kh, kw, stride, pad, relu, bias is not None, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, scale, y = ctx.saved_tensors
+        kh, kw, stride, pad, relu, has_bias, has_res = ctx.cfg
+        gy = _chk(gy, name="grad")
+        g = relu_backward_raw(gy, y) if relu else gy
+        w = weight_ohwi(weight)
+        gx = gw = gb = gres = None
+        if ctx.needs_input_grad[0]:
+            gx = conv2d_dgrad_raw(g, w, scale, tuple(x.shape), kh, kw, stride, pad)
+        if ctx.needs_input_grad[1]:
+            gw = grad_like_weight(conv2d_wgrad_raw(g, x, scale, w.shape[0], kh, kw, stride, pad), weight)
+        if has_bias and ctx.needs_input_grad[3]:
+            gb = bias_grad_raw(g, g.shape[-1])
+        if has_res and ctx.needs_input_grad[4]:
+            gres = g
+        return gx, gw, None, gb, gres, None, None, None
+
+
+def conv_bn_act(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0, relu=False):
+    """act(conv(x, weight) * scale + bias + residual); x NHWC, weight [Cout,Cin,KH,KW]."""
+    return _ConvBnAct.apply(x, weight, scale, bias, residual, stride, pad, relu)
+
+
+def linear(x, weight, bias=None, relu=False):
+    """F.linear (+ReLU) on [R, Cin] through the same implicit-GEMM kernels (a 1x1 conv on R 1x1 'images')."""
+    r, cin = x.shape
+    y = _ConvBnAct.apply(x.view(r, 1, 1, cin), weight, None, bias, None, 1, 0, relu)
+    return y.view(r, weight.shape[0])
+
+
+class _AvgPoolHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x, name="x")
+        k, h, w, c = x.shape
+        y = torch.empty((k, c), dtype=torch.float32, device=x.device)
+        _lib.call("dd_avgpool_forward", _ptr(x), _ptr(y), k, h * w, c, _stream())
+        ctx.shape = (k, h, w, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        k, h, w, c = ctx.shape
+        gy = _chk(gy, name="grad")
+        gx = torch.empty(ctx.shape, dtype=torch.float32, device=gy.device)
+        _lib.call("dd_avgpool_backward", _ptr(gy), _ptr(gx), k, h * w, c, _stream())
+        return gx
+
+
+def avgpool_hw(x):
+    """nn.AvgPool2d(7) on a [K,7,7,C] NHWC ROI feature -> [K,C]."""
+    return _AvgPoolHW.apply(x)
+
+
+class _RoIAlign(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, rois, spatial_scale, pooled, sampling_ratio, bin_step):
+        feat = _chk(feat, name="feat")
+        rois = _chk(rois, name="rois")
+        n, h, w, c = feat.shape
+        k = rois.shape[0]
+        o = (pooled + bin_step - 1) // bin_step
+        out = torch.empty((k, o, o, c), dtype=torch.float32, device=feat.device)
+        _lib.call("dd_roi_align_forward", _ptr(feat), _ptr(rois), _ptr(out), n, h, w, c, k, float(spatial_scale),
+                  pooled, pooled, sampling_ratio, bin_step, _stream())
+        ctx.save_for_backward(rois)
+        ctx.meta = (n, h, w, c, k, float(spatial_scale), pooled, sampling_ratio, bin_step)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (rois,) = ctx.saved_tensors
+        n, h, w, c, k, scale, pooled, sr, bin_step = ctx.meta
+        g = _chk(g, name="grad")
+        gfeat = torch.zeros((n, h, w, c), dtype=torch.float32, device=g.device)
+        _lib.call("dd_roi_align_backward", _ptr(g), _ptr(rois), _ptr(gfeat), n, h, w, c, k, scale, pooled, pooled, sr,
+                  bin_step, _stream())
+        return gfeat, None, None, None, None, None
+
+
+def roi_align(feat, rois, spatial_scale, pooled, sampling_ratio, bin_step=1):
+    """ROIAlign on an NHWC map; bin_step=2 returns only the even bins (see include/dadetect_b200.h)."""
+    return _RoIAlign.apply(feat, rois, spatial_scale, pooled, sampling_ratio, bin_step)
+
+
+class _GradientScalar(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        ctx.weight = float(weight)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _chk(g, name="grad")
+        out = torch.empty_like(g)
+        _lib.call("dd_grl_backward", _ptr(g), ctx.weight, _ptr(out), g.numel(), 0, _stream())
+        return out, None
+
+
+def gradient_scalar(x, weight):
+    return _GradientScalar.apply(x, weight)
+
+
+class _GradientScalarDev(torch.autograd.Function):
+    """GRL whose weight lives in a device float[1] that may be written AFTER the forward pass."""
+
+    @staticmethod
+    def forward(ctx, x, weight_dev):
+        ctx.weight_dev = weight_dev
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _chk(g, name="grad")
+        out = torch.empty_like(g)
+        _lib.call("dd_grl_backward_dev", _ptr(g), _ptr(ctx.weight_dev), _ptr(out), g.numel(), 0, _stream())
+        return out, None
+
+
+def gradient_scalar_dev(x, weight_dev):
+    return _GradientScalarDev.apply(x, weight_dev)
+
+
+def adv_grl_weight(loss, bce, lam, lam_adv, threshold, out=None):
+    """Device-side AdvGRL weight from a device loss scalar (no host sync)."""
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=loss.device)
+    _lib.call("dd_adv_grl_weight", _ptr(loss.detach().view(1)), float(bce), float(lam), float(lam_adv),
+              float(threshold), _ptr(out), _stream())
+    return out
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, keep):
+        x = _chk(x, name="x")
+        keep = _chk(keep, name="keep")
+        out = torch.empty_like(x)
+        _lib.call("dd_dropout_apply", _ptr(x), _ptr(keep), _ptr(out), x.numel(), _stream())
+        ctx.save_for_backward(keep)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (keep,) = ctx.saved_tensors
+        g = _chk(g, name="grad")
+        out = torch.empty_like(g)
+        _lib.call("dd_dropout_apply", _ptr(g), _ptr(keep), _ptr(out), g.numel(), _stream())
+        return out, None
+
+
+def dropout_with_mask(x, keep):
+    """F.dropout(p=0.5, training=True) with a caller-supplied {0,1} keep mask."""
+    return _Dropout.apply(x, keep)
+
+
+# ----------------------------------------------------------------------------------------- losses
+class _ScaledGradLoss(torch.autograd.Function):
+    """Common tail: forward computed (loss, grads) in one fused kernel; backward multiplies the stored
+    gradients by the upstream scalar without reading it on the host."""
+
+    @staticmethod
+    def forward(ctx, loss, n_inputs, *tensors):
+        inputs, grads = tensors[:n_inputs], tensors[n_inputs:]
+        ctx.save_for_backward(*grads)
+        ctx.n = n_inputs
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        outs = [None, None]
+        for i, gr in enumerate(ctx.saved_tensors):
+            outs.append(gr * g if ctx.needs_input_grad[2 + i] else None)
+        outs.extend([None] * ctx.n)
+        return tuple(outs)
+
+
+def _finish(loss, inputs, grads):
+    need = any(t.requires_grad for t in inputs)
+    if not need:
+        return loss.view(())
+    return _ScaledGradLoss.apply(loss, len(inputs), *inputs, *grads)
+
+
+def bce_with_logits_mean(x, targets=None, seg_labels=None, seg_len=0):
+    """mean BCE-with-logits; targets float tensor of x's shape, or per-segment uint8 labels."""
+    xc = _chk(x, name="logits").view(-1)
+    loss = torch.empty(1, dtype=torch.float32, device=x.device)
+    grad = torch.empty_like(xc)
+    t = _chk(targets, name="targets")
+    sl = _chk(seg_labels, torch.uint8, "seg_labels")
+    _lib.call("dd_bce_logits_mean", _ptr(xc), _ptr(t), _ptr(sl), int(seg_len), xc.numel(), _ptr(loss), _ptr(grad),
+              _stream())
+    return _finish(loss, (x,), (grad.view_as(x),))
+
+
+def softmax_ce_mean(logits, labels, row_mask):
+    lg = _chk(logits, name="logits")
+    rows, c = lg.shape
+    loss = torch.empty(1, dtype=torch.float32, device=lg.device)
+    grad = torch.empty_like(lg)
+    _lib.call("dd_softmax_ce_mean", _ptr(lg), _ptr(_chk(labels, torch.int64, "labels")),
+              _ptr(_chk(row_mask, torch.uint8, "row_mask")), rows, c, _ptr(loss), _ptr(grad), _stream())
+    return _finish(loss, (logits,), (grad,))
+
+
+def box_reg_loss(box_reg, reg_targets, labels, row_mask):
+    br = _chk(box_reg, name="box_regression")
+    rows, c4 = br.shape
+    loss = torch.empty(1, dtype=torch.float32, device=br.device)
+    grad = torch.empty_like(br)
+    _lib.call("dd_box_reg_loss", _ptr(br), _ptr(_chk(reg_targets, name="regression_targets")),
+              _ptr(_chk(labels, torch.int64, "labels")), _ptr(_chk(row_mask, torch.uint8, "row_mask")), rows, c4 // 4,
+              _ptr(loss), _ptr(grad), _stream())
+    return _finish(loss, (box_reg,), (grad,))
+
+
+def smooth_l1_sum(x, t, beta, divisor):
+    xc = _chk(x, name="x")
+    tc = _chk(t, name="t")
+    loss = torch.empty(1, dtype=torch.float32, device=x.device)
+    grad = torch.empty_like(xc)
+    _lib.call("dd_smooth_l1_sum", _ptr(xc), _ptr(tc), xc.numel(), float(beta), float(divisor), _ptr(loss), _ptr(grad),
+              _stream())
+    return _finish(loss, (x,), (grad,))
+
+
+def consistency_loss(img_logits, ins_logits, n_src):
+    """img_logits [2, hw] (any trailing shape), ins_logits [K] or [K,1]; sigmoid folded into the kernel."""
+    il = _chk(img_logits, name="img_logits")
+    sl = _chk(ins_logits, name="ins_logits")
+    if il.shape[0] != 2:
+        raise AssertionError("only batch size=2 is supported for consistency loss now, received batch size: {}".format(
+            il.shape[0]))
+    hw = il.numel() // 2
+    k = sl.numel()
+    loss = torch.empty(1, dtype=torch.float32, device=il.device)
+    gi, gs = torch.empty_like(il), torch.empty_like(sl)
+    ws = torch.empty(4, dtype=torch.float32, device=il.device)
+    _lib.call("dd_consistency_loss", _ptr(il), hw, _ptr(sl), k, int(n_src), _ptr(loss), _ptr(gi), _ptr(gs), _ptr(ws),
+              _stream())
+    return _finish(loss, (img_logits, ins_logits), (gi, gs))
+
+
+def triplet_margin_loss(a, p, n, margin, rows, d, inner):
+    """nn.TripletMarginLoss(margin, p=2) with the distance over `d` elements strided by `inner`."""
+    ac, pc, nc = _chk(a, name="anchor"), _chk(p, name="positive"), _chk(n, name="negative")
+    loss = torch.empty(1, dtype=torch.float32, device=ac.device)
+    need = a.requires_grad or p.requires_grad or n.requires_grad
+    ga = torch.empty_like(ac) if need else None
+    gp = torch.empty_like(pc) if need else None
+    gn = torch.empty_like(nc) if need else None
+    _lib.call("dd_triplet_margin_loss", _ptr(ac), _ptr(pc), _ptr(nc), int(rows), int(d), int(inner), float(margin),
+              _ptr(loss), _ptr(ga), _ptr(gp), _ptr(gn), _stream())
+    if not need:
+        return loss.view(())
+    return _ScaledGradLoss.apply(loss, 3, a, p, n, ga, gp, gn)
+
+
+# ----------------------------------------------------------------------------------------- detection ops
+def anchor_grid(cell_anchors, fh, fw, stride, img_w, img_h, straddle):
+    a = cell_anchors.shape[0]
+    anchors = torch.empty((fh * fw * a, 4), dtype=torch.float32, device=cell_anchors.device)
+    vis = torch.empty((fh * fw * a,), dtype=torch.uint8, device=cell_anchors.device)
+    _lib.call("dd_anchor_grid", _ptr(_chk(cell_anchors, name="cell_anchors")), a, fh, fw, int(stride), int(img_w),
+              int(img_h), int(straddle), _ptr(anchors), _ptr(vis), _stream())
+    return anchors, vis
+
+
+def rpn_topk_decode(logits, deltas, anchors, k, img_w, img_h, min_size):
+    """logits [N,FH,FW,A], deltas [N,FH,FW,4A] NHWC -> boxes [N,k,4], scores [N,k], idx [N,k], valid [N]."""
+    n, fh, fw, a = logits.shape
+    dev = logits.device
+    boxes = torch.empty((n, k, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((n, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+    valid = torch.empty((n,), dtype=torch.int32, device=dev)
+    _lib.call("dd_rpn_topk_decode", _ptr(_chk(logits, name="logits")), _ptr(_chk(deltas, name="deltas")),
+              _ptr(_chk(anchors, name="anchors")), n, fh, fw, a, int(k), int(img_w), int(img_h), float(min_size),
+              _ptr(boxes), _ptr(scores), _ptr(idx), _ptr(valid), None, _stream())
+    return boxes, scores, idx, valid
+
+
+def nms_sorted(boxes_sorted, thresh, max_keep=0):
+    """boxes sorted by descending score -> (keep positions int64 [n] buffer, device count int32[1])."""
+    b = _chk(boxes_sorted, name="boxes")
+    n = b.shape[0]
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=b.device)
+    count = torch.zeros((1,), dtype=torch.int32, device=b.device)
+    ws = _workspace(_lib.load().dd_nms_workspace_bytes(n), b.device, "nms")
+    _lib.call("dd_nms_sorted", _ptr(b), n, float(thresh), int(max_keep), _ptr(keep), _ptr(count), _ptr(ws), _stream())
+    return keep, count
+
+
+def nms(boxes, scores, thresh):
+    """`_C.nms` semantics (csrc/nms.h:10-28, GPU variant): kept original indices, ascending, int64."""
+    b = _chk(boxes, name="boxes")
+    s = _chk(scores, name="scores")
+    n = b.shape[0]
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=b.device)
+    keep = torch.empty((n,), dtype=torch.int64, device=b.device)
+    count = torch.zeros((1,), dtype=torch.int32, device=b.device)
+    ws = _workspace(_lib.load().dd_nms_workspace_bytes(n), b.device, "nms")
+    _lib.call("dd_nms", _ptr(b), _ptr(s), n, float(thresh), _ptr(keep), _ptr(count), _ptr(ws), _stream())
+    return keep[: int(count.item())]
+
+
+def match(gt, pred, high, low, allow_low_quality):
+    """Fused boxlist_iou + Matcher: int64 [N] with -1 (below low) / -2 (between) sentinels."""
+    g = _chk(gt, name="gt")
+    p = _chk(pred, name="pred")
+    m, n = g.shape[0], p.shape[0]
+    if m == 0:
+        raise ValueError("No ground-truth boxes available for one of the images during training")
+    if n == 0:
+        raise ValueError("No proposal boxes available for one of the images during training")
+    matches = torch.empty((n,), dtype=torch.int64, device=p.device)
+    vals = torch.empty((n,), dtype=torch.float32, device=p.device)
+    best = torch.empty((m,), dtype=torch.float32, device=p.device)
+    _lib.call("dd_match", _ptr(g), m, _ptr(p), n, float(high), float(low), 1 if allow_low_quality else 0,
+              _ptr(matches), _ptr(vals), _ptr(best), _stream())
+    return matches, vals
+
+
+def box_encode(gt, pred, matches, weights, wrap_negative=False):
+    g = _chk(gt, name="gt")
+    p = _chk(pred, name="pred")
+    out = torch.empty((p.shape[0], 4), dtype=torch.float32, device=p.device)
+    wx, wy, ww, wh = (float(v) for v in weights)
+    _lib.call("dd_box_encode", _ptr(g), g.shape[0], _ptr(p), _ptr(_chk(matches, torch.int64, "matches")), p.shape[0],
+              wx, wy, ww, wh, 1 if wrap_negative else 0, _ptr(out), _stream())
+    return out
+
+
+def box_decode(codes, boxes, weights):
+    c = _chk(codes, name="codes")
+    b = _chk(boxes, name="boxes")
+    r, k4 = c.shape
+    out = torch.empty_like(c)
+    wx, wy, ww, wh = (float(v) for v in weights)
+    _lib.call("dd_box_decode", _ptr(c), _ptr(b), r, k4 // 4, wx, wy, ww, wh, _ptr(out), _stream())
+    return out
+
+
+def sgd_momentum_(p, g, buf, lr, momentum, wd, grad_scale, first_step):
+    _lib.call("dd_sgd_momentum", _ptr(p), _ptr(g), _ptr(buf), p.numel(), float(lr), float(momentum), float(wd),
+              float(grad_scale), 1 if first_step else 0, _stream())

@@ -1,0 +1,192 @@
+/* dadetect_b200 — C ABI of the B200 (sm_100a) DA Faster R-CNN training hot path.
+ *
+ * Drop-in boundary: the reference reaches native code through the pybind
+ * module `maskrcnn_benchmark._C` (maskrcnn_benchmark/csrc/vision.cpp:7-15) and through
+ * ATen/cuDNN/cuBLAS library calls made by its Python layers.  This header is the C-ABI
+ * replacement for BOTH: every entry point takes plain device pointers, sizes and a CUDA
+ * stream (as void*), no torch types.  The Python binding (`da-detect_b200/_lib.py`, ctypes)
+ * and the `_C`-compatible shim (`da-detect_b200/_C.py`) sit on top; INTEGRATION.md shows the
+ * reference-side stub.
+ *
+ * Conventions
+ *   - all pointers are device pointers unless named h_*; float = IEEE fp32;
+ *   - activations are NHWC ([N][H][W][C], C fastest); conv weights are OHWI
+ *     ([Cout][KH][KW][Cin]); the *_nchw entry points accept the reference's NCHW layout;
+ *   - boxes are xyxy in pixels with the reference's inclusive "+1" width convention;
+ *   - every function returns 0 on success, otherwise a cudaError_t value (or -1 for an
+ *     argument error); dd_last_error() returns a static description of the last failure;
+ *   - work is enqueued on `stream` and is asynchronous w.r.t. the host unless stated.
+ */
+#ifndef DADETECT_B200_H_
+#define DADETECT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* dd_last_error(void);
+int dd_abi_version(void);
+/* number of kernels launched by this library since process start (bench.py's gpu_launches) */
+long long dd_launch_count(void);
+
+/* ---------------------------------------------------------------- maskrcnn_benchmark._C ops */
+
+/* Replaces ROIAlign_forward (csrc/ROIAlign.h:11-25 -> cuda/ROIAlign_cuda.cu:64-122,257-299).
+ * feat [N,H,W,C] NHWC, rois [K,5] = (batch_idx, x1, y1, x2, y2), out [K, PH/bin_step, PW/bin_step, C].
+ * bin_step = 1 is the reference op.  bin_step = 2 computes only the even (ph,pw) bins of the
+ * PH x PW bin geometry — exactly what res5's stride-2 1x1 convs consume. */
+int dd_roi_align_forward(const float* feat, const float* rois, float* out, int N, int H, int W, int C,
+                         int K, float spatial_scale, int PH, int PW, int sampling_ratio, int bin_step,
+                         void* stream);
+/* Replaces ROIAlign_backward (csrc/ROIAlign.h:27-45 -> cuda/ROIAlign_cuda.cu:177-254,302-346).
+ * grad_feat [N,H,W,C] must be zero-filled by the caller (as the reference does, :316) or hold a
+ * gradient to accumulate into. */
+int dd_roi_align_backward(const float* grad_out, const float* rois, float* grad_feat, int N, int H, int W,
+                          int C, int K, float spatial_scale, int PH, int PW, int sampling_ratio,
+                          int bin_step, void* stream);
+/* NCHW wrappers with the reference's exact tensor layout ([N,C,H,W] in, [K,C,PH,PW] out). */
+int dd_roi_align_forward_nchw(const float* feat, const float* rois, float* out, int N, int C, int H, int W,
+                              int K, float spatial_scale, int PH, int PW, int sampling_ratio, void* stream);
+int dd_roi_align_backward_nchw(const float* grad_out, const float* rois, float* grad_feat, int N, int C,
+                               int H, int W, int K, float spatial_scale, int PH, int PW, int sampling_ratio,
+                               void* stream);
+
+/* Replaces nms (csrc/nms.h:10-28 -> cuda/nms.cu:70-131), GPU semantics: suppress when IoU > thresh.
+ * boxes [n,4], scores [n] in ANY order; keep_out int64[n] receives the kept ORIGINAL indices in
+ * ascending order, *keep_count (device int) their number.  Entirely on device: no D2H mask copy,
+ * no host scan.  n <= 16384.  workspace: dd_nms_workspace_bytes(n) bytes. */
+size_t dd_nms_workspace_bytes(int n);
+int dd_nms(const float* boxes, const float* scores, int n, float thresh, int64_t* keep_out, int* keep_count,
+           void* workspace, void* stream);
+/* Same, for boxes already sorted by descending score (the RPN path): keep_out holds positions in
+ * that order (ascending).  max_keep > 0 stops after that many kept boxes — identical to
+ * boxlist_nms(max_proposals) (structures/boxlist_ops.py:30-33) because positions ARE score order. */
+int dd_nms_sorted(const float* boxes_sorted, int n, float thresh, int max_keep, int64_t* keep_out,
+                  int* keep_count, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------- RPN proposal generation */
+
+/* AnchorGenerator.grid_anchors + add_visibility_to (rpn/anchor_generator.py:73-111):
+ * anchors [FH*FW*A,4] in (y, x, a) order, visibility uint8. */
+int dd_anchor_grid(const float* cell_anchors, int A, int FH, int FW, int stride, int img_w, int img_h,
+                   int straddle_thresh, float* anchors, uint8_t* visibility, void* stream);
+/* RPNPostProcessor.forward_for_single_feature_map up to (not including) NMS
+ * (rpn/inference.py:87-115): per image sigmoid -> top-k (sorted, ties by lower index) ->
+ * gather deltas+anchors -> BoxCoder.decode(1,1,1,1) -> clip_to_image -> small-box filter.
+ * logits [N,FH,FW,A] NHWC, deltas [N,FH,FW,4A]; boxes [N,k,4], scores [N,k], topk_idx int32[N,k];
+ * valid[N] = boxes surviving the min_size filter (compacted to the front, order preserved).
+ * k <= 16384.  workspace: dd_rpn_topk_workspace_bytes(N, FH*FW*A). */
+size_t dd_rpn_topk_workspace_bytes(int N, int num_anchors);
+int dd_rpn_topk_decode(const float* logits, const float* deltas, const float* anchors, int N, int FH, int FW,
+                       int A, int k, int img_w, int img_h, float min_size, float* boxes, float* scores,
+                       int32_t* topk_idx, int32_t* valid, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------- matching / box coding */
+
+/* boxlist_iou + Matcher (structures/boxlist_ops.py:56-91, modeling/matcher.py:42-112) fused: never
+ * materialises the [M,N] matrix.  gt [M,4], pred [N,4]; matches int64[N] in {-2,-1,0..M-1};
+ * matched_vals float[N] (may be NULL).  gt_best is workspace float[M]. */
+int dd_match(const float* gt, int M, const float* pred, int N, float high, float low, int allow_low_quality,
+             int64_t* matches, float* matched_vals, float* gt_best, void* stream);
+/* BoxCoder.encode (box_coder.py:22-50) of gt[matches[i] clamped at 0] against pred[i];
+ * wrap_negative != 0 reproduces the reference's negative-index wrap for target images
+ * (box_head/loss.py:47-51). */
+int dd_box_encode(const float* gt, int M, const float* pred, const int64_t* matches, int N, float wx, float wy,
+                  float ww, float wh, int wrap_negative, float* targets, void* stream);
+/* BoxCoder.decode (box_coder.py:52-95) for codes [R, 4*k] against boxes [R,4]. */
+int dd_box_decode(const float* codes, const float* boxes, int R, int k, float wx, float wy, float ww, float wh,
+                  float* out, void* stream);
+
+/* ---------------------------------------------------------------- dense layers (implicit GEMM) */
+
+/* impl: 0 = fp32 SIMT tiles (bit-faithful fp32 accumulate), 1 = tcgen05 TF32 (TMA-staged, TMEM accum). */
+#define DD_IMPL_SIMT 0
+#define DD_IMPL_TCGEN05 1
+#define DD_ACT_NONE 0
+#define DD_ACT_RELU 1
+
+/* y = act( conv(x, w) * scale[co] + bias[co] + residual ).  Conv2d + FrozenBatchNorm2d (+ residual
+ * add + ReLU) of resnet.py:294-314 / batch_norm.py:19-24 in one kernel; scale/bias/residual may be
+ * NULL.  x [N,H,W,Cin], w [Cout,KH,KW,Cin], y [N,OH,OW,Cout], OH = (H+2p-KH)/s+1. */
+int dd_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias,
+                      const float* residual, float* y, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                      int stride, int pad, int act, int impl, void* stream);
+/* gx = conv_transpose(gy, w * scale[co]) (+ addend) (* (mask_act > 0) if mask_act).  gx [N,H,W,Cin]
+ * is fully written (positions a strided conv never read receive addend or 0). */
+int dd_conv2d_dgrad(const float* gy, const float* w, const float* scale, const float* addend,
+                    const float* mask_act, float* gx, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                    int stride, int pad, int impl, void* stream);
+/* gw[co,kh,kw,ci] (+)= scale[co] * sum_{n,oh,ow} gy[n,oh,ow,co] * x[n,oh*s+kh-p,ow*s+kw-p,ci].
+ * workspace: dd_conv2d_wgrad_workspace_bytes(...) (split-K partials). */
+size_t dd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
+int dd_conv2d_wgrad(const float* gy, const float* x, const float* scale, float* gw, int N, int H, int W, int Cin,
+                    int Cout, int KH, int KW, int stride, int pad, int accumulate, int impl, void* workspace,
+                    void* stream);
+/* gb[c] (+)= sum over rows of gy [rows, C]. */
+int dd_bias_grad(const float* gy, float* gb, int rows, int C, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------- pooling / elementwise */
+int dd_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W, void* stream);
+int dd_nhwc_to_nchw(const float* x, float* y, int N, int C, int H, int W, void* stream);
+/* F.max_pool2d(k=3, s=2, p=1) of the stem (resnet.py:335), NHWC; forward only (stem is frozen). */
+int dd_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, void* stream);
+/* nn.AvgPool2d(7) on [K,HW,C] -> [K,C] and its backward. */
+int dd_avgpool_forward(const float* x, float* y, int K, int HW, int C, void* stream);
+int dd_avgpool_backward(const float* gy, float* gx, int K, int HW, int C, void* stream);
+/* out = g * (act > 0 ? 1 : 0); ReLU backward applied to a gradient that fans in from several consumers. */
+int dd_relu_backward(const float* g, const float* act, float* out, long long n, void* stream);
+/* GradientScalarLayer backward (layers/gradient_scalar_layer.py:11-13): out = w * g (no clone);
+ * accumulate != 0: out += w * g. */
+int dd_grl_backward(const float* g, float w, float* out, long long n, int accumulate, void* stream);
+/* Same with the weight read from device memory at execution time (AdvGRL: the weight depends on a loss
+ * value that is never brought to the host). */
+int dd_grl_backward_dev(const float* g, const float* w_dev, float* out, long long n, int accumulate, void* stream);
+/* AdvGRL weight (da_heads/da_heads.py:173-195; intent per README of the reference):
+ * *w_out = (*loss <= bce) ? -lam_adv * min(threshold, 1 / *loss) : -lam.  loss, w_out: device float[1]. */
+int dd_adv_grl_weight(const float* loss, float bce, float lam, float lam_adv, float threshold, float* w_out,
+                      void* stream);
+/* x * keep * 2 (F.dropout p=0.5 with a caller-supplied keep mask, da_heads.py:63,65); same op is its backward. */
+int dd_dropout_apply(const float* x, const float* keep, float* out, long long n, void* stream);
+
+/* ---------------------------------------------------------------- losses (fused forward + gradient) */
+
+/* F.binary_cross_entropy_with_logits(x, t) mean over n.  Targets: `targets` float[n] if non-NULL, else
+ * segment labels: element i belongs to segment i / seg_len and takes seg_labels[segment] (uint8) — the
+ * per-image domain label of da_heads/loss.py:153-167.  loss: device float[1]; grad float[n] = dL/dx. */
+int dd_bce_logits_mean(const float* x, const float* targets, const uint8_t* seg_labels, long long seg_len,
+                       long long n, float* loss, float* grad, void* stream);
+/* F.cross_entropy(logits[rows,C], labels) mean over rows with row_mask != 0 (box_head/loss.py:193-200).
+ * grad [rows,C] (zero for masked-out rows). */
+int dd_softmax_ce_mean(const float* logits, const int64_t* labels, const uint8_t* row_mask, int rows, int C,
+                       float* loss, float* grad, void* stream);
+/* smooth_l1_loss(x, t, beta, size_average=False) / divisor (layers/smooth_l1_loss.py:6-16). */
+int dd_smooth_l1_sum(const float* x, const float* t, long long n, float beta, float divisor, float* loss,
+                     float* grad, void* stream);
+/* Box-head regression loss (box_head/loss.py:202-219): for rows with mask && label>0 gathers the 4
+ * columns 4*label..4*label+3 of box_reg [rows, 4*C], smooth-L1(beta=1) sum / (#masked rows). */
+int dd_box_reg_loss(const float* box_reg, const float* reg_targets, const int64_t* labels, const uint8_t* row_mask,
+                    int rows, int C, float* loss, float* grad, void* stream);
+/* consistency_loss (layers/consistency_loss.py:3-27) on LOGITS: img_logits [2, hw], ins_logits [K];
+ * first n_src ROIs belong to image 0.  Returns loss and gradients w.r.t. both logit tensors
+ * (sigmoid folded in). */
+int dd_consistency_loss(const float* img_logits, long long hw, const float* ins_logits, int K, int n_src,
+                        float* loss, float* grad_img, float* grad_ins, float* workspace2, void* stream);
+/* nn.TripletMarginLoss(margin, p=2) (da_heads/loss.py:198-200): a,p,n [rows, D] with the norm over D
+ * computed on rows gathered with element stride `inner` (NHWC feature maps: D = W taken with stride C);
+ * see SURVEY §2.3/§9.8.  rows = number of distance vectors.  Layout: element (r, d) of a tensor lives at
+ * base[(r / inner) * D * inner + d * inner + (r % inner)].  grads may be NULL. */
+int dd_triplet_margin_loss(const float* a, const float* p, const float* n, long long rows, int D, long long inner,
+                           float margin, float* loss, float* grad_a, float* grad_p, float* grad_n, void* stream);
+
+/* ---------------------------------------------------------------- optimiser */
+/* torch.optim.SGD step over a flat segment: g' = g*grad_scale + wd*p; buf = momentum*buf + g'; p -= lr*buf
+ * (solver/build.py:7-20; first step semantics buf = g' selected by first_step != 0). */
+int dd_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, float wd,
+                    float grad_scale, int first_step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DADETECT_B200_H_ */

@@ -1,0 +1,446 @@
+"""GPU parity tests: every C-ABI kernel against the CPU oracle (oracle/da_frcnn_ref.py, pinned to the
+reference by tests/test_oracle_pins.py) or a plain torch fp32 CPU reference for the dense ops.
+Bit-exact for anchors / indices / match labels / NMS keep lists; stated tolerances for fp32 math."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import da_frcnn_ref as orc
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def ops():
+    from dadetect_b200 import ops as o
+    return o
+
+
+def rand_boxes(g, n, w, h, min_size=4.0):
+    x1 = torch.rand(n, generator=g) * w * 0.8
+    y1 = torch.rand(n, generator=g) * h * 0.8
+    bw = min_size + torch.rand(n, generator=g) * w * 0.4
+    bh = min_size + torch.rand(n, generator=g) * h * 0.4
+    return torch.stack([x1, y1, (x1 + bw).clamp(max=w - 1), (y1 + bh).clamp(max=h - 1)], 1)
+
+
+# ------------------------------------------------------------------------------ ROIAlign
+@pytest.mark.parametrize("sampling_ratio", [0, 2])
+@pytest.mark.parametrize("channels", [8, 6])
+def test_roi_align_forward_backward(sampling_ratio, channels):
+    g = torch.Generator().manual_seed(1)
+    feat = torch.randn(2, channels, 12, 20, generator=g)
+    rois = torch.cat([torch.randint(0, 2, (40, 1), generator=g).float(), rand_boxes(g, 40, 320, 192)], 1)
+    rois[0, 1:] = torch.tensor([-40.0, -30.0, 500.0, 400.0])
+    rois[1, 1:] = torch.tensor([50.0, 60.0, 50.2, 60.1])
+    go = torch.randn(40, channels, 14, 14, generator=g)
+    fr = feat.clone().requires_grad_(True)
+    want = orc.roi_align(fr, rois, 1 / 16, 14, 14, sampling_ratio)
+    (gwant,) = torch.autograd.grad(want, fr, go)
+
+    fd = feat.permute(0, 2, 3, 1).contiguous().to(DEV).requires_grad_(True)
+    got = ops().roi_align(fd, rois.to(DEV), 1 / 16, 14, sampling_ratio, 1)
+    (ggot,) = torch.autograd.grad(got, fd, go.permute(0, 2, 3, 1).contiguous().to(DEV))
+    torch.testing.assert_close(got.permute(0, 3, 1, 2).cpu(), want, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(ggot.permute(0, 3, 1, 2).cpu(), gwant, atol=1e-5, rtol=1e-4)
+
+    # even-bin variant == the even bins of the full op (what res5's stride-2 1x1 convs read)
+    got2 = ops().roi_align(fd, rois.to(DEV), 1 / 16, 14, sampling_ratio, 2)
+    assert torch.equal(got2, got[:, ::2, ::2, :])
+    go2 = torch.zeros_like(go)
+    go2[:, :, ::2, ::2] = go[:, :, ::2, ::2]
+    (gwant2,) = torch.autograd.grad(want, fr, go2)
+    (ggot2,) = torch.autograd.grad(got2, fd, go[:, :, ::2, ::2].permute(0, 2, 3, 1).contiguous().to(DEV))
+    torch.testing.assert_close(ggot2.permute(0, 3, 1, 2).cpu(), gwant2, atol=1e-5, rtol=1e-4)
+
+
+def test_roi_align_nchw_c_abi_matches_reference_layout(golden_dir):
+    """The `_C.roi_align_forward/backward` boundary: NCHW in, [K,C,PH,PW] out (csrc/ROIAlign.h:11-45),
+    checked against outputs of the reference's own compiled CPU kernel (tests/golden/ref_ops.pt)."""
+    from dadetect_b200 import _C
+    o = torch.load(os.path.join(golden_dir, "ref_ops.pt"), weights_only=False)
+    feat, rois = o["ra_feat"].to(DEV), o["ra_rois"].to(DEV)
+    torch.testing.assert_close(_C.roi_align_forward(feat, rois, 1 / 16, 14, 14, 0).cpu(), o["ra_out_s0"],
+                               atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(_C.roi_align_forward(feat, rois, 1 / 16, 7, 7, 2).cpu(), o["ra_out_s2"],
+                               atol=1e-5, rtol=1e-5)
+    g = torch.randn(rois.shape[0], feat.shape[1], 7, 7, generator=torch.Generator().manual_seed(2))
+    fr = o["ra_feat"].clone().requires_grad_(True)
+    (want,) = torch.autograd.grad(orc.roi_align(fr, o["ra_rois"], 1 / 16, 7, 7, 2), fr, g)
+    got = _C.roi_align_backward(g.to(DEV), rois, 1 / 16, 7, 7, feat.shape[0], feat.shape[1], feat.shape[2],
+                                feat.shape[3], 2)
+    torch.testing.assert_close(got.cpu(), want, atol=1e-5, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------ NMS
+def test_nms_reference_kats(golden_dir):
+    k = torch.load(os.path.join(golden_dir, "ref_kats.pt"), weights_only=False)
+    for thr, want in zip(k["nms5_thresh"], k["nms5_keep"]):
+        got = ops().nms(k["nms5_boxes"].to(DEV), k["nms5_scores"].to(DEV), thr)
+        assert got.cpu().tolist() == sorted(want)
+    got = ops().nms(k["nms53_boxes"].to(DEV), k["nms53_scores"].to(DEV), 0.5)
+    assert got.cpu().tolist() == k["nms53_keep"].tolist()
+
+
+@pytest.mark.parametrize("n,thr", [(1, 0.5), (63, 0.3), (64, 0.5), (65, 0.7), (3000, 0.7), (12000, 0.7)])
+def test_nms_matches_oracle_bit_exact(n, thr):
+    g = torch.Generator().manual_seed(n)
+    boxes = rand_boxes(g, n, 2048, 1024, 8.0)
+    if n > 100:      # cluster boxes so that a realistic fraction is suppressed
+        centers = rand_boxes(g, 40, 2048, 1024, 30.0)
+        boxes = centers[torch.randint(0, 40, (n,), generator=g)] + torch.randn(n, 4, generator=g) * 6
+        boxes[:, 2:] = torch.maximum(boxes[:, 2:], boxes[:, :2] + 1)
+    scores = torch.rand(n, generator=g)
+    want = orc.nms(boxes, scores, thr, strict=True)
+    got = ops().nms(boxes.to(DEV), scores.to(DEV), thr)
+    assert torch.equal(got.cpu(), want)
+    # sorted-input variant with early exit == boxlist_nms(max_proposals) (boxlist_ops.py:30-33)
+    order = torch.sort(scores, descending=True, stable=True)[1]
+    keep, cnt = ops().nms_sorted(boxes[order].contiguous().to(DEV), thr, 50)
+    kept = order[keep[: int(cnt.item())].cpu()]
+    want_first = order[torch.isin(order, want)][:50]
+    assert torch.equal(kept, want_first)
+
+
+def test_nms_empty():
+    got = ops().nms(torch.zeros(0, 4, device=DEV), torch.zeros(0, device=DEV), 0.5)
+    assert got.numel() == 0 and got.dtype == torch.int64
+
+
+# ------------------------------------------------------------------------------ anchors / proposals
+def test_anchor_grid_exact():
+    cell = orc.cell_anchors(16, (32, 64, 128, 256, 512), (0.5, 1.0, 2.0))
+    for fh, fw, iw, ih in ((12, 20, 320, 192), (64, 128, 2048, 1024)):
+        want = orc.grid_anchors(fh, fw, 16, cell)
+        vis = orc.anchor_visibility(want, iw, ih, 0)
+        a, v = ops().anchor_grid(cell.to(DEV), fh, fw, 16, iw, ih, 0)
+        assert torch.equal(a.cpu(), want)
+        assert torch.equal(v.cpu().bool(), vis)
+
+
+@pytest.mark.parametrize("fh,fw,k", [(12, 20, 2000), (64, 128, 12000), (5, 7, 525)])
+def test_rpn_topk_decode(fh, fw, k):
+    g = torch.Generator().manual_seed(fh * fw)
+    a = 15
+    n = 2
+    logits = torch.randn(n, a, fh, fw, generator=g) * 2
+    deltas = torch.randn(n, 4 * a, fh, fw, generator=g) * 0.5
+    deltas[0, 2] = 6.0          # exercises the log(1000/16) clamp on dw
+    cell = orc.cell_anchors(16, (32, 64, 128, 256, 512), (0.5, 1.0, 2.0))
+    anchors = orc.grid_anchors(fh, fw, 16, cell)
+    iw, ih = fw * 16, fh * 16
+    obj = orc.permute_and_flatten(logits, n, 1, fh, fw).view(n, -1)
+    reg = orc.permute_and_flatten(deltas, n, 4, fh, fw)
+    k = min(k, a * fh * fw)
+    sc_want, idx_want = obj.sigmoid().topk(k, dim=1, sorted=True)
+    boxes, scores, idx, valid = ops().rpn_topk_decode(logits.permute(0, 2, 3, 1).contiguous().to(DEV),
+                                                      deltas.permute(0, 2, 3, 1).contiguous().to(DEV),
+                                                      anchors.to(DEV), k, iw, ih, 0)
+    assert valid.cpu().tolist() == [k, k]
+    assert torch.equal(idx.cpu().long(), idx_want)            # no ties in the random logits
+    torch.testing.assert_close(scores.cpu(), sc_want, atol=1e-6, rtol=1e-6)
+    for i in range(n):
+        want = orc.clip_boxes(orc.box_decode(reg[i][idx_want[i]], anchors[idx_want[i]], (1.0, 1.0, 1.0, 1.0)), iw, ih)
+        torch.testing.assert_close(boxes[i].cpu(), want, atol=2e-3, rtol=1e-5)
+
+
+def test_rpn_topk_ties_take_lowest_index_and_min_size_filter():
+    fh, fw, a = 4, 4, 3
+    logits = torch.zeros(1, fh, fw, a)
+    logits[0, 1, 1, 1] = 3.0
+    deltas = torch.zeros(1, fh, fw, 4 * a)
+    anchors = orc.grid_anchors(fh, fw, 16, orc.cell_anchors(16, (32, 64, 128), (1.0,)))
+    boxes, scores, idx, valid = ops().rpn_topk_decode(logits.to(DEV), deltas.to(DEV), anchors.to(DEV), 10, 64, 64, 0)
+    assert idx[0].cpu().tolist() == [(1 * fw + 1) * a + 1] + list(range(9))
+    _, _, _, valid2 = ops().rpn_topk_decode(logits.to(DEV), deltas.to(DEV), anchors.to(DEV), 10, 64, 64, 1000.0)
+    assert valid2.cpu().tolist() == [0]
+
+
+# ------------------------------------------------------------------------------ matcher / coder
+@pytest.mark.parametrize("m,n", [(1, 5), (7, 300), (20, 122880)])
+def test_match_bit_exact(m, n):
+    g = torch.Generator().manual_seed(m * 1000 + n)
+    gt = rand_boxes(g, m, 2048, 1024, 16.0).floor()
+    if n == 122880:
+        pred = orc.grid_anchors(64, 128, 16, orc.cell_anchors(16, (32, 64, 128, 256, 512), (0.5, 1.0, 2.0)))
+    else:
+        pred = rand_boxes(g, n, 2048, 1024)
+        pred[: min(m, n)] = gt[: min(m, n)] + 0.25
+    iou = orc.box_iou(gt, pred)
+    for hi, lo, lq in ((0.7, 0.3, True), (0.5, 0.5, False)):
+        want = orc.matcher(iou.clone(), hi, lo, lq)
+        got, vals = ops().match(gt.to(DEV), pred.to(DEV), hi, lo, lq)
+        assert torch.equal(got.cpu(), want)
+        assert torch.equal(vals.cpu(), iou.max(dim=0)[0])
+
+
+def test_match_raises_on_empty():
+    with pytest.raises(ValueError):
+        ops().match(torch.zeros(0, 4, device=DEV), torch.zeros(3, 4, device=DEV), 0.5, 0.5, False)
+    with pytest.raises(ValueError):
+        ops().match(torch.zeros(3, 4, device=DEV), torch.zeros(0, 4, device=DEV), 0.5, 0.5, False)
+
+
+def test_box_encode_decode():
+    g = torch.Generator().manual_seed(9)
+    gt, pred = rand_boxes(g, 7, 320, 192), rand_boxes(g, 300, 320, 192)
+    matches = torch.randint(-2, 7, (300,), generator=g)
+    for wts in ((1.0, 1.0, 1.0, 1.0), (10.0, 10.0, 5.0, 5.0)):
+        want = orc.box_encode(gt[matches.clamp(min=0)], pred, wts)
+        got = ops().box_encode(gt.to(DEV), pred.to(DEV), matches.to(DEV), wts)
+        torch.testing.assert_close(got.cpu(), want, atol=1e-5, rtol=1e-5)
+        want_wrap = orc.box_encode(gt[matches], pred, wts)
+        got_wrap = ops().box_encode(gt.to(DEV), pred.to(DEV), matches.to(DEV), wts, wrap_negative=True)
+        torch.testing.assert_close(got_wrap.cpu(), want_wrap, atol=1e-5, rtol=1e-5)
+        codes = torch.randn(300, 36, generator=g)
+        want_d = orc.box_decode(codes, pred, wts)
+        got_d = ops().box_decode(codes.to(DEV), pred.to(DEV), wts)
+        torch.testing.assert_close(got_d.cpu(), want_d, atol=1e-3, rtol=1e-5)
+
+
+def test_box_decode_reference_kat(golden_dir):
+    k = torch.load(os.path.join(golden_dir, "ref_kats.pt"), weights_only=False)
+    got = ops().box_decode(k["coder_deltas"].to(DEV), k["coder_boxes"].to(DEV), (1.0, 1.0, 1.0, 1.0))
+    torch.testing.assert_close(got.cpu(), k["coder_decoded"], atol=1e-4, rtol=0)
+
+
+# ------------------------------------------------------------------------------ dense tier
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, pad
+    (2, 16, 24, 64, 64, 1, 1, 0),
+    (2, 16, 24, 64, 128, 1, 2, 0),
+    (1, 15, 23, 32, 48, 3, 1, 1),
+    (2, 32, 40, 3, 64, 7, 2, 3),
+    (3, 7, 7, 128, 256, 3, 1, 1),
+    (2, 8, 12, 256, 15, 1, 1, 0),
+    (2, 8, 12, 64, 1, 1, 1, 0),
+    (1, 9, 11, 16, 20, 3, 2, 1),
+]
+
+
+def _to_nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_forward_dgrad_wgrad_simt(case):
+    n, h, w, cin, cout, k, stride, pad = case
+    o = ops()
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    scale = 0.5 + torch.rand(cout, generator=g)
+    bias = torch.randn(cout, generator=g) * 0.1
+    xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    y0 = F.conv2d(xr, wr, stride=stride, padding=pad) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    res = torch.randn(y0.shape, generator=g)
+    want = F.relu(y0 + res)
+    go = torch.randn(want.shape, generator=g)
+    gx_want, gw_want = torch.autograd.grad(want, (xr, wr), go)
+
+    xd = _to_nhwc(x).to(DEV)
+    wd = wt.permute(0, 2, 3, 1).contiguous().to(DEV)
+    sd, bd, rd = scale.to(DEV), bias.to(DEV), _to_nhwc(res).to(DEV)
+    got = o.conv2d_forward_raw(xd, wd, sd, bd, rd, k, k, stride, pad, True, impl=o.IMPL_SIMT)
+    torch.testing.assert_close(got.permute(0, 3, 1, 2).cpu(), want, atol=2e-5, rtol=1e-4)
+    gpre = o.relu_backward_raw(_to_nhwc(go).to(DEV), got)
+    gx = o.conv2d_dgrad_raw(gpre, wd, sd, tuple(xd.shape), k, k, stride, pad, impl=o.IMPL_SIMT)
+    torch.testing.assert_close(gx.permute(0, 3, 1, 2).cpu(), gx_want, atol=2e-5, rtol=1e-4)
+    if cin % 4 == 0:
+        gw = o.conv2d_wgrad_raw(gpre, xd, sd, cout, k, k, stride, pad, impl=o.IMPL_SIMT)
+        torch.testing.assert_close(gw.permute(0, 3, 1, 2).cpu(), gw_want, atol=1e-4, rtol=1e-4)
+    # fused dgrad epilogue: (acc + addend) * (mask_act > 0)
+    addend = torch.randn(x.shape, generator=g)
+    act = torch.randn(x.shape, generator=g)
+    gx2 = o.conv2d_dgrad_raw(gpre, wd, sd, tuple(xd.shape), k, k, stride, pad, addend=_to_nhwc(addend).to(DEV),
+                             mask_act=_to_nhwc(act).to(DEV), impl=o.IMPL_SIMT)
+    torch.testing.assert_close(gx2.permute(0, 3, 1, 2).cpu(), (gx_want + addend) * (act > 0), atol=2e-5, rtol=1e-4)
+
+
+def test_conv_autograd_function_and_linear():
+    o = ops()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 32, 10, 12, generator=g)
+    wt = torch.randn(48, 32, 3, 3, generator=g) * 0.05
+    b = torch.randn(48, generator=g) * 0.1
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, wt, b))
+    want = F.relu(F.conv2d(xr, wr, br, padding=1))
+    go = torch.randn(want.shape, generator=g)
+    gw = torch.autograd.grad(want, (xr, wr, br), go)
+    xd = _to_nhwc(x).to(DEV).requires_grad_(True)
+    wd = wt.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    bd = b.to(DEV).requires_grad_(True)
+    got = o.conv_bn_act(xd, wd, None, bd, pad=1, relu=True)
+    gg = torch.autograd.grad(got, (xd, wd, bd), _to_nhwc(go).to(DEV))
+    torch.testing.assert_close(got.permute(0, 3, 1, 2).cpu(), want, atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(gg[0].permute(0, 3, 1, 2).cpu(), gw[0], atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(gg[1].cpu(), gw[1], atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(gg[2].cpu(), gw[2], atol=1e-4, rtol=1e-4)
+
+    xl = torch.randn(37, 64, generator=g)
+    wl = torch.randn(9, 64, generator=g) * 0.1
+    bl = torch.randn(9, generator=g)
+    xlr, wlr, blr = (t.clone().requires_grad_(True) for t in (xl, wl, bl))
+    want = F.linear(xlr, wlr, blr)
+    go = torch.randn(want.shape, generator=g)
+    gw = torch.autograd.grad(want, (xlr, wlr, blr), go)
+    xld, wld, bld = (t.to(DEV).requires_grad_(True) for t in (xl, wl, bl))
+    got = o.linear(xld, wld, bld)
+    gg = torch.autograd.grad(got, (xld, wld, bld), go.to(DEV))
+    torch.testing.assert_close(got.cpu(), want, atol=2e-5, rtol=1e-4)
+    for a, b_ in zip(gg, gw):
+        torch.testing.assert_close(a.cpu(), b_, atol=1e-4, rtol=1e-4)
+
+
+def test_pooling_and_layout():
+    o = ops()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 64, 17, 22, generator=g)
+    torch.testing.assert_close(o.nchw_to_nhwc(x.to(DEV)).cpu(), _to_nhwc(x))
+    torch.testing.assert_close(o.nhwc_to_nchw(_to_nhwc(x).to(DEV)).cpu(), x)
+    want = F.max_pool2d(x, 3, 2, 1)
+    assert torch.equal(o.maxpool3x3s2(_to_nhwc(x).to(DEV)).permute(0, 3, 1, 2).cpu(), want)
+    r = torch.randn(5, 32, 7, 7, generator=g, requires_grad=True)
+    want = F.avg_pool2d(r, 7).view(5, -1)
+    go = torch.randn(5, 32, generator=g)
+    (gw,) = torch.autograd.grad(want, r, go)
+    rd = _to_nhwc(r.detach()).to(DEV).requires_grad_(True)
+    got = o.avgpool_hw(rd)
+    (gg,) = torch.autograd.grad(got, rd, go.to(DEV))
+    torch.testing.assert_close(got.cpu(), want, atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(gg.permute(0, 3, 1, 2).cpu(), gw, atol=1e-7, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------ losses
+def test_bce_losses():
+    o = ops()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 12, 20, 1, generator=g) * 3
+    xr = x.clone().requires_grad_(True)
+    want = orc.da_img_loss(xr.permute(0, 3, 1, 2), [True, False])
+    (gw,) = torch.autograd.grad(want * 0.7, xr)
+    xd = x.to(DEV).requires_grad_(True)
+    got = o.bce_with_logits_mean(xd, None, torch.tensor([1, 0], dtype=torch.uint8, device=DEV), 240)
+    (gg,) = torch.autograd.grad(got * 0.7, xd)
+    assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want))     # fp32-sum tier: 1e-4 rel
+    torch.testing.assert_close(gg.cpu(), gw, atol=1e-7, rtol=1e-4)
+    t = (torch.rand(77, generator=g) > 0.5).float()
+    z = torch.randn(77, generator=g)
+    zr = z.clone().requires_grad_(True)
+    want = F.binary_cross_entropy_with_logits(zr, t)
+    (gw,) = torch.autograd.grad(want, zr)
+    zd = z.to(DEV).requires_grad_(True)
+    got = o.bce_with_logits_mean(zd, t.to(DEV))
+    (gg,) = torch.autograd.grad(got, zd)
+    assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want))
+    torch.testing.assert_close(gg.cpu(), gw, atol=1e-7, rtol=1e-4)
+
+
+def test_fastrcnn_losses():
+    o = ops()
+    g = torch.Generator().manual_seed(6)
+    rows, c = 300, 9
+    logits = torch.randn(rows, c, generator=g)
+    reg = torch.randn(rows, 4 * c, generator=g)
+    labels = torch.randint(0, c, (rows,), generator=g)
+    regt = torch.randn(rows, 4, generator=g) * 0.5
+    dom = torch.cat([torch.ones(180, dtype=torch.bool), torch.zeros(120, dtype=torch.bool)])
+    samples = [dict(labels=labels, regression_targets=regt, domain_labels=dom)]
+    lr, rr = logits.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+    wc, wb, _ = orc.fastrcnn_loss(lr, rr, samples)
+    gwc, gwb = torch.autograd.grad(wc + wb, (lr, rr))
+    ld, rd = logits.to(DEV).requires_grad_(True), reg.to(DEV).requires_grad_(True)
+    gc = o.softmax_ce_mean(ld, labels.to(DEV), dom.to(torch.uint8).to(DEV))
+    gb = o.box_reg_loss(rd, regt.to(DEV), labels.to(DEV), dom.to(torch.uint8).to(DEV))
+    ggc, ggb = torch.autograd.grad(gc + gb, (ld, rd))
+    assert abs(float(gc) - float(wc)) <= 1e-4 * abs(float(wc))
+    assert abs(float(gb) - float(wb)) <= 1e-4 * abs(float(wb))
+    torch.testing.assert_close(ggc.cpu(), gwc, atol=1e-7, rtol=1e-4)
+    torch.testing.assert_close(ggb.cpu(), gwb, atol=1e-7, rtol=1e-4)
+
+
+def test_smooth_l1_consistency_triplet():
+    o = ops()
+    g = torch.Generator().manual_seed(7)
+    x, t = torch.randn(50, 4, generator=g), torch.randn(50, 4, generator=g) * 0.2
+    xr = x.clone().requires_grad_(True)
+    want = orc.smooth_l1(xr, t, 1 / 9, False) / 256
+    (gw,) = torch.autograd.grad(want, xr)
+    xd = x.to(DEV).requires_grad_(True)
+    got = o.smooth_l1_sum(xd, t.to(DEV), 1 / 9, 256.0)
+    (gg,) = torch.autograd.grad(got, xd)
+    assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want))
+    torch.testing.assert_close(gg.cpu(), gw, atol=1e-7, rtol=1e-4)
+    assert float(o.smooth_l1_sum(torch.zeros(0, 4, device=DEV), torch.zeros(0, 4, device=DEV), 1 / 9, 256.0)) == 0.0
+
+    img = torch.randn(2, 1, 12, 20, generator=g)
+    ins = torch.randn(37, 1, generator=g)
+    dom = torch.cat([torch.ones(21, dtype=torch.bool), torch.zeros(16, dtype=torch.bool)])
+    ir, sr = img.clone().requires_grad_(True), ins.clone().requires_grad_(True)
+    want = orc.consistency_loss(ir.sigmoid(), sr.sigmoid(), dom)
+    gwi, gws = torch.autograd.grad(want, (ir, sr))
+    idv, sdv = img.reshape(2, -1).to(DEV).requires_grad_(True), ins.reshape(-1).to(DEV).requires_grad_(True)
+    got = o.consistency_loss(idv, sdv, 21)
+    ggi, ggs = torch.autograd.grad(got, (idv, sdv))
+    assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want))
+    torch.testing.assert_close(ggi.cpu().view_as(gwi), gwi, atol=1e-8, rtol=1e-3)
+    torch.testing.assert_close(ggs.cpu().view_as(gws), gws, atol=1e-8, rtol=1e-3)
+
+    # image-level triplet: NCHW [1,C,H,W], distance over W
+    a, p, n = (torch.randn(1, 8, 5, 16, generator=g) for _ in range(3))
+    ar, pr, nr = (v.clone().requires_grad_(True) for v in (a, p, n))
+    want = orc.triplet_margin_loss(ar, pr, nr, 1.0)
+    gw = torch.autograd.grad(want, (ar, pr, nr))
+    ad, pd, nd = (_to_nhwc(v).to(DEV).requires_grad_(True) for v in (a, p, n))
+    got = o.triplet_margin_loss(ad, pd, nd, 1.0, 5 * 8, 16, 8)
+    gg = torch.autograd.grad(got, (ad, pd, nd))
+    assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want))
+    for x1, x2 in zip(gg, gw):
+        torch.testing.assert_close(x1.permute(0, 3, 1, 2).cpu(), x2, atol=1e-7, rtol=1e-3)
+    # instance-level triplet: [R, D]
+    a, p, n = (torch.randn(9, 64, generator=g) for _ in range(3))
+    ar, pr, nr = (v.clone().requires_grad_(True) for v in (a, p, n))
+    want = orc.triplet_margin_loss(ar, pr, nr, 0.7)
+    gw = torch.autograd.grad(want, (ar, pr, nr))
+    ad, pd, nd = (v.to(DEV).requires_grad_(True) for v in (a, p, n))
+    got = o.triplet_margin_loss(ad, pd, nd, 0.7, 9, 64, 1)
+    gg = torch.autograd.grad(got, (ad, pd, nd))
+    assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want))
+    for x1, x2 in zip(gg, gw):
+        torch.testing.assert_close(x1.cpu(), x2, atol=1e-7, rtol=1e-3)
+
+
+def test_grl_dropout_advgrl_sgd(golden_dir):
+    o = ops()
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(33, 7, generator=g)
+    xd = x.to(DEV).requires_grad_(True)
+    y = o.gradient_scalar(xd, -0.1)
+    assert torch.equal(y, xd)
+    (gx,) = torch.autograd.grad(y, xd, torch.ones_like(y))
+    torch.testing.assert_close(gx.cpu(), torch.full_like(x, -0.1))
+    keep = (torch.rand(33, 7, generator=g) > 0.5).float()
+    yd = o.dropout_with_mask(xd, keep.to(DEV))
+    torch.testing.assert_close(yd.cpu(), x * keep * 2)
+    ref = torch.load(os.path.join(golden_dir, "ref_ops.pt"), weights_only=False)
+    for L, w in ref["adv_grl"]:                       # weights produced by the reference's Adv_GRL
+        wd = o.adv_grl_weight(torch.tensor([L], device=DEV), ref["adv_bce"], 0.1, 0.1, 30)
+        assert abs(float(wd) - w) <= 1e-6 * max(1.0, abs(w))
+    wdev = torch.tensor([-2.5], device=DEV)
+    y = o.gradient_scalar_dev(xd, wdev)
+    (gx,) = torch.autograd.grad(y, xd, torch.ones_like(y))
+    torch.testing.assert_close(gx.cpu(), torch.full_like(x, -2.5))
+
+    p = torch.randn(1000, generator=g)
+    grads = [torch.randn(1000, generator=g) for _ in range(3)]
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.SGD([pr], lr=0.01, momentum=0.9, weight_decay=5e-4)
+    pd, buf = p.to(DEV), torch.zeros(1000, device=DEV)
+    for i, gr in enumerate(grads):
+        pr.grad = gr.clone()
+        opt.step()
+        o.sgd_momentum_(pd, gr.to(DEV), buf, 0.01, 0.9, 5e-4, 1.0, i == 0)
+    torch.testing.assert_close(pd.cpu(), pr.detach(), atol=1e-6, rtol=1e-5)
