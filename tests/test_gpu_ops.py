@@ -39,11 +39,11 @@ def test_roi_align_forward_backward(sampling_ratio, channels):
     go = torch.randn(40, channels, 14, 14, generator=g)
     fr = feat.clone().requires_grad_(True)
     want = orc.roi_align(fr, rois, 1 / 16, 14, 14, sampling_ratio)
-    (gwant,) = torch.autograd.grad(want, fr, go)
+    (gwant,) = torch.autograd.grad(want, fr, go, retain_graph=True)
 
     fd = feat.permute(0, 2, 3, 1).contiguous().to(DEV).requires_grad_(True)
     got = ops().roi_align(fd, rois.to(DEV), 1 / 16, 14, sampling_ratio, 1)
-    (ggot,) = torch.autograd.grad(got, fd, go.permute(0, 2, 3, 1).contiguous().to(DEV))
+    (ggot,) = torch.autograd.grad(got, fd, go.permute(0, 2, 3, 1).contiguous().to(DEV), retain_graph=True)
     torch.testing.assert_close(got.permute(0, 3, 1, 2).cpu(), want, atol=1e-5, rtol=1e-5)
     torch.testing.assert_close(ggot.permute(0, 3, 1, 2).cpu(), gwant, atol=1e-5, rtol=1e-4)
 
@@ -126,7 +126,9 @@ def test_rpn_topk_decode(fh, fw, k):
     g = torch.Generator().manual_seed(fh * fw)
     a = 15
     n = 2
-    logits = torch.randn(n, a, fh, fw, generator=g) * 2
+    # distinct values => no top-k ties (tie order is unspecified in the reference)
+    total = n * a * fh * fw
+    logits = ((torch.randperm(total, generator=g).float() / total - 0.5) * 8).view(n, a, fh, fw)
     deltas = torch.randn(n, 4 * a, fh, fw, generator=g) * 0.5
     deltas[0, 2] = 6.0          # exercises the log(1000/16) clamp on dw
     cell = orc.cell_anchors(16, (32, 64, 128, 256, 512), (0.5, 1.0, 2.0))
