@@ -17,6 +17,7 @@ _SIGS = {
     "dd_last_error": (ctypes.c_char_p, ""),
     "dd_abi_version": (_I, ""),
     "dd_launch_count": (_Q, ""),
+    "dd_tcgen05_built": (_I, ""),
     "dd_roi_align_forward": (_I, "pppiiiiifiiiip"),
     "dd_roi_align_backward": (_I, "pppiiiiifiiiip"),
     "dd_roi_align_forward_nchw": (_I, "pppiiiiifiiip"),

@@ -2,6 +2,7 @@
 // dispatcher uses the fp32 SIMT arm.
 #include "common.cuh"
 
+extern "C" int dd_tcgen05_built(void) { return 0; }
 bool dd_tc_supports(int, int, int, int, int, int, int, int, int, int) { return false; }
 int dd_tc_conv2d_forward(const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
                          int, int, int, int, int, int, int, cudaStream_t) { return dd::fail(-1, "tcgen05 arm not built", __FILE__, __LINE__); }

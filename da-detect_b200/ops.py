@@ -32,6 +32,10 @@ def get_default_impl():
     return _default_impl
 
 
+def tcgen05_available():
+    return bool(_lib.load().dd_tcgen05_built())
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -30,6 +30,8 @@ const char* dd_last_error(void);
 int dd_abi_version(void);
 /* number of kernels launched by this library since process start (bench.py's gpu_launches) */
 long long dd_launch_count(void);
+/* 1 when the tcgen05/TMA arm of the dense tier is compiled into this library, else 0 */
+int dd_tcgen05_built(void);
 
 /* ---------------------------------------------------------------- maskrcnn_benchmark._C ops */
 
