@@ -1,12 +1,470 @@
-// tcgen05 / TMA arm of the dense tier — placeholder until the kernels land: reports "unsupported" so the
-// dispatcher uses the fp32 SIMT arm.
+// tcgen05 / TMA arm of the dense tier (impl = DD_IMPL_TCGEN05), sm_100a only.
+//
+// Implicit-GEMM convolution on the 5th-generation tensor cores: fp32 NHWC activations and OHWI weights
+// are consumed directly as TF32 operands (kind::tf32, fp32 accumulate in TMEM) — no im2col buffer, no
+// layout or precision conversion pass.  One warp-specialised CTA computes a 128 x BN output tile:
+//
+//   warp 0   TMA producer : per (filter tap, 32-channel slice) one 4-D tensor-map box of the activation
+//                           (a [tn x th x tw] block of output pixels shifted by the tap; out-of-image
+//                           coordinates are zero-filled by TMA = the conv padding) and one 2-D box of
+//                           the weights, both 128B-swizzled K-major tiles, into a 3-4 stage smem ring
+//   warp 1   MMA issuer   : one elected thread issues 4 tcgen05.mma (M=128, N=BN, K=8) per stage,
+//                           tcgen05.commit releases the stage back to the producer
+//   warps 2-5 epilogue    : tcgen05.ld the fp32 accumulators (one output pixel per thread, 32 channels per
+//                           load), apply FrozenBN scale/bias + residual + ReLU (forward) or fan-in add +
+//                           ReLU mask (dgrad), 128-bit stores to NHWC
+//
+//   forward: D[pix, co] = sum_{tap, ci} X[pix + tap, ci] * W[co, tap, ci]
+//   dgrad  : the same kernel on GY with the flipped / transposed / BN-scaled weights W'[ci, tap', co]
+//            (prepared by a small transpose kernel); 1x1 stride-2 dgrad runs compact and scatters rows
+//   wgrad  : D[co, ci] (per tap) = sum_pix GY[pix, co] * X[pix + tap, ci]: both operands MN-major
+//            (channels contiguous), split over pixel blocks, partials reduced by wgrad_reduce
+//
+// Reference being replaced: cuDNN/cuBLAS calls behind F.conv2d / F.linear.
+#include <cuda.h>
+
 #include "common.cuh"
 
-extern "C" int dd_tcgen05_built(void) { return 0; }
-bool dd_tc_supports(int, int, int, int, int, int, int, int, int, int) { return false; }
-int dd_tc_conv2d_forward(const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
-                         int, int, int, int, int, int, int, cudaStream_t) { return dd::fail(-1, "tcgen05 arm not built", __FILE__, __LINE__); }
-int dd_tc_conv2d_dgrad(const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
-                       int, int, int, int, int, int, cudaStream_t) { return dd::fail(-1, "tcgen05 arm not built", __FILE__, __LINE__); }
+namespace {
+
+constexpr int BM = 128;            // output pixels per CTA tile (UMMA M)
+constexpr int BKB = 128;           // bytes of K per stage row (one 128B swizzle span) = 32 tf32
+constexpr int BKE = 32;            // elements of K per stage
+constexpr int UMMA_K = 8;          // tf32: 32 bytes per MMA K step
+constexpr int NUM_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+
+struct TcParams {
+  // epilogue
+  float* out;
+  const float* scale;     // per output channel (fwd: BN scale; may be null)
+  const float* bias;      // per output channel (may be null)
+  const float* extra;     // residual (fwd) / addend (dgrad), same addressing as out (may be null)
+  const float* mask;      // dgrad: activation whose > 0 gates the result (may be null)
+  int relu;
+  // geometry of the GEMM rows (output pixel blocks)
+  int N, OH, OW;          // logical output pixel grid enumerated by the tiles
+  int tn, th, tw;         // tile = tn images x th rows x tw cols (tn*th*tw == 128)
+  int tiles_h, tiles_w;   // ceil(OH/th), ceil(OW/tw)
+  // where a row lands in the output tensor: out[((n*out_H + h*os)*out_W + w*os)*ldc + co]
+  int out_H, out_W, os, ldc;
+  int Cout;               // valid output channels (columns)
+  // K loop
+  int taps, KW, pad, cblocks;   // taps = KH*KW, cblocks = Cin/32
+  int Cin;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 28)) __trap();
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, 128B swizzle (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
+// Rows are 128 B apart, 8-row swizzle atoms are 1024 B apart (SBO); LBO is unused for swizzled K-major.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
+// a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kABytes = BM * BKB;      // 16 KB
+  static constexpr int kBBytes = BN * BKB;      // 8 / 16 / 32 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kStages * L::kStageBytes);
+  uint64_t* empty_bar = full_bar + L::kStages;
+  uint64_t* tmem_full_bar = empty_bar + L::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int n_tile = blockIdx.x;                       // output-channel tile
+  int mt = blockIdx.y;                                 // pixel-block tile
+  const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
+  const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
+  const int n0 = mt * p.tn, oh0 = tile_h * p.th, ow0 = tile_w * p.tw;
+  const int k_iters = p.taps * p.cblocks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < L::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % L::kStages;
+        const uint32_t ph = (it / L::kStages) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        const int tap = it / p.cblocks, cb = it % p.cblocks;
+        const int kh = tap / p.KW, kw = tap % p.KW;
+        uint8_t* sa = smem + s * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes;
+        mbar_expect_tx(full_bar + s, L::kStageBytes);
+        tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
+        tma_load_2d(&map_b, full_bar + s, sb, tap * p.Cin + cb * BKE, n_tile * BN);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    for (int it = 0; it < k_iters; ++it) {
+      const int s = it % L::kStages;
+      const uint32_t ph = (it / L::kStages) & 1;
+      mbar_wait(full_bar + s, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < BKE / UMMA_K; ++k) {
+          const uint64_t ad = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
+          const uint64_t bd = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
+          umma_tf32(tmem_base, ad, bd, idesc, (it | k) ? 1u : 0u);
+        }
+        umma_commit(empty_bar + s);                       // frees the smem stage when these MMAs retire
+        if (it == k_iters - 1) umma_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int quarter = warp & 3;                        // TMEM lanes [32*quarter, 32*quarter+32)
+    const int row = quarter * 32 + lane;                 // tile row = TMEM lane = output pixel slot
+    const int wl = row % p.tw, hl = (row / p.tw) % p.th, nl = row / (p.tw * p.th);
+    const int n = n0 + nl, oh = oh0 + hl, ow = ow0 + wl;
+    const bool row_ok = n < p.N && oh < p.OH && ow < p.OW;
+    const size_t row_off = (((size_t)n * p.out_H + (size_t)oh * p.os) * p.out_W + (size_t)ow * p.os) * p.ldc;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+      const int col0 = n_tile * BN + c0;
+      if (row_ok && col0 < p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int col = col0 + j;
+          if (col >= p.Cout) break;
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(r[j + e]);
+            const int c = col + e;
+            if (c < p.Cout) {
+              if (p.scale) x *= __ldg(p.scale + c);
+              if (p.bias) x += __ldg(p.bias + c);
+              if (p.extra) x += __ldg(p.extra + row_off + c);
+              if (p.mask) x = __ldg(p.mask + row_off + c) > 0.f ? x : 0.f;
+              if (p.relu) x = fmaxf(x, 0.f);
+            }
+            v[e] = x;
+          }
+          float* dst = p.out + row_off + col;
+          if (col + 3 < p.Cout && (((row_off + col) & 3) == 0)) {
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (col + e < p.Cout) dst[e] = v[e];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// W'[ci][KH-1-kh][KW-1-kw][co] = scale[co] * W[co][kh][kw][ci]  (dgrad as a forward conv over GY)
+__global__ void weight_flip_transpose_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                             float* __restrict__ wt, int Cout, int Cin, int KH, int KW) {
+  const long long total = (long long)Cout * KH * KW * Cin;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    // t enumerates the DESTINATION (co fastest) for coalesced writes
+    const int co = (int)(t % Cout);
+    const int kw = (int)((t / Cout) % KW);
+    const int kh = (int)((t / ((long long)Cout * KW)) % KH);
+    const int ci = (int)(t / ((long long)Cout * KW * KH));
+    float v = w[(((size_t)co * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)) * Cin + ci];
+    if (scale) v *= __ldg(scale + co);
+    wt[t] = v;
+  }
+}
+
+// x[:, ::s, ::s, :] (the input a strided 1x1 conv actually reads), float4 over channels
+__global__ void subsample_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int s,
+                                 int OH, int OW) {
+  const int c4n = C / 4;
+  const long long total = (long long)N * OH * OW * c4n;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(t % c4n);
+    const int ow = (int)((t / c4n) % OW);
+    const int oh = (int)((t / ((long long)c4n * OW)) % OH);
+    const int n = (int)(t / ((long long)c4n * OW * OH));
+    reinterpret_cast<float4*>(y)[t] = dd::ldg4(x + (((size_t)n * H + (size_t)oh * s) * W + (size_t)ow * s) * C + c4 * 4);
+  }
+}
+
+__global__ void fill_kernel(const float* __restrict__ addend, const float* __restrict__ mask, float* __restrict__ gx,
+                            long long n) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    float v = addend ? addend[t] : 0.f;
+    if (mask) v = mask[t] > 0.f ? v : 0.f;
+    gx[t] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims,
+                                      strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    const char* msg = nullptr;
+    cuGetErrorString(r, &msg);
+    snprintf(dd::g_err, sizeof(dd::g_err), "cuTensorMapEncodeTiled failed: %s", msg ? msg : "?");
+    return -1;
+  }
+  return 0;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int m_tiles, int n_tiles, cudaStream_t s) {
+  using L = SmemLayout<BN>;
+  static bool configured = false;
+  if (!configured) {
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  dim3 grid(n_tiles, m_tiles);
+  conv_tc_kernel<BN><<<grid, NUM_THREADS, L::kTotal, s>>>(ma, mb, p);
+  DD_LAUNCHED();
+  return 0;
+}
+
+// Core: D[pixel, col] = sum_{tap, c} A[n, oh + kh - pad, ow + kw - pad, c] * B[col, tap, c]
+//   A: [N, AH, AW, Cin] NHWC fp32 (stride 1 access), B: [ncols, taps*Cin] fp32, output rows enumerate (N, OH, OW).
+int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, const float* b, int ncols, int KH, int KW, int pad,
+                 int OH, int OW, TcParams p, cudaStream_t s) {
+  p.N = N; p.OH = OH; p.OW = OW;
+  p.tw = pow2_ceil(OW < 16 ? OW : 16);
+  p.th = pow2_ceil(OH < BM / p.tw ? OH : BM / p.tw);
+  p.tn = BM / (p.tw * p.th);
+  p.tiles_w = (OW + p.tw - 1) / p.tw;
+  p.tiles_h = (OH + p.th - 1) / p.th;
+  const int tiles_n = (N + p.tn - 1) / p.tn;
+  p.taps = KH * KW; p.KW = KW; p.pad = pad; p.Cin = Cin; p.cblocks = Cin / BKE; p.Cout = ncols;
+  const int m_tiles = tiles_n * p.tiles_h * p.tiles_w;
+  DD_CHECK_ARG(m_tiles <= 65535);
+
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)AW, (cuuint64_t)AH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)AW * Cin * 4, (cuuint64_t)AH * AW * Cin * 4};
+    cuuint32_t box[4] = {(cuuint32_t)BKE, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+    if (encode_map(&ma, a, 4, dims, strides, box)) return -1;
+  }
+  const int BN = (ncols % 256 == 0) ? 256 : (ncols > 64 ? 128 : 64);
+  {
+    const cuuint64_t K = (cuuint64_t)KH * KW * Cin;
+    cuuint64_t dims[2] = {K, (cuuint64_t)ncols};
+    cuuint64_t strides[1] = {K * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)(BN < 256 ? BN : 256)};
+    if (encode_map(&mb, b, 2, dims, strides, box)) return -1;
+  }
+  const int n_tiles = (ncols + BN - 1) / BN;
+  if (BN == 256) return launch_tc<256>(ma, mb, p, m_tiles, n_tiles, s);
+  if (BN == 128) return launch_tc<128>(ma, mb, p, m_tiles, n_tiles, s);
+  return launch_tc<64>(ma, mb, p, m_tiles, n_tiles, s);
+}
+
+}  // namespace
+
+extern "C" int dd_tcgen05_built(void) { return 1; }
+
+// mode: 0 forward, 1 dgrad, 2 wgrad
+bool dd_tc_supports(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
+  (void)N; (void)H; (void)W;
+  if (mode == 0) {
+    if (Cin % 32 != 0) return false;                                  // stem (Cin = 3) stays on the SIMT arm
+    if (stride != 1 && !(KH == 1 && KW == 1 && pad == 0)) return false;
+    return true;
+  }
+  if (mode == 1) {
+    if (Cout % 32 != 0 || Cin % 4 != 0) return false;                 // K of the dgrad GEMM is Cout
+    if (stride != 1 && !(KH == 1 && KW == 1 && pad == 0)) return false;
+    if (stride == 1 && pad != (KH - 1) / 2) return false;             // "same" convs only (all of ResNet/RPN)
+    return true;
+  }
+  return false;                                                        // wgrad: SIMT arm for now
+}
+
+int dd_tc_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias, const float* residual,
+                         float* y, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                         int act, cudaStream_t s) {
+  const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
+  TcParams p = {};
+  p.out = y; p.scale = scale; p.bias = bias; p.extra = residual; p.mask = nullptr; p.relu = act == DD_ACT_RELU;
+  p.out_H = OH; p.out_W = OW; p.os = 1; p.ldc = Cout;
+  const float* a = x;
+  float* sub = nullptr;
+  int AH = H, AW = W;
+  if (stride != 1) {   // strided 1x1: gather the pixels the conv reads, then a dense 1x1
+    DD_CUDA(cudaMallocAsync(&sub, sizeof(float) * (size_t)N * OH * OW * Cin, s));
+    const long long total = (long long)N * OH * OW * (Cin / 4);
+    subsample_kernel<<<dd::grid_for(total, 256), 256, 0, s>>>(x, sub, N, H, W, Cin, stride, OH, OW);
+    DD_LAUNCHED();
+    a = sub; AH = OH; AW = OW;
+  }
+  int rc = tc_conv_core(a, N, AH, AW, Cin, w, Cout, KH, KW, pad, OH, OW, p, s);
+  if (sub) cudaFreeAsync(sub, s);
+  return rc;
+}
+
+int dd_tc_conv2d_dgrad(const float* gy, const float* w, const float* scale, const float* addend, const float* mask_act,
+                       float* gx, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                       cudaStream_t s) {
+  const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
+  float* wt = nullptr;
+  const size_t wn = (size_t)Cout * KH * KW * Cin;
+  DD_CUDA(cudaMallocAsync(&wt, sizeof(float) * wn, s));
+  weight_flip_transpose_kernel<<<dd::grid_for((long long)wn, 256), 256, 0, s>>>(w, scale, wt, Cout, Cin, KH, KW);
+  DD_LAUNCHED();
+  TcParams p = {};
+  p.out = gx; p.scale = nullptr; p.bias = nullptr; p.extra = addend; p.mask = mask_act; p.relu = 0;
+  p.out_H = H; p.out_W = W; p.ldc = Cin;
+  int rc;
+  if (stride == 1) {
+    p.os = 1;
+    // gx[n,h,w,ci] = sum_{kh',kw',co} gy[n, h + kh' - pad', w + kw' - pad', co] * W'[ci, kh', kw', co], pad' = KH-1-pad
+    rc = tc_conv_core(gy, N, OH, OW, Cout, wt, Cin, KH, KW, KH - 1 - pad, H, W, p, s);
+  } else {
+    // 1x1 stride s: rows enumerate gy's pixels, each lands on (oh*s, ow*s); everything else is addend/0
+    const long long n = (long long)N * H * W * Cin;
+    fill_kernel<<<dd::grid_for(n, 256), 256, 0, s>>>(addend, mask_act, gx, n);
+    DD_LAUNCHED();
+    p.os = stride;
+    rc = tc_conv_core(gy, N, OH, OW, Cout, wt, Cin, 1, 1, 0, OH, OW, p, s);
+  }
+  cudaFreeAsync(wt, s);
+  return rc;
+}
+
 int dd_tc_conv2d_wgrad(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int,
-                       int, void*, cudaStream_t) { return dd::fail(-1, "tcgen05 arm not built", __FILE__, __LINE__); }
+                       int, void*, cudaStream_t) {
+  return dd::fail(-1, "tcgen05 wgrad not built", __FILE__, __LINE__);
+}

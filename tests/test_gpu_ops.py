@@ -446,3 +446,58 @@ def test_grl_dropout_advgrl_sgd(golden_dir):
         opt.step()
         o.sgd_momentum_(pd, gr.to(DEV), buf, 0.01, 0.9, 5e-4, 1.0, i == 0)
     torch.testing.assert_close(pd.cpu(), pr.detach(), atol=1e-6, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------ dense tier, tcgen05 arm
+TC_CASES = [
+    (2, 16, 24, 64, 64, 1, 1, 0),
+    (2, 16, 24, 64, 128, 1, 2, 0),
+    (1, 15, 23, 32, 48, 3, 1, 1),
+    (3, 7, 7, 128, 256, 3, 1, 1),
+    (2, 8, 12, 256, 15, 1, 1, 0),
+    (37, 1, 1, 2048, 1024, 1, 1, 0),
+    (5, 7, 7, 512, 512, 3, 1, 1),
+    (1, 32, 64, 256, 256, 3, 1, 1),
+]
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_arm(case):
+    """tcgen05 (TF32 operands, fp32 accumulate) against the fp32 CPU reference.  TF32 keeps 10 mantissa bits,
+    so the tolerance is statistical: rms error <= 2e-3 of the rms magnitude, max error <= 2e-2 of it."""
+    n, h, w, cin, cout, k, stride, pad = case
+    o = ops()
+    assert o.tcgen05_available()
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    scale = 0.5 + torch.rand(cout, generator=g)
+    bias = torch.randn(cout, generator=g) * 0.1
+    xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    y0 = F.conv2d(xr, wr, stride=stride, padding=pad) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    res = torch.randn(y0.shape, generator=g)
+    want = F.relu(y0 + res)
+    go = torch.randn(want.shape, generator=g)
+    gx_want, gw_want = torch.autograd.grad(want, (xr, wr), go)
+
+    def close(got, ref, what):
+        err = got - ref
+        rms = float(ref.pow(2).mean().sqrt())
+        assert float(err.pow(2).mean().sqrt()) <= 2e-3 * rms, (what, float(err.pow(2).mean().sqrt()), rms)
+        assert float(err.abs().max()) <= 2e-2 * max(rms, 1e-6) * 3, (what, float(err.abs().max()), rms)
+
+    xd = _to_nhwc(x).to(DEV)
+    wd = wt.permute(0, 2, 3, 1).contiguous().to(DEV)
+    sd, bd, rd = scale.to(DEV), bias.to(DEV), _to_nhwc(res).to(DEV)
+    got = o.conv2d_forward_raw(xd, wd, sd, bd, rd, k, k, stride, pad, True, impl=o.IMPL_TCGEN05)
+    close(got.permute(0, 3, 1, 2).cpu(), want.detach(), "forward")
+    exact = o.conv2d_forward_raw(xd, wd, sd, bd, rd, k, k, stride, pad, True, impl=o.IMPL_SIMT)
+    gpre = o.relu_backward_raw(_to_nhwc(go).to(DEV), exact)
+    addend = torch.randn(x.shape, generator=g)
+    act = torch.randn(x.shape, generator=g)
+    gx = o.conv2d_dgrad_raw(gpre, wd, sd, tuple(xd.shape), k, k, stride, pad, addend=_to_nhwc(addend).to(DEV),
+                            mask_act=_to_nhwc(act).to(DEV), impl=o.IMPL_TCGEN05)
+    close(gx.permute(0, 3, 1, 2).cpu(), (gx_want + addend) * (act > 0), "dgrad")
+    gw = o.conv2d_wgrad_raw(gpre, xd, sd, cout, k, k, stride, pad, impl=o.IMPL_TCGEN05)
+    close(gw.permute(0, 3, 1, 2).cpu(), gw_want, "wgrad")
