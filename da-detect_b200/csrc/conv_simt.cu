@@ -315,6 +315,16 @@ int wgrad_splits(int M, int Ncols, int K) {
 
 }  // namespace
 
+int dd_simt_wgrad_splits(int M, int Ncols, int K) { return wgrad_splits(M, Ncols, K); }
+
+int dd_wgrad_reduce(const float* partial, int splits, int M, int Ncols, const float* scale, float* gw, int accumulate,
+                    cudaStream_t s) {
+  const long long total = (long long)M * Ncols;
+  wgrad_reduce_kernel<<<dd::grid_for(total, 256), 256, 0, s>>>(partial, splits, M, Ncols, scale, gw, accumulate);
+  DD_LAUNCHED();
+  return 0;
+}
+
 // ---- entry points for the SIMT arm (dispatch from conv_dispatch.cu) -------------------------------------
 int dd_simt_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias,
                            const float* residual, float* y, int N, int H, int W, int Cin, int Cout, int KH, int KW,

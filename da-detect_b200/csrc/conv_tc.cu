@@ -284,6 +284,159 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ wgrad kernel
+// D[co, ci] (one filter tap per CTA column) = sum over a range of pixel blocks of GY[pix, co] * X[pix + tap, ci].
+// Both operands are MN-major: a TMA box is [32 pixels x 32 channels] with the 32 channels (128 B) contiguous,
+// i.e. one UMMA "MN-major, 128B-swizzle" column block; 4 (co) + BN/32 (ci) such boxes per stage.
+struct TcWgradParams {
+  float* partial;          // [splits][Cout][taps*Cin]
+  int Cout, Cin, taps, KW, pad;
+  int tn, th, tw;          // pixel block = tn*th*tw == 32
+  int tiles_h, tiles_w, pix_blocks, blocks_per_split;
+  int ci_tiles;
+};
+
+constexpr int WG_KPIX = 32;                       // pixels per stage (4 MMA K-steps of 8)
+constexpr int WG_BOX_BYTES = WG_KPIX * 128;       // one [32 pix x 32 ch] box = 4 KB
+
+// MN-major TF32 operands exist only in the "128B swizzle with 32B atom" layout (cute::UMMA::LayoutType::
+// SWIZZLE_128B_BASE32B = 1; CUTLASS sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only
+// available smem layout"), produced by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: rows of 128 B
+// (32 channels), 32-byte chunks XOR-swizzled with (row & 3), pattern period 4 rows = 512 B.
+// LBO = byte distance between 32-channel column blocks, SBO = between 4-pixel row groups.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(WG_BOX_BYTES >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int m, int n) {
+  return make_idesc_tf32(m, n) | (1u << 15) | (1u << 16);
+}
+
+template <int BN>
+struct WgradSmem {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kABytes = 4 * WG_BOX_BYTES;            // 128 co
+  static constexpr int kBBytes = (BN / 32) * WG_BOX_BYTES;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_x,
+                const TcWgradParams p) {
+  using L = WgradSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kStages * L::kStageBytes);
+  uint64_t* empty_bar = full_bar + L::kStages;
+  uint64_t* tmem_full_bar = empty_bar + L::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tap = blockIdx.x / p.ci_tiles, ci_tile = blockIdx.x % p.ci_tiles;
+  const int co0 = blockIdx.y * BM, ci0 = ci_tile * BN;
+  const int kh = tap / p.KW, kw = tap % p.KW;
+  const int pb_begin = blockIdx.z * p.blocks_per_split;
+  const int pb_end = min(p.pix_blocks, pb_begin + p.blocks_per_split);
+  const int k_iters = max(pb_end - pb_begin, 0);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_gy);
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < L::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % L::kStages;
+        const uint32_t ph = (it / L::kStages) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        int pb = pb_begin + it;
+        const int bw = pb % p.tiles_w; pb /= p.tiles_w;
+        const int bh = pb % p.tiles_h; pb /= p.tiles_h;
+        const int n0 = pb * p.tn, oh0 = bh * p.th, ow0 = bw * p.tw;
+        uint8_t* sa = smem + s * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes;
+        mbar_expect_tx(full_bar + s, L::kStageBytes);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          tma_load_4d(&map_gy, full_bar + s, sa + j * WG_BOX_BYTES, co0 + j * 32, ow0, oh0, n0);
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j)
+          tma_load_4d(&map_x, full_bar + s, sb + j * WG_BOX_BYTES, ci0 + j * 32, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_tf32_mn(BM, BN);
+    for (int it = 0; it < k_iters; ++it) {
+      const int s = it % L::kStages;
+      const uint32_t ph = (it / L::kStages) & 1;
+      mbar_wait(full_bar + s, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < WG_KPIX / UMMA_K; ++k) {
+          const uint64_t ad = make_mnmajor_sw128_desc(a_addr + k * 1024);
+          const uint64_t bd = make_mnmajor_sw128_desc(b_addr + k * 1024);
+          umma_tf32(tmem_base, ad, bd, idesc, (it | k) ? 1u : 0u);
+        }
+        umma_commit(empty_bar + s);
+        if (it == k_iters - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int co = co0 + quarter * 32 + lane;
+    const size_t ldp = (size_t)p.taps * p.Cin;
+    float* dst_row = p.partial + ((size_t)blockIdx.z * p.Cout + co) * ldp + (size_t)tap * p.Cin + ci0;
+    if (k_iters > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      if (k_iters > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (co < p.Cout && ci0 + c0 < p.Cin) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst_row + c0 + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                          __uint_as_float(r[j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
 // W'[ci][KH-1-kh][KW-1-kw][co] = scale[co] * W[co][kh][kw][ci]  (dgrad as a forward conv over GY)
 __global__ void weight_flip_transpose_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                              float* __restrict__ wt, int Cout, int Cin, int KH, int KW) {
@@ -327,11 +480,11 @@ __global__ void fill_kernel(const float* __restrict__ addend, const float* __res
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box) {
+               const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims,
                                       strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     const char* msg = nullptr;
@@ -392,6 +545,20 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, const float* b,
   return launch_tc<64>(ma, mb, p, m_tiles, n_tiles, s);
 }
 
+
+template <int BN>
+int launch_wgrad(const CUtensorMap& mg, const CUtensorMap& mx, const TcWgradParams& p, dim3 grid, cudaStream_t s) {
+  using L = WgradSmem<BN>;
+  static bool configured = false;
+  if (!configured) {
+    DD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  wgrad_tc_kernel<BN><<<grid, NUM_THREADS, L::kTotal, s>>>(mg, mx, p);
+  DD_LAUNCHED();
+  return 0;
+}
+
 }  // namespace
 
 extern "C" int dd_tcgen05_built(void) { return 1; }
@@ -410,7 +577,10 @@ bool dd_tc_supports(int mode, int N, int H, int W, int Cin, int Cout, int KH, in
     if (stride == 1 && pad != (KH - 1) / 2) return false;             // "same" convs only (all of ResNet/RPN)
     return true;
   }
-  return false;                                                        // wgrad: SIMT arm for now
+  // wgrad: both channel counts are TMA inner dimensions
+  if (Cin % 32 != 0 || Cout % 32 != 0) return false;
+  if (stride != 1 && !(KH == 1 && KW == 1 && pad == 0)) return false;
+  return true;
 }
 
 int dd_tc_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias, const float* residual,
@@ -464,7 +634,66 @@ int dd_tc_conv2d_dgrad(const float* gy, const float* w, const float* scale, cons
   return rc;
 }
 
-int dd_tc_conv2d_wgrad(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int,
-                       int, void*, cudaStream_t) {
-  return dd::fail(-1, "tcgen05 wgrad not built", __FILE__, __LINE__);
+int dd_simt_wgrad_splits(int M, int Ncols, int K);
+int dd_wgrad_reduce(const float* partial, int splits, int M, int Ncols, const float* scale, float* gw, int accumulate,
+                    cudaStream_t s);
+
+int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, float* gw, int N, int H, int W, int Cin,
+                       int Cout, int KH, int KW, int stride, int pad, int accumulate, void* workspace, cudaStream_t s) {
+  DD_CHECK_ARG(workspace != nullptr);
+  const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
+  const float* xa = x;
+  float* sub = nullptr;
+  int AH = H, AW = W;
+  if (stride != 1) {
+    DD_CUDA(cudaMallocAsync(&sub, sizeof(float) * (size_t)N * OH * OW * Cin, s));
+    const long long total = (long long)N * OH * OW * (Cin / 4);
+    subsample_kernel<<<dd::grid_for(total, 256), 256, 0, s>>>(x, sub, N, H, W, Cin, stride, OH, OW);
+    DD_LAUNCHED();
+    xa = sub; AH = OH; AW = OW;
+  }
+  TcWgradParams p = {};
+  p.partial = (float*)workspace;
+  p.Cout = Cout; p.Cin = Cin; p.taps = KH * KW; p.KW = KW; p.pad = pad;
+  p.tw = pow2_ceil(OW < 16 ? OW : 16);
+  p.th = pow2_ceil(OH < WG_KPIX / p.tw ? OH : WG_KPIX / p.tw);
+  p.tn = WG_KPIX / (p.tw * p.th);
+  p.tiles_w = (OW + p.tw - 1) / p.tw;
+  p.tiles_h = (OH + p.th - 1) / p.th;
+  p.pix_blocks = ((N + p.tn - 1) / p.tn) * p.tiles_h * p.tiles_w;
+  const int BN = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : 32));
+  p.ci_tiles = (Cin + BN - 1) / BN;
+  const int co_tiles = (Cout + BM - 1) / BM;
+  // split the pixel range so that ~2 waves of CTAs exist, within the workspace the SIMT sizing function grants
+  const int max_splits = dd_simt_wgrad_splits(Cout, KH * KW * Cin, N * OH * OW);
+  const int tiles = co_tiles * p.ci_tiles * p.taps;
+  int splits = (2 * dd::kNumSMs + tiles - 1) / tiles;
+  if (splits > max_splits) splits = max_splits;
+  if (splits > p.pix_blocks) splits = p.pix_blocks;
+  if (splits < 1) splits = 1;
+  p.blocks_per_split = (p.pix_blocks + splits - 1) / splits;
+  splits = (p.pix_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
+
+  CUtensorMap mg, mx;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)OW * Cout * 4, (cuuint64_t)OH * OW * Cout * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+    if (encode_map(&mg, gy, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)AW, (cuuint64_t)AH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)AW * Cin * 4, (cuuint64_t)AH * AW * Cin * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+    if (encode_map(&mx, xa, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
+  }
+  dim3 grid(p.ci_tiles * p.taps, co_tiles, splits);
+  int rc;
+  if (BN == 256) rc = launch_wgrad<256>(mg, mx, p, grid, s);
+  else if (BN == 128) rc = launch_wgrad<128>(mg, mx, p, grid, s);
+  else if (BN == 64) rc = launch_wgrad<64>(mg, mx, p, grid, s);
+  else rc = launch_wgrad<32>(mg, mx, p, grid, s);
+  if (!rc) rc = dd_wgrad_reduce(p.partial, splits, Cout, KH * KW * Cin, scale, gw, accumulate, s);
+  if (sub) cudaFreeAsync(sub, s);
+  return rc;
 }

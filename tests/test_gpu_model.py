@@ -46,9 +46,28 @@ def scenario(name):
     return cfg, sd, images, targets, (H, W)
 
 
+# Tolerances per dense-tier arm.  simt = fp32 FMA (the parity arm: 1e-4 on losses, BASELINE north_star);
+# tcgen05 = TF32 operands / fp32 accumulate (10-bit mantissa inputs): losses within 2e-3, gradients within 3e-2
+# globally — the documented cost of feeding fp32 storage straight to the tensor cores.
+TOL = {"simt": dict(loss=1e-4, grad_tensor=1e-2, grad_global=2e-3),
+       "tcgen05": dict(loss=2e-3, grad_tensor=2.5e-1, grad_global=3e-2)}
+
+
+@pytest.fixture(autouse=True)
+def _restore_impl():
+    from dadetect_b200 import ops
+    yield
+    ops.set_default_impl(ops.IMPL_SIMT)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("dense", ["simt", "tcgen05"])
 @pytest.mark.parametrize("name", sorted(SCENARIOS))
-def test_training_step_matches_oracle(name):
+def test_training_step_matches_oracle(name, dense):
+    from dadetect_b200 import ops
     from dadetect_b200.utils.random_source import ReplaySource
+    ops.set_default_impl(ops.IMPL_TCGEN05 if dense == "tcgen05" else ops.IMPL_SIMT)
+    tol = TOL[dense]
     cfg, sd, images, targets, hw = scenario(name)
     torch.manual_seed(77)
     rec = orc.RecordingHooks()
@@ -66,7 +85,8 @@ def test_training_step_matches_oracle(name):
     # index-exact tier: the sampled ROIs are the same boxes with the same labels
     box = model.roi_heads.box
     ref_samples = aux["samples"] if "samples" in aux else None
-    if ref_samples is not None and not cfg.MODEL.DA_HEADS.ALIGNMENT:
+    exact = dense == "simt"      # TF32 logits may legitimately reorder near-tied proposals
+    if exact and ref_samples is not None and not cfg.MODEL.DA_HEADS.ALIGNMENT:
         for p, s in zip(box.loss_evaluator._proposals, ref_samples):
             assert torch.equal(p.get_field("labels").cpu(), s["labels"])
             assert torch.equal(p.get_field("domain_labels").cpu(), s["domain_labels"])
@@ -80,9 +100,15 @@ def test_training_step_matches_oracle(name):
     assert torch.equal(model.rpn.last["pos"].cpu(), aux["rpn_pos"])
     assert torch.equal(model.rpn.last["neg"].cpu(), aux["rpn_neg"])
     assert not replay.perms and not replay.masks
+    print(dense, name, {k: (float(got[k]), float(want[k])) for k in want})
     for k in want:
         g, w = float(got[k]), float(want[k])
-        assert abs(g - w) <= 1e-4 * max(abs(w), 1e-3), (k, g, w)
+        # relative to the loss value, floored at 0.05: the consistency term is a mean |p_img - p_ins| of
+        # probabilities near 0.5, so its natural scale is the probabilities, not its own small value
+        # the triplet terms are differences of two nearly equal feature distances (d(a,p) - d(a,n)), which
+        # amplifies the TF32 operand rounding ~10x: 1e-2 for those keys on the tcgen05 arm
+        t_k = 1e-2 if (dense == "tcgen05" and k.startswith("triplet")) else tol["loss"]
+        assert abs(g - w) <= t_k * max(abs(w), 0.05 if dense == "tcgen05" else 1e-3), (k, g, w)
     sum(got.values()).backward()
     named = dict(model.named_parameters())
     worst, num, den = [], 0.0, 0.0
@@ -100,9 +126,9 @@ def test_training_step_matches_oracle(name):
         # Per-tensor bound is loose on purpose: the domain-classifier gradients are sums over source ROIs
         # (negative terms) and target ROIs (positive terms) that nearly cancel at chance level, so fp32
         # round-off of the per-ROI terms is amplified ~1e3x in the relative error of the sum.
-        assert rel < 1e-2, (k, rel, float(b.norm()))
+        assert rel < tol["grad_tensor"], (k, rel, float(b.norm()))
     print("worst gradient rel-L2 errors:", sorted(worst)[-3:], "global:", (num / den) ** 0.5)
-    assert (num / den) ** 0.5 < 2e-3
+    assert (num / den) ** 0.5 < tol["grad_global"]
 
 
 def test_eval_mode_runs_and_returns_boxlists():
