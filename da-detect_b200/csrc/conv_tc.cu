@@ -479,17 +479,35 @@ __global__ void fill_kernel(const float* __restrict__ addend, const float* __res
 // ------------------------------------------------------------------------------------------------ host side
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
+// cuTensorMapEncodeTiled is a driver-API entry point; it is resolved through the runtime
+// (cudaGetDriverEntryPoint) so that the library has no link-time dependency on libcuda.so and still loads on
+// a machine without a driver (the CPU build/ABI check).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return dd::fail(-1, "cuTensorMapEncodeTiled is unavailable (no CUDA driver)", __FILE__, __LINE__);
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims,
-                                      strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    const char* msg = nullptr;
-    cuGetErrorString(r, &msg);
-    snprintf(dd::g_err, sizeof(dd::g_err), "cuTensorMapEncodeTiled failed: %s", msg ? msg : "?");
+    snprintf(dd::g_err, sizeof(dd::g_err), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return -1;
   }
   return 0;

@@ -14,6 +14,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
+from ..structures import is_source_image
 from .backbone import Conv2dParams
 
 
@@ -60,7 +61,7 @@ class DAInsHead(nn.Module):
 
 def _image_domain_labels(targets, device):
     """prepare_masks (da_heads/loss.py:45-53): one bit per image, is_source.any()."""
-    return torch.tensor([1 if bool(t.get_field("is_source").any()) else 0 for t in targets],
+    return torch.tensor([1 if is_source_image(t) else 0 for t in targets],
                         dtype=torch.uint8, device=device)
 
 

@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..structures import to_image_list
+from ..structures import cache_source_flags, is_source_image, to_image_list
 from ..utils.random_source import RandomSource
 from .backbone import build_backbone
 from .da_heads import build_da_heads, build_da_heads_triplet
@@ -23,9 +23,61 @@ from .roi_heads import build_roi_heads
 from .rpn import build_rpn
 
 
+class _Trunk(nn.Module):
+    """Static-shape segment 1: backbone + RPN head.  Not registered in the model tree (shares its modules)."""
+
+    def __init__(self, backbone, rpn_head):
+        super().__init__()
+        self.backbone, self.rpn_head = backbone, rpn_head
+
+    def forward(self, x):
+        feat = self.backbone(x)[0]
+        logits, deltas = self.rpn_head(feat)
+        return feat, logits, deltas
+
+
+class _BoxBranch(nn.Module):
+    """Static-shape segment 2 (for a fixed number of ROIs): ROIAlign -> res5 -> 7x7 average -> predictor."""
+
+    def __init__(self, feature_extractor, predictor):
+        super().__init__()
+        self.fe, self.predictor = feature_extractor, predictor
+
+    def forward(self, feat, rois):
+        x = ops.roi_align(feat, rois, self.fe.pooler.scale, self.fe.pooler.output_size, self.fe.pooler.sampling_ratio,
+                          2 if self.fe.even_bins else 1)
+        x = self.fe.head(x, self.fe.even_bins)
+        pooled = ops.avgpool_hw(x)
+        cls, box = self.predictor(pooled)
+        return pooled, cls, box
+
+
+class SegmentRunner(object):
+    """Runs static-shape segments either eagerly or as CUDA graphs (torch.cuda.make_graphed_callables captures
+    the forward AND backward kernel sequences of a segment once per input-shape signature; replay removes the
+    per-launch Python/ctypes/autograd overhead, which is ~3x the GPU time of the step otherwise)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.cache = {}
+
+    def run(self, name, factory, args):
+        if not self.enabled or not torch.is_grad_enabled():
+            return factory()(*args)
+        key = (name,) + tuple((tuple(a.shape), a.requires_grad) for a in args)
+        fn = self.cache.get(key)
+        if fn is None:
+            sample = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in args)
+            torch.cuda.synchronize()
+            fn = torch.cuda.make_graphed_callables(factory(), sample)
+            self.cache[key] = fn
+        return fn(*args)
+
+
 class GeneralizedRCNN(nn.Module):
     def __init__(self, cfg):
         super().__init__()
+        self.__dict__["segments"] = SegmentRunner()
         self.rng = RandomSource()
         self.backbone = build_backbone(cfg)
         self.rpn = build_rpn(cfg, self.rng)
@@ -35,6 +87,12 @@ class GeneralizedRCNN(nn.Module):
         self.da_heads_triplet = build_da_heads_triplet(cfg, self.rng) if self.triplet_use else False
         self.Aligned = cfg.MODEL.DA_HEADS.ALIGNMENT
         self.size_divisible = cfg.DATALOADER.SIZE_DIVISIBILITY
+
+    def enable_cuda_graphs(self, flag=True):
+        """Replay the static-shape segments (backbone + RPN head; box branch per ROI count) as CUDA graphs."""
+        self.segments.enabled = bool(flag)
+        if self.roi_heads:
+            self.roi_heads.box.__dict__["segments"] = self.segments
 
     def set_random_source(self, rng):
         """Swap the source of randperm/dropout draws (parity tests replay oracle draws)."""
@@ -49,9 +107,12 @@ class GeneralizedRCNN(nn.Module):
         if self.training and targets is None:
             raise ValueError("In training mode, targets should be passed")
         images = to_image_list(images)
+        if targets is not None:
+            cache_source_flags(targets)
         x = ops.nchw_to_nhwc(images.tensors)
-        features = self.backbone(x)
-        proposals, proposal_losses = self.rpn(images, features, targets)
+        feat, logits, deltas = self.segments.run("trunk", lambda: _Trunk(self.backbone, self.rpn.head), (x,))
+        features = [feat]
+        proposals, proposal_losses = self.rpn(images, features, targets, head_out=(logits, deltas))
         da_losses = {}
         if self.roi_heads:
             if self.training:
@@ -64,7 +125,7 @@ class GeneralizedRCNN(nn.Module):
                     _, _, detector_losses, _, dom = self.roi_heads(ori_features, proposals[0:2], ori_targets)
                     pooled = box.last_pooled
                     n_src = sum(len(p) for p, t in zip(box.loss_evaluator._proposals, ori_targets)
-                                if bool(t.get_field("is_source").any()))
+                                if is_source_image(t))
                     pooled_set = [0, 0, 0]
                     if self.Aligned:                         # :109-114 — all three with the TARGET image's proposals
                         pooled_set = []
@@ -78,7 +139,7 @@ class GeneralizedRCNN(nn.Module):
                     box = self.roi_heads.box
                     _, _, detector_losses, _, dom = self.roi_heads(features, proposals, targets)
                     n_src = sum(len(p) for p, t in zip(box.loss_evaluator._proposals, targets)
-                                if bool(t.get_field("is_source").any()))
+                                if is_source_image(t))
                     da_losses = self.da_heads(features, box.last_pooled, dom, n_src, targets)
                 else:
                     # The reference leaves `detector_losses` unbound here; plain Faster R-CNN

@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..structures import BoxList
+from ..structures import BoxList, is_source_image
 from .backbone import ResNetHead
 from .sampling import BELOW_LOW_THRESHOLD, BETWEEN_THRESHOLDS, balanced_sample
 
@@ -92,7 +92,7 @@ class FastRCNNLossComputation(object):
     def prepare_targets(self, proposals, targets, sample_for_da=False):
         labels, regs, domains = [], [], []
         for p, t in zip(proposals, targets):
-            src = bool(t.get_field("is_source").any())
+            src = is_source_image(t)
             gt = t.convert("xyxy").bbox
             m, _ = ops.match(gt, p.bbox, self.high, self.low, False)
             gl = t.get_field("labels")
@@ -162,9 +162,17 @@ class ROIBoxHead(nn.Module):
         box_head/box_head.py:36-117, plus the shared pooled vector as attribute `last_pooled`."""
         if self.training:
             proposals = self.loss_evaluator.subsample(proposals, targets)
-        x = self.feature_extractor(features, proposals)
-        pooled = ops.avgpool_hw(x)
-        class_logits, box_regression = self.predictor(pooled)
+        segments = self.__dict__.get("segments")
+        if segments is not None and self.training:
+            from .detector import _BoxBranch
+            rois = Pooler.convert_to_roi_format(proposals)
+            pooled, class_logits, box_regression = segments.run(
+                "box", lambda: _BoxBranch(self.feature_extractor, self.predictor), (features[0], rois))
+            x = None          # the [K,7,7,2048] map stays inside the segment; consumers use `pooled`
+        else:
+            x = self.feature_extractor(features, proposals)
+            pooled = ops.avgpool_hw(x)
+            class_logits, box_regression = self.predictor(pooled)
         self.last_pooled = pooled
         if not self.training:
             from .inference import box_post_process

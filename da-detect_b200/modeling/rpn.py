@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..structures import BoxList
+from ..structures import BoxList, is_source_image
 from .backbone import Conv2dParams
 from .sampling import BELOW_LOW_THRESHOLD, BETWEEN_THRESHOLDS, balanced_sample
 
@@ -136,7 +136,7 @@ class RPNModule(nn.Module):
             out.append(bl)
         if train and targets is not None:       # add_gt_proposals: source images only (:51-74)
             for i, t in enumerate(targets):
-                if bool(t.get_field("is_source").any()):
+                if is_source_image(t):
                     gt = t.bbox.to(out[i].bbox.dtype)
                     bl = BoxList(torch.cat([out[i].bbox, gt]), out[i].size, mode="xyxy")
                     bl.add_field("objectness", torch.cat([out[i].get_field("objectness"),
@@ -150,7 +150,7 @@ class RPNModule(nn.Module):
         labels, reg_targets = [], []
         vis = visibility.bool()
         for t in targets:                                   # labels exist for source images only (:66-67)
-            if not bool(t.get_field("is_source").any()):
+            if not is_source_image(t):
                 continue
             gt = t.convert("xyxy").bbox
             m, _ = ops.match(gt, anchors, R.FG_IOU_THRESHOLD, R.BG_IOU_THRESHOLD, True)
@@ -173,9 +173,9 @@ class RPNModule(nn.Module):
         self.last = dict(labels=labels, pos=pos, neg=neg, reg_targets=reg_targets)
         return obj_loss, box_loss
 
-    def forward(self, images, features, targets=None):
+    def forward(self, images, features, targets=None, head_out=None):
         feat = features[0]
-        logits, deltas = self.head(feat)
+        logits, deltas = head_out if head_out is not None else self.head(feat)
         n, fh, fw, _ = feat.shape
         ih, iw = images.image_sizes[0]
         anchors, vis = self.anchor_generator.grid(fh, fw, int(iw), int(ih))

@@ -133,3 +133,24 @@ class BoxList(object):
     def __repr__(self):
         return "BoxList(num_boxes={}, image_width={}, image_height={}, mode={})".format(
             len(self), self.size[0], self.size[1], self.mode)
+
+
+def is_source_image(target):
+    """True when the image's boxes carry is_source=True (reference: `is_source.any()`, e.g. rpn/loss.py:63-67).
+    The answer is cached on the BoxList so the device->host read happens once per image, not once per use."""
+    flag = getattr(target, "_is_source_image", None)
+    if flag is None:
+        flag = bool(target.get_field("is_source").any())
+        target._is_source_image = flag
+    return flag
+
+
+def cache_source_flags(targets):
+    """One device->host transfer for the whole batch instead of one sync per image per consumer."""
+    import torch
+    todo = [t for t in targets if getattr(t, "_is_source_image", None) is None]
+    if not todo:
+        return
+    flags = torch.stack([t.get_field("is_source").any() for t in todo]).tolist()
+    for t, f in zip(todo, flags):
+        t._is_source_image = bool(f)

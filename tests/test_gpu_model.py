@@ -150,3 +150,34 @@ def test_product_path_does_not_import_oracle():
     code = ("import sys; sys.path.insert(0, %r); import dadetect_b200.modeling, dadetect_b200.ops, dadetect_b200._C; "
             "bad=[m for m in sys.modules if 'da_frcnn_ref' in m or m.startswith('oracle')]; assert not bad, bad" % ROOT)
     subprocess.check_call([sys.executable, "-c", code])
+
+
+@pytest.mark.timeout(900)
+def test_cuda_graph_segments_match_eager():
+    """Replaying the static-shape segments as CUDA graphs must not change results (same kernels, same order)."""
+    from dadetect_b200.utils.random_source import ReplaySource
+    cfg, sd, images, targets, hw = scenario("da_img_ins_cst")
+    dev = torch.device("cuda")
+    rec = orc.RecordingHooks()
+    torch.manual_seed(5)
+    with torch.no_grad():
+        orc.forward_train({k: v.clone() for k, v in sd.items()}, cfg, images, targets, hooks=rec, nms_strict=True)
+    results = []
+    for graphs in (False, True):
+        model = build(cfg, sd, dev)
+        model.enable_cuda_graphs(graphs)
+        for rep in range(2):                                   # second pass replays the captured graphs
+            model.set_random_source(ReplaySource(rec.perms, rec.masks))
+            model.zero_grad(set_to_none=True)
+            losses = model(images.to(dev), to_boxlists(targets, hw, dev))
+            sum(losses.values()).backward()
+        results.append(({k: float(v) for k, v in losses.items()},
+                        {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = results
+    assert l0.keys() == l1.keys()
+    for k in l0:
+        assert abs(l0[k] - l1[k]) <= 1e-6 * max(1.0, abs(l0[k])), (k, l0[k], l1[k])
+    assert g0.keys() == g1.keys()
+    for k in g0:
+        rel = float((g0[k] - g1[k]).norm() / (g0[k].norm() + 1e-30))
+        assert rel < 1e-4, (k, rel)       # only atomics ordering (ROIAlign backward, loss partial sums) may differ
