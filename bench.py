@@ -22,7 +22,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -55,31 +54,45 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region (the B200_PROFILING.md clocks line), read
+    in-process through NVML: forking `nvidia-smi` five times a second from a process that holds a CUDA context
+    stalls the launching thread and roughly doubles the measured step time."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
 
     def run(self):
-        while not self.stop_flag:
+        n = self.nvml
+        while not self.stop_flag and n is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([x.strip() for x in out.strip().split(",")])
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, mx, reasons))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.25)
 
     def summary(self):
-        good = [s for s in self.samples if len(s) == 6 and s[0].isdigit()]
-        if not good:
+        if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in good)]
-        return {"sm_mhz": statistics.median(int(s[0]) for s in good), "sm_max_mhz": int(good[0][1]), "reasons": reasons}
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = [k for k, b in bits.items() if any(s[2] & b for s in self.samples)]
+        return {"sm_mhz": statistics.median(s[0] for s in self.samples), "sm_max_mhz": self.samples[0][1],
+                "reasons": reasons, "samples": len(self.samples)}
 
 
 # ------------------------------------------------------------------------------------------ CPU port arm

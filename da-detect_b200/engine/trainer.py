@@ -21,6 +21,7 @@ import torch
 import torch.distributed as dist
 
 from .. import ops
+from ..utils.sections import section
 
 
 class WarmupMultiStepLR(object):
@@ -125,10 +126,13 @@ class FlatSGDTrainer(object):
 
     def step(self, images, targets):
         """images: ImageList/tensor on the device; returns the (unreduced) loss dict of this rank."""
-        loss_dict = self.model(images, targets)
-        losses = sum(loss_dict.values())
-        self.zero_grad()
-        losses.backward()
-        self.all_reduce()
-        self.optimizer_step()
+        with section("forward"):
+            loss_dict = self.model(images, targets)
+            losses = sum(loss_dict.values())
+        with section("backward"):
+            self.zero_grad()
+            losses.backward()
+        with section("allreduce+sgd"):
+            self.all_reduce()
+            self.optimizer_step()
         return loss_dict

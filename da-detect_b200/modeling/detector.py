@@ -17,6 +17,7 @@ from torch import nn
 from .. import ops
 from ..structures import cache_source_flags, is_source_image, to_image_list
 from ..utils.random_source import RandomSource
+from ..utils.sections import section
 from .backbone import build_backbone
 from .da_heads import build_da_heads, build_da_heads_triplet
 from .roi_heads import build_roi_heads
@@ -109,10 +110,12 @@ class GeneralizedRCNN(nn.Module):
         images = to_image_list(images)
         if targets is not None:
             cache_source_flags(targets)
-        x = ops.nchw_to_nhwc(images.tensors)
-        feat, logits, deltas = self.segments.run("trunk", lambda: _Trunk(self.backbone, self.rpn.head), (x,))
+        with section("trunk_fwd"):
+            x = ops.nchw_to_nhwc(images.tensors)
+            feat, logits, deltas = self.segments.run("trunk", lambda: _Trunk(self.backbone, self.rpn.head), (x,))
         features = [feat]
-        proposals, proposal_losses = self.rpn(images, features, targets, head_out=(logits, deltas))
+        with section("rpn_proposals_and_loss"):
+            proposals, proposal_losses = self.rpn(images, features, targets, head_out=(logits, deltas))
         da_losses = {}
         if self.roi_heads:
             if self.training:
@@ -137,10 +140,12 @@ class GeneralizedRCNN(nn.Module):
                                                       ori_targets)
                 elif self.da_heads:
                     box = self.roi_heads.box
-                    _, _, detector_losses, _, dom = self.roi_heads(features, proposals, targets)
+                    with section("box_head_fwd"):
+                        _, _, detector_losses, _, dom = self.roi_heads(features, proposals, targets)
                     n_src = sum(len(p) for p, t in zip(box.loss_evaluator._proposals, targets)
                                 if is_source_image(t))
-                    da_losses = self.da_heads(features, box.last_pooled, dom, n_src, targets)
+                    with section("da_heads_fwd"):
+                        da_losses = self.da_heads(features, box.last_pooled, dom, n_src, targets)
                 else:
                     # The reference leaves `detector_losses` unbound here; plain Faster R-CNN
                     # training is the obvious intent.

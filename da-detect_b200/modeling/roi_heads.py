@@ -17,6 +17,7 @@ from torch import nn
 from .. import ops
 from ..structures import BoxList, is_source_image
 from .backbone import ResNetHead
+from ..utils.sections import section
 from .sampling import BELOW_LOW_THRESHOLD, BETWEEN_THRESHOLDS, balanced_sample
 
 
@@ -161,7 +162,8 @@ class ROIBoxHead(nn.Module):
         """Training: returns (x, proposals, losses, da_ins_feas, da_ins_labels) like
         box_head/box_head.py:36-117, plus the shared pooled vector as attribute `last_pooled`."""
         if self.training:
-            proposals = self.loss_evaluator.subsample(proposals, targets)
+            with section("  box_subsample"):
+                proposals = self.loss_evaluator.subsample(proposals, targets)
         segments = self.__dict__.get("segments")
         if segments is not None and self.training:
             from .detector import _BoxBranch

@@ -11,6 +11,7 @@ from torch import nn
 from .. import ops
 from ..structures import BoxList, is_source_image
 from .backbone import Conv2dParams
+from ..utils.sections import section
 from .sampling import BELOW_LOW_THRESHOLD, BETWEEN_THRESHOLDS, balanced_sample
 
 
@@ -179,10 +180,12 @@ class RPNModule(nn.Module):
         n, fh, fw, _ = feat.shape
         ih, iw = images.image_sizes[0]
         anchors, vis = self.anchor_generator.grid(fh, fw, int(iw), int(ih))
-        boxes = self.proposals(anchors, logits.detach(), deltas.detach(), images.image_sizes, targets)
+        with section("  rpn_proposals"):
+            boxes = self.proposals(anchors, logits.detach(), deltas.detach(), images.image_sizes, targets)
         if not self.training:
             return boxes, {}
-        obj_loss, box_loss = self.losses(anchors, vis, logits, deltas, targets)
+        with section("  rpn_loss"):
+            obj_loss, box_loss = self.losses(anchors, vis, logits, deltas, targets)
         return boxes, {"loss_objectness": obj_loss, "loss_rpn_box_reg": box_loss}
 
 
