@@ -1,0 +1,93 @@
+"""CPU-only: host-side logic of the data-parallel tail (engine/trainer.py) with world_size 2 over gloo —
+flat parameter/gradient buffers, [weights..., biases...] ordering, one all_reduce of the flat gradient whose
+1/world average is applied by the optimiser's grad_scale — and the LR schedules."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch import nn
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _Toy(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv = nn.Conv2d(4, 8, 3, bias=True)
+        self.fc = nn.Linear(8, 3)
+        self.frozen = nn.Linear(2, 2)
+        for p in self.frozen.parameters():
+            p.requires_grad = False
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dadetect_b200.config import get_cfg_defaults
+    from dadetect_b200.engine import FlatSGDTrainer
+    torch.manual_seed(0)
+    model = _Toy()
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    tr = FlatSGDTrainer(model, get_cfg_defaults())
+    assert tr.world == world
+    # parameters are views of the flat buffer and kept their values; weights precede biases
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    names = [n for n, _ in tr.order]
+    assert names == ["conv.weight", "fc.weight", "conv.bias", "fc.bias"]
+    assert tr.n_weight == 8 * 4 * 9 + 3 * 8
+    off = 0
+    for n, p in tr.order:
+        assert p.data_ptr() == tr.flat_param.data_ptr() + 4 * off, n
+        assert p.grad.data_ptr() == tr.flat_grad.data_ptr() + 4 * off, n
+        off += (p.numel() + 3) // 4 * 4
+    # rank-dependent gradients written through p.grad land in the flat buffer; one all_reduce sums them
+    tr.zero_grad()
+    x = torch.randn(2, 4, 5, 5, generator=torch.Generator().manual_seed(100 + rank))
+    y = model.fc(model.conv(x).mean(dim=(2, 3))).sum()
+    y.backward()
+    local = tr.flat_grad.clone()
+    tr.all_reduce()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    assert torch.allclose(tr.flat_grad, sum(gathered), atol=1e-6)
+    if rank == 0:
+        out.put("ok")
+    dist.destroy_process_group()
+
+
+def test_flat_buffers_and_all_reduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get() == "ok"
+
+
+def test_lr_schedules():
+    from dadetect_b200.engine import WarmupCosineLR, WarmupMultiStepLR
+    s = WarmupMultiStepLR(0.001, (50000,), 0.1, 1.0 / 3, 500, "linear")
+    assert s.lr_at(0) == pytest.approx(0.001 / 3)
+    assert s.lr_at(250) == pytest.approx(0.001 * (1 / 3 * 0.5 + 0.5))
+    assert s.lr_at(500) == pytest.approx(0.001)
+    assert s.lr_at(50000) == pytest.approx(0.0001)
+    with pytest.raises(ValueError):
+        WarmupMultiStepLR(0.001, (5, 3))
+    c = WarmupCosineLR(0.001, 170000, 1e-6, 1e-4, 33200)
+    assert c.lr_at(0) == pytest.approx(1e-4)
+    assert c.lr_at(33200) < 0.001 and c.lr_at(33200) > 0.0009
+    assert c.lr_at(170000) == pytest.approx(1e-6)
