@@ -45,6 +45,8 @@ struct TcParams {
   int N, OH, OW;          // logical output pixel grid enumerated by the tiles
   int tn, th, tw;         // tile = tn images x th rows x tw cols (tn*th*tw == 128)
   int tiles_h, tiles_w;   // ceil(OH/th), ceil(OW/tw)
+  int m_tiles, n_tiles;   // persistent tile space: t -> (n_tile = t % n_tiles, m_tile = t / n_tiles)
+  int tma_store;          // 1: staged chunks leave through a TMA tensor store; 0: guarded scalar stores
   // where a row lands in the output tensor: out[((n*out_H + h*os)*out_W + w*os)*ldc + co]
   int out_H, out_W, os, ldc;
   int Cout;               // valid output channels (columns)
@@ -83,6 +85,13 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
@@ -151,43 +160,70 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 
 template <int BN>
 struct SmemLayout {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kABytes = BM * BKB;      // 16 KB
   static constexpr int kBBytes = BN * BKB;      // 8 / 16 / 32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTotal = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = BM * 128;                 // one 128-row x 32-column fp32 chunk
+  static constexpr int kStagingOff = kStages * kStageBytes;      // 2 staging buffers (1024-aligned)
+  static constexpr int kRowOff = kStagingOff + 2 * kStagingBytes;  // int32 pixel index per tile row
+  static constexpr int kBarOff = kRowOff + BM * 4;
+  static constexpr int kTotal = kBarOff + 256 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------ kernel
+// Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence t = blockIdx.x + i*gridDim.x.
+// Two TMEM accumulators (2 x BN columns) let the MMAs of tile i+1 run while the epilogue drains tile i; the TMA
+// producer runs ahead across tile boundaries through the smem ring.
+//
+// Epilogue per 32-column chunk: tcgen05.ld (thread = one tile row) -> 128B-swizzled smem staging ->
+// re-mapped pass (8 threads per row => coalesced 128-bit reads of residual / mask, per-channel scale + bias,
+// ReLU) -> one TMA tensor store of the [rows x 32 ch] box, which also clips the tile against the tensor edges.
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, const TcParams p) {
   using L = SmemLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kStages * L::kStageBytes);
+  uint8_t* staging = smem + L::kStagingOff;
+  int* row_pix = reinterpret_cast<int*>(smem + L::kRowOff);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* empty_bar = full_bar + L::kStages;
-  uint64_t* tmem_full_bar = empty_bar + L::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + L::kStages;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int n_tile = blockIdx.x;                       // output-channel tile
-  int mt = blockIdx.y;                                 // pixel-block tile
-  const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
-  const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
-  const int n0 = mt * p.tn, oh0 = tile_h * p.th, ow0 = tile_w * p.tw;
   const int k_iters = p.taps * p.cblocks;
+  const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (p.tma_store) tma_prefetch_desc(&map_c);
     for (int s = 0; s < L::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -196,99 +232,177 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % L::kStages;
-        const uint32_t ph = (it / L::kStages) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        const int tap = it / p.cblocks, cb = it % p.cblocks;
-        const int kh = tap / p.KW, kw = tap % p.KW;
-        uint8_t* sa = smem + s * L::kStageBytes;
-        uint8_t* sb = sa + L::kABytes;
-        mbar_expect_tx(full_bar + s, L::kStageBytes);
-        tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
-        tma_load_2d(&map_b, full_bar + s, sb, tap * p.Cin + cb * BKE, n_tile * BN);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_tile = t % p.n_tiles;
+        int mt = t / p.n_tiles;
+        const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
+        const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
+        const int n0 = mt * p.tn, oh0 = tile_h * p.th, ow0 = tile_w * p.tw;
+        for (int kit = 0; kit < k_iters; ++kit, ++it) {
+          const int s = it % L::kStages;
+          const uint32_t ph = (it / L::kStages) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          const int tap = kit / p.cblocks, cb = kit - tap * p.cblocks;
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          uint8_t* sa = smem + s * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(full_bar + s, L::kStageBytes);
+          tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
+          tma_load_2d(&map_b, full_bar + s, sb, tap * p.Cin + cb * BKE, n_tile * BN);
+        }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-    for (int it = 0; it < k_iters; ++it) {
-      const int s = it % L::kStages;
-      const uint32_t ph = (it / L::kStages) & 1;
-      mbar_wait(full_bar + s, ph);
+    uint32_t it = 0;
+    int local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t aph = (local >> 1) & 1;
+      mbar_wait(tmem_empty_bar + acc, aph ^ 1);            // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint32_t b_addr = a_addr + L::kABytes;
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kit = 0; kit < k_iters; ++kit, ++it) {
+        const int s = it % L::kStages;
+        const uint32_t ph = (it / L::kStages) & 1;
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
 #pragma unroll
-        for (int k = 0; k < BKE / UMMA_K; ++k) {
-          const uint64_t ad = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
-          const uint64_t bd = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
-          umma_tf32(tmem_base, ad, bd, idesc, (it | k) ? 1u : 0u);
+          for (int k = 0; k < BKE / UMMA_K; ++k) {
+            const uint64_t ad = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
+            const uint64_t bd = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
+            umma_tf32(tmem_d, ad, bd, idesc, (kit | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + s);                              // frees the smem stage when these MMAs retire
+          if (kit == k_iters - 1) umma_commit(tmem_full_bar + acc);  // accumulator complete
         }
-        umma_commit(empty_bar + s);                       // frees the smem stage when these MMAs retire
-        if (it == k_iters - 1) umma_commit(tmem_full_bar);  // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ================================ epilogue (warps 2..5) ================================
     const int quarter = warp & 3;                        // TMEM lanes [32*quarter, 32*quarter+32)
-    const int row = quarter * 32 + lane;                 // tile row = TMEM lane = output pixel slot
+    const int row = quarter * 32 + lane;                 // tile row owned in the TMEM -> smem pass
+    const int te = threadIdx.x - 64;                     // 0..127, mapping of the re-mapped pass:
+    const int pc = te & 7;                               //   16-byte column group inside the 32-column chunk
+    const int pr0 = te >> 3;                             //   rows pr0 + 16*i
     const int wl = row % p.tw, hl = (row / p.tw) % p.th, nl = row / (p.tw * p.th);
-    const int n = n0 + nl, oh = oh0 + hl, ow = ow0 + wl;
-    const bool row_ok = n < p.N && oh < p.OH && ow < p.OW;
-    const size_t row_off = (((size_t)n * p.out_H + (size_t)oh * p.os) * p.out_W + (size_t)ow * p.os) * p.ldc;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    uint32_t chunk_ctr = 0;
+    int local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t aph = (local >> 1) & 1;
+      const int n_tile = t % p.n_tiles;
+      int mt = t / p.n_tiles;
+      const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
+      const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
+      const int n0 = mt * p.tn, oh0 = tile_h * p.th, ow0 = tile_w * p.tw;
+      epi_bar_sync();                                    // every reader of the previous tile's row table is done
+      {
+        const int n = n0 + nl, oh = oh0 + hl, ow = ow0 + wl;
+        const bool ok = n < p.N && oh < p.OH && ow < p.OW;
+        row_pix[row] = ok ? (n * p.out_H + oh * p.os) * p.out_W + ow * p.os : -1;
+      }
+      const int cols_here = min(BN, p.Cout - n_tile * BN);
+      const int n_chunks = (cols_here + 31) >> 5;
+      mbar_wait(tmem_full_bar + acc, aph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-      const int col0 = n_tile * BN + c0;
-      if (row_ok && col0 < p.Cout) {
+      for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
+        if (ch == n_chunks - 1) {                        // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tmem_empty_bar + acc);
+        }
+        uint8_t* stg = staging + (chunk_ctr & 1) * L::kStagingBytes;
+        if (te == 0) tma_store_wait_read<1>();           // the store that last read this buffer has drained
+        epi_bar_sync();
+        {
+          uint8_t* dst = stg + row * 128;
+          const int sw = row & 7;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int col = col0 + j;
-          if (col >= p.Cout) break;
-          float v[4];
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst + ((j ^ sw) << 4)) =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                            __uint_as_float(r[4 * j + 3]));
+        }
+        epi_bar_sync();
+        // ---- re-mapped pass: thread = (column group pc, rows pr0 + 16 i)
+        const int col = n_tile * BN + ch * 32 + pc * 4;
+        float sc[4], bi[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = __uint_as_float(r[j + e]);
-            const int c = col + e;
-            if (c < p.Cout) {
-              if (p.scale) x *= __ldg(p.scale + c);
-              if (p.bias) x += __ldg(p.bias + c);
-              if (p.extra) x += __ldg(p.extra + row_off + c);
-              if (p.mask) x = __ldg(p.mask + row_off + c) > 0.f ? x : 0.f;
-              if (p.relu) x = fmaxf(x, 0.f);
+        for (int e = 0; e < 4; ++e) {
+          const bool cok = col + e < p.Cout;
+          sc[e] = (p.scale && cok) ? __ldg(p.scale + col + e) : 1.f;
+          bi[e] = (p.bias && cok) ? __ldg(p.bias + col + e) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = pr0 + 16 * i;
+          const int pix = row_pix[rr];
+          float4* sp = reinterpret_cast<float4*>(stg + rr * 128 + ((pc ^ (rr & 7)) << 4));
+          float4 v4 = *sp;
+          float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = fmaf(v[e], sc[e], bi[e]);
+          if (pix >= 0 && col < p.Cout) {
+            const size_t off = (size_t)pix * p.ldc + col;
+            if (p.tma_store) {                           // ldc % 4 == 0: 128-bit side reads, TMA writes
+              if (p.extra) { const float4 x = dd::ldg4(p.extra + off); v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; }
+              if (p.mask) {
+                const float4 m = dd::ldg4(p.mask + off);
+                v[0] = m.x > 0.f ? v[0] : 0.f; v[1] = m.y > 0.f ? v[1] : 0.f;
+                v[2] = m.z > 0.f ? v[2] : 0.f; v[3] = m.w > 0.f ? v[3] : 0.f;
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+              }
+            } else {                                     // narrow / unaligned outputs: scalar guarded path
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (col + e < p.Cout) {
+                  float x = v[e];
+                  if (p.extra) x += __ldg(p.extra + off + e);
+                  if (p.mask) x = __ldg(p.mask + off + e) > 0.f ? x : 0.f;
+                  if (p.relu) x = fmaxf(x, 0.f);
+                  p.out[off + e] = x;
+                }
+              }
             }
-            v[e] = x;
           }
-          float* dst = p.out + row_off + col;
-          if (col + 3 < p.Cout && (((row_off + col) & 3) == 0)) {
-            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (col + e < p.Cout) dst[e] = v[e];
-          }
+          if (p.tma_store) *sp = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        if (p.tma_store) {
+          fence_async_smem();
+          epi_bar_sync();
+          if (te == 0) tma_store_4d(&map_c, stg, n_tile * BN + ch * 32, ow0, oh0, n0);
         }
       }
     }
+    if (te == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
 
 // ------------------------------------------------------------------------------------------------ wgrad kernel
 // D[co, ci] (one filter tap per CTA column) = sum over a range of pixel blocks of GY[pix, co] * X[pix + tap, ci].
-// Both operands are MN-major: a TMA box is [32 pixels x 32 channels] with the 32 channels (128 B) contiguous,
-// i.e. one UMMA "MN-major, 128B-swizzle" column block; 4 (co) + BN/32 (ci) such boxes per stage.
+// Both operands are MN-major: a [32 pixels x 32 channels] block with the 32 channels (128 B) contiguous is one
+// UMMA "MN-major, 128B-swizzle" column block; a stage holds 4 (co) + BN/32 (ci) of them, each operand landed by
+// ONE 5-D TMA box whose outermost dimension walks the 32-channel blocks.  1x1 convs see the pixels as one
+// dense axis (no padding of 7x7 ROI maps to 8x8).
 struct TcWgradParams {
   float* partial;          // [splits][Cout][taps*Cin]
   int Cout, Cin, taps, KW, pad;
@@ -373,12 +487,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
         uint8_t* sa = smem + s * L::kStageBytes;
         uint8_t* sb = sa + L::kABytes;
         mbar_expect_tx(full_bar + s, L::kStageBytes);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          tma_load_4d(&map_gy, full_bar + s, sa + j * WG_BOX_BYTES, co0 + j * 32, ow0, oh0, n0);
-#pragma unroll
-        for (int j = 0; j < BN / 32; ++j)
-          tma_load_4d(&map_x, full_bar + s, sb + j * WG_BOX_BYTES, ci0 + j * 32, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
+        // 5-D views {32 ch, W, H, N, channel block}: one instruction lands all [32 pix x 32 ch] column blocks
+        tma_load_5d(&map_gy, full_bar + s, sa, 0, ow0, oh0, n0, co0 / 32);
+        tma_load_5d(&map_x, full_bar + s, sb, 0, ow0 + kw - p.pad, oh0 + kh - p.pad, n0, ci0 / 32);
       }
     }
   } else if (warp == 1) {
@@ -437,33 +548,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
   }
 }
 
-// W'[ci][KH-1-kh][KW-1-kw][co] = scale[co] * W[co][kh][kw][ci]  (dgrad as a forward conv over GY)
+// W'[ci][KH-1-kh][KW-1-kw][co] = scale[co] * W[co][kh][kw][ci]  (dgrad as a forward conv over GY).
+// One 32x32 smem-tiled transpose per (tap, co block, ci block): coalesced on both sides.
 __global__ void weight_flip_transpose_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                             float* __restrict__ wt, int Cout, int Cin, int KH, int KW) {
-  const long long total = (long long)Cout * KH * KW * Cin;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    // t enumerates the DESTINATION (co fastest) for coalesced writes
-    const int co = (int)(t % Cout);
-    const int kw = (int)((t / Cout) % KW);
-    const int kh = (int)((t / ((long long)Cout * KW)) % KH);
-    const int ci = (int)(t / ((long long)Cout * KW * KH));
-    float v = w[(((size_t)co * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)) * Cin + ci];
-    if (scale) v *= __ldg(scale + co);
-    wt[t] = v;
+                                             float* __restrict__ wt, int Cout, int Cin, int taps) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int co = co0 + ty + j, ci = ci0 + tx;
+    float v = 0.f;
+    if (co < Cout && ci < Cin) {
+      v = w[((size_t)co * taps + tap) * Cin + ci];
+      if (scale) v *= __ldg(scale + co);
+    }
+    tile[ty + j][tx] = v;
   }
-}
-
-// x[:, ::s, ::s, :] (the input a strided 1x1 conv actually reads), float4 over channels
-__global__ void subsample_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int s,
-                                 int OH, int OW) {
-  const int c4n = C / 4;
-  const long long total = (long long)N * OH * OW * c4n;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(t % c4n);
-    const int ow = (int)((t / c4n) % OW);
-    const int oh = (int)((t / ((long long)c4n * OW)) % OH);
-    const int n = (int)(t / ((long long)c4n * OW * OH));
-    reinterpret_cast<float4*>(y)[t] = dd::ldg4(x + (((size_t)n * H + (size_t)oh * s) * W + (size_t)ow * s) * C + c4 * 4);
+  __syncthreads();
+  const int tflip = taps - 1 - tap;                  // (KH-1-kh)*KW + (KW-1-kw)
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int ci = ci0 + ty + j, co = co0 + tx;
+    if (co < Cout && ci < Cin) wt[((size_t)ci * taps + tflip) * Cout + co] = tile[tx][ty + j];
   }
 }
 
@@ -514,42 +621,58 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
 }
 
 template <int BN>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int m_tiles, int n_tiles, cudaStream_t s) {
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcParams& p, cudaStream_t s) {
   using L = SmemLayout<BN>;
   static bool configured = false;
   if (!configured) {
     DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  dim3 grid(n_tiles, m_tiles);
-  conv_tc_kernel<BN><<<grid, NUM_THREADS, L::kTotal, s>>>(ma, mb, p);
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < dd::kNumSMs ? total : dd::kNumSMs;
+  conv_tc_kernel<BN><<<grid, NUM_THREADS, L::kTotal, s>>>(ma, mb, mc, p);
   DD_LAUNCHED();
   return 0;
 }
 
-// Core: D[pixel, col] = sum_{tap, c} A[n, oh + kh - pad, ow + kw - pad, c] * B[col, tap, c]
-//   A: [N, AH, AW, Cin] NHWC fp32 (stride 1 access), B: [ncols, taps*Cin] fp32, output rows enumerate (N, OH, OW).
-int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, const float* b, int ncols, int KH, int KW, int pad,
-                 int OH, int OW, TcParams p, cudaStream_t s) {
+// Core: D[pixel, col] = sum_{tap, c} A[n, (oh + kh - pad) * as, (ow + kw - pad) * as, c] * B[col, tap, c]
+//   A: [N, AH, AW, Cin] NHWC fp32 read with pixel stride `as` (as > 1 only for 1x1 taps: the TMA view simply
+//      has doubled strides, nothing is gathered), B: [ncols, taps*Cin] fp32, output rows enumerate (N, OH, OW)
+//   and land at out[((n*out_H + oh*os)*out_W + ow*os)*ldc + col].
+int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const float* b, int ncols, int KH, int KW,
+                 int pad, int OH, int OW, TcParams p, cudaStream_t s) {
+  const bool flat = KH == 1 && KW == 1 && pad == 0 && as == 1 && p.os == 1 && OH == AH && OW == AW &&
+                    p.out_H == OH && p.out_W == OW;
+  if (flat) {                               // 1x1 stride 1: pixels are one dense axis, no tile padding at all
+    const long long P = (long long)N * OH * OW;
+    DD_CHECK_ARG(P < (1ll << 31));
+    N = 1; OH = AH = 1; OW = AW = (int)P;
+    p.out_H = 1; p.out_W = (int)P;
+    p.tw = BM; p.th = 1; p.tn = 1;
+  } else {
+    p.tw = pow2_ceil(OW < 16 ? OW : 16);
+    p.th = pow2_ceil(OH < BM / p.tw ? OH : BM / p.tw);
+    p.tn = BM / (p.tw * p.th);
+  }
   p.N = N; p.OH = OH; p.OW = OW;
-  p.tw = pow2_ceil(OW < 16 ? OW : 16);
-  p.th = pow2_ceil(OH < BM / p.tw ? OH : BM / p.tw);
-  p.tn = BM / (p.tw * p.th);
   p.tiles_w = (OW + p.tw - 1) / p.tw;
   p.tiles_h = (OH + p.th - 1) / p.th;
   const int tiles_n = (N + p.tn - 1) / p.tn;
   p.taps = KH * KW; p.KW = KW; p.pad = pad; p.Cin = Cin; p.cblocks = Cin / BKE; p.Cout = ncols;
-  const int m_tiles = tiles_n * p.tiles_h * p.tiles_w;
-  DD_CHECK_ARG(m_tiles <= 65535);
+  p.m_tiles = tiles_n * p.tiles_h * p.tiles_w;
+  const int BN = (ncols % 256 == 0) ? 256 : (ncols > 64 ? 128 : 64);
+  p.n_tiles = (ncols + BN - 1) / BN;
+  DD_CHECK_ARG((long long)p.m_tiles * p.n_tiles < (1ll << 31));
+  p.tma_store = (p.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
 
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mc;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)AW, (cuuint64_t)AH, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)AW * Cin * 4, (cuuint64_t)AH * AW * Cin * 4};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 4 * as, (cuuint64_t)AW * Cin * 4 * as, (cuuint64_t)AH * AW * Cin * 4};
+    if (as > 1) { dims[1] = (cuuint64_t)OW; dims[2] = (cuuint64_t)OH; }   // view of every as-th pixel of [AH, AW]
     cuuint32_t box[4] = {(cuuint32_t)BKE, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
     if (encode_map(&ma, a, 4, dims, strides, box)) return -1;
   }
-  const int BN = (ncols % 256 == 0) ? 256 : (ncols > 64 ? 128 : 64);
   {
     const cuuint64_t K = (cuuint64_t)KH * KW * Cin;
     cuuint64_t dims[2] = {K, (cuuint64_t)ncols};
@@ -557,10 +680,18 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, const float* b,
     cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)(BN < 256 ? BN : 256)};
     if (encode_map(&mb, b, 2, dims, strides, box)) return -1;
   }
-  const int n_tiles = (ncols + BN - 1) / BN;
-  if (BN == 256) return launch_tc<256>(ma, mb, p, m_tiles, n_tiles, s);
-  if (BN == 128) return launch_tc<128>(ma, mb, p, m_tiles, n_tiles, s);
-  return launch_tc<64>(ma, mb, p, m_tiles, n_tiles, s);
+  if (p.tma_store) {
+    cuuint64_t dims[4] = {(cuuint64_t)ncols, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)p.ldc * 4 * p.os, (cuuint64_t)p.out_W * p.ldc * 4 * p.os,
+                             (cuuint64_t)p.out_H * p.out_W * p.ldc * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+    if (encode_map(&mc, p.out, 4, dims, strides, box)) return -1;
+  } else {
+    mc = ma;
+  }
+  if (BN == 256) return launch_tc<256>(ma, mb, mc, p, s);
+  if (BN == 128) return launch_tc<128>(ma, mb, mc, p, s);
+  return launch_tc<64>(ma, mb, mc, p, s);
 }
 
 
@@ -608,19 +739,8 @@ int dd_tc_conv2d_forward(const float* x, const float* w, const float* scale, con
   TcParams p = {};
   p.out = y; p.scale = scale; p.bias = bias; p.extra = residual; p.mask = nullptr; p.relu = act == DD_ACT_RELU;
   p.out_H = OH; p.out_W = OW; p.os = 1; p.ldc = Cout;
-  const float* a = x;
-  float* sub = nullptr;
-  int AH = H, AW = W;
-  if (stride != 1) {   // strided 1x1: gather the pixels the conv reads, then a dense 1x1
-    DD_CUDA(cudaMallocAsync(&sub, sizeof(float) * (size_t)N * OH * OW * Cin, s));
-    const long long total = (long long)N * OH * OW * (Cin / 4);
-    subsample_kernel<<<dd::grid_for(total, 256), 256, 0, s>>>(x, sub, N, H, W, Cin, stride, OH, OW);
-    DD_LAUNCHED();
-    a = sub; AH = OH; AW = OW;
-  }
-  int rc = tc_conv_core(a, N, AH, AW, Cin, w, Cout, KH, KW, pad, OH, OW, p, s);
-  if (sub) cudaFreeAsync(sub, s);
-  return rc;
+  // strided 1x1: the TMA view of x addresses every stride-th pixel directly
+  return tc_conv_core(x, N, H, W, Cin, stride, w, Cout, KH, KW, pad, OH, OW, p, s);
 }
 
 int dd_tc_conv2d_dgrad(const float* gy, const float* w, const float* scale, const float* addend, const float* mask_act,
@@ -630,8 +750,11 @@ int dd_tc_conv2d_dgrad(const float* gy, const float* w, const float* scale, cons
   float* wt = nullptr;
   const size_t wn = (size_t)Cout * KH * KW * Cin;
   DD_CUDA(cudaMallocAsync(&wt, sizeof(float) * wn, s));
-  weight_flip_transpose_kernel<<<dd::grid_for((long long)wn, 256), 256, 0, s>>>(w, scale, wt, Cout, Cin, KH, KW);
-  DD_LAUNCHED();
+  {
+    dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, KH * KW);
+    weight_flip_transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(w, scale, wt, Cout, Cin, KH * KW);
+    DD_LAUNCHED();
+  }
   TcParams p = {};
   p.out = gx; p.scale = nullptr; p.bias = nullptr; p.extra = addend; p.mask = mask_act; p.relu = 0;
   p.out_H = H; p.out_W = W; p.ldc = Cin;
@@ -639,14 +762,14 @@ int dd_tc_conv2d_dgrad(const float* gy, const float* w, const float* scale, cons
   if (stride == 1) {
     p.os = 1;
     // gx[n,h,w,ci] = sum_{kh',kw',co} gy[n, h + kh' - pad', w + kw' - pad', co] * W'[ci, kh', kw', co], pad' = KH-1-pad
-    rc = tc_conv_core(gy, N, OH, OW, Cout, wt, Cin, KH, KW, KH - 1 - pad, H, W, p, s);
+    rc = tc_conv_core(gy, N, OH, OW, Cout, 1, wt, Cin, KH, KW, KH - 1 - pad, H, W, p, s);
   } else {
     // 1x1 stride s: rows enumerate gy's pixels, each lands on (oh*s, ow*s); everything else is addend/0
     const long long n = (long long)N * H * W * Cin;
     fill_kernel<<<dd::grid_for(n, 256), 256, 0, s>>>(addend, mask_act, gx, n);
     DD_LAUNCHED();
     p.os = stride;
-    rc = tc_conv_core(gy, N, OH, OW, Cout, wt, Cin, 1, 1, 0, OH, OW, p, s);
+    rc = tc_conv_core(gy, N, OH, OW, Cout, 1, wt, Cin, 1, 1, 0, OH, OW, p, s);
   }
   cudaFreeAsync(wt, s);
   return rc;
@@ -660,29 +783,32 @@ int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, floa
                        int Cout, int KH, int KW, int stride, int pad, int accumulate, void* workspace, cudaStream_t s) {
   DD_CHECK_ARG(workspace != nullptr);
   const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
-  const float* xa = x;
-  float* sub = nullptr;
-  int AH = H, AW = W;
-  if (stride != 1) {
-    DD_CUDA(cudaMallocAsync(&sub, sizeof(float) * (size_t)N * OH * OW * Cin, s));
-    const long long total = (long long)N * OH * OW * (Cin / 4);
-    subsample_kernel<<<dd::grid_for(total, 256), 256, 0, s>>>(x, sub, N, H, W, Cin, stride, OH, OW);
-    DD_LAUNCHED();
-    xa = sub; AH = OH; AW = OW;
-  }
   TcWgradParams p = {};
   p.partial = (float*)workspace;
   p.Cout = Cout; p.Cin = Cin; p.taps = KH * KW; p.KW = KW; p.pad = pad;
-  p.tw = pow2_ceil(OW < 16 ? OW : 16);
-  p.th = pow2_ceil(OH < WG_KPIX / p.tw ? OH : WG_KPIX / p.tw);
-  p.tn = WG_KPIX / (p.tw * p.th);
-  p.tiles_w = (OW + p.tw - 1) / p.tw;
-  p.tiles_h = (OH + p.th - 1) / p.th;
-  p.pix_blocks = ((N + p.tn - 1) / p.tn) * p.tiles_h * p.tiles_w;
+  // pixel axes as the kernel sees them (gy side: PN x PH x PW; x side may be a strided view of the same grid)
+  int PN = N, PH = OH, PW = OW;
+  cuuint64_t xs_w = (cuuint64_t)Cin * 4 * stride, xs_h = (cuuint64_t)W * Cin * 4 * stride, xs_n = (cuuint64_t)H * W * Cin * 4;
+  cuuint64_t x_w = stride == 1 ? W : OW, x_h = stride == 1 ? H : OH;
+  if (KH == 1 && KW == 1 && pad == 0 && stride == 1) {        // flat: one dense pixel axis
+    const long long P = (long long)N * OH * OW;
+    DD_CHECK_ARG(P < (1ll << 31));
+    PN = 1; PH = 1; PW = (int)P;
+    x_w = (cuuint64_t)P; x_h = 1;
+    xs_h = xs_n = (cuuint64_t)P * Cin * 4;
+    p.tw = WG_KPIX; p.th = 1; p.tn = 1;
+  } else {
+    p.tw = pow2_ceil(PW < 16 ? PW : 16);
+    p.th = pow2_ceil(PH < WG_KPIX / p.tw ? PH : WG_KPIX / p.tw);
+    p.tn = WG_KPIX / (p.tw * p.th);
+  }
+  p.tiles_w = (PW + p.tw - 1) / p.tw;
+  p.tiles_h = (PH + p.th - 1) / p.th;
+  p.pix_blocks = ((PN + p.tn - 1) / p.tn) * p.tiles_h * p.tiles_w;
   const int BN = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : 32));
   p.ci_tiles = (Cin + BN - 1) / BN;
   const int co_tiles = (Cout + BM - 1) / BM;
-  // split the pixel range so that ~2 waves of CTAs exist, within the workspace the SIMT sizing function grants
+  // split the pixel range so that whole waves of CTAs exist, within the workspace the sizing function grants
   const int max_splits = dd_simt_wgrad_splits(Cout, KH * KW * Cin, N * OH * OW);
   const int tiles = co_tiles * p.ci_tiles * p.taps;
   int splits = (2 * dd::kNumSMs + tiles - 1) / tiles;
@@ -694,16 +820,17 @@ int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, floa
 
   CUtensorMap mg, mx;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)OW * Cout * 4, (cuuint64_t)OH * OW * Cout * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
-    if (encode_map(&mg, gy, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
+    cuuint64_t dims[5] = {32, (cuuint64_t)PW, (cuuint64_t)PH, (cuuint64_t)PN, (cuuint64_t)(Cout / 32)};
+    cuuint64_t strides[4] = {(cuuint64_t)Cout * 4, (cuuint64_t)PW * Cout * 4, (cuuint64_t)PH * PW * Cout * 4, 128};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn, 4};
+    if (encode_map(&mg, gy, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
   }
   {
-    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)AW, (cuuint64_t)AH, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)AW * Cin * 4, (cuuint64_t)AH * AW * Cin * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
-    if (encode_map(&mx, xa, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
+    // strided 1x1: a view of every stride-th pixel of x (no gather pass)
+    cuuint64_t dims[5] = {32, x_w, x_h, (cuuint64_t)PN, (cuuint64_t)(Cin / 32)};
+    cuuint64_t strides[4] = {xs_w, xs_h, xs_n, 128};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn, (cuuint32_t)(BN / 32)};
+    if (encode_map(&mx, x, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
   }
   dim3 grid(p.ci_tiles * p.taps, co_tiles, splits);
   int rc;
@@ -712,6 +839,5 @@ int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, floa
   else if (BN == 64) rc = launch_wgrad<64>(mg, mx, p, grid, s);
   else rc = launch_wgrad<32>(mg, mx, p, grid, s);
   if (!rc) rc = dd_wgrad_reduce(p.partial, splits, Cout, KH * KW * Cin, scale, gw, accumulate, s);
-  if (sub) cudaFreeAsync(sub, s);
   return rc;
 }

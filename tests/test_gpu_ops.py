@@ -458,6 +458,11 @@ TC_CASES = [
     (37, 1, 1, 2048, 1024, 1, 1, 0),
     (5, 7, 7, 512, 512, 3, 1, 1),
     (1, 32, 64, 256, 256, 3, 1, 1),
+    (2, 128, 128, 64, 64, 1, 1, 0),       # 256 flat tiles: the persistent loop wraps (> 148 CTAs' worth)
+    (2, 32, 48, 256, 128, 1, 2, 0),       # strided TMA views (forward / wgrad), scattered TMA store (dgrad)
+    (2, 16, 24, 128, 60, 1, 1, 0),        # Cout % 32 != 0: the last staged chunk is clipped by the TMA store
+    (1, 24, 40, 64, 512, 3, 1, 1),        # several column tiles per pixel tile
+    (300, 7, 7, 64, 96, 1, 1, 0),         # 1x1 on ROI maps: flat pixel axis, ragged last tile
 ]
 
 
