@@ -32,7 +32,8 @@ _SIGS = {
     "dd_box_encode": (_I, "pippiffffipp"),
     "dd_box_decode": (_I, "ppiiffffpp"),
     "dd_conv2d_forward": (_I, "ppppppiiiiiiiiiiip"),
-    "dd_conv2d_dgrad": (_I, "ppppppiiiiiiiiiip"),
+    "dd_conv2d_dgrad_workspace_bytes": (_Z, "iiii"),
+    "dd_conv2d_dgrad": (_I, "ppppppiiiiiiiiiipip"),
     "dd_conv2d_wgrad_workspace_bytes": (_Z, "iiiiiiiii"),
     "dd_conv2d_wgrad": (_I, "ppppiiiiiiiiiiipp"),
     "dd_bias_grad": (_I, "ppiiip"),

@@ -13,7 +13,7 @@ int dd_simt_conv2d_wgrad(const float*, const float*, const float*, float*, int, 
 int dd_tc_conv2d_forward(const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
                          int, int, int, int, int, int, int, cudaStream_t);
 int dd_tc_conv2d_dgrad(const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
-                       int, int, int, int, int, int, cudaStream_t);
+                       int, int, int, int, int, int, float*, int, cudaStream_t);
 int dd_tc_conv2d_wgrad(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int,
                        int, void*, cudaStream_t);
 bool dd_tc_supports(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
@@ -29,13 +29,19 @@ extern "C" int dd_conv2d_forward(const float* x, const float* w, const float* sc
                                 dd::S(stream));
 }
 
+extern "C" size_t dd_conv2d_dgrad_workspace_bytes(int Cin, int Cout, int KH, int KW) {
+  return sizeof(float) * (size_t)Cin * Cout * KH * KW;
+}
+
 extern "C" int dd_conv2d_dgrad(const float* gy, const float* w, const float* scale, const float* addend,
                                const float* mask_act, float* gx, int N, int H, int W, int Cin, int Cout, int KH,
-                               int KW, int stride, int pad, int impl, void* stream) {
+                               int KW, int stride, int pad, int impl, void* workspace, int prepared, void* stream) {
   DD_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0);
-  if (impl == DD_IMPL_TCGEN05 && dd_tc_supports(1, N, H, W, Cin, Cout, KH, KW, stride, pad))
+  if (impl == DD_IMPL_TCGEN05 && dd_tc_supports(1, N, H, W, Cin, Cout, KH, KW, stride, pad)) {
+    DD_CHECK_ARG(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0);
     return dd_tc_conv2d_dgrad(gy, w, scale, addend, mask_act, gx, N, H, W, Cin, Cout, KH, KW, stride, pad,
-                              dd::S(stream));
+                              (float*)workspace, prepared, dd::S(stream));
+  }
   return dd_simt_conv2d_dgrad(gy, w, scale, addend, mask_act, gx, N, H, W, Cin, Cout, KH, KW, stride, pad,
                               dd::S(stream));
 }

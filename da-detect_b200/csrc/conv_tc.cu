@@ -47,6 +47,7 @@ struct TcParams {
   int tiles_h, tiles_w;   // ceil(OH/th), ceil(OW/tw)
   int m_tiles, n_tiles;   // persistent tile space: t -> (n_tile = t % n_tiles, m_tile = t / n_tiles)
   int tma_store;          // 1: staged chunks leave through a TMA tensor store; 0: guarded scalar stores
+  int prefetch_side;      // 1: map_e / map_m are valid and the producer prefetches extra / mask tiles to L2
   // where a row lands in the output tensor: out[((n*out_H + h*os)*out_W + w*os)*ldc + co]
   int out_H, out_W, os, ldc;
   int Cout;               // valid output channels (columns)
@@ -100,6 +101,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -140,6 +146,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // Shared-memory matrix descriptor, K-major, 128B swizzle (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
 // Rows are 128 B apart, 8-row swizzle atoms are 1024 B apart (SBO); LBO is unused for swizzled K-major.
@@ -174,7 +194,6 @@ struct SmemLayout {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -199,7 +218,8 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_c, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_e,
+               const __grid_constant__ CUtensorMap map_m, const TcParams p) {
   using L = SmemLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -239,6 +259,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
         const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
         const int n0 = mt * p.tn, oh0 = tile_h * p.th, ow0 = tile_w * p.tw;
+        if (p.prefetch_side) {
+          // pull the tile of the residual / addend / mask tensors towards L2 while the MMAs of this tile run, so
+          // the epilogue's side reads are L2 hits
+          const int cols_here = min(BN, p.Cout - n_tile * BN);
+          for (int c = 0; c < cols_here; c += 32) {
+            if (p.extra) tma_prefetch_l2_4d(&map_e, n_tile * BN + c, ow0, oh0, n0);
+            if (p.mask) tma_prefetch_l2_4d(&map_m, n_tile * BN + c, ow0, oh0, n0);
+          }
+        }
         for (int kit = 0; kit < k_iters; ++kit, ++it) {
           const int s = it % L::kStages;
           const uint32_t ph = (it / L::kStages) & 1;
@@ -286,12 +315,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ================================ epilogue (warps 2..5) ================================
-    const int quarter = warp & 3;                        // TMEM lanes [32*quarter, 32*quarter+32)
+    // Each warp owns TMEM lanes / tile rows [32q, 32q+32) end to end (its own staging slices, its own TMA
+    // stores), so the chunk loop needs only __syncwarp.
+    const int quarter = warp & 3;
     const int row = quarter * 32 + lane;                 // tile row owned in the TMEM -> smem pass
-    const int te = threadIdx.x - 64;                     // 0..127, mapping of the re-mapped pass:
-    const int pc = te & 7;                               //   16-byte column group inside the 32-column chunk
-    const int pr0 = te >> 3;                             //   rows pr0 + 16*i
+    const int pc = lane & 7;                             // re-mapped pass: 16-byte column group of the chunk,
+    const int pr0 = quarter * 32 + (lane >> 3);          //   rows pr0 + 4 i
     const int wl = row % p.tw, hl = (row / p.tw) % p.th, nl = row / (p.tw * p.th);
+    // the warp's 32 rows as a sub-box of the tile (tw is a power of two, or 128 on the flat axis)
+    const int r0 = quarter * 32;
+    const int sub_w = r0 % p.tw, sub_h = (r0 / p.tw) % p.th, sub_n = r0 / (p.tw * p.th);
+    uint8_t* my_stage = staging + quarter * 4096;        // + (chunk & 1) * kStagingBytes
     uint32_t chunk_ctr = 0;
     int local = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
@@ -302,91 +336,125 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
       const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
       const int n0 = mt * p.tn, oh0 = tile_h * p.th, ow0 = tile_w * p.tw;
-      epi_bar_sync();                                    // every reader of the previous tile's row table is done
+      __syncwarp();                                      // lanes are done reading the previous tile's row table
       {
         const int n = n0 + nl, oh = oh0 + hl, ow = ow0 + wl;
         const bool ok = n < p.N && oh < p.OH && ow < p.OW;
         row_pix[row] = ok ? (n * p.out_H + oh * p.os) * p.out_W + ow * p.os : -1;
       }
+      __syncwarp();
+      int pix[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pix[i] = row_pix[pr0 + 4 * i];
       const int cols_here = min(BN, p.Cout - n_tile * BN);
       const int n_chunks = (cols_here + 31) >> 5;
+      const int colbase = n_tile * BN + pc * 4;
+      // per-channel scale / bias of chunk 0 (later chunks are fetched one chunk ahead)
+      float sc[4], bi[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool cok = colbase + e < p.Cout;
+        sc[e] = (p.scale && cok) ? __ldg(p.scale + colbase + e) : 1.f;
+        bi[e] = (p.bias && cok) ? __ldg(p.bias + colbase + e) : 0.f;
+      }
       mbar_wait(tmem_full_bar + acc, aph);
       tc_fence_after();
+      const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      uint32_t ra[32], rb[32];
+      tmem_ld32_nowait(tm, ra);
 #pragma unroll 1
       for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
-        if (ch == n_chunks - 1) {                        // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(tmem_empty_bar + acc);
+        tmem_ld_wait();
+        const bool odd = ch & 1;
+        // next chunk's accumulators start moving while this one is processed
+        if (ch + 1 < n_chunks) {
+          if (odd) tmem_ld32_nowait(tm + (uint32_t)((ch + 1) * 32), ra);
+          else tmem_ld32_nowait(tm + (uint32_t)((ch + 1) * 32), rb);
         }
-        uint8_t* stg = staging + (chunk_ctr & 1) * L::kStagingBytes;
-        if (te == 0) tma_store_wait_read<1>();           // the store that last read this buffer has drained
-        epi_bar_sync();
+        uint8_t* stg = my_stage + (chunk_ctr & 1) * L::kStagingBytes;
+        if (lane == 0) tma_store_wait_read<1>();         // the store that last read this slice has drained
+        __syncwarp();
         {
-          uint8_t* dst = stg + row * 128;
-          const int sw = row & 7;
+          uint8_t* dst = stg + lane * 128;
+          const int sw = lane & 7;                       // == row & 7
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(dst + ((j ^ sw) << 4)) =
-                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                            __uint_as_float(r[4 * j + 3]));
+          for (int j = 0; j < 8; ++j) {
+            float4 v;
+            if (odd) v = make_float4(__uint_as_float(rb[4 * j]), __uint_as_float(rb[4 * j + 1]),
+                                     __uint_as_float(rb[4 * j + 2]), __uint_as_float(rb[4 * j + 3]));
+            else v = make_float4(__uint_as_float(ra[4 * j]), __uint_as_float(ra[4 * j + 1]),
+                                 __uint_as_float(ra[4 * j + 2]), __uint_as_float(ra[4 * j + 3]));
+            *reinterpret_cast<float4*>(dst + ((j ^ sw) << 4)) = v;
+          }
         }
-        epi_bar_sync();
-        // ---- re-mapped pass: thread = (column group pc, rows pr0 + 16 i)
-        const int col = n_tile * BN + ch * 32 + pc * 4;
-        float sc[4], bi[4];
+        // ---- re-mapped pass: lane = (column group pc, rows (lane >> 3) + 4 i of the warp's 32)
+        const int col = colbase + ch * 32;
+        const bool col_ok = col < p.Cout;
+        float4 ex[8], mk[8];
+        if (p.tma_store) {                               // all side reads of the chunk in flight at once
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = pix[i] >= 0 && col_ok;
+            const size_t off = (size_t)(ok ? pix[i] : 0) * p.ldc + (ok ? col : 0);
+            if (p.extra) ex[i] = ok ? dd::ldg4(p.extra + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.mask) mk[i] = ok ? dd::ldg4(p.mask + off) : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+        }
+        float scn[4], bin[4];                            // scale / bias of the next chunk
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const bool cok = col + e < p.Cout;
-          sc[e] = (p.scale && cok) ? __ldg(p.scale + col + e) : 1.f;
-          bi[e] = (p.bias && cok) ? __ldg(p.bias + col + e) : 0.f;
+          const bool cok = ch + 1 < n_chunks && col + 32 + e < p.Cout;
+          scn[e] = (p.scale && cok) ? __ldg(p.scale + col + 32 + e) : 1.f;
+          bin[e] = (p.bias && cok) ? __ldg(p.bias + col + 32 + e) : 0.f;
         }
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int rr = pr0 + 16 * i;
-          const int pix = row_pix[rr];
-          float4* sp = reinterpret_cast<float4*>(stg + rr * 128 + ((pc ^ (rr & 7)) << 4));
-          float4 v4 = *sp;
+          const int rl = (lane >> 3) + 4 * i;            // row inside the warp's slice
+          float4* sp = reinterpret_cast<float4*>(stg + rl * 128 + ((pc ^ (rl & 7)) << 4));
+          const float4 v4 = *sp;
           float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[e] = fmaf(v[e], sc[e], bi[e]);
-          if (pix >= 0 && col < p.Cout) {
-            const size_t off = (size_t)pix * p.ldc + col;
-            if (p.tma_store) {                           // ldc % 4 == 0: 128-bit side reads, TMA writes
-              if (p.extra) { const float4 x = dd::ldg4(p.extra + off); v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; }
-              if (p.mask) {
-                const float4 m = dd::ldg4(p.mask + off);
-                v[0] = m.x > 0.f ? v[0] : 0.f; v[1] = m.y > 0.f ? v[1] : 0.f;
-                v[2] = m.z > 0.f ? v[2] : 0.f; v[3] = m.w > 0.f ? v[3] : 0.f;
-              }
-              if (p.relu) {
+          if (p.tma_store) {                             // ldc % 4 == 0: 128-bit side reads, TMA writes
+            if (p.extra) { v[0] += ex[i].x; v[1] += ex[i].y; v[2] += ex[i].z; v[3] += ex[i].w; }
+            if (p.mask) {
+              v[0] = mk[i].x > 0.f ? v[0] : 0.f; v[1] = mk[i].y > 0.f ? v[1] : 0.f;
+              v[2] = mk[i].z > 0.f ? v[2] : 0.f; v[3] = mk[i].w > 0.f ? v[3] : 0.f;
+            }
+            if (p.relu) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-              }
-            } else {                                     // narrow / unaligned outputs: scalar guarded path
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            *sp = make_float4(v[0], v[1], v[2], v[3]);
+          } else if (pix[i] >= 0 && col_ok) {            // narrow / unaligned outputs: scalar guarded path
+            const size_t off = (size_t)pix[i] * p.ldc + col;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (col + e < p.Cout) {
-                  float x = v[e];
-                  if (p.extra) x += __ldg(p.extra + off + e);
-                  if (p.mask) x = __ldg(p.mask + off + e) > 0.f ? x : 0.f;
-                  if (p.relu) x = fmaxf(x, 0.f);
-                  p.out[off + e] = x;
-                }
+            for (int e = 0; e < 4; ++e) {
+              if (col + e < p.Cout) {
+                float x = v[e];
+                if (p.extra) x += __ldg(p.extra + off + e);
+                if (p.mask) x = __ldg(p.mask + off + e) > 0.f ? x : 0.f;
+                if (p.relu) x = fmaxf(x, 0.f);
+                p.out[off + e] = x;
               }
             }
           }
-          if (p.tma_store) *sp = make_float4(v[0], v[1], v[2], v[3]);
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { sc[e] = scn[e]; bi[e] = bin[e]; }
         if (p.tma_store) {
           fence_async_smem();
-          epi_bar_sync();
-          if (te == 0) tma_store_4d(&map_c, stg, n_tile * BN + ch * 32, ow0, oh0, n0);
+          __syncwarp();
+          if (lane == 0)
+            tma_store_4d(&map_c, stg, n_tile * BN + ch * 32, ow0 + sub_w, oh0 + sub_h, n0 + sub_n);
         }
       }
+      // every tcgen05.ld of this accumulator has completed (the loop's last wait): hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar + acc);
     }
-    if (te == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -621,7 +689,8 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
 }
 
 template <int BN>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const TcParams& p, cudaStream_t s) {
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
+              const CUtensorMap& mm, const TcParams& p, cudaStream_t s) {
   using L = SmemLayout<BN>;
   static bool configured = false;
   if (!configured) {
@@ -630,7 +699,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < dd::kNumSMs ? total : dd::kNumSMs;
-  conv_tc_kernel<BN><<<grid, NUM_THREADS, L::kTotal, s>>>(ma, mb, mc, p);
+  conv_tc_kernel<BN><<<grid, NUM_THREADS, L::kTotal, s>>>(ma, mb, mc, me, mm, p);
   DD_LAUNCHED();
   return 0;
 }
@@ -663,7 +732,9 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
   const int BN = (ncols % 256 == 0) ? 256 : (ncols > 64 ? 128 : 64);
   p.n_tiles = (ncols + BN - 1) / BN;
   DD_CHECK_ARG((long long)p.m_tiles * p.n_tiles < (1ll << 31));
-  p.tma_store = (p.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
+  const uintptr_t align_bits = reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.extra) |
+                               reinterpret_cast<uintptr_t>(p.mask);
+  p.tma_store = (p.ldc % 4 == 0 && (align_bits & 15) == 0) ? 1 : 0;
 
   CUtensorMap ma, mb, mc;
   {
@@ -684,14 +755,29 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
     cuuint64_t dims[4] = {(cuuint64_t)ncols, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)p.ldc * 4 * p.os, (cuuint64_t)p.out_W * p.ldc * 4 * p.os,
                              (cuuint64_t)p.out_H * p.out_W * p.ldc * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+    // each epilogue warp stores its own 32 tile rows: a [bn x bh x bw] sub-box of the tile
+    const int bw = p.tw < 32 ? p.tw : 32;
+    const int bh = p.th < 32 / bw ? p.th : 32 / bw;
+    const int bn = 32 / (bw * bh);
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
     if (encode_map(&mc, p.out, 4, dims, strides, box)) return -1;
   } else {
     mc = ma;
   }
-  if (BN == 256) return launch_tc<256>(ma, mb, mc, p, s);
-  if (BN == 128) return launch_tc<128>(ma, mb, mc, p, s);
-  return launch_tc<64>(ma, mb, mc, p, s);
+  CUtensorMap me = ma, mm = ma;
+  p.prefetch_side = 0;
+  if (p.tma_store && (p.extra || p.mask)) {
+    cuuint64_t dims[4] = {(cuuint64_t)ncols, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)p.ldc * 4 * p.os, (cuuint64_t)p.out_W * p.ldc * 4 * p.os,
+                             (cuuint64_t)p.out_H * p.out_W * p.ldc * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+    if (p.extra && encode_map(&me, p.extra, 4, dims, strides, box)) return -1;
+    if (p.mask && encode_map(&mm, p.mask, 4, dims, strides, box)) return -1;
+    p.prefetch_side = 1;
+  }
+  if (BN == 256) return launch_tc<256>(ma, mb, mc, me, mm, p, s);
+  if (BN == 128) return launch_tc<128>(ma, mb, mc, me, mm, p, s);
+  return launch_tc<64>(ma, mb, mc, me, mm, p, s);
 }
 
 
@@ -745,12 +831,9 @@ int dd_tc_conv2d_forward(const float* x, const float* w, const float* scale, con
 
 int dd_tc_conv2d_dgrad(const float* gy, const float* w, const float* scale, const float* addend, const float* mask_act,
                        float* gx, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                       cudaStream_t s) {
+                       float* wt, int prepared, cudaStream_t s) {
   const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
-  float* wt = nullptr;
-  const size_t wn = (size_t)Cout * KH * KW * Cin;
-  DD_CUDA(cudaMallocAsync(&wt, sizeof(float) * wn, s));
-  {
+  if (!prepared) {
     dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, KH * KW);
     weight_flip_transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(w, scale, wt, Cout, Cin, KH * KW);
     DD_LAUNCHED();
@@ -771,7 +854,6 @@ int dd_tc_conv2d_dgrad(const float* gy, const float* w, const float* scale, cons
     p.os = stride;
     rc = tc_conv_core(gy, N, OH, OW, Cout, 1, wt, Cin, 1, 1, 0, OH, OW, p, s);
   }
-  cudaFreeAsync(wt, s);
   return rc;
 }
 

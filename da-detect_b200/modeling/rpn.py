@@ -105,6 +105,14 @@ class RPNModule(nn.Module):
         self.anchor_generator = AnchorGenerator(R.ANCHOR_SIZES, R.ASPECT_RATIOS, R.ANCHOR_STRIDE[0], R.STRADDLE_THRESH)
         self.head = RPNHead(cfg.MODEL.BACKBONE.OUT_CHANNELS, self.anchor_generator.num_anchors_per_location()[0])
         self.rng = rng
+        self.proposal_hook = None
+
+    def set_proposal_hook(self, fn):
+        """fn(list[BoxList]) -> list[BoxList], called on the proposals of every forward (None = off).
+        Like set_random_source this exists for parity tests: the TF32 arm is compared with the fp32 arm on
+        IDENTICAL hard decisions (top-k order, NMS survivors), so that the comparison measures arithmetic
+        error instead of a flipped near-tie."""
+        self.proposal_hook = fn
 
     # ---- proposals (RPNPostProcessor, rpn/inference.py:76-152) -------------------------------------
     @torch.no_grad()
@@ -182,6 +190,8 @@ class RPNModule(nn.Module):
         anchors, vis = self.anchor_generator.grid(fh, fw, int(iw), int(ih))
         with section("  rpn_proposals"):
             boxes = self.proposals(anchors, logits.detach(), deltas.detach(), images.image_sizes, targets)
+            if self.proposal_hook is not None:
+                boxes = self.proposal_hook(boxes)
         if not self.training:
             return boxes, {}
         with section("  rpn_loss"):

@@ -100,13 +100,23 @@ def conv2d_forward_raw(x, w_ohwi, scale, bias, residual, kh, kw, stride, pad, re
     return y
 
 
-def conv2d_dgrad_raw(gy, w_ohwi, scale, x_shape, kh, kw, stride, pad, addend=None, mask_act=None, impl=None):
+def conv2d_dgrad_raw(gy, w_ohwi, scale, x_shape, kh, kw, stride, pad, addend=None, mask_act=None, impl=None,
+                     prepared_ws=None):
+    """prepared_ws: a float buffer that already holds this layer's dgrad weights W' (see dgrad_workspace)."""
     n, h, wd, cin = x_shape
     cout = w_ohwi.shape[0]
     gx = torch.empty(x_shape, dtype=torch.float32, device=gy.device)
+    ws = prepared_ws if prepared_ws is not None else dgrad_workspace(cin, cout, kh, kw, gy.device)
     _lib.call("dd_conv2d_dgrad", _ptr(gy), _ptr(w_ohwi), _ptr(scale), _ptr(addend), _ptr(mask_act), _ptr(gx),
-              n, h, wd, cin, cout, kh, kw, stride, pad, _default_impl if impl is None else impl, _stream())
+              n, h, wd, cin, cout, kh, kw, stride, pad, _default_impl if impl is None else impl, _ptr(ws),
+              1 if prepared_ws is not None else 0, _stream())
     return gx
+
+
+def dgrad_workspace(cin, cout, kh, kw, device):
+    """Scratch for the tcgen05 arm's prepared dgrad weights (stream-ordered reuse through torch's allocator)."""
+    nbytes = _lib.load().dd_conv2d_dgrad_workspace_bytes(cin, cout, kh, kw)
+    return torch.empty(max(int(nbytes) // 4, 4), dtype=torch.float32, device=device)
 
 
 def conv2d_wgrad_raw(gy, x, scale, cout, kh, kw, stride, pad, out=None, accumulate=False, impl=None):

@@ -116,10 +116,14 @@ int dd_conv2d_forward(const float* x, const float* w, const float* scale, const 
                       const float* residual, float* y, int N, int H, int W, int Cin, int Cout, int KH, int KW,
                       int stride, int pad, int act, int impl, void* stream);
 /* gx = conv_transpose(gy, w * scale[co]) (+ addend) (* (mask_act > 0) if mask_act).  gx [N,H,W,Cin]
- * is fully written (positions a strided conv never read receive addend or 0). */
+ * is fully written (positions a strided conv never read receive addend or 0).
+ * workspace: dd_conv2d_dgrad_workspace_bytes(...) bytes (16-byte aligned) — the tcgen05 arm keeps the
+ * BN-scaled, tap-flipped, transposed weights W'[ci,kh',kw',co] there.  prepared != 0: the workspace already
+ * holds W' for this (w, scale) from an earlier call and the preparation kernel is skipped. */
+size_t dd_conv2d_dgrad_workspace_bytes(int Cin, int Cout, int KH, int KW);
 int dd_conv2d_dgrad(const float* gy, const float* w, const float* scale, const float* addend,
                     const float* mask_act, float* gx, int N, int H, int W, int Cin, int Cout, int KH, int KW,
-                    int stride, int pad, int impl, void* stream);
+                    int stride, int pad, int impl, void* workspace, int prepared, void* stream);
 /* gw[co,kh,kw,ci] (+)= scale[co] * sum_{n,oh,ow} gy[n,oh,ow,co] * x[n,oh*s+kh-p,ow*s+kw-p,ci].
  * workspace: dd_conv2d_wgrad_workspace_bytes(...) (split-K partials). */
 size_t dd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
