@@ -22,6 +22,7 @@
 //
 // Reference being replaced: cuDNN/cuBLAS calls behind F.conv2d / F.linear.
 #include <cuda.h>
+#include <math.h>
 
 #include "common.cuh"
 
@@ -195,9 +196,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -207,6 +208,38 @@ __device__ __forceinline__ void tma_store_wait_read() {
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, int v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lds32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void load_scale_bias(const TcParams& p, int col, float (&sc)[4], float (&bi)[4]) {
+  if (col + 3 < p.Cout && (p.Cout & 3) == 0) {           // aligned 128-bit loads (all multi-of-4 channel counts)
+    const float4 s4 = p.scale ? dd::ldg4(p.scale + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 b4 = p.bias ? dd::ldg4(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
+    bi[0] = b4.x; bi[1] = b4.y; bi[2] = b4.z; bi[3] = b4.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool cok = col + e < p.Cout;
+      sc[e] = (p.scale && cok) ? __ldg(p.scale + col + e) : 1.f;
+      bi[e] = (p.bias && cok) ? __ldg(p.bias + col + e) : 0.f;
+    }
+  }
+}
+
+enum { EPI_EXTRA = 1, EPI_MASK = 2, EPI_SCALAR = 4 };
+
 // ------------------------------------------------------------------------------------------------ kernel
 // Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence t = blockIdx.x + i*gridDim.x.
 // Two TMEM accumulators (2 x BN columns) let the MMAs of tile i+1 run while the epilogue drains tile i; the TMA
@@ -215,7 +248,7 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // Epilogue per 32-column chunk: tcgen05.ld (thread = one tile row) -> 128B-swizzled smem staging ->
 // re-mapped pass (8 threads per row => coalesced 128-bit reads of residual / mask, per-channel scale + bias,
 // ReLU) -> one TMA tensor store of the [rows x 32 ch] box, which also clips the tile against the tensor edges.
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_e,
@@ -316,16 +349,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ================================ epilogue (warps 2..5) ================================
     // Each warp owns TMEM lanes / tile rows [32q, 32q+32) end to end (its own staging slices, its own TMA
-    // stores), so the chunk loop needs only __syncwarp.
+    // stores), so the chunk loop needs only __syncwarp.  EPI selects the compiled side-input handling.
+    constexpr bool kExtra = (EPI & EPI_EXTRA) != 0, kMask = (EPI & EPI_MASK) != 0, kScalar = (EPI & EPI_SCALAR) != 0;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;                 // tile row owned in the TMEM -> smem pass
     const int pc = lane & 7;                             // re-mapped pass: 16-byte column group of the chunk,
-    const int pr0 = quarter * 32 + (lane >> 3);          //   rows pr0 + 4 i
+    const int pr = lane >> 3;                            //   rows pr + 4 i of the warp's 32
     const int wl = row % p.tw, hl = (row / p.tw) % p.th, nl = row / (p.tw * p.th);
-    // the warp's 32 rows as a sub-box of the tile (tw is a power of two, or 128 on the flat axis)
-    const int r0 = quarter * 32;
+    const int r0 = quarter * 32;                         // the warp's rows as a sub-box of the tile
     const int sub_w = r0 % p.tw, sub_h = (r0 / p.tw) % p.th, sub_n = r0 / (p.tw * p.th);
-    uint8_t* my_stage = staging + quarter * 4096;        // + (chunk & 1) * kStagingBytes
+    const uint32_t my_stage = smem_u32(staging) + quarter * 4096;      // + (chunk & 1) * kStagingBytes
+    const uint32_t my_rows = smem_u32(row_pix) + quarter * 128;
+    const uint32_t st_off = lane * 128;                  // TMEM -> smem pass: own row, chunk j at (j ^ (lane & 7)) * 16
+    const uint32_t st_sw = lane & 7;
+    const float lo = p.relu ? 0.f : -INFINITY;
     uint32_t chunk_ctr = 0;
     int local = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
@@ -336,97 +373,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
       const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
       const int n0 = mt * p.tn, oh0 = tile_h * p.th, ow0 = tile_w * p.tw;
-      __syncwarp();                                      // lanes are done reading the previous tile's row table
-      {
+      int pix[8];
+      if (kExtra || kMask || kScalar) {                  // side reads / scalar stores need the rows' pixel index
+        __syncwarp();                                    // lanes are done reading the previous tile's row table
         const int n = n0 + nl, oh = oh0 + hl, ow = ow0 + wl;
         const bool ok = n < p.N && oh < p.OH && ow < p.OW;
-        row_pix[row] = ok ? (n * p.out_H + oh * p.os) * p.out_W + ow * p.os : -1;
-      }
-      __syncwarp();
-      int pix[8];
+        sts32(my_rows + lane * 4, ok ? (n * p.out_H + oh * p.os) * p.out_W + ow * p.os : -1);
+        __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pix[i] = row_pix[pr0 + 4 * i];
+        for (int i = 0; i < 8; ++i) pix[i] = lds32(my_rows + (pr + 4 * i) * 4);
+      }
       const int cols_here = min(BN, p.Cout - n_tile * BN);
       const int n_chunks = (cols_here + 31) >> 5;
       const int colbase = n_tile * BN + pc * 4;
-      // per-channel scale / bias of chunk 0 (later chunks are fetched one chunk ahead)
-      float sc[4], bi[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool cok = colbase + e < p.Cout;
-        sc[e] = (p.scale && cok) ? __ldg(p.scale + colbase + e) : 1.f;
-        bi[e] = (p.bias && cok) ? __ldg(p.bias + colbase + e) : 0.f;
-      }
+      float sc[4], bi[4];                                // per-channel scale / bias, fetched one chunk ahead
+      load_scale_bias(p, colbase, sc, bi);
       mbar_wait(tmem_full_bar + acc, aph);
       tc_fence_after();
       const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      uint32_t ra[32], rb[32];
-      tmem_ld32_nowait(tm, ra);
-#pragma unroll 1
-      for (int ch = 0; ch < n_chunks; ++ch, ++chunk_ctr) {
-        tmem_ld_wait();
-        const bool odd = ch & 1;
-        // next chunk's accumulators start moving while this one is processed
-        if (ch + 1 < n_chunks) {
-          if (odd) tmem_ld32_nowait(tm + (uint32_t)((ch + 1) * 32), ra);
-          else tmem_ld32_nowait(tm + (uint32_t)((ch + 1) * 32), rb);
+
+      auto process = [&](const uint32_t (&r)[32], int ch) {
+        const uint32_t stg = my_stage + (chunk_ctr & 1) * L::kStagingBytes;
+        if (!kScalar) {
+          if (lane == 0) tma_store_wait_read<1>();       // the store that last read this slice has drained
+          __syncwarp();
         }
-        uint8_t* stg = my_stage + (chunk_ctr & 1) * L::kStagingBytes;
-        if (lane == 0) tma_store_wait_read<1>();         // the store that last read this slice has drained
-        __syncwarp();
-        {
-          uint8_t* dst = stg + lane * 128;
-          const int sw = lane & 7;                       // == row & 7
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 v;
-            if (odd) v = make_float4(__uint_as_float(rb[4 * j]), __uint_as_float(rb[4 * j + 1]),
-                                     __uint_as_float(rb[4 * j + 2]), __uint_as_float(rb[4 * j + 3]));
-            else v = make_float4(__uint_as_float(ra[4 * j]), __uint_as_float(ra[4 * j + 1]),
-                                 __uint_as_float(ra[4 * j + 2]), __uint_as_float(ra[4 * j + 3]));
-            *reinterpret_cast<float4*>(dst + ((j ^ sw) << 4)) = v;
-          }
-        }
-        // ---- re-mapped pass: lane = (column group pc, rows (lane >> 3) + 4 i of the warp's 32)
+        for (int j = 0; j < 8; ++j)
+          sts128(stg + st_off + ((j ^ st_sw) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        // ---- re-mapped pass: lane = (column group pc, rows pr + 4 i)
         const int col = colbase + ch * 32;
         const bool col_ok = col < p.Cout;
         float4 ex[8], mk[8];
-        if (p.tma_store) {                               // all side reads of the chunk in flight at once
+        if (!kScalar) {                                  // all side reads of the chunk in flight at once
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const bool ok = pix[i] >= 0 && col_ok;
-            const size_t off = (size_t)(ok ? pix[i] : 0) * p.ldc + (ok ? col : 0);
-            if (p.extra) ex[i] = ok ? dd::ldg4(p.extra + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.mask) mk[i] = ok ? dd::ldg4(p.mask + off) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const size_t off = ok ? (size_t)pix[i] * p.ldc + col : 0;
+            if (kExtra) ex[i] = ok ? dd::ldg4(p.extra + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kMask) mk[i] = ok ? dd::ldg4(p.mask + off) : make_float4(1.f, 1.f, 1.f, 1.f);
           }
         }
-        float scn[4], bin[4];                            // scale / bias of the next chunk
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const bool cok = ch + 1 < n_chunks && col + 32 + e < p.Cout;
-          scn[e] = (p.scale && cok) ? __ldg(p.scale + col + 32 + e) : 1.f;
-          bin[e] = (p.bias && cok) ? __ldg(p.bias + col + 32 + e) : 0.f;
-        }
+        float scn[4], bin[4];
+        if (ch + 1 < n_chunks) load_scale_bias(p, col + 32, scn, bin);
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int rl = (lane >> 3) + 4 * i;            // row inside the warp's slice
-          float4* sp = reinterpret_cast<float4*>(stg + rl * 128 + ((pc ^ (rl & 7)) << 4));
-          const float4 v4 = *sp;
-          float v[4] = {v4.x, v4.y, v4.z, v4.w};
+          const int rl = pr + 4 * i;
+          const uint32_t sp = stg + rl * 128 + ((pc ^ (rl & 7)) << 4);
+          float v[4];
+          lds128(sp, v);
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[e] = fmaf(v[e], sc[e], bi[e]);
-          if (p.tma_store) {                             // ldc % 4 == 0: 128-bit side reads, TMA writes
-            if (p.extra) { v[0] += ex[i].x; v[1] += ex[i].y; v[2] += ex[i].z; v[3] += ex[i].w; }
-            if (p.mask) {
+          if (!kScalar) {
+            if (kExtra) { v[0] += ex[i].x; v[1] += ex[i].y; v[2] += ex[i].z; v[3] += ex[i].w; }
+            if (kMask) {
               v[0] = mk[i].x > 0.f ? v[0] : 0.f; v[1] = mk[i].y > 0.f ? v[1] : 0.f;
               v[2] = mk[i].z > 0.f ? v[2] : 0.f; v[3] = mk[i].w > 0.f ? v[3] : 0.f;
             }
-            if (p.relu) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-            }
-            *sp = make_float4(v[0], v[1], v[2], v[3]);
+            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], lo);
+            sts128(sp, v[0], v[1], v[2], v[3]);
           } else if (pix[i] >= 0 && col_ok) {            // narrow / unaligned outputs: scalar guarded path
             const size_t off = (size_t)pix[i] * p.ldc + col;
 #pragma unroll
@@ -435,22 +443,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 float x = v[e];
                 if (p.extra) x += __ldg(p.extra + off + e);
                 if (p.mask) x = __ldg(p.mask + off + e) > 0.f ? x : 0.f;
-                if (p.relu) x = fmaxf(x, 0.f);
-                p.out[off + e] = x;
+                p.out[off + e] = fmaxf(x, lo);
               }
             }
           }
         }
+        if (ch + 1 < n_chunks) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { sc[e] = scn[e]; bi[e] = bin[e]; }
-        if (p.tma_store) {
+          for (int e = 0; e < 4; ++e) { sc[e] = scn[e]; bi[e] = bin[e]; }
+        }
+        if (!kScalar) {
           fence_async_smem();
           __syncwarp();
-          if (lane == 0)
-            tma_store_4d(&map_c, stg, n_tile * BN + ch * 32, ow0 + sub_w, oh0 + sub_h, n0 + sub_n);
+          if (lane == 0) tma_store_4d(&map_c, stg, n_tile * BN + ch * 32, ow0 + sub_w, oh0 + sub_h, n0 + sub_n);
+        } else {
+          __syncwarp();
+        }
+        ++chunk_ctr;
+      };
+
+      uint32_t ra[32], rb[32];
+      tmem_ld32_nowait(tm, ra);
+#pragma unroll 1
+      for (int ch = 0; ch < n_chunks; ch += 2) {
+        tmem_ld_wait();
+        if (ch + 1 < n_chunks) tmem_ld32_nowait(tm + (uint32_t)((ch + 1) * 32), rb);   // moves while ra is processed
+        process(ra, ch);
+        if (ch + 1 < n_chunks) {
+          tmem_ld_wait();
+          if (ch + 2 < n_chunks) tmem_ld32_nowait(tm + (uint32_t)((ch + 2) * 32), ra);
+          process(rb, ch + 1);
         }
       }
-      // every tcgen05.ld of this accumulator has completed (the loop's last wait): hand it back to the MMA warp
+      // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(tmem_empty_bar + acc);
     }
@@ -688,20 +713,33 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
   return 0;
 }
 
-template <int BN>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
-              const CUtensorMap& mm, const TcParams& p, cudaStream_t s) {
+template <int BN, int EPI>
+int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
+               const CUtensorMap& mm, const TcParams& p, cudaStream_t s) {
   using L = SmemLayout<BN>;
   static bool configured = false;
   if (!configured) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < dd::kNumSMs ? total : dd::kNumSMs;
-  conv_tc_kernel<BN><<<grid, NUM_THREADS, L::kTotal, s>>>(ma, mb, mc, me, mm, p);
+  conv_tc_kernel<BN, EPI><<<grid, NUM_THREADS, L::kTotal, s>>>(ma, mb, mc, me, mm, p);
   DD_LAUNCHED();
   return 0;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
+              const CUtensorMap& mm, const TcParams& p, cudaStream_t s) {
+  if (!p.tma_store) return launch_tc2<BN, EPI_SCALAR>(ma, mb, mc, me, mm, p, s);
+  const int epi = (p.extra ? EPI_EXTRA : 0) | (p.mask ? EPI_MASK : 0);
+  switch (epi) {
+    case 0: return launch_tc2<BN, 0>(ma, mb, mc, me, mm, p, s);
+    case EPI_EXTRA: return launch_tc2<BN, EPI_EXTRA>(ma, mb, mc, me, mm, p, s);
+    case EPI_MASK: return launch_tc2<BN, EPI_MASK>(ma, mb, mc, me, mm, p, s);
+    default: return launch_tc2<BN, EPI_EXTRA | EPI_MASK>(ma, mb, mc, me, mm, p, s);
+  }
 }
 
 // Core: D[pixel, col] = sum_{tap, c} A[n, (oh + kh - pad) * as, (ow + kw - pad) * as, c] * B[col, tap, c]
