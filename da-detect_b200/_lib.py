@@ -25,6 +25,8 @@ _SIGS = {
     "dd_nms_workspace_bytes": (_Z, "i"),
     "dd_nms": (_I, "ppifpppp"),
     "dd_nms_sorted": (_I, "pifipppp"),
+    "dd_nms_batched_workspace_bytes": (_Z, "ii"),
+    "dd_nms_sorted_batched": (_I, "ppiifipippp"),
     "dd_anchor_grid": (_I, "piiiiiiippp"),
     "dd_rpn_topk_workspace_bytes": (_Z, "ii"),
     "dd_rpn_topk_decode": (_I, "pppiiiiiiifpppppp"),

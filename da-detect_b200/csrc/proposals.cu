@@ -208,10 +208,17 @@ __device__ __forceinline__ float iou_plus1(const float4 a, const float4 b) {
 }
 
 // mask[i][cb] bit j: box (cb*64+j) is suppressed by box i (j > i only).  Upper triangle only.
-__global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ boxes, int n, float thresh,
-                                                      unsigned long long* __restrict__ mask, int col_blocks) {
+// Batched over images (blockIdx.z): image g has n = n_dev ? n_dev[g] : n_cap boxes at boxes + g * n_cap and its own
+// [n_cap x cb_cap] mask.
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ n_dev,
+                                                      int n_cap, float thresh, unsigned long long* __restrict__ mask,
+                                                      int cb_cap) {
+  const int img = blockIdx.z;
+  const int n = n_dev ? min(n_dev[img], n_cap) : n_cap;
   const int rb = blockIdx.y, cb = blockIdx.x;
-  if (cb < rb) return;
+  if (cb < rb || cb * 64 >= n || rb * 64 >= n) return;
+  boxes += (size_t)img * n_cap;
+  mask += (size_t)img * n_cap * cb_cap;
   __shared__ float4 cols[64];
   const int col_size = min(n - cb * 64, 64);
   if ((int)threadIdx.x < col_size) cols[threadIdx.x] = boxes[cb * 64 + threadIdx.x];
@@ -223,57 +230,73 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__
     const int start = (rb == cb) ? threadIdx.x + 1 : 0;
     for (int j = start; j < col_size; ++j)
       if (iou_plus1(me, cols[j]) > thresh) bits |= 1ull << j;
-    mask[(size_t)i * col_blocks + cb] = bits;
+    mask[(size_t)i * cb_cap + cb] = bits;
   }
 }
 
-// Single-CTA greedy scan over the bitmask.  keep_pos receives kept positions (ascending = score order).
-__global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long* __restrict__ mask, int n,
-                                                       int col_blocks, int max_keep, int64_t* __restrict__ keep_pos,
-                                                       int* __restrict__ keep_count) {
-  extern __shared__ unsigned long long remv[];   // col_blocks words
-  __shared__ unsigned long long diag[64];
-  __shared__ unsigned long long s_kept_bits;
-  __shared__ int s_nkeep;
-  for (int j = threadIdx.x; j < col_blocks; j += blockDim.x) remv[j] = 0ull;
-  if (threadIdx.x == 0) s_nkeep = 0;
+// Greedy scan over the bitmask, one CTA per image.  Per 64-box block: one thread walks the surviving boxes
+// (find-first-set over the not-yet-suppressed bits, the block's diagonal words staged in shared memory and
+// prefetched one block ahead); then the whole CTA ORs the mask rows of the boxes just kept into the running
+// suppression words of all later blocks — rows are spread over four thread groups so that the L2 loads of one
+// block are independent and in flight together.  keep_pos receives kept positions (ascending = score order).
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const unsigned long long* __restrict__ mask,
+                                                                const int* __restrict__ n_dev, int n_cap, int cb_cap,
+                                                                int max_keep, int64_t* __restrict__ keep_pos,
+                                                                int keep_stride, int* __restrict__ keep_count) {
+  extern __shared__ unsigned long long remv[];   // cb_cap words
+  __shared__ unsigned long long diag[2][64];
+  __shared__ int kept_rows[64];
+  __shared__ int s_cnt, s_nkeep, s_done;
+  const int img = blockIdx.x;
+  const int n = n_dev ? min(n_dev[img], n_cap) : n_cap;
+  const int col_blocks = (n + 63) / 64;
+  mask += (size_t)img * n_cap * cb_cap;
+  keep_pos += (size_t)img * keep_stride;
+  const int tid = threadIdx.x;
+  for (int j = tid; j < col_blocks; j += blockDim.x) remv[j] = 0ull;
+  if (tid == 0) { s_nkeep = 0; s_done = 0; }
+  if (tid < 64 && tid < n) diag[0][tid] = mask[(size_t)tid * cb_cap];
   __syncthreads();
   for (int b = 0; b < col_blocks; ++b) {
     const int size = min(n - b * 64, 64);
-    if ((int)threadIdx.x < size) diag[threadIdx.x] = mask[(size_t)(b * 64 + threadIdx.x) * col_blocks + b];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long cur = remv[b], kept = 0ull;
-      int nk = s_nkeep;
-      for (int i = 0; i < size; ++i) {
-        if (!((cur >> i) & 1ull)) {
-          if (max_keep > 0 && nk >= max_keep) break;
-          kept |= 1ull << i;
-          keep_pos[nk++] = (int64_t)(b * 64 + i);
-          cur |= diag[i];
-        }
+    if (tid >= 64 && tid < 128 && b + 1 < col_blocks) {           // next block's diagonal words
+      const int r = (b + 1) * 64 + tid - 64;
+      if (r < n) diag[(b + 1) & 1][tid - 64] = mask[(size_t)r * cb_cap + (b + 1)];
+    }
+    if (tid == 0) {
+      unsigned long long cur = remv[b];
+      if (size < 64) cur |= ~0ull << size;
+      int nk = s_nkeep, cnt = 0;
+      unsigned long long avail = ~cur;
+      while (avail) {
+        if (max_keep > 0 && nk >= max_keep) break;
+        const int i = __ffsll((long long)avail) - 1;
+        kept_rows[cnt++] = i;
+        keep_pos[nk++] = (int64_t)(b * 64 + i);
+        cur |= diag[b & 1][i];
+        avail = ~cur & ~((2ull << i) - 1ull);
       }
-      s_kept_bits = kept;
+      s_cnt = cnt;
       s_nkeep = nk;
+      s_done = (max_keep > 0 && nk >= max_keep) ? 1 : 0;
     }
     __syncthreads();
-    const unsigned long long kept = s_kept_bits;
-    if (max_keep > 0 && s_nkeep >= max_keep) break;
-    if (kept) {
-      for (int j = b + 1 + threadIdx.x; j < col_blocks; j += blockDim.x) {
-        unsigned long long acc = remv[j];
-        unsigned long long kb = kept;
-        while (kb) {
-          const int i = __ffsll((long long)kb) - 1;
-          kb &= kb - 1;
-          acc |= mask[(size_t)(b * 64 + i) * col_blocks + j];
-        }
-        remv[j] = acc;
+    if (s_done) break;
+    const int cnt = s_cnt;
+    if (cnt > 0) {
+      const int slot = tid >> 8, j = b + 1 + (tid & 255);
+      if (j < col_blocks) {
+        unsigned long long acc = 0ull;
+        const unsigned long long* base = mask + (size_t)(b * 64) * cb_cap + j;
+#pragma unroll 4
+        for (int r = slot; r < cnt; r += 4) acc |= base[(size_t)kept_rows[r] * cb_cap];
+        if (acc) atomicOr(&remv[j], acc);
       }
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *keep_count = s_nkeep;
+  if (tid == 0) keep_count[img] = s_nkeep;
 }
 
 // Sort (score desc, index asc) -> order; gather boxes.  Single CTA, n <= kSortCap.
@@ -337,13 +360,16 @@ NmsWs carve(void* ws, int n) {
   return w;
 }
 
-int nms_sorted_impl(const float* boxes_sorted, int n, float thresh, int max_keep, int64_t* keep, int* keep_count,
-                    unsigned long long* mask, cudaStream_t s) {
-  const int cb = (n + 63) / 64;
-  dim3 grid(cb, cb);
-  nms_mask_kernel<<<grid, 64, 0, s>>>(reinterpret_cast<const float4*>(boxes_sorted), n, thresh, mask, cb);
+// images: number of images; n_dev: optional per-image box counts on the device (<= n_cap)
+int nms_sorted_impl(const float* boxes_sorted, int images, const int* n_dev, int n_cap, float thresh, int max_keep,
+                    int64_t* keep, int keep_stride, int* keep_count, unsigned long long* mask, cudaStream_t s) {
+  const int cb = (n_cap + 63) / 64;
+  DD_CHECK_ARG(cb <= 256 && images > 0 && images <= 65535);
+  dim3 grid(cb, cb, images);
+  nms_mask_kernel<<<grid, 64, 0, s>>>(reinterpret_cast<const float4*>(boxes_sorted), n_dev, n_cap, thresh, mask, cb);
   DD_LAUNCHED();
-  nms_scan_kernel<<<1, 256, cb * sizeof(unsigned long long), s>>>(mask, n, cb, max_keep, keep, keep_count);
+  nms_scan_kernel<<<images, kScanThreads, cb * sizeof(unsigned long long), s>>>(mask, n_dev, n_cap, cb, max_keep, keep,
+                                                                               keep_stride, keep_count);
   DD_LAUNCHED();
   return 0;
 }
@@ -399,7 +425,21 @@ extern "C" int dd_nms_sorted(const float* boxes_sorted, int n, float thresh, int
     return 0;
   }
   NmsWs w = carve(workspace, n);
-  return nms_sorted_impl(boxes_sorted, n, thresh, max_keep, keep_out, keep_count, w.mask, dd::S(stream));
+  return nms_sorted_impl(boxes_sorted, 1, nullptr, n, thresh, max_keep, keep_out, 0, keep_count, w.mask, dd::S(stream));
+}
+
+extern "C" size_t dd_nms_batched_workspace_bytes(int images, int n_cap) {
+  if (n_cap <= 0 || images <= 0) return 256;
+  const int cb = (n_cap + 63) / 64;
+  return align_up((size_t)images * n_cap * cb * 8, 256) + 256;
+}
+
+extern "C" int dd_nms_sorted_batched(const float* boxes_sorted, const int* n_dev, int images, int n_cap, float thresh,
+                                     int max_keep, int64_t* keep_out, int keep_stride, int* keep_count,
+                                     void* workspace, void* stream) {
+  DD_CHECK_ARG(images > 0 && n_cap > 0 && n_cap <= kSortCap && workspace != nullptr && n_dev != nullptr);
+  return nms_sorted_impl(boxes_sorted, images, n_dev, n_cap, thresh, max_keep, keep_out, keep_stride, keep_count,
+                         (unsigned long long*)workspace, dd::S(stream));
 }
 
 extern "C" int dd_nms(const float* boxes, const float* scores, int n, float thresh, int64_t* keep_out,
@@ -423,8 +463,8 @@ extern "C" int dd_nms(const float* boxes, const float* scores, int n, float thre
   sort_scores_gather_kernel<<<1, 1024, (size_t)p2 * 8, s>>>(scores, reinterpret_cast<const float4*>(boxes), n,
                                                             w.order, w.boxes_sorted);
   DD_LAUNCHED();
-  int rc = nms_sorted_impl(reinterpret_cast<const float*>(w.boxes_sorted), n, thresh, 0, keep_out, keep_count,
-                           w.mask, s);
+  int rc = nms_sorted_impl(reinterpret_cast<const float*>(w.boxes_sorted), 1, nullptr, n, thresh, 0, keep_out, 0,
+                           keep_count, w.mask, s);
   if (rc) return rc;
   keep_to_sorted_indices_kernel<<<1, 1024, (size_t)p2 * 8, s>>>(w.order, keep_count, keep_out, p2);
   DD_LAUNCHED();

@@ -87,12 +87,37 @@ class Bottleneck(nn.Module):
         return ops.conv_bn_act(out, self.conv3.weight, s3, b3, residual=identity, relu=True)
 
 
+class Stage(nn.Sequential):
+    """make_stage (resnet.py:197-224): the blocks keep their reference names (``layerN.i.*``); the forward of
+    the whole stage is one fused autograd node (ops.bottleneck_stage) unless `fused` is switched off."""
+
+    fused = True
+
+    def forward(self, x, first_stride_override=None, input_is_relu=False, grad_premasked=False):
+        if not self.fused:
+            for i, blk in enumerate(self):
+                x = blk(x, stride_override=first_stride_override if i == 0 else None)
+            return x
+        blocks, strides = [], []
+        for i, blk in enumerate(self):
+            d = {}
+            for j, (conv, bn) in enumerate(((blk.conv1, blk.bn1), (blk.conv2, blk.bn2), (blk.conv3, blk.bn3)), 1):
+                sc, bi = bn.affine()
+                d["w%d" % j], d["s%d" % j], d["b%d" % j] = conv.weight, sc, bi
+            if blk.downsample is not None:
+                sc, bi = blk.downsample[1].affine()
+                d["wd"], d["sd"], d["bd"] = blk.downsample[0].weight, sc, bi
+            blocks.append(d)
+            strides.append(first_stride_override if (i == 0 and first_stride_override is not None) else blk.stride)
+        return ops.bottleneck_stage(x, blocks, strides, input_is_relu, grad_premasked)
+
+
 def make_stage(cin, mid, cout, blocks, first_stride):
     layers = []
     for i in range(blocks):
         layers.append(Bottleneck(cin, mid, cout, first_stride if i == 0 else 1))
         cin = cout
-    return nn.Sequential(*layers)
+    return Stage(*layers)
 
 
 class Stem(nn.Module):
@@ -142,8 +167,11 @@ class ResNetC4(nn.Module):
 
     def forward(self, x):
         x = self.stem(x)
-        for name in self.stages:
-            x = getattr(self, name)(x)
+        last = len(self.stages) - 1
+        for i, name in enumerate(self.stages):
+            # every stage output is a ReLU output consumed only by the next stage, so the mask (x > 0) of the
+            # gradient crossing a stage boundary is applied by the consumer's dgrad epilogue
+            x = getattr(self, name)(x, input_is_relu=i > 0, grad_premasked=i < last)
         return [x]
 
 
@@ -161,9 +189,7 @@ class ResNetHead(nn.Module):
         self.out_channels = cout
 
     def forward(self, x, input_is_even_bins):
-        for i, blk in enumerate(self.layer4):
-            x = blk(x, stride_override=1 if (i == 0 and input_is_even_bins) else None)
-        return x
+        return self.layer4(x, first_stride_override=1 if input_is_even_bins else None)
 
 
 def build_backbone(cfg):

@@ -128,21 +128,21 @@ class RPNModule(nn.Module):
             raise NotImplementedError("images of different un-padded sizes in one batch")
         ih, iw = sizes.pop()
         boxes, scores, _, valid = ops.rpn_topk_decode(logits, deltas, anchors, k, iw, ih, R.MIN_SIZE)
-        valid_h = valid.tolist()
-        pending = []
-        for i in range(n):
-            b = boxes[i, : valid_h[i]]
-            keep, cnt = ops.nms_sorted(b, R.NMS_THRESH, post) if R.NMS_THRESH > 0 else (None, None)
-            pending.append((b, scores[i, : valid_h[i]], keep.clone() if keep is not None else None, cnt))
-        counts = torch.cat([c for _, _, _, c in pending if c is not None]).tolist() if R.NMS_THRESH > 0 else []
         out = []
-        for i, (b, s, keep, cnt) in enumerate(pending):
-            if keep is not None:
-                sel = keep[: counts[i]]
-                b, s = b[sel], s[sel]
-            bl = BoxList(b, (iw, ih), mode="xyxy")
-            bl.add_field("objectness", s)
-            out.append(bl)
+        if R.NMS_THRESH > 0:
+            keep, cnt = ops.nms_sorted_batched(boxes, valid, R.NMS_THRESH, post)     # whole batch, 2 launches
+            counts = cnt.tolist()                                                    # the one host read
+            for i in range(n):
+                sel = keep[i, : counts[i]]
+                bl = BoxList(boxes[i][sel], (iw, ih), mode="xyxy")
+                bl.add_field("objectness", scores[i][sel])
+                out.append(bl)
+        else:
+            valid_h = valid.tolist()
+            for i in range(n):
+                bl = BoxList(boxes[i, : valid_h[i]], (iw, ih), mode="xyxy")
+                bl.add_field("objectness", scores[i, : valid_h[i]])
+                out.append(bl)
         if train and targets is not None:       # add_gt_proposals: source images only (:51-74)
             for i, t in enumerate(targets):
                 if is_source_image(t):

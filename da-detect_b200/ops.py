@@ -207,6 +207,120 @@ def conv_bn_act(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0
     return _ConvBnAct.apply(x, weight, scale, bias, residual, stride, pad, relu)
 
 
+class _BottleneckStage(torch.autograd.Function):
+    """A whole ResNet stage (make_stage, resnet.py:197-224: a run of BottleneckWithFixedBatchNorm blocks) as ONE
+    autograd node.  Forward = the same fused conv+FrozenBN(+residual)+ReLU kernels as conv_bn_act.  Backward is
+    written out explicitly so that every ReLU mask and every residual fan-in add rides in a dgrad epilogue:
+
+        g2 = dgrad3(g_out)            * (y2 > 0)
+        g1 = dgrad2(g2)               * (y1 > 0)
+        gx = (dgrad1(g1) + g_out)     * (x > 0)      identity block   (x is the previous block's ReLU output, so
+        gx = (dgrad1(g1) + dgradD(g_out)) * (x > 0)  downsample block  gx is already that block's masked g_out)
+
+    i.e. no relu_backward and no gradient-add kernels inside a stage (the reference's autograd graph runs
+    threshold_backward, the BN-scale multiply and the add as separate passes over every activation).
+
+    flags: input_is_relu  — the stage input is a ReLU output whose ONLY consumer is this stage, and its producer
+                            accepts an already-masked gradient (then gx is returned masked by x > 0);
+           grad_premasked — the incoming gradient is already masked by (output > 0).
+    """
+
+    @staticmethod
+    def forward(ctx, x, meta, *tensors):
+        strides, has_down, input_is_relu, grad_premasked = meta
+        x = _chk(x, name="x")
+        need_graph = x.requires_grad or any(t.requires_grad for t in tensors)
+        saved, per_block = [], []
+        k = 0
+        cur = x
+        for bi, stride in enumerate(strides):
+            w1, s1, b1, w2, s2, b2, w3, s3, b3 = tensors[k:k + 9]
+            k += 9
+            wd = sd = bd = None
+            if has_down[bi]:
+                wd, sd, bd = tensors[k:k + 3]
+                k += 3
+            y1 = conv2d_forward_raw(cur, weight_ohwi(w1), s1, b1, None, 1, 1, stride, 0, True)
+            y2 = conv2d_forward_raw(y1, weight_ohwi(w2), s2, b2, None, 3, 3, 1, 1, True)
+            identity = cur
+            if wd is not None:
+                identity = conv2d_forward_raw(cur, weight_ohwi(wd), sd, bd, None, 1, 1, stride, 0, False)
+            out = conv2d_forward_raw(y2, weight_ohwi(w3), s3, b3, identity, 1, 1, 1, 0, True)
+            if need_graph:
+                saved.extend([cur, y1, y2])
+            cur = out
+        if need_graph:
+            saved.append(cur)
+            ctx.save_for_backward(*saved, *tensors)
+            ctx.n_saved = len(saved)
+            ctx.meta = meta
+        return cur
+
+    @staticmethod
+    def backward(ctx, g):
+        strides, has_down, input_is_relu, grad_premasked = ctx.meta
+        all_saved = ctx.saved_tensors
+        acts, tensors = all_saved[:ctx.n_saved], all_saved[ctx.n_saved:]
+        y_last = acts[-1]
+        g = _chk(g, name="grad")
+        g_out = g if grad_premasked else relu_backward_raw(g, y_last)
+        grads = [None] * len(tensors)
+        # tensor offsets of each block
+        offs, k = [], 0
+        for bi in range(len(strides)):
+            offs.append(k)
+            k += 12 if has_down[bi] else 9
+        need_x = ctx.needs_input_grad[0]
+        gx = None
+        for bi in reversed(range(len(strides))):
+            o = offs[bi]
+            w1, s1, _, w2, s2, _, w3, s3, _ = tensors[o:o + 9]
+            x_in, y1, y2 = acts[3 * bi:3 * bi + 3]
+            stride = strides[bi]
+            first = bi == 0
+            w1o, w2o, w3o = weight_ohwi(w1), weight_ohwi(w2), weight_ohwi(w3)
+            if ctx.needs_input_grad[2 + o + 6]:
+                grads[o + 6] = grad_like_weight(conv2d_wgrad_raw(g_out, y2, s3, w3o.shape[0], 1, 1, 1, 0), w3)
+            g2 = conv2d_dgrad_raw(g_out, w3o, s3, tuple(y2.shape), 1, 1, 1, 0, mask_act=y2)
+            if ctx.needs_input_grad[2 + o + 3]:
+                grads[o + 3] = grad_like_weight(conv2d_wgrad_raw(g2, y1, s2, w2o.shape[0], 3, 3, 1, 1), w2)
+            g1 = conv2d_dgrad_raw(g2, w2o, s2, tuple(y1.shape), 3, 3, 1, 1, mask_act=y1)
+            del g2
+            if ctx.needs_input_grad[2 + o]:
+                grads[o] = grad_like_weight(conv2d_wgrad_raw(g1, x_in, s1, w1o.shape[0], 1, 1, stride, 0), w1)
+            wd = sd = None
+            if has_down[bi]:
+                wd, sd = tensors[o + 9], tensors[o + 10]
+                if ctx.needs_input_grad[2 + o + 9]:
+                    wdo = weight_ohwi(wd)
+                    grads[o + 9] = grad_like_weight(conv2d_wgrad_raw(g_out, x_in, sd, wdo.shape[0], 1, 1, stride, 0), wd)
+            if first and not need_x:
+                break
+            # data gradient of the block input: conv1 path + residual path, masked by the producer's ReLU
+            mask = x_in if (not first or input_is_relu) else None
+            if wd is not None:
+                t = conv2d_dgrad_raw(g_out, weight_ohwi(wd), sd, tuple(x_in.shape), 1, 1, stride, 0)
+            else:
+                t = g_out
+            g_out = conv2d_dgrad_raw(g1, w1o, s1, tuple(x_in.shape), 1, 1, stride, 0, addend=t, mask_act=mask)
+            del g1, t
+            if first:
+                gx = g_out
+        return (gx, None) + tuple(grads)
+
+
+def bottleneck_stage(x, blocks, strides, input_is_relu=False, grad_premasked=False):
+    """blocks: list of dicts with w1,s1,b1,w2,s2,b2,w3,s3,b3 and optionally wd,sd,bd (tensors)."""
+    tensors, has_down = [], []
+    for b in blocks:
+        tensors.extend([b["w1"], b["s1"], b["b1"], b["w2"], b["s2"], b["b2"], b["w3"], b["s3"], b["b3"]])
+        has_down.append("wd" in b)
+        if "wd" in b:
+            tensors.extend([b["wd"], b["sd"], b["bd"]])
+    meta = (tuple(int(s) for s in strides), tuple(has_down), bool(input_is_relu), bool(grad_premasked))
+    return _BottleneckStage.apply(x, meta, *tensors)
+
+
 def linear(x, weight, bias=None, relu=False):
     """F.linear (+ReLU) on [R, Cin] through the same implicit-GEMM kernels (a 1x1 conv on R 1x1 'images')."""
     r, cin = x.shape
@@ -475,6 +589,20 @@ def nms_sorted(boxes_sorted, thresh, max_keep=0):
     count = torch.zeros((1,), dtype=torch.int32, device=b.device)
     ws = _workspace(_lib.load().dd_nms_workspace_bytes(n), b.device, "nms")
     _lib.call("dd_nms_sorted", _ptr(b), n, float(thresh), int(max_keep), _ptr(keep), _ptr(count), _ptr(ws), _stream())
+    return keep, count
+
+
+def nms_sorted_batched(boxes_sorted, valid, thresh, max_keep):
+    """boxes [N, cap, 4] sorted by descending score per image, valid int32 [N] on the device ->
+    (keep positions int64 [N, max_keep], counts int32 [N]); two launches for the whole batch, no host sync."""
+    b = _chk(boxes_sorted, name="boxes")
+    v = _chk(valid, torch.int32, "valid")
+    n_img, cap = b.shape[0], b.shape[1]
+    keep = torch.empty((n_img, max_keep), dtype=torch.int64, device=b.device)
+    count = torch.empty((n_img,), dtype=torch.int32, device=b.device)
+    ws = _workspace(_lib.load().dd_nms_batched_workspace_bytes(n_img, cap), b.device, "nms_batched")
+    _lib.call("dd_nms_sorted_batched", _ptr(b), _ptr(v), n_img, cap, float(thresh), int(max_keep), _ptr(keep),
+              int(max_keep), _ptr(count), _ptr(ws), _stream())
     return keep, count
 
 

@@ -67,6 +67,14 @@ int dd_nms(const float* boxes, const float* scores, int n, float thresh, int64_t
  * boxlist_nms(max_proposals) (structures/boxlist_ops.py:30-33) because positions ARE score order. */
 int dd_nms_sorted(const float* boxes_sorted, int n, float thresh, int max_keep, int64_t* keep_out,
                   int* keep_count, void* workspace, void* stream);
+/* The same for a batch of images in two launches: boxes_sorted [images, n_cap, 4], image g holds n_dev[g]
+ * (device int32, <= n_cap) boxes; keep_out + g * keep_stride receives image g's kept positions, keep_count[g]
+ * their number.  No host knowledge of the counts is needed (rpn/inference.py:87-127 loops over images on the
+ * host and synchronises per image).  workspace: dd_nms_batched_workspace_bytes(images, n_cap). */
+size_t dd_nms_batched_workspace_bytes(int images, int n_cap);
+int dd_nms_sorted_batched(const float* boxes_sorted, const int* n_dev, int images, int n_cap, float thresh,
+                          int max_keep, int64_t* keep_out, int keep_stride, int* keep_count, void* workspace,
+                          void* stream);
 
 /* ---------------------------------------------------------------- RPN proposal generation */
 

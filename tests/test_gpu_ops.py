@@ -105,6 +105,26 @@ def test_nms_matches_oracle_bit_exact(n, thr):
     assert torch.equal(kept, want_first)
 
 
+def test_nms_batched_ragged_counts_match_single_image():
+    """One batched call (device-side per-image counts, incl. an empty image) == per-image calls == oracle."""
+    g = torch.Generator().manual_seed(5)
+    cap, counts, thr, post = 3000, [3000, 1234, 0, 65], 0.7, 300
+    centers = rand_boxes(g, 40, 2048, 1024, 30.0)
+    batch = torch.zeros(len(counts), cap, 4)
+    want = []
+    for i, n in enumerate(counts):
+        b = centers[torch.randint(0, 40, (cap,), generator=g)] + torch.randn(cap, 4, generator=g) * 6
+        b[:, 2:] = torch.maximum(b[:, 2:], b[:, :2] + 1)
+        batch[i] = b                                    # rows >= n are garbage the kernel must ignore
+        scores = torch.arange(n, 0, -1, dtype=torch.float32)          # already in descending-score order
+        want.append(orc.nms(b[:n], scores, thr, strict=True)[:post] if n else torch.zeros(0, dtype=torch.int64))
+    keep, cnt = ops().nms_sorted_batched(batch.to(DEV), torch.tensor(counts, dtype=torch.int32, device=DEV), thr, post)
+    cnt = cnt.cpu().tolist()
+    for i in range(len(counts)):
+        assert cnt[i] == len(want[i])
+        assert torch.equal(keep[i, : cnt[i]].cpu(), want[i])
+
+
 def test_nms_empty():
     got = ops().nms(torch.zeros(0, 4, device=DEV), torch.zeros(0, device=DEV), 0.5)
     assert got.numel() == 0 and got.dtype == torch.int64
@@ -295,6 +315,44 @@ def test_conv_autograd_function_and_linear():
     torch.testing.assert_close(got.cpu(), want, atol=2e-5, rtol=1e-4)
     for a, b_ in zip(gg, gw):
         torch.testing.assert_close(a.cpu(), b_, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("first_stride,in_relu,premasked", [(2, True, True), (1, False, False)])
+def test_fused_stage_matches_per_layer_autograd(impl, first_stride, in_relu, premasked):
+    """ops.bottleneck_stage (explicit backward, masks and fan-in adds in dgrad epilogues) against the same
+    blocks run layer by layer through conv_bn_act + autograd."""
+    from dadetect_b200.modeling.backbone import make_stage
+    o = ops()
+    o.set_default_impl(o.IMPL_TCGEN05 if impl == "tcgen05" else o.IMPL_SIMT)
+    try:
+        torch.manual_seed(3)
+        stage = make_stage(32, 32, 64, 3, first_stride).to(DEV)
+        for m in stage.modules():
+            if hasattr(m, "running_var"):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+        x0 = torch.randn(2, 12, 20, 32, device=DEV)
+        if in_relu:
+            x0 = x0.relu()
+        go = torch.randn(2, 12 // first_stride, 20 // first_stride, 64, device=DEV)
+        res = []
+        for fused in (False, True):
+            stage.fused = fused
+            x = x0.clone().requires_grad_(True)
+            y = stage(x, input_is_relu=in_relu, grad_premasked=premasked)
+            g = go * (y > 0) if premasked else go          # a pre-masked upstream gradient
+            grads = torch.autograd.grad(y, [x] + list(stage.parameters()), g)
+            gx = grads[0] * (x0 > 0) if (in_relu and not fused) else grads[0]
+            res.append((y.detach(), gx, grads[1:]))
+        tol = dict(atol=1e-5, rtol=1e-4) if impl == "simt" else dict(atol=2e-2, rtol=2e-2)
+        torch.testing.assert_close(res[1][0], res[0][0], **tol)
+        torch.testing.assert_close(res[1][1], res[0][1], **tol)
+        for a, b in zip(res[1][2], res[0][2]):
+            torch.testing.assert_close(a, b, atol=tol["atol"] * 10, rtol=tol["rtol"])
+    finally:
+        o.set_default_impl(o.IMPL_SIMT)
 
 
 def test_pooling_and_layout():
