@@ -284,20 +284,39 @@ __global__ void dgrad_fill_kernel(const float* __restrict__ addend, const float*
   }
 }
 
-__global__ void bias_grad_kernel(const float* __restrict__ gy, float* __restrict__ gb, int rows, int C, int accumulate) {
-  // one CTA per 32 channels; threads (32 x 8): coalesced along channels, strided over rows
-  __shared__ float part[8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  float acc = 0.f;
-  if (c < C)
-    for (int r = threadIdx.y; r < rows; r += 8) acc += gy[(size_t)r * C + c];
-  part[threadIdx.y][threadIdx.x] = acc;
+// Column sums of gy [rows, C].  grid (channel groups of 32 x `vec`, row slices): coalesced (vector) reads along
+// channels, in-CTA tree over the 8 row lanes, one atomicAdd per channel per CTA into the zero-initialised /
+// accumulated gb.
+template <int VEC>
+__global__ void bias_grad_kernel(const float* __restrict__ gy, float* __restrict__ gb, int rows, int C,
+                                 int rows_per_cta) {
+  __shared__ float part[8][32 * VEC + 1];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * VEC;
+  const int r_begin = blockIdx.y * rows_per_cta, r_end = min(rows, r_begin + rows_per_cta);
+  float acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+  if (c < C) {
+    for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
+      if (VEC == 4) {
+        const float4 v = dd::ldg4(gy + (size_t)r * C + c);
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      } else {
+        acc[0] += gy[(size_t)r * C + c];
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) part[threadIdx.y][threadIdx.x * VEC + e] = acc[e];
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-    float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
-    gb[c] = accumulate ? gb[c] + s : s;
+    for (int e = 0; e < VEC; ++e) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x * VEC + e];
+      atomicAdd(gb + c + e, s);
+    }
   }
 }
 
@@ -394,8 +413,18 @@ int dd_simt_conv2d_wgrad(const float* gy, const float* x, const float* scale, fl
 
 extern "C" int dd_bias_grad(const float* gy, float* gb, int rows, int C, int accumulate, void* stream) {
   DD_CHECK_ARG(rows > 0 && C > 0);
+  cudaStream_t s = dd::S(stream);
+  if (!accumulate) DD_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)C, s));
   dim3 block(32, 8);
-  bias_grad_kernel<<<(C + 31) / 32, block, 0, dd::S(stream)>>>(gy, gb, rows, C, accumulate);
+  const bool vec = C % 4 == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
+  const int groups = vec ? (C + 127) / 128 : (C + 31) / 32;
+  int slices = (4 * dd::kNumSMs + groups - 1) / groups;
+  if (slices > (rows + 63) / 64) slices = (rows + 63) / 64;
+  if (slices < 1) slices = 1;
+  const int rows_per_cta = (rows + slices - 1) / slices;
+  dim3 grid(groups, (rows + rows_per_cta - 1) / rows_per_cta);
+  if (vec) bias_grad_kernel<4><<<grid, block, 0, s>>>(gy, gb, rows, C, rows_per_cta);
+  else bias_grad_kernel<1><<<grid, block, 0, s>>>(gy, gb, rows, C, rows_per_cta);
   DD_LAUNCHED();
   return 0;
 }

@@ -48,6 +48,7 @@ struct TcParams {
   int tiles_h, tiles_w;   // ceil(OH/th), ceil(OW/tw)
   int m_tiles, n_tiles;   // persistent tile space: t -> (n_tile = t % n_tiles, m_tile = t / n_tiles)
   int tma_store;          // 1: staged chunks leave through a TMA tensor store; 0: guarded scalar stores
+  int stem;               // 1: A is the 5-D overlapping-window view of the padded NHWC4 image (7x7/2 stem)
   int prefetch_side;      // 1: map_e / map_m are valid and the producer prefetches extra / mask tiles to L2
   // where a row lands in the output tensor: out[((n*out_H + h*os)*out_W + w*os)*ldc + co]
   int out_H, out_W, os, ldc;
@@ -310,7 +311,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* sa = smem + s * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_expect_tx(full_bar + s, L::kStageBytes);
-          tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
+          if (p.stem) tma_load_5d(&map_a, full_bar + s, sa, 0, ow0, oh0 + (tap >> 1), tap & 1, n0);
+          else tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
           tma_load_2d(&map_b, full_bar + s, sb, tap * p.Cin + cb * BKE, n_tile * BN);
         }
       }
@@ -497,12 +499,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ONE 5-D TMA box whose outermost dimension walks the 32-channel blocks.  1x1 convs see the pixels as one
 // dense axis (no padding of 7x7 ROI maps to 8x8).
 struct TcWgradParams {
-  float* partial;          // [splits][Cout][taps*Cin]
+  float* gw;               // [Cout][taps*Cin], accumulated into
+  const float* scale;      // per-Cout BN scale (may be null)
   int Cout, Cin, taps, KW, pad;
   int tn, th, tw;          // pixel block = tn*th*tw == 32
   int tiles_h, tiles_w, pix_blocks, blocks_per_split;
   int ci_tiles;
 };
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 constexpr int WG_KPIX = 32;                       // pixels per stage (4 MMA K-steps of 8)
 constexpr int WG_BOX_BYTES = WG_KPIX * 128;       // one [32 pix x 32 ch] box = 4 KB
@@ -607,29 +614,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
       __syncwarp();
     }
   } else {
+    // epilogue: BN scale, then fp32 vector reductions straight into gw (split-K partial sums meet in L2; no
+    // partial buffers, no reduce pass)
     const int quarter = warp & 3;
     const int co = co0 + quarter * 32 + lane;
     const size_t ldp = (size_t)p.taps * p.Cin;
-    float* dst_row = p.partial + ((size_t)blockIdx.z * p.Cout + co) * ldp + (size_t)tap * p.Cin + ci0;
+    float* dst_row = p.gw + (size_t)co * ldp + (size_t)tap * p.Cin + ci0;
+    const float sc = (p.scale && co < p.Cout) ? __ldg(p.scale + co) : 1.f;
     if (k_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
-    }
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      if (k_iters > 0) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-      } else {
+        if (co < p.Cout && ci0 + c0 < p.Cin) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-      if (co < p.Cout && ci0 + c0 < p.Cin) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst_row + c0 + j) =
-              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                          __uint_as_float(r[j + 3]));
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(dst_row + c0 + j, __uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc,
+                       __uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
+        }
       }
     }
   }
@@ -832,6 +836,92 @@ int launch_wgrad(const CUtensorMap& mg, const CUtensorMap& mx, const TcWgradPara
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- 7x7/2 stem
+// The stem conv (3 -> 64, 7x7, stride 2, pad 3; resnet.py:317-336) has Cin = 3, far too narrow for a TMA box.
+// Re-cast: copy the NCHW image once into a zero-haloed NHWC4 buffer P[N, H+6, W+8, 4]; then the 7 taps of one
+// filter ROW that an output pixel reads are 8 consecutive pixels x 4 channels = 32 contiguous floats of P
+// (the 8th pixel and the 4th channel meet zero weights).  A TMA view with OVERLAPPING windows — pixel stride
+// 32 B, row pairs split into (row/2, parity) so that the stride-2 row walk is a plain dimension — hands the
+// tensor cores a K-major [128 pixels x 32] tile per filter row: an implicit GEMM with K = 7 x 32 = 224.
+__global__ void stem_pad_kernel(const float* __restrict__ x, float* __restrict__ P, int N, int H, int W, int hp, int wp) {
+  // one thread per padded pixel; reads of the three planes are coalesced along w
+  const long long total = (long long)N * hp * wp;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(t % wp) - 3;
+    const int h = (int)((t / wp) % hp) - 3;
+    const int n = (int)(t / ((long long)wp * hp));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (w >= 0 && w < W && h >= 0 && h < H) {
+      const size_t plane = (size_t)H * W, o = (size_t)n * 3 * plane + (size_t)h * W + w;
+      v.x = __ldg(x + o); v.y = __ldg(x + o + plane); v.z = __ldg(x + o + 2 * plane);
+    }
+    reinterpret_cast<float4*>(P)[t] = v;
+  }
+}
+
+// W2[co][kh][kw*4 + c] = w[co][kh][kw][c] (OHWI, 7x7x3), zero for kw == 7 or c == 3
+__global__ void stem_weight_kernel(const float* __restrict__ w, float* __restrict__ w2, int Cout) {
+  const int total = Cout * 7 * 32;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int c = t & 3, kw = (t >> 2) & 7, kh = (t >> 5) % 7, co = t / (7 * 32);
+    w2[t] = (c < 3 && kw < 7) ? w[((co * 7 + kh) * 7 + kw) * 3 + c] : 0.f;
+  }
+}
+
+}  // namespace
+
+extern "C" size_t dd_stem_workspace_bytes(int N, int H, int W, int Cout) {
+  return sizeof(float) * ((size_t)N * (H + 6) * (W + 8) * 4 + (size_t)Cout * 7 * 32) + 256;
+}
+
+extern "C" int dd_stem_conv7x7s2_forward(const float* x_nchw, const float* w_ohwi, const float* scale,
+                                         const float* bias, float* y, int N, int H, int W, int Cout, int act,
+                                         void* workspace, void* stream) {
+  DD_CHECK_ARG(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && Cout > 0 && Cout % 4 == 0 && Cout <= 64);
+  DD_CHECK_ARG(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
+               (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  cudaStream_t s = dd::S(stream);
+  const int hp = H + 6, wp = W + 8, OH = H / 2, OW = W / 2;
+  float* P = (float*)workspace;
+  float* w2 = P + (((size_t)N * hp * wp * 4 + 63) / 64) * 64;
+  stem_pad_kernel<<<dd::grid_for((long long)N * hp * wp, 256), 256, 0, s>>>(x_nchw, P, N, H, W, hp, wp);
+  DD_LAUNCHED();
+  stem_weight_kernel<<<(Cout * 7 * 32 + 255) / 256, 256, 0, s>>>(w_ohwi, w2, Cout);
+  DD_LAUNCHED();
+
+  TcParams p = {};
+  p.out = y; p.scale = scale; p.bias = bias; p.relu = act == DD_ACT_RELU;
+  p.N = N; p.OH = OH; p.OW = OW;
+  p.tw = 16; p.th = 8; p.tn = 1;
+  p.tiles_w = (OW + 15) / 16; p.tiles_h = (OH + 7) / 8;
+  p.m_tiles = N * p.tiles_h * p.tiles_w; p.n_tiles = 1;
+  p.tma_store = 1; p.stem = 1;
+  p.out_H = OH; p.out_W = OW; p.os = 1; p.ldc = Cout; p.Cout = Cout;
+  p.taps = 7; p.KW = 1; p.pad = 0; p.cblocks = 1; p.Cin = 32;
+  CUtensorMap ma, mb, mc;
+  {
+    // (32 floats of the window, ow, row pair, row parity, n)
+    cuuint64_t dims[5] = {32, (cuuint64_t)OW, (cuuint64_t)(hp / 2), 2, (cuuint64_t)N};
+    cuuint64_t strides[4] = {32, (cuuint64_t)wp * 32, (cuuint64_t)wp * 16, (cuuint64_t)hp * wp * 16};
+    cuuint32_t box[5] = {32, 16, 8, 1, 1};
+    if (encode_map(&ma, P, 5, dims, strides, box)) return -1;
+  }
+  {
+    cuuint64_t dims[2] = {224, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {224 * 4};
+    cuuint32_t box[2] = {32, 64};
+    if (encode_map(&mb, w2, 2, dims, strides, box)) return -1;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)OW * Cout * 4, (cuuint64_t)OH * OW * Cout * 4};
+    cuuint32_t box[4] = {32, 16, 2, 1};
+    if (encode_map(&mc, y, 4, dims, strides, box)) return -1;
+  }
+  return launch_tc<64>(ma, mb, mc, ma, ma, p, s);
+}
+
+namespace {
 }  // namespace
 
 extern "C" int dd_tcgen05_built(void) { return 1; }
@@ -895,16 +985,14 @@ int dd_tc_conv2d_dgrad(const float* gy, const float* w, const float* scale, cons
   return rc;
 }
 
-int dd_simt_wgrad_splits(int M, int Ncols, int K);
-int dd_wgrad_reduce(const float* partial, int splits, int M, int Ncols, const float* scale, float* gw, int accumulate,
-                    cudaStream_t s);
-
 int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, float* gw, int N, int H, int W, int Cin,
                        int Cout, int KH, int KW, int stride, int pad, int accumulate, void* workspace, cudaStream_t s) {
-  DD_CHECK_ARG(workspace != nullptr);
+  (void)workspace;
   const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
+  DD_CHECK_ARG((reinterpret_cast<uintptr_t>(gw) & 15) == 0);
+  if (!accumulate) DD_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * KH * KW * Cin, s));
   TcWgradParams p = {};
-  p.partial = (float*)workspace;
+  p.gw = gw; p.scale = scale;
   p.Cout = Cout; p.Cin = Cin; p.taps = KH * KW; p.KW = KW; p.pad = pad;
   // pixel axes as the kernel sees them (gy side: PN x PH x PW; x side may be a strided view of the same grid)
   int PN = N, PH = OH, PW = OW;
@@ -928,12 +1016,10 @@ int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, floa
   const int BN = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : 32));
   p.ci_tiles = (Cin + BN - 1) / BN;
   const int co_tiles = (Cout + BM - 1) / BM;
-  // split the pixel range so that whole waves of CTAs exist, within the workspace the sizing function grants
-  const int max_splits = dd_simt_wgrad_splits(Cout, KH * KW * Cin, N * OH * OW);
+  // split the pixel range so that about two waves of CTAs exist and every CTA still runs >= 8 K-iterations
   const int tiles = co_tiles * p.ci_tiles * p.taps;
   int splits = (2 * dd::kNumSMs + tiles - 1) / tiles;
-  if (splits > max_splits) splits = max_splits;
-  if (splits > p.pix_blocks) splits = p.pix_blocks;
+  if (splits > (p.pix_blocks + 7) / 8) splits = (p.pix_blocks + 7) / 8;
   if (splits < 1) splits = 1;
   p.blocks_per_split = (p.pix_blocks + splits - 1) / splits;
   splits = (p.pix_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
@@ -958,6 +1044,5 @@ int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, floa
   else if (BN == 128) rc = launch_wgrad<128>(mg, mx, p, grid, s);
   else if (BN == 64) rc = launch_wgrad<64>(mg, mx, p, grid, s);
   else rc = launch_wgrad<32>(mg, mx, p, grid, s);
-  if (!rc) rc = dd_wgrad_reduce(p.partial, splits, Cout, KH * KW * Cin, scale, gw, accumulate, s);
   return rc;
 }

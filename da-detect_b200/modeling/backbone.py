@@ -128,14 +128,18 @@ class Stem(nn.Module):
         self.conv1 = Conv2dParams(3, cout, 7, 2, 3)
         self.bn1 = FrozenBatchNorm2d(cout)
 
-    def forward(self, x):
+    def forward(self, x_nchw):
+        """x_nchw: the reference's input layout [N,3,H,W]; everything downstream is NHWC."""
         s, b = self.bn1.affine()
-        x = ops.conv_bn_act(x, self.conv1.weight, s, b, stride=2, pad=3, relu=True)
+        if ops.stem_tc_supported(x_nchw, self.conv1.weight):
+            x = ops.stem_conv7x7s2(x_nchw, self.conv1.weight, s, b, relu=True)
+        else:
+            x = ops.conv_bn_act(ops.nchw_to_nhwc(x_nchw), self.conv1.weight, s, b, stride=2, pad=3, relu=True)
         return ops.maxpool3x3s2(x)
 
 
 class ResNetC4(nn.Module):
-    """ResNet.forward for the *-C4 bodies: returns [res4 feature map] (NHWC)."""
+    """ResNet.forward for the *-C4 bodies: NCHW image in, returns [res4 feature map] (NHWC)."""
 
     def __init__(self, cfg):
         super().__init__()

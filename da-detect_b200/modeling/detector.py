@@ -111,7 +111,7 @@ class GeneralizedRCNN(nn.Module):
         if targets is not None:
             cache_source_flags(targets)
         with section("trunk_fwd"):
-            x = ops.nchw_to_nhwc(images.tensors)
+            x = ops._chk(images.tensors, name="images")            # NCHW; the stem consumes it directly
             feat, logits, deltas = self.segments.run("trunk", lambda: _Trunk(self.backbone, self.rpn.head), (x,))
         features = [feat]
         with section("rpn_proposals_and_loss"):

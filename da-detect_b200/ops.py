@@ -159,6 +159,28 @@ def nhwc_to_nchw(x):
     return y
 
 
+def stem_conv7x7s2(x_nchw, weight, scale, bias, relu=True):
+    """BaseStem conv (7x7/2, 3 -> Cout<=64) + FrozenBN + ReLU on the tensor cores, straight from the
+    reference's NCHW image (the layout conversion is part of the operand staging); returns NHWC.  The stem is
+    frozen in every DA config (FREEZE_CONV_BODY_AT = 2), so this op is forward-only."""
+    x = _chk(x_nchw, name="images")
+    n, c, h, w = x.shape
+    cout = weight.shape[0]
+    if c != 3 or tuple(weight.shape[1:]) != (3, 7, 7):
+        raise RuntimeError("dadetect_b200: stem_conv7x7s2 expects [N,3,H,W] images and a [Cout,3,7,7] weight")
+    y = torch.empty((n, h // 2, w // 2, cout), dtype=torch.float32, device=x.device)
+    ws = _workspace(_lib.load().dd_stem_workspace_bytes(n, h, w, cout), x.device, "stem")
+    _lib.call("dd_stem_conv7x7s2_forward", _ptr(x), _ptr(weight_ohwi(weight.detach())), _ptr(scale), _ptr(bias),
+              _ptr(y), n, h, w, cout, 1 if relu else 0, _ptr(ws), _stream())
+    return y
+
+
+def stem_tc_supported(x_nchw, weight):
+    return (_default_impl == IMPL_TCGEN05 and x_nchw.shape[1] == 3 and x_nchw.shape[2] % 2 == 0
+            and x_nchw.shape[3] % 2 == 0 and tuple(weight.shape[1:]) == (3, 7, 7) and weight.shape[0] % 4 == 0
+            and weight.shape[0] <= 64 and not weight.requires_grad)
+
+
 def maxpool3x3s2(x):
     n, h, w, c = x.shape
     oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1

@@ -123,6 +123,13 @@ int dd_box_decode(const float* codes, const float* boxes, int R, int k, float wx
 int dd_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias,
                       const float* residual, float* y, int N, int H, int W, int Cin, int Cout, int KH, int KW,
                       int stride, int pad, int act, int impl, void* stream);
+/* The ResNet stem (BaseStem, resnet.py:317-336: 7x7 stride-2 pad-3 conv of the 3-channel image + FrozenBN
+ * + ReLU) on the tensor cores, reading the reference's NCHW image directly: x_nchw [N,3,H,W] (H, W even),
+ * w [Cout,7,7,3] (OHWI), y [N,H/2,W/2,Cout] NHWC, Cout <= 64.  workspace: dd_stem_workspace_bytes(...) bytes,
+ * 256-byte aligned (zero-haloed NHWC4 copy of the image + re-packed weights). */
+size_t dd_stem_workspace_bytes(int N, int H, int W, int Cout);
+int dd_stem_conv7x7s2_forward(const float* x_nchw, const float* w_ohwi, const float* scale, const float* bias,
+                              float* y, int N, int H, int W, int Cout, int act, void* workspace, void* stream);
 /* gx = conv_transpose(gy, w * scale[co]) (+ addend) (* (mask_act > 0) if mask_act).  gx [N,H,W,Cin]
  * is fully written (positions a strided conv never read receive addend or 0).
  * workspace: dd_conv2d_dgrad_workspace_bytes(...) bytes (16-byte aligned) — the tcgen05 arm keeps the

@@ -355,6 +355,24 @@ def test_fused_stage_matches_per_layer_autograd(impl, first_stride, in_relu, pre
         o.set_default_impl(o.IMPL_SIMT)
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 34, 50)])
+def test_stem_tensor_core_path(shape):
+    """7x7/2 stem as an overlapping-window implicit GEMM on tcgen05 (TF32) against F.conv2d fp32."""
+    n, h, w = shape
+    o = ops()
+    g = torch.Generator().manual_seed(h)
+    x = torch.rand(n, 3, h, w, generator=g) * 255 - 110
+    wt = torch.randn(64, 3, 7, 7, generator=g) / 12.0
+    scale = 0.5 + torch.rand(64, generator=g)
+    bias = torch.randn(64, generator=g) * 0.1
+    want = F.relu(F.conv2d(x, wt, stride=2, padding=3) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    got = o.stem_conv7x7s2(x.to(DEV), wt.to(DEV), scale.to(DEV), bias.to(DEV))
+    err = got.permute(0, 3, 1, 2).cpu() - want
+    rms = float(want.pow(2).mean().sqrt())
+    assert float(err.pow(2).mean().sqrt()) <= 2e-3 * rms
+    assert float(err.abs().max()) <= 6e-2 * rms
+
+
 def test_pooling_and_layout():
     o = ops()
     g = torch.Generator().manual_seed(4)
