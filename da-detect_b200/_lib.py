@@ -55,7 +55,10 @@ _SIGS = {
     "dd_softmax_ce_mean": (_I, "pppiippp"),
     "dd_smooth_l1_sum": (_I, "ppqffppp"),
     "dd_box_reg_loss": (_I, "ppppiippp"),
-    "dd_consistency_loss": (_I, "pqpiippppp"),
+    "dd_consistency_loss": (_I, "pqpiipppppp"),
+    "dd_proposals_gather": (_I, "pppppppiiiipppp"),
+    "dd_balanced_sample": (_I, "pppiiiippp"),
+    "dd_sgd_momentum_dev": (_I, "pppqpffffp"),
     "dd_triplet_margin_loss": (_I, "pppqiqfppppp"),
     "dd_sgd_momentum": (_I, "pppqffffip"),
 }

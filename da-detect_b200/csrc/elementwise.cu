@@ -120,7 +120,9 @@ __global__ void dropout_kernel(const float* __restrict__ x, const float* __restr
 }
 
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
-                           float lr, float momentum, float wd, float grad_scale, int first_step) {
+                           float lr, const float* __restrict__ lr_dev, float momentum, float wd, float grad_scale,
+                           int first_step) {
+  if (lr_dev) lr = lr * __ldg(lr_dev);     // learning rate kept on the device (a captured graph replays it)
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
     const float pv = p[t];
     float gv = g[t] * grad_scale;
@@ -204,8 +206,18 @@ extern "C" int dd_sgd_momentum(float* p, const float* g, float* buf, long long n
                                float grad_scale, int first_step, void* stream) {
   DD_CHECK_ARG(n >= 0);
   if (n == 0) return 0;
-  sgd_kernel<<<dd::grid_for(n, 256), 256, 0, dd::S(stream)>>>(p, g, buf, n, lr, momentum, wd, grad_scale,
+  sgd_kernel<<<dd::grid_for(n, 256), 256, 0, dd::S(stream)>>>(p, g, buf, n, lr, nullptr, momentum, wd, grad_scale,
                                                               first_step);
+  DD_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dd_sgd_momentum_dev(float* p, const float* g, float* buf, long long n, const float* lr_dev,
+                                   float lr_factor, float momentum, float wd, float grad_scale, void* stream) {
+  DD_CHECK_ARG(n >= 0 && lr_dev != nullptr);
+  if (n == 0) return 0;
+  sgd_kernel<<<dd::grid_for(n, 256), 256, 0, dd::S(stream)>>>(p, g, buf, n, lr_factor, lr_dev, momentum, wd,
+                                                              grad_scale, 0);
   DD_LAUNCHED();
   return 0;
 }

@@ -132,13 +132,24 @@ __global__ void __launch_bounds__(256) cst_img_mean_kernel(const float* __restri
 
 // single CTA over the K ROIs
 __global__ void __launch_bounds__(256) cst_ins_kernel(const float* __restrict__ ins_logits, int K, int n_src,
-                                                      float inv_hw, float* __restrict__ ws, float* __restrict__ loss,
+                                                      const uint8_t* __restrict__ row_valid, float inv_hw,
+                                                      float* __restrict__ ws, float* __restrict__ loss,
                                                       float* __restrict__ grad_ins) {
   __shared__ float red[32];
+  __shared__ float s_cnt;
   const float mean0 = ws[0] * inv_hw, mean1 = ws[1] * inv_hw;
-  const float invK = 1.0f / (float)K;
+  float cnt = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) cnt += (!row_valid || row_valid[k]) ? 1.f : 0.f;
+  cnt = dd::block_sum(cnt, red);
+  if (threadIdx.x == 0) s_cnt = cnt;
+  __syncthreads();
+  const float invK = 1.0f / s_cnt;                 // mean over the ROIs that exist (padding rows are skipped)
   float acc = 0.f, d0 = 0.f, d1 = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    if (row_valid && !row_valid[k]) {
+      if (grad_ins) grad_ins[k] = 0.f;
+      continue;
+    }
     const float s = sigmoidf_(ins_logits[k]);
     const bool src = k < n_src;
     const float diff = (src ? mean0 : mean1) - s;
@@ -288,14 +299,15 @@ extern "C" int dd_box_reg_loss(const float* box_reg, const float* reg_targets, c
 }
 
 extern "C" int dd_consistency_loss(const float* img_logits, long long hw, const float* ins_logits, int K, int n_src,
-                                   float* loss, float* grad_img, float* grad_ins, float* workspace2, void* stream) {
+                                   const uint8_t* row_valid, float* loss, float* grad_img, float* grad_ins,
+                                   float* workspace2, void* stream) {
   DD_CHECK_ARG(hw > 0 && K > 0 && n_src >= 0 && n_src <= K && workspace2 != nullptr);
   cudaStream_t s = dd::S(stream);
   DD_CUDA(cudaMemsetAsync(workspace2, 0, 4 * sizeof(float), s));
   dim3 grid(dd::grid_for(hw, 256, 1), 2);
   cst_img_mean_kernel<<<grid, 256, 0, s>>>(img_logits, hw, workspace2);
   DD_LAUNCHED();
-  cst_ins_kernel<<<1, 256, 0, s>>>(ins_logits, K, n_src, 1.0f / (float)hw, workspace2, loss, grad_ins);
+  cst_ins_kernel<<<1, 256, 0, s>>>(ins_logits, K, n_src, row_valid, 1.0f / (float)hw, workspace2, loss, grad_ins);
   DD_LAUNCHED();
   if (grad_img) {
     cst_img_grad_kernel<<<grid, 256, 0, s>>>(img_logits, hw, 1.0f / (float)hw, workspace2, grad_img);

@@ -1,0 +1,198 @@
+// Device-resident proposal bookkeeping and fg/bg subsampling: fixed-capacity buffers with on-device counts,
+// so that one training step has no host synchronisation between the RPN head and the box-head losses (the
+// reference reads sizes back on the host in rpn/inference.py:87-127, boxlist_ops.py:30-34,
+// balanced_positive_negative_sampler.py:35-76 and box_head/loss.py:55-130).
+//
+//   dd_proposals_gather   NMS survivors (+ ground-truth boxes for source images, inference.py:51-74) ->
+//                         [N, cap, 4] / [N, cap] / count[N]
+//   dd_balanced_sample    BalancedPositiveNegativeSampler: `num_pos = min(#pos, max_pos)` positives and
+//                         `min(#neg, batch - num_pos)` negatives chosen uniformly at random.  The reference
+//                         takes a prefix of randperm(#pos); here every candidate carries a random key and the
+//                         smallest keys win (an exact radix select, ties broken by lower index) — the same
+//                         distribution, and with keys = rank in a recorded permutation the identical choice.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 1024;
+
+__global__ void __launch_bounds__(256) proposals_gather_kernel(
+    const float4* __restrict__ boxes, const float* __restrict__ scores, const int64_t* __restrict__ keep,
+    const int* __restrict__ keep_count, const float4* __restrict__ gt, const int* __restrict__ gt_off,
+    const uint8_t* __restrict__ append_gt, int k, int post, int cap, float4* __restrict__ out_boxes,
+    float* __restrict__ out_obj, int* __restrict__ out_count) {
+  const int img = blockIdx.x;
+  const int nk = min(keep_count[img], post);
+  const int g0 = gt_off[img], ng = append_gt[img] ? gt_off[img + 1] - g0 : 0;
+  const int total = min(nk + ng, cap);
+  for (int r = threadIdx.x; r < cap; r += blockDim.x) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    float s = 0.f;
+    if (r < nk) {
+      const int pos = (int)keep[(size_t)img * post + r];
+      b = boxes[(size_t)img * k + pos];
+      s = scores[(size_t)img * k + pos];
+    } else if (r < total) {
+      b = gt[g0 + r - nk];
+      s = 1.f;
+    }
+    out_boxes[(size_t)img * cap + r] = b;
+    out_obj[(size_t)img * cap + r] = s;
+  }
+  if (threadIdx.x == 0) out_count[img] = total;
+}
+
+__device__ __forceinline__ uint32_t ordered_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// class of a candidate: 0 = positive (label >= 1), 1 = negative (label == 0), 2 = ignored
+__device__ __forceinline__ int cls_of(int label) { return label >= 1 ? 0 : (label == 0 ? 1 : 2); }
+
+// Exclusive rank of `flag` among the CTA's threads in thread order; `total` = number of set flags.
+__device__ __forceinline__ int block_rank(bool flag, int* warp_tot, int& total) {
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int within = __popc(bal & ((1u << lane) - 1u));
+  __syncthreads();
+  if (lane == 0) warp_tot[wid] = __popc(bal);
+  __syncthreads();
+  int base = 0, tot = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+    const int c = warp_tot[w];
+    if (w < wid) base += c;
+    tot += c;
+  }
+  total = tot;
+  return base + within;
+}
+
+// One CTA per image.
+__global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
+    const int* __restrict__ labels, const int* __restrict__ n_dev, const float* __restrict__ keys, int n_cap,
+    int batch, int max_pos, int64_t* __restrict__ sel_idx, int* __restrict__ counts) {
+  __shared__ int hist[2][256];
+  __shared__ int warp_tot[32];
+  __shared__ int s_cnt[2];
+  __shared__ uint32_t s_prefix[2];
+  __shared__ int s_need[2];
+  const int img = blockIdx.x;
+  labels += (size_t)img * n_cap;
+  keys += (size_t)img * n_cap;
+  sel_idx += (size_t)img * batch;
+  const int n = n_dev ? min(n_dev[img], n_cap) : n_cap;
+  const int tid = threadIdx.x;
+
+  // ---- population of the two classes
+  if (tid < 2) s_cnt[tid] = 0;
+  __syncthreads();
+  {
+    int c0 = 0, c1 = 0;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int c = cls_of(labels[i]);
+      c0 += c == 0;
+      c1 += c == 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&s_cnt[0], c0); atomicAdd(&s_cnt[1], c1); }
+  }
+  __syncthreads();
+  const int n_pos = s_cnt[0], n_neg = s_cnt[1];
+  const int num_pos = min(n_pos, max_pos);
+  const int num_neg = min(n_neg, batch - num_pos);
+  const int want[2] = {num_pos, num_neg};
+
+  // ---- exact radix select (both classes in the same sweeps): key of the want[c]-th smallest candidate
+  uint32_t prefix[2] = {0u, 0u}, mask = 0u;
+  int need[2] = {want[0], want[1]};
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 512; i += blockDim.x) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int c = cls_of(labels[i]);
+      if (c < 2) {
+        const uint32_t key = ordered_key(keys[i]);
+        if ((key & mask) == prefix[c]) atomicAdd(&hist[c][(key >> shift) & 0xFF], 1);
+      }
+    }
+    __syncthreads();
+    if (tid < 2) {
+      const int c = tid;
+      int acc = 0, b = 0;
+      if (need[c] > 0) {
+        for (; b < 255; ++b) {
+          if (acc + hist[c][b] >= need[c]) break;
+          acc += hist[c][b];
+        }
+      }
+      s_prefix[c] = prefix[c] | ((uint32_t)b << shift);
+      s_need[c] = need[c] - acc;
+    }
+    __syncthreads();
+    prefix[0] = s_prefix[0]; prefix[1] = s_prefix[1];
+    need[0] = s_need[0]; need[1] = s_need[1];
+    mask |= 0xFFu << shift;
+    __syncthreads();
+  }
+  // candidates with key < prefix[c] are taken, plus the first need[c] (by index) with key == prefix[c]
+
+  // ---- ordered compaction: selected indices in ascending order (== nonzero(pos_mask | neg_mask))
+  int out_base = 0, ties[2] = {0, 0};
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + tid;
+    int c = 2;
+    bool lt = false, eq = false;
+    if (i < n) {
+      c = cls_of(labels[i]);
+      if (c < 2 && want[c] > 0) {
+        const uint32_t key = ordered_key(keys[i]);
+        lt = key < prefix[c];
+        eq = key == prefix[c];
+      }
+    }
+    int tot0, tot1;
+    const int r0 = block_rank(eq && c == 0, warp_tot, tot0);
+    const int r1 = block_rank(eq && c == 1, warp_tot, tot1);
+    const bool take = lt || (eq && c == 0 && ties[0] + r0 < need[0]) || (eq && c == 1 && ties[1] + r1 < need[1]);
+    ties[0] += tot0;
+    ties[1] += tot1;
+    int tot;
+    const int r = block_rank(take, warp_tot, tot);
+    if (take && out_base + r < batch) sel_idx[out_base + r] = (int64_t)i;
+    out_base += tot;
+  }
+  const int total = min(out_base, batch);
+  for (int r = total + tid; r < batch; r += blockDim.x) sel_idx[r] = 0;   // padding rows point at candidate 0
+  if (tid == 0) {
+    counts[img * 2 + 0] = num_pos;
+    counts[img * 2 + 1] = total;
+  }
+}
+
+}  // namespace
+
+extern "C" int dd_proposals_gather(const float* boxes, const float* scores, const int64_t* keep, const int* keep_count,
+                                   const float* gt, const int* gt_offsets, const uint8_t* append_gt, int N, int k,
+                                   int post, int cap, float* out_boxes, float* out_objectness, int* out_count,
+                                   void* stream) {
+  DD_CHECK_ARG(N > 0 && k > 0 && post > 0 && cap >= post);
+  proposals_gather_kernel<<<N, 256, 0, dd::S(stream)>>>(
+      reinterpret_cast<const float4*>(boxes), scores, keep, keep_count, reinterpret_cast<const float4*>(gt), gt_offsets,
+      append_gt, k, post, cap, reinterpret_cast<float4*>(out_boxes), out_objectness, out_count);
+  DD_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dd_balanced_sample(const int* labels, const int* n_dev, const float* keys, int images, int n_cap,
+                                  int batch, int max_pos, int64_t* sel_idx, int* counts, void* stream) {
+  DD_CHECK_ARG(images > 0 && n_cap > 0 && batch > 0 && max_pos >= 0 && max_pos <= batch);
+  balanced_sample_kernel<<<images, kThreads, 0, dd::S(stream)>>>(labels, n_dev, keys, n_cap, batch, max_pos, sel_idx,
+                                                               counts);
+  DD_LAUNCHED();
+  return 0;
+}

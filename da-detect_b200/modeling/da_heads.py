@@ -49,13 +49,13 @@ class DAInsHead(nn.Module):
         nn.init.constant_(self.fc3_da.bias, 0)
         self.rng = rng
 
-    def forward(self, x):
+    def forward(self, x, row_valid=None):
         x = ops.linear(x, self.fc1_da.weight, self.fc1_da.bias, relu=True)
         if self.training:
-            x = ops.dropout_with_mask(x, self.rng.dropout_keep(tuple(x.shape), x.device))
+            x = ops.dropout_with_mask(x, self.rng.dropout_keep(tuple(x.shape), x.device, row_valid))
         x = ops.linear(x, self.fc2_da.weight, self.fc2_da.bias, relu=True)
         if self.training:
-            x = ops.dropout_with_mask(x, self.rng.dropout_keep(tuple(x.shape), x.device))
+            x = ops.dropout_with_mask(x, self.rng.dropout_keep(tuple(x.shape), x.device, row_valid))
         return ops.linear(x, self.fc3_da.weight, self.fc3_da.bias)
 
 
@@ -65,16 +65,26 @@ def _image_domain_labels(targets, device):
                         dtype=torch.uint8, device=device)
 
 
-def da_img_loss(img_logits, targets):
+def da_img_loss(img_logits, targets, seg=None):
     """Per-pixel BCE against the image's domain label, mean over N*h*w (loss.py:140-168)."""
     n = img_logits.shape[0]
-    seg = _image_domain_labels(targets, img_logits.device)
+    if seg is None:
+        seg = _image_domain_labels(targets, img_logits.device)
     return ops.bce_with_logits_mean(img_logits, None, seg, img_logits.numel() // n)
 
 
-def da_ins_loss(ins_logits, dom):
-    """Per-ROI BCE against the ROI's domain (loss.py:170-174)."""
-    return ops.bce_with_logits_mean(ins_logits.reshape(-1), dom.to(torch.float32))
+def da_ins_loss(ins_logits, dom, row_valid=None):
+    """Per-ROI BCE against the ROI's domain (loss.py:170-174).  row_valid: slots of the fixed-capacity ROI
+    layout that hold no proposal are neutralised (logit +100 vs target 1: exactly zero loss and gradient) and
+    the mean is rescaled to the existing ROIs."""
+    x = ins_logits.reshape(-1)
+    t = dom.to(torch.float32)
+    if row_valid is None:
+        return ops.bce_with_logits_mean(x, t)
+    v = row_valid.bool()
+    x = torch.where(v, x, torch.full_like(x[:1], 100.0))
+    t = torch.where(v, t, torch.ones_like(t))
+    return ops.bce_with_logits_mean(x, t) * (float(x.numel()) / v.sum().to(torch.float32))
 
 
 def _num_source(dom_sizes):
@@ -96,7 +106,9 @@ class _Base(nn.Module):
 class DomainAdaptationModule(_Base):
     """The original DA module (da_heads.py:354-440 + DALossComputation loss.py:28-104)."""
 
-    def forward(self, img_features, pooled_ins, dom, n_src, targets):
+    def forward(self, img_features, pooled_ins, dom, n_src, targets, row_valid=None, seg=None):
+        """row_valid / seg: fixed-capacity ROI slots that exist, and the cached per-image domain labels (both
+        optional; supplied by the sync-free training path)."""
         if not self.training:
             return {}
         D = self.cfg.MODEL.DA_HEADS
@@ -106,12 +118,12 @@ class DomainAdaptationModule(_Base):
         img_c = ops.gradient_scalar(feat, 1.0 * D.DA_IMG_GRL_WEIGHT)
         ins_c = ops.gradient_scalar(pooled_ins, 1.0 * D.DA_INS_GRL_WEIGHT)
         da_img = self.imghead(img_g)
-        da_ins = self.inshead(ins_g)
+        da_ins = self.inshead(ins_g, row_valid)
         da_img_c = self.imghead(img_c)
-        da_ins_c = self.inshead(ins_c)
-        l_img = da_img_loss(da_img, targets)
-        l_ins = da_ins_loss(da_ins, dom)
-        l_cst = ops.consistency_loss(da_img_c.reshape(da_img_c.shape[0], -1), da_ins_c.reshape(-1), n_src)
+        da_ins_c = self.inshead(ins_c, row_valid)
+        l_img = da_img_loss(da_img, targets, seg)
+        l_ins = da_ins_loss(da_ins, dom, row_valid)
+        l_cst = ops.consistency_loss(da_img_c.reshape(da_img_c.shape[0], -1), da_ins_c.reshape(-1), n_src, row_valid)
         losses = {}
         if self.img_weight > 0:
             losses["loss_da_image"] = self.img_weight * l_img

@@ -88,6 +88,46 @@ class GeneralizedRCNN(nn.Module):
         self.da_heads_triplet = build_da_heads_triplet(cfg, self.rng) if self.triplet_use else False
         self.Aligned = cfg.MODEL.DA_HEADS.ALIGNMENT
         self.size_divisible = cfg.DATALOADER.SIZE_DIVISIBILITY
+        self.static_shapes = True
+        self.__dict__["_meta_cache"] = {}
+
+    def enable_static_shapes(self, flag=True):
+        """Training without host reads (plain DA / no-DA modes): proposals and sampled ROIs live in fixed-capacity
+        device buffers with device-side counts, so a whole step can be captured into one CUDA graph."""
+        self.static_shapes = bool(flag)
+
+    def _batch_meta(self, targets):
+        """Per-batch-signature device constants (GT offsets, which images take GT proposals, per-image domain
+        labels); built once per signature, outside any graph capture."""
+        key = tuple((len(t), bool(is_source_image(t))) for t in targets)
+        meta = self._meta_cache.get(key)
+        if meta is None:
+            dev = targets[0].bbox.device
+            offs = [0]
+            for n, _ in key:
+                offs.append(offs[-1] + n)
+            meta = dict(gt_offsets=torch.tensor(offs, dtype=torch.int32, device=dev),
+                        append_gt=torch.tensor([1 if s else 0 for _, s in key], dtype=torch.uint8, device=dev),
+                        seg=torch.tensor([1 if s else 0 for _, s in key], dtype=torch.uint8, device=dev),
+                        max_gt=max([n for n, s in key if s] + [0]))
+            self._meta_cache[key] = meta
+        meta = dict(meta)
+        meta["gt_cat"] = torch.cat([t.convert("xyxy").bbox.to(torch.float32) for t in targets], dim=0)
+        return meta
+
+    def _forward_static(self, images, targets, feat, logits, deltas):
+        meta = self._batch_meta(targets)
+        features = [feat]
+        props, proposal_losses = self.rpn.forward_static(images, features, targets, (logits, deltas), meta)
+        losses = {}
+        box = self.roi_heads.box
+        detector_losses, pooled, dom, row_valid = box.forward_static(features, props, targets)
+        losses.update(detector_losses)
+        losses.update(proposal_losses)
+        if self.da_heads:
+            losses.update(self.da_heads(features, pooled, dom, box.loss_evaluator.batch, targets, row_valid=row_valid,
+                                        seg=meta["seg"]))
+        return losses
 
     def enable_cuda_graphs(self, flag=True):
         """Replay the static-shape segments (backbone + RPN head; box branch per ROI count) as CUDA graphs."""
@@ -113,6 +153,8 @@ class GeneralizedRCNN(nn.Module):
         with section("trunk_fwd"):
             x = ops._chk(images.tensors, name="images")            # NCHW; the stem consumes it directly
             feat, logits, deltas = self.segments.run("trunk", lambda: _Trunk(self.backbone, self.rpn.head), (x,))
+        if self.training and self.static_shapes and self.roi_heads and not self.da_heads_triplet:
+            return self._forward_static(images, targets, feat, logits, deltas)
         features = [feat]
         with section("rpn_proposals_and_loss"):
             proposals, proposal_losses = self.rpn(images, features, targets, head_out=(logits, deltas))

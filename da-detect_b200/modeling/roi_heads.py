@@ -137,6 +137,68 @@ class FastRCNNLossComputation(object):
                 raise AssertionError("subsample_for_da would drop proposals; not reachable from subsample()")
         return proposals
 
+    @torch.no_grad()
+    def subsample_static(self, props, targets):
+        """subsample (loss.py:100-130) on a ProposalBatch with the sampler on the device: every image contributes
+        exactly `batch` ROI slots; `valid` marks the slots that hold a sampled proposal (all of them unless an
+        image has fewer than `batch` labelled candidates).  Returns the flat per-ROI tensors of the batch."""
+        boxes, nprop = props.boxes, props.count
+        n_img, cap = boxes.shape[0], boxes.shape[1]
+        B = self.batch
+        dev = boxes.device
+        ar_cap = torch.arange(cap, device=dev)
+        labs, ms = [], []
+        for i, t in enumerate(targets):
+            gt = t.convert("xyxy").bbox
+            m, _ = ops.match(gt, boxes[i], self.high, self.low, False)
+            if is_source_image(t):
+                lab = t.get_field("labels").to(torch.int64)[m.clamp(min=0)]
+                lab = torch.where(m == BELOW_LOW_THRESHOLD, torch.zeros_like(lab), lab)
+                lab = torch.where(m == BETWEEN_THRESHOLDS, torch.full_like(lab, -1), lab)
+            else:                                            # loss.py:84-85: target-domain labels are all 0
+                lab = torch.zeros_like(m)
+            lab = torch.where(ar_cap < nprop[i], lab, torch.full_like(lab, -1))
+            labs.append(lab.to(torch.int32))
+            ms.append(m)
+        lab_all = torch.stack(labs)
+        keys = torch.stack([self.rng.sample_keys(l) for l in labs])
+        sel, cnt = ops.balanced_sample(lab_all, nprop, keys, B, int(B * self.pos_fraction))
+        valid = torch.arange(B, device=dev).unsqueeze(0) < cnt[:, 1:2]
+        rois, labels, regs, doms = [], [], [], []
+        for i, t in enumerate(targets):
+            src = is_source_image(t)
+            bx = boxes[i][sel[i]]
+            rois.append(torch.cat([torch.full((B, 1), float(i), dtype=bx.dtype, device=dev), bx], dim=1))
+            labels.append(torch.where(valid[i], labs[i][sel[i]].to(torch.int64), torch.zeros_like(sel[i])))
+            regs.append(ops.box_encode(t.convert("xyxy").bbox, bx, ms[i][sel[i]], self.weights, wrap_negative=not src))
+            doms.append(torch.full((B,), src, dtype=torch.bool, device=dev))
+        st = dict(rois=torch.cat(rois), labels=torch.cat(labels), regression_targets=torch.cat(regs),
+                  domain_labels=torch.cat(doms), valid=valid.reshape(-1), counts=cnt[:, 1], size=props.size,
+                  objectness=torch.stack([props.objectness[i][sel[i]] for i in range(n_img)]).reshape(-1))
+        self._static = st
+        self.rng.consume_da_draws(st["counts"])
+        return st
+
+    def static_proposals(self):
+        """The sampled proposals of the last static step as list[BoxList] (host reads; for tests / inspection)."""
+        st = self._static
+        B = self.batch
+        out = []
+        for i, c in enumerate(st["counts"].tolist()):
+            sl = slice(i * B, i * B + c)
+            q = BoxList(st["rois"][sl, 1:], st["size"], mode="xyxy")
+            for f in ("objectness", "labels", "regression_targets", "domain_labels"):
+                q.add_field(f, st[f][sl])
+            out.append(q)
+        return out
+
+    def loss_static(self, class_logits, box_regression):
+        st = self._static
+        mask = (st["valid"] & st["domain_labels"]).to(torch.uint8)
+        cls_loss = ops.softmax_ce_mean(class_logits, st["labels"], mask)
+        box_loss = ops.box_reg_loss(box_regression, st["regression_targets"], st["labels"], mask)
+        return cls_loss, box_loss
+
     def __call__(self, class_logits, box_regression):
         props = self._proposals
         labels = torch.cat([p.get_field("labels") for p in props], dim=0)
@@ -157,6 +219,27 @@ class ROIBoxHead(nn.Module):
         self.predictor = FastRCNNPredictor(cfg)
         self.loss_evaluator = FastRCNNLossComputation(cfg, rng)
         self.cfg = cfg.clone()
+
+    def forward_static(self, features, props, targets):
+        """Training on a ProposalBatch without host reads: returns (losses, pooled [K,2048], domain labels [K],
+        row_valid uint8 [K]) with K = images x BATCH_SIZE_PER_IMAGE."""
+        st = self.loss_evaluator.subsample_static(props, targets)
+        segments = self.__dict__.get("segments")
+        if segments is not None:
+            from .detector import _BoxBranch
+            pooled, class_logits, box_regression = segments.run(
+                "box", lambda: _BoxBranch(self.feature_extractor, self.predictor), (features[0], st["rois"]))
+        else:
+            fe = self.feature_extractor
+            x = ops.roi_align(features[0], st["rois"], fe.pooler.scale, fe.pooler.output_size,
+                              fe.pooler.sampling_ratio, 2 if fe.even_bins else 1)
+            pooled = ops.avgpool_hw(fe.head(x, fe.even_bins))
+            class_logits, box_regression = self.predictor(pooled)
+        self.last_pooled = pooled
+        loss_classifier, loss_box_reg = self.loss_evaluator.loss_static(class_logits, box_regression)
+        self.last = dict(class_logits=class_logits, box_regression=box_regression)
+        return (dict(loss_classifier=loss_classifier, loss_box_reg=loss_box_reg), pooled, st["domain_labels"],
+                st["valid"].to(torch.uint8))
 
     def forward(self, features, proposals, targets=None):
         """Training: returns (x, proposals, losses, da_ins_feas, da_ins_labels) like

@@ -95,6 +95,22 @@ class RPNHead(nn.Module):
         return logits, deltas
 
 
+class ProposalBatch(object):
+    """Fixed-capacity proposals of a batch: boxes [N,cap,4], objectness [N,cap], count int32 [N] (device)."""
+
+    def __init__(self, boxes, objectness, count, size):
+        self.boxes, self.objectness, self.count, self.size = boxes, objectness, count, size
+
+    def to_boxlists(self):
+        """list[BoxList] like RPNPostProcessor returns (reads the counts on the host)."""
+        out = []
+        for i, c in enumerate(self.count.tolist()):
+            bl = BoxList(self.boxes[i, :c], self.size, mode="xyxy")
+            bl.add_field("objectness", self.objectness[i, :c])
+            out.append(bl)
+        return out
+
+
 class RPNModule(nn.Module):
     def __init__(self, cfg, rng):
         super().__init__()
@@ -106,6 +122,7 @@ class RPNModule(nn.Module):
         self.head = RPNHead(cfg.MODEL.BACKBONE.OUT_CHANNELS, self.anchor_generator.num_anchors_per_location()[0])
         self.rng = rng
         self.proposal_hook = None
+        self.keep_debug = False       # tests: keep label / sample index tensors of the last step (host reads)
 
     def set_proposal_hook(self, fn):
         """fn(list[BoxList]) -> list[BoxList], called on the proposals of every forward (None = off).
@@ -181,6 +198,82 @@ class RPNModule(nn.Module):
         obj_loss = ops.bce_with_logits_mean(obj[sampled], labels[sampled])
         self.last = dict(labels=labels, pos=pos, neg=neg, reg_targets=reg_targets)
         return obj_loss, box_loss
+
+    # ---- fixed-capacity, sync-free variants (training) --------------------------------------------------
+    @torch.no_grad()
+    def proposals_static(self, anchors, logits, deltas, image_sizes, meta):
+        """RPNPostProcessor without host reads: (proposals [N,cap,4], objectness [N,cap], count int32 [N]) with
+        cap = POST_NMS_TOP_N_TRAIN + max GT boxes per image; 4 launches for the whole batch."""
+        R = self.cfg.MODEL.RPN
+        n, fh, fw, a = logits.shape
+        k = min(R.PRE_NMS_TOP_N_TRAIN, fh * fw * a)
+        post = min(R.POST_NMS_TOP_N_TRAIN, k)
+        sizes = set((int(h), int(w)) for h, w in image_sizes)
+        if len(sizes) != 1:
+            raise NotImplementedError("images of different un-padded sizes in one batch")
+        ih, iw = sizes.pop()
+        boxes, scores, _, valid = ops.rpn_topk_decode(logits, deltas, anchors, k, iw, ih, R.MIN_SIZE)
+        keep, cnt = ops.nms_sorted_batched(boxes, valid, R.NMS_THRESH, post)
+        return ProposalBatch(*ops.proposals_gather(boxes, scores, keep, cnt, meta["gt_cat"], meta["gt_offsets"],
+                                                   meta["append_gt"], post + meta["max_gt"]), size=(iw, ih))
+
+    def losses_static(self, anchors, visibility, logits, deltas, targets):
+        """RPNLossComputation (rpn/loss.py:57-143) with the sampler on the device.  Per source image the 256
+        sampled anchors sit in a fixed [256] index vector with a device-side count; rows beyond the count are
+        neutralised (logit +100 against target 1 has exactly zero BCE and zero gradient in fp32)."""
+        R = self.cfg.MODEL.RPN
+        B = R.BATCH_SIZE_PER_IMAGE
+        max_pos = int(B * R.POSITIVE_FRACTION)
+        A = anchors.shape[0]
+        vis = visibility.bool()
+        obj = logits.reshape(-1)                             # (n, h, w, a) order == permute_and_flatten
+        reg = deltas.reshape(-1, 4)
+        ar = torch.arange(B, device=obj.device)
+        bce_sum = l1_sum = total = None
+        dbg = dict(labels=[], pos=[], neg=[]) if self.keep_debug else None
+        ordinal = 0
+        for t in targets:                                   # labels exist for source images only (:66-67)
+            if not is_source_image(t):
+                continue
+            gt = t.convert("xyxy").bbox
+            m, _ = ops.match(gt, anchors, R.FG_IOU_THRESHOLD, R.BG_IOU_THRESHOLD, True)
+            lab = (m >= 0).to(torch.int32)
+            lab = torch.where((m == BETWEEN_THRESHOLDS) | ~vis, torch.full_like(lab, -1), lab)
+            sel, cnt = ops.balanced_sample(lab.view(1, -1), None, self.rng.sample_keys(lab).view(1, -1), B, max_pos)
+            sel, n_tot = sel[0], cnt[0, 1]
+            valid = ar < n_tot
+            lab_s = lab[sel]
+            rows = sel + ordinal * A
+            x = torch.where(valid, obj[rows], torch.full_like(obj[:1], 100.0))
+            tgt = torch.where(valid, lab_s.to(torch.float32), torch.ones_like(x))
+            bce_i = ops.bce_with_logits_mean(x, tgt) * float(B)
+            posm = (valid & (lab_s == 1)).to(torch.float32).unsqueeze(1)
+            tg = ops.box_encode(gt, anchors[sel], m[sel], (1.0, 1.0, 1.0, 1.0))
+            l1_i = ops.smooth_l1_sum(reg[rows] * posm, tg * posm, 1.0 / 9, 1.0)
+            bce_sum = bce_i if bce_sum is None else bce_sum + bce_i
+            l1_sum = l1_i if l1_sum is None else l1_sum + l1_i
+            total = n_tot if total is None else total + n_tot
+            if dbg is not None:
+                dbg["labels"].append(lab.to(torch.float32))
+                dbg["pos"].append(rows[valid & (lab_s == 1)])
+                dbg["neg"].append(rows[valid & (lab_s == 0)])
+            ordinal += 1
+        inv = 1.0 / total.to(torch.float32)
+        if dbg is not None:
+            self.last = dict(labels=torch.cat(dbg["labels"]), pos=torch.cat(dbg["pos"]), neg=torch.cat(dbg["neg"]))
+        return bce_sum * inv, l1_sum * inv
+
+    def forward_static(self, images, features, targets, head_out, meta):
+        feat = features[0]
+        logits, deltas = head_out
+        n, fh, fw, _ = feat.shape
+        ih, iw = images.image_sizes[0]
+        anchors, vis = self.anchor_generator.grid(fh, fw, int(iw), int(ih))
+        props = self.proposals_static(anchors, logits.detach(), deltas.detach(), images.image_sizes, meta)
+        if self.proposal_hook is not None:
+            props = self.proposal_hook(props)
+        obj_loss, box_loss = self.losses_static(anchors, vis, logits, deltas, targets)
+        return props, {"loss_objectness": obj_loss, "loss_rpn_box_reg": box_loss}
 
     def forward(self, images, features, targets=None, head_out=None):
         feat = features[0]

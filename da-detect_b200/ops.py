@@ -547,8 +547,9 @@ def smooth_l1_sum(x, t, beta, divisor):
     return _finish(loss, (x,), (grad,))
 
 
-def consistency_loss(img_logits, ins_logits, n_src):
-    """img_logits [2, hw] (any trailing shape), ins_logits [K] or [K,1]; sigmoid folded into the kernel."""
+def consistency_loss(img_logits, ins_logits, n_src, row_valid=None):
+    """img_logits [2, hw] (any trailing shape), ins_logits [K] or [K,1]; sigmoid folded into the kernel.
+    row_valid (uint8 [K], optional): padding ROIs of the fixed-capacity layout are skipped."""
     il = _chk(img_logits, name="img_logits")
     sl = _chk(ins_logits, name="ins_logits")
     if il.shape[0] != 2:
@@ -559,8 +560,8 @@ def consistency_loss(img_logits, ins_logits, n_src):
     loss = torch.empty(1, dtype=torch.float32, device=il.device)
     gi, gs = torch.empty_like(il), torch.empty_like(sl)
     ws = torch.empty(4, dtype=torch.float32, device=il.device)
-    _lib.call("dd_consistency_loss", _ptr(il), hw, _ptr(sl), k, int(n_src), _ptr(loss), _ptr(gi), _ptr(gs), _ptr(ws),
-              _stream())
+    _lib.call("dd_consistency_loss", _ptr(il), hw, _ptr(sl), k, int(n_src), _ptr(_chk(row_valid, torch.uint8, "row_valid")),
+              _ptr(loss), _ptr(gi), _ptr(gs), _ptr(ws), _stream())
     return _finish(loss, (img_logits, ins_logits), (gi, gs))
 
 
@@ -677,6 +678,40 @@ def box_decode(codes, boxes, weights):
     wx, wy, ww, wh = (float(v) for v in weights)
     _lib.call("dd_box_decode", _ptr(c), _ptr(b), r, k4 // 4, wx, wy, ww, wh, _ptr(out), _stream())
     return out
+
+
+def proposals_gather(boxes, scores, keep, keep_count, gt_cat, gt_offsets, append_gt, cap):
+    """boxes [N,k,4], scores [N,k], keep int64 [N,post], keep_count int32 [N], gt_cat [G,4], gt_offsets int32 [N+1],
+    append_gt uint8 [N] -> (proposals [N,cap,4], objectness [N,cap], count int32 [N]); no host read."""
+    n, k = scores.shape
+    post = keep.shape[1]
+    dev = boxes.device
+    out_b = torch.empty((n, cap, 4), dtype=torch.float32, device=dev)
+    out_s = torch.empty((n, cap), dtype=torch.float32, device=dev)
+    out_c = torch.empty((n,), dtype=torch.int32, device=dev)
+    _lib.call("dd_proposals_gather", _ptr(_chk(boxes, name="boxes")), _ptr(_chk(scores, name="scores")),
+              _ptr(_chk(keep, torch.int64, "keep")), _ptr(_chk(keep_count, torch.int32, "keep_count")),
+              _ptr(_chk(gt_cat, name="gt")), _ptr(_chk(gt_offsets, torch.int32, "gt_offsets")),
+              _ptr(_chk(append_gt, torch.uint8, "append_gt")), n, k, post, int(cap), _ptr(out_b), _ptr(out_s),
+              _ptr(out_c), _stream())
+    return out_b, out_s, out_c
+
+
+def balanced_sample(labels, n_dev, keys, batch, max_pos):
+    """labels int32 [images, n_cap], n_dev int32 [images] or None, keys float [images, n_cap] ->
+    (sel_idx int64 [images, batch] ascending, counts int32 [images, 2] = {positives, total})."""
+    lab = _chk(labels, torch.int32, "labels")
+    images, n_cap = lab.shape
+    sel = torch.empty((images, batch), dtype=torch.int64, device=lab.device)
+    cnt = torch.empty((images, 2), dtype=torch.int32, device=lab.device)
+    _lib.call("dd_balanced_sample", _ptr(lab), _ptr(_chk(n_dev, torch.int32, "n_dev")), _ptr(_chk(keys, name="keys")),
+              images, n_cap, int(batch), int(max_pos), _ptr(sel), _ptr(cnt), _stream())
+    return sel, cnt
+
+
+def sgd_momentum_dev_(p, g, buf, lr_dev, lr_factor, momentum, wd, grad_scale):
+    _lib.call("dd_sgd_momentum_dev", _ptr(p), _ptr(g), _ptr(buf), p.numel(), _ptr(lr_dev), float(lr_factor),
+              float(momentum), float(wd), float(grad_scale), _stream())
 
 
 def sgd_momentum_(p, g, buf, lr, momentum, wd, grad_scale, first_step):

@@ -109,6 +109,24 @@ int dd_box_encode(const float* gt, int M, const float* pred, const int64_t* matc
 int dd_box_decode(const float* codes, const float* boxes, int R, int k, float wx, float wy, float ww, float wh,
                   float* out, void* stream);
 
+/* ---------------------------------------------------------------- device-resident proposals / sampling */
+
+/* RPNPostProcessor tail (rpn/inference.py:116-127 + add_gt_proposals :51-74) without host reads: image g keeps
+ * its first min(keep_count[g], post) NMS survivors boxes[g, keep[g, r]] and, when append_gt[g] != 0, is extended
+ * with its ground-truth boxes gt[gt_offsets[g] .. gt_offsets[g+1]) (objectness 1).  out_boxes [N, cap, 4],
+ * out_objectness [N, cap] (rows beyond out_count[g] are zero). */
+int dd_proposals_gather(const float* boxes, const float* scores, const int64_t* keep, const int* keep_count,
+                        const float* gt, const int* gt_offsets, const uint8_t* append_gt, int N, int k, int post,
+                        int cap, float* out_boxes, float* out_objectness, int* out_count, void* stream);
+/* BalancedPositiveNegativeSampler (balanced_positive_negative_sampler.py:27-76) per image on the device:
+ * labels int32 [images, n_cap] (>= 1 positive, 0 negative, < 0 ignored), image g has n_dev[g] candidates
+ * (n_dev NULL: n_cap), keys float [images, n_cap] the random draw.  Chooses min(#pos, max_pos) positives and
+ * min(#neg, batch - that) negatives with the smallest keys (ties: lower index).  sel_idx int64 [images, batch]
+ * = chosen candidate indices in ascending order (rows beyond the total are 0); counts int32 [images, 2] =
+ * {positives chosen, total chosen}. */
+int dd_balanced_sample(const int* labels, const int* n_dev, const float* keys, int images, int n_cap, int batch,
+                       int max_pos, int64_t* sel_idx, int* counts, void* stream);
+
 /* ---------------------------------------------------------------- dense layers (implicit GEMM) */
 
 /* impl: 0 = fp32 SIMT tiles (bit-faithful fp32 accumulate), 1 = tcgen05 TF32 (TMA-staged, TMEM accum). */
@@ -193,7 +211,10 @@ int dd_box_reg_loss(const float* box_reg, const float* reg_targets, const int64_
  * first n_src ROIs belong to image 0.  Returns loss and gradients w.r.t. both logit tensors
  * (sigmoid folded in). */
 int dd_consistency_loss(const float* img_logits, long long hw, const float* ins_logits, int K, int n_src,
-                        float* loss, float* grad_img, float* grad_ins, float* workspace2, void* stream);
+                        const uint8_t* row_valid, float* loss, float* grad_img, float* grad_ins, float* workspace2,
+                        void* stream);
+/* row_valid (nullable, uint8 [K]): ROIs of the fixed-capacity layout that do not exist are skipped and the
+ * mean runs over the existing ones. */
 /* nn.TripletMarginLoss(margin, p=2) (da_heads/loss.py:198-200): a,p,n [rows, D] with the norm over D
  * computed on rows gathered with element stride `inner` (NHWC feature maps: D = W taken with stride C);
  * see SURVEY §2.3/§9.8.  rows = number of distance vectors.  Layout: element (r, d) of a tensor lives at
@@ -206,6 +227,10 @@ int dd_triplet_margin_loss(const float* a, const float* p, const float* n, long 
  * (solver/build.py:7-20; first step semantics buf = g' selected by first_step != 0). */
 int dd_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, float wd,
                     float grad_scale, int first_step, void* stream);
+/* The same with lr = lr_factor * (*lr_dev) read on the device, so that a captured CUDA graph of the whole step
+ * follows the LR schedule; buf must be zero before the first step (then buf = g' falls out of the recurrence). */
+int dd_sgd_momentum_dev(float* p, const float* g, float* buf, long long n, const float* lr_dev, float lr_factor,
+                        float momentum, float wd, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

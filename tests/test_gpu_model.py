@@ -85,7 +85,7 @@ def test_training_step_matches_oracle(name, dense):
         probe = build(cfg, sd, dev)
         probe.set_random_source(ReplaySource(list(rec.perms), list(rec.masks)))
         forced = []
-        probe.rpn.set_proposal_hook(lambda bl: forced.extend(bl) or bl)
+        probe.rpn.set_proposal_hook(lambda props: forced.append(props) or props)
         with torch.no_grad():
             probe(images.to(dev), to_boxlists(targets, hw, dev))
         del probe
@@ -93,8 +93,9 @@ def test_training_step_matches_oracle(name, dense):
     model = build(cfg, sd, dev)
     replay = ReplaySource(rec.perms, rec.masks)
     model.set_random_source(replay)
+    model.rpn.keep_debug = True
     if forced is not None:
-        model.rpn.set_proposal_hook(lambda bl: list(forced))
+        model.rpn.set_proposal_hook(lambda props: forced[0])
     got = model(images.to(dev), to_boxlists(targets, hw, dev))
     assert list(got.keys()) == list(want.keys())
     # index-exact tier: the sampled ROIs are the same boxes with the same labels
@@ -102,7 +103,11 @@ def test_training_step_matches_oracle(name, dense):
     ref_samples = aux["samples"] if "samples" in aux else None
     exact = dense == "simt"      # TF32 logits may legitimately reorder near-tied proposals
     if exact and ref_samples is not None and not cfg.MODEL.DA_HEADS.ALIGNMENT:
-        for p, s in zip(box.loss_evaluator._proposals, ref_samples):
+        static = model.static_shapes and not cfg.MODEL.DA_HEADS.TRIPLET_USE
+        sampled = box.loss_evaluator.static_proposals() if static else box.loss_evaluator._proposals
+        assert len(sampled) == len(ref_samples)
+        for p, s in zip(sampled, ref_samples):
+            assert len(p) == len(s["labels"])
             assert torch.equal(p.get_field("labels").cpu(), s["labels"])
             assert torch.equal(p.get_field("domain_labels").cpu(), s["domain_labels"])
             # Boxes agree to fp32 tolerance, except where two proposals have EQUAL objectness: top-k tie

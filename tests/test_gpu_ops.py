@@ -125,6 +125,56 @@ def test_nms_batched_ragged_counts_match_single_image():
         assert torch.equal(keep[i, : cnt[i]].cpu(), want[i])
 
 
+@pytest.mark.parametrize("n_cap,n,batch,max_pos,p_pos,p_neg,int_keys", [
+    (5000, 4321, 256, 64, 0.1, 0.6, False), (122880, 122880, 256, 128, 0.0005, 0.9, False),
+    (600, 600, 256, 128, 0.02, 0.1, False), (300, 150, 256, 64, 0.3, 0.3, True), (64, 64, 16, 4, 0.0, 0.5, True)])
+def test_balanced_sample_matches_reference_semantics(n_cap, n, batch, max_pos, p_pos, p_neg, int_keys):
+    """Device sampler == BalancedPositiveNegativeSampler with `keys` standing for the random permutation:
+    min(#pos, max_pos) positives and min(#neg, batch - num_pos) negatives with the smallest keys (ties -> lower
+    index), returned as ascending indices; candidates beyond the device-side count are ignored."""
+    g = torch.Generator().manual_seed(n_cap + batch)
+    u = torch.rand(2, n_cap, generator=g)
+    labels = torch.where(u < p_pos, 3, torch.where(u < p_pos + p_neg, 0, -1)).to(torch.int32)
+    keys = torch.randint(0, 40, (2, n_cap), generator=g).float() if int_keys else torch.rand(2, n_cap, generator=g)
+    counts = torch.tensor([n, max(n - 7, 1)], dtype=torch.int32)
+    sel, cnt = ops().balanced_sample(labels.to(DEV), counts.to(DEV), keys.to(DEV), batch, max_pos)
+    sel, cnt = sel.cpu(), cnt.cpu()
+    for i in range(2):
+        lab, key = labels[i, : counts[i]], keys[i, : counts[i]]
+        pos, neg = torch.nonzero(lab >= 1).squeeze(1), torch.nonzero(lab == 0).squeeze(1)
+        num_pos = min(pos.numel(), max_pos)
+        num_neg = min(neg.numel(), batch - num_pos)
+        pick = lambda idx, k: idx[torch.sort(key[idx], stable=True)[1][:k]]
+        want = torch.sort(torch.cat([pick(pos, num_pos), pick(neg, num_neg)]))[0]
+        assert cnt[i].tolist() == [num_pos, num_pos + num_neg]
+        assert torch.equal(sel[i, : want.numel()], want)
+        assert int(sel[i, want.numel():].abs().sum()) == 0
+
+
+def test_proposals_gather_appends_gt_and_pads():
+    g = torch.Generator().manual_seed(9)
+    n, k, post, cap = 3, 50, 10, 14
+    boxes, scores = torch.rand(n, k, 4, generator=g), torch.rand(n, k, generator=g)
+    keep = torch.stack([torch.randperm(k, generator=g)[:post] for _ in range(n)])
+    cnt = torch.tensor([10, 4, 0], dtype=torch.int32)
+    gt = torch.rand(7, 4, generator=g)
+    offs = torch.tensor([0, 3, 5, 7], dtype=torch.int32)
+    app = torch.tensor([1, 0, 1], dtype=torch.uint8)
+    ob, os_, oc = ops().proposals_gather(boxes.to(DEV), scores.to(DEV), keep.to(DEV), cnt.to(DEV), gt.to(DEV),
+                                         offs.to(DEV), app.to(DEV), cap)
+    ob, os_, oc = ob.cpu(), os_.cpu(), oc.cpu()
+    assert oc.tolist() == [13, 4, 2]
+    for i in range(n):
+        want_b = boxes[i][keep[i, : cnt[i]]]
+        want_s = scores[i][keep[i, : cnt[i]]]
+        if app[i]:
+            want_b = torch.cat([want_b, gt[offs[i]: offs[i + 1]]])
+            want_s = torch.cat([want_s, torch.ones(offs[i + 1] - offs[i])])
+        c = oc[i]
+        assert torch.equal(ob[i, :c], want_b) and torch.equal(os_[i, :c], want_s)
+        assert float(ob[i, c:].abs().sum()) == 0.0 and float(os_[i, c:].abs().sum()) == 0.0
+
+
 def test_nms_empty():
     got = ops().nms(torch.zeros(0, 4, device=DEV), torch.zeros(0, device=DEV), 0.5)
     assert got.numel() == 0 and got.dtype == torch.int64
