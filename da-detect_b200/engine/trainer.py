@@ -101,6 +101,20 @@ class FlatSGDTrainer(object):
                 p.grad = vg
                 off += pad4(n)
         self.total = total
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.step_graphs = None          # signature -> captured whole-step CUDA graph (enable_step_graph)
+        self.graph_launches = 0          # kernels of ours replayed through step graphs so far
+        self.graph_stream = None
+
+    def enable_step_graph(self, flag=True):
+        """Capture zero_grad + forward + backward + all-reduce + SGD of one iteration into ONE CUDA graph per
+        batch signature (image shape, GT boxes per image, source flags) and replay it afterwards: the step has
+        no host reads (model.enable_static_shapes), the learning rate is read from device memory, and new
+        batches are copied into the graph's static input buffers."""
+        self.step_graphs = {} if flag else None
+        if flag:
+            self.model.enable_static_shapes(True)
+            self.model.enable_cuda_graphs(False)
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -124,8 +138,89 @@ class FlatSGDTrainer(object):
                               self.momentum, self.wd_bias, scale, first)
         self.iteration += 1
 
+    def _optimizer_step_dev(self):
+        scale = 1.0 / self.world
+        nw = self.n_weight
+        ops.sgd_momentum_dev_(self.flat_param[:nw], self.flat_grad[:nw], self.flat_buf[:nw], self.lr_dev, 1.0,
+                              self.momentum, self.wd, scale)
+        if self.total > nw:
+            ops.sgd_momentum_dev_(self.flat_param[nw:], self.flat_grad[nw:], self.flat_buf[nw:], self.lr_dev,
+                                  self.bias_lr_factor, self.momentum, self.wd_bias, scale)
+
+    def _graph_step(self, images, targets):
+        from .. import _lib
+        from ..structures import BoxList, cache_source_flags, is_source_image
+        from ..structures.image_list import ImageList
+        tensors = images.tensors if isinstance(images, ImageList) else images
+        if not torch.is_tensor(tensors) or self.model.da_heads_triplet or not self.model.roi_heads:
+            return None                  # triplet modes still read sizes on the host: eager path
+        cache_source_flags(targets)
+        key = (tuple(tensors.shape),) + tuple((len(t), bool(is_source_image(t)), tuple(t.size)) for t in targets)
+        ent = self.step_graphs.get(key)
+        if ent is None:
+            st_targets = []
+            for t in targets:
+                b = BoxList(t.convert("xyxy").bbox.to(torch.float32).clone(), t.size, mode="xyxy")
+                b.add_field("labels", t.get_field("labels").clone())
+                b._is_source_image = bool(is_source_image(t))
+                st_targets.append(b)
+            ent = dict(images=tensors.clone(), targets=st_targets, graph=None, losses=None, calls=0, launches=0)
+            self.step_graphs[key] = ent
+        else:
+            ent["images"].copy_(tensors, non_blocking=True)
+            for st, t in zip(ent["targets"], targets):
+                st.bbox.copy_(t.convert("xyxy").bbox, non_blocking=True)
+                st.get_field("labels").copy_(t.get_field("labels"), non_blocking=True)
+        self.lr_dev.fill_(self.lr())
+        ent["calls"] += 1
+        # Eager warm-up and capture run on ONE dedicated stream, and nothing returned keeps the autograd graph
+        # alive: a stale AccumulateGrad node bound to another stream would invalidate the capture.
+        if self.graph_stream is None:
+            self.graph_stream = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        if ent["calls"] == 1:
+            # first sight of a signature: one eager step (lazy workspaces, cached constants, kernel attributes)
+            self.graph_stream.wait_stream(cur)
+            with torch.cuda.stream(self.graph_stream):
+                ld = self._eager_step(ent["images"], ent["targets"], dev_lr=True)
+                loss_dict = {k: v.detach().clone() for k, v in ld.items()}
+                del ld
+            cur.wait_stream(self.graph_stream)
+        else:
+            if ent["graph"] is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                before = _lib.launch_count()
+                with torch.cuda.graph(g, stream=self.graph_stream):
+                    ld = self._eager_step(ent["images"], ent["targets"], dev_lr=True)
+                    ent["losses"] = {k: v.detach() for k, v in ld.items()}
+                    del ld
+                ent["launches"] = _lib.launch_count() - before
+                ent["graph"] = g
+            ent["graph"].replay()
+            self.graph_launches += ent["launches"]
+            loss_dict = ent["losses"]
+        self.iteration += 1
+        return loss_dict
+
+    def _eager_step(self, images, targets, dev_lr=False):
+        loss_dict = self.model(images, targets)
+        losses = sum(loss_dict.values())
+        self.zero_grad()
+        losses.backward()
+        self.all_reduce()
+        if dev_lr:
+            self._optimizer_step_dev()
+        else:
+            self.optimizer_step()
+        return loss_dict
+
     def step(self, images, targets):
         """images: ImageList/tensor on the device; returns the (unreduced) loss dict of this rank."""
+        if self.step_graphs is not None and self.model.training:
+            out = self._graph_step(images, targets)
+            if out is not None:
+                return out
         with section("forward"):
             loss_dict = self.model(images, targets)
             losses = sum(loss_dict.values())

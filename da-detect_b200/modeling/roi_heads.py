@@ -235,9 +235,9 @@ class ROIBoxHead(nn.Module):
                               fe.pooler.sampling_ratio, 2 if fe.even_bins else 1)
             pooled = ops.avgpool_hw(fe.head(x, fe.even_bins))
             class_logits, box_regression = self.predictor(pooled)
-        self.last_pooled = pooled
         loss_classifier, loss_box_reg = self.loss_evaluator.loss_static(class_logits, box_regression)
-        self.last = dict(class_logits=class_logits, box_regression=box_regression)
+        # detached: a kept reference into the autograd graph would pin its AccumulateGrad nodes across steps
+        self.last = dict(class_logits=class_logits.detach(), box_regression=box_regression.detach())
         return (dict(loss_classifier=loss_classifier, loss_box_reg=loss_box_reg), pooled, st["domain_labels"],
                 st["valid"].to(torch.uint8))
 

@@ -65,3 +65,21 @@ class ReplaySource(RandomSource):
             return full
         assert tuple(m.shape) == tuple(shape), (tuple(m.shape), tuple(shape))
         return m.contiguous()
+
+
+class HashSource(RandomSource):
+    """Deterministic, capture-safe pseudo-random draws (a pure function of the element index and the shape):
+    lets a test compare a captured whole-step graph with the eager step on identical random choices."""
+
+    def _u(self, shape, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        i = torch.arange(n, dtype=torch.float32, device=device)
+        return torch.frac(torch.sin(i * 12.9898 + float(n % 7) * 78.233) * 43758.5453).abs().reshape(shape)
+
+    def sample_keys(self, labels):
+        return self._u(tuple(labels.shape), labels.device)
+
+    def dropout_keep(self, shape, device, row_valid=None):
+        return (self._u(tuple(shape), device) < 0.5).to(torch.float32)

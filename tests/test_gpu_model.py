@@ -201,3 +201,34 @@ def test_cuda_graph_segments_match_eager():
     for k in g0:
         rel = float((g0[k] - g1[k]).norm() / (g0[k].norm() + 1e-30))
         assert rel < 1e-4, (k, rel)       # only atomics ordering (ROIAlign backward, loss partial sums) may differ
+
+
+@pytest.mark.timeout(900)
+def test_whole_step_graph_matches_eager_training():
+    """FlatSGDTrainer.enable_step_graph: three SGD steps replayed from ONE captured CUDA graph (zero_grad, forward,
+    backward, SGD with the learning rate read on the device) == the same three steps launched eagerly."""
+    from dadetect_b200.engine import FlatSGDTrainer
+    from dadetect_b200.utils.random_source import HashSource
+    cfg, sd, images, targets, hw = scenario("da_img_ins_cst")
+    dev = torch.device("cuda")
+    out = []
+    for graph in (False, True):
+        model = build(cfg, sd, dev)
+        model.set_random_source(HashSource())
+        trainer = FlatSGDTrainer(model, cfg, world_size=1)
+        if graph:
+            trainer.enable_step_graph(True)
+        losses = []
+        for it in range(4):
+            tg = to_boxlists(targets, hw, dev)
+            ld = trainer.step(images.to(dev) + 0.01 * it, tg)
+            losses.append({k: float(v) for k, v in ld.items()})
+        if graph:
+            assert trainer.graph_launches > 0 and len(trainer.step_graphs) == 1
+        out.append((losses, trainer.flat_param.clone()))
+    (l0, p0), (l1, p1) = out
+    for a, b in zip(l0, l1):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 2e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    rel = float((p0 - p1).norm() / p0.norm())
+    assert rel < 1e-5, rel
