@@ -169,6 +169,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (no whole-step CUDA graph)")
     args = ap.parse_args()
+    if os.environ.get("DD_BENCH_WATCHDOG"):          # developer aid: dump all stacks and exit if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["DD_BENCH_WATCHDOG"]), exit=True)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -300,11 +303,6 @@ def main():
                 "peak_source": pk["source"] + ", dense bf16 burst",
                 "step_frac_of_flop_roofline": (2.0 * 1000.0 / ms_step) * TFLOP_PER_IMAGE / pk["bf16_sustained"]}
 
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        return
     images_per_step = 2 * world
     line = {
         "metric": "DA-FRCNN R-50-C4 train images/sec", "value": images_per_step * 1000.0 / ms_step, "unit": "images/s",
@@ -320,9 +318,23 @@ def main():
         "gpu_launches": launches,
         "roofline": roofline,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(cfg)
-    print(json.dumps(line))
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        # Tear down in dependency order: captured graphs hold NCCL kernels, so they go before the communicator;
+        # the destroy itself runs under a deadline (a wedged communicator must not hang the launcher).
+        import gc
+        dist.barrier()
+        trainer.step_graphs = None
+        gc.collect()
+        torch.cuda.synchronize()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(timeout=20.0)
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

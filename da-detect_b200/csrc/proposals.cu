@@ -103,8 +103,13 @@ __global__ void __launch_bounds__(kTopkThreads) rpn_topk_decode_kernel(
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < num_anchors; i += blockDim.x) {
+      // objectness logits share their leading bytes, so nearly every lane hits the same bin in the first passes:
+      // aggregate equal bins inside the warp and issue ONE shared-memory atomic per distinct bin
       const uint32_t key = float_to_ordered(lg[i]);
-      if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
+      const bool in = (key & prefix_mask) == prefix;
+      const uint32_t bin = in ? ((key >> shift) & 0xFF) : 0xFFFFFFFFu;
+      const unsigned peers = __match_any_sync(__activemask(), bin);
+      if (in && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
     }
     __syncthreads();
     if (threadIdx.x == 0) {

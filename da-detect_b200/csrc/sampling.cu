@@ -50,30 +50,30 @@ __device__ __forceinline__ uint32_t ordered_key(float f) {
 // class of a candidate: 0 = positive (label >= 1), 1 = negative (label == 0), 2 = ignored
 __device__ __forceinline__ int cls_of(int label) { return label >= 1 ? 0 : (label == 0 ? 1 : 2); }
 
-// Exclusive rank of `flag` among the CTA's threads in thread order; `total` = number of set flags.
-__device__ __forceinline__ int block_rank(bool flag, int* warp_tot, int& total) {
-  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+// Exclusive scan of one int per warp across the CTA (32 warps): returns the sum of the values of lower warps.
+__device__ __forceinline__ int warp_totals_exclusive(int my_warp_total, int* sm32, int& grand_total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int within = __popc(bal & ((1u << lane) - 1u));
   __syncthreads();
-  if (lane == 0) warp_tot[wid] = __popc(bal);
+  if (lane == 0) sm32[wid] = my_warp_total;
   __syncthreads();
-  int base = 0, tot = 0;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-    const int c = warp_tot[w];
-    if (w < wid) base += c;
-    tot += c;
+  int v = lane < (int)(blockDim.x >> 5) ? sm32[lane] : 0;
+  int incl = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
   }
-  total = tot;
-  return base + within;
+  grand_total = __shfl_sync(0xffffffffu, incl, 31);
+  return __shfl_sync(0xffffffffu, incl - v, wid);
 }
 
-// One CTA per image.
+// One CTA per image.  Every warp owns a CONTIGUOUS slice of the candidates (lanes interleaved inside it, so the
+// loads are coalesced and the index order inside a warp is the ballot order); ordering across warps needs one
+// scan of 32 warp totals per phase instead of a block-wide rank per 1024 candidates.
 __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
     const int* __restrict__ labels, const int* __restrict__ n_dev, const float* __restrict__ keys, int n_cap,
     int batch, int max_pos, int64_t* __restrict__ sel_idx, int* __restrict__ counts) {
   __shared__ int hist[2][256];
-  __shared__ int warp_tot[32];
+  __shared__ int sm32[32];
   __shared__ int s_cnt[2];
   __shared__ uint32_t s_prefix[2];
   __shared__ int s_need[2];
@@ -82,7 +82,10 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
   keys += (size_t)img * n_cap;
   sel_idx += (size_t)img * batch;
   const int n = n_dev ? min(n_dev[img], n_cap) : n_cap;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int per_warp = ((n + nwarps - 1) / nwarps + 31) & ~31;       // slice length, multiple of 32
+  const int w_begin = min(wid * per_warp, n), w_end = min(w_begin + per_warp, n);
 
   // ---- population of the two classes
   if (tid < 2) s_cnt[tid] = 0;
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
       c0 += __shfl_xor_sync(0xffffffffu, c0, o);
       c1 += __shfl_xor_sync(0xffffffffu, c1, o);
     }
-    if ((tid & 31) == 0) { atomicAdd(&s_cnt[0], c0); atomicAdd(&s_cnt[1], c1); }
+    if (lane == 0) { atomicAdd(&s_cnt[0], c0); atomicAdd(&s_cnt[1], c1); }
   }
   __syncthreads();
   const int n_pos = s_cnt[0], n_neg = s_cnt[1];
@@ -141,32 +144,55 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
   }
   // candidates with key < prefix[c] are taken, plus the first need[c] (by index) with key == prefix[c]
 
-  // ---- ordered compaction: selected indices in ascending order (== nonzero(pos_mask | neg_mask))
-  int out_base = 0, ties[2] = {0, 0};
-  for (int base = 0; base < n; base += blockDim.x) {
-    const int i = base + tid;
-    int c = 2;
-    bool lt = false, eq = false;
-    if (i < n) {
-      c = cls_of(labels[i]);
-      if (c < 2 && want[c] > 0) {
-        const uint32_t key = ordered_key(keys[i]);
-        lt = key < prefix[c];
-        eq = key == prefix[c];
-      }
-    }
-    int tot0, tot1;
-    const int r0 = block_rank(eq && c == 0, warp_tot, tot0);
-    const int r1 = block_rank(eq && c == 1, warp_tot, tot1);
-    const bool take = lt || (eq && c == 0 && ties[0] + r0 < need[0]) || (eq && c == 1 && ties[1] + r1 < need[1]);
-    ties[0] += tot0;
-    ties[1] += tot1;
-    int tot;
-    const int r = block_rank(take, warp_tot, tot);
-    if (take && out_base + r < batch) sel_idx[out_base + r] = (int64_t)i;
-    out_base += tot;
+  // ---- phase A: ties (key == prefix) per warp slice and class -> tie rank base of every warp
+  int eq_w[2] = {0, 0};
+  for (int i = w_begin + lane; i < w_end; i += 32) {
+    const int c = cls_of(labels[i]);
+    if (c < 2 && want[c] > 0 && ordered_key(keys[i]) == prefix[c]) eq_w[c] += 1;
   }
-  const int total = min(out_base, batch);
+  for (int o = 16; o > 0; o >>= 1) {
+    eq_w[0] += __shfl_xor_sync(0xffffffffu, eq_w[0], o);
+    eq_w[1] += __shfl_xor_sync(0xffffffffu, eq_w[1], o);
+  }
+  int dummy;
+  int tie_base[2];
+  tie_base[0] = warp_totals_exclusive(eq_w[0], sm32, dummy);
+  tie_base[1] = warp_totals_exclusive(eq_w[1], sm32, dummy);
+
+  // ---- phase B: number of selected candidates per warp slice -> output base of every warp
+  // ---- phase C: write them in index order.  (B and C walk the slice identically; `write` switches.)
+  int out_base = 0, total = 0;
+  for (int write = 0; write < 2; ++write) {
+    int ties[2] = {tie_base[0], tie_base[1]};
+    int taken = 0;
+    for (int i0 = w_begin; i0 < w_end; i0 += 32) {
+      const int i = i0 + lane;
+      int c = 2;
+      bool lt = false, eq = false;
+      if (i < w_end) {
+        c = cls_of(labels[i]);
+        if (c < 2 && want[c] > 0) {
+          const uint32_t key = ordered_key(keys[i]);
+          lt = key < prefix[c];
+          eq = key == prefix[c];
+        }
+      }
+      const unsigned e0 = __ballot_sync(0xffffffffu, eq && c == 0), e1 = __ballot_sync(0xffffffffu, eq && c == 1);
+      const unsigned below = (1u << lane) - 1u;
+      const bool take = lt || (eq && c == 0 && ties[0] + __popc(e0 & below) < need[0]) ||
+                        (eq && c == 1 && ties[1] + __popc(e1 & below) < need[1]);
+      ties[0] += __popc(e0);
+      ties[1] += __popc(e1);
+      const unsigned tk = __ballot_sync(0xffffffffu, take);
+      if (write && take) {
+        const int slot = out_base + taken + __popc(tk & below);
+        if (slot < batch) sel_idx[slot] = (int64_t)i;
+      }
+      taken += __popc(tk);
+    }
+    if (!write) out_base = warp_totals_exclusive(taken, sm32, total);
+  }
+  total = min(total, batch);
   for (int r = total + tid; r < batch; r += blockDim.x) sel_idx[r] = 0;   // padding rows point at candidate 0
   if (tid == 0) {
     counts[img * 2 + 0] = num_pos;

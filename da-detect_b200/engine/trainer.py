@@ -112,6 +112,7 @@ class FlatSGDTrainer(object):
         no host reads (model.enable_static_shapes), the learning rate is read from device memory, and new
         batches are copied into the graph's static input buffers."""
         self.step_graphs = {} if flag else None
+        ops.set_direct_weight_grad(flag)     # wgrad kernels accumulate into the flat gradient buffer directly
         if flag:
             self.model.enable_static_shapes(True)
             self.model.enable_cuda_graphs(False)

@@ -32,6 +32,28 @@ def get_default_impl():
     return _default_impl
 
 
+_direct_wgrad = False
+
+
+def set_direct_weight_grad(flag):
+    """When on, the weight-gradient kernels ACCUMULATE straight into `param.grad` (which must exist, be zeroed
+    before backward and keep its address — FlatSGDTrainer's flat gradient buffer) and autograd receives no
+    weight gradient: no per-parameter AccumulateGrad add kernels.  Off: gradients are returned to autograd."""
+    global _direct_wgrad
+    _direct_wgrad = bool(flag)
+
+
+def _wgrad_into(param, gy, x, scale, cout, kh, kw, stride, pad):
+    """Weight gradient of one conv: returned for autograd, or (direct mode) accumulated into param.grad."""
+    if _direct_wgrad and param.is_leaf and param.grad is not None:
+        g = param.grad
+        phys = g.permute(0, 2, 3, 1) if g.dim() == 4 else g
+        if phys.is_contiguous() and phys.data_ptr() % 16 == 0:
+            conv2d_wgrad_raw(gy, x, scale, cout, kh, kw, stride, pad, out=phys, accumulate=True)
+            return None
+    return grad_like_weight(conv2d_wgrad_raw(gy, x, scale, cout, kh, kw, stride, pad), param)
+
+
 def tcgen05_available():
     return bool(_lib.load().dd_tcgen05_built())
 
@@ -203,6 +225,7 @@ class _ConvBnAct(torch.autograd.Function):
         y = conv2d_forward_raw(x, w, scale, bias, residual, kh, kw, stride, pad, relu)
         ctx.save_for_backward(x, weight, scale, y if relu else None)
         ctx.cfg = (kh, kw, stride, pad, relu, bias is not None, residual is not None)
+        ctx.weight_ref = weight
         return y
 
     @staticmethod
@@ -216,7 +239,7 @@ class _ConvBnAct(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = conv2d_dgrad_raw(g, w, scale, tuple(x.shape), kh, kw, stride, pad)
         if ctx.needs_input_grad[1]:
-            gw = grad_like_weight(conv2d_wgrad_raw(g, x, scale, w.shape[0], kh, kw, stride, pad), weight)
+            gw = _wgrad_into(ctx.weight_ref, g, x, scale, w.shape[0], kh, kw, stride, pad)
         if has_bias and ctx.needs_input_grad[3]:
             gb = bias_grad_raw(g, g.shape[-1])
         if has_res and ctx.needs_input_grad[4]:
@@ -276,6 +299,7 @@ class _BottleneckStage(torch.autograd.Function):
             ctx.save_for_backward(*saved, *tensors)
             ctx.n_saved = len(saved)
             ctx.meta = meta
+            ctx.param_refs = tensors
         return cur
 
     @staticmethod
@@ -301,21 +325,22 @@ class _BottleneckStage(torch.autograd.Function):
             stride = strides[bi]
             first = bi == 0
             w1o, w2o, w3o = weight_ohwi(w1), weight_ohwi(w2), weight_ohwi(w3)
+            refs = ctx.param_refs
             if ctx.needs_input_grad[2 + o + 6]:
-                grads[o + 6] = grad_like_weight(conv2d_wgrad_raw(g_out, y2, s3, w3o.shape[0], 1, 1, 1, 0), w3)
+                grads[o + 6] = _wgrad_into(refs[o + 6], g_out, y2, s3, w3o.shape[0], 1, 1, 1, 0)
             g2 = conv2d_dgrad_raw(g_out, w3o, s3, tuple(y2.shape), 1, 1, 1, 0, mask_act=y2)
             if ctx.needs_input_grad[2 + o + 3]:
-                grads[o + 3] = grad_like_weight(conv2d_wgrad_raw(g2, y1, s2, w2o.shape[0], 3, 3, 1, 1), w2)
+                grads[o + 3] = _wgrad_into(refs[o + 3], g2, y1, s2, w2o.shape[0], 3, 3, 1, 1)
             g1 = conv2d_dgrad_raw(g2, w2o, s2, tuple(y1.shape), 3, 3, 1, 1, mask_act=y1)
             del g2
             if ctx.needs_input_grad[2 + o]:
-                grads[o] = grad_like_weight(conv2d_wgrad_raw(g1, x_in, s1, w1o.shape[0], 1, 1, stride, 0), w1)
+                grads[o] = _wgrad_into(refs[o], g1, x_in, s1, w1o.shape[0], 1, 1, stride, 0)
             wd = sd = None
             if has_down[bi]:
                 wd, sd = tensors[o + 9], tensors[o + 10]
                 if ctx.needs_input_grad[2 + o + 9]:
                     wdo = weight_ohwi(wd)
-                    grads[o + 9] = grad_like_weight(conv2d_wgrad_raw(g_out, x_in, sd, wdo.shape[0], 1, 1, stride, 0), wd)
+                    grads[o + 9] = _wgrad_into(refs[o + 9], g_out, x_in, sd, wdo.shape[0], 1, 1, stride, 0)
             if first and not need_x:
                 break
             # data gradient of the block input: conv1 path + residual path, masked by the producer's ReLU

@@ -58,6 +58,7 @@ def _restore_impl():
     from dadetect_b200 import ops
     yield
     ops.set_default_impl(ops.IMPL_SIMT)
+    ops.set_direct_weight_grad(False)
 
 
 @pytest.mark.timeout(900)
