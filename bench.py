@@ -178,7 +178,7 @@ def main():
     import torch
     import torch.distributed as dist
     from dadetect_b200 import _lib, ops
-    from dadetect_b200.engine import FlatSGDTrainer
+    from dadetect_b200.engine import DevicePrefetcher, FlatSGDTrainer
     from dadetect_b200.modeling import build_detection_model
     from dadetect_b200.structures import BoxList
     from dadetect_b200.utils.synthetic import make_batch, make_state_dict
@@ -259,9 +259,17 @@ def main():
 
     loss_host = torch.empty(16, dtype=torch.float32).pin_memory()
 
+    prefetch = DevicePrefetcher(dev, (W, H))
+
     def step_e2e(s):
-        img, tg = to_device(*host[s % n_host])
+        # public API end to end: every step moves its own batch from pinned host memory (on the copy stream, one
+        # batch ahead of the compute stream), runs trainer.step and reads the loss vector back to the host
+        if s == 0:
+            prefetch.put(0, *host[0])
+        img, tg = prefetch.get(s)
+        prefetch.put(s + 1, *host[(s + 1) % n_host])
         ld = trainer.step(img, tg)
+        prefetch.release(s)
         vec = torch.stack([v.detach() for v in ld.values()])
         loss_host[: vec.numel()].copy_(vec, non_blocking=False)       # D2H read of the step's result
         last_losses["n"] = vec.numel()
@@ -297,9 +305,13 @@ def main():
     k_flops = 2.0 * 2 * (H // 16) * (W // 16) * 9 * 1024 * 1024
     pk = peaks()
     achieved_tf = k_flops / (k_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01b_roofline_traffic.json")      # dram bytes/launch from the ncu capture
+    if os.path.exists(tpath) and dense == "tcgen05":
+        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
-                "frac": achieved_tf / pk["bf16_burst"], "traffic": None,
-                "kernel": "conv_gemm (RPN 3x3 1024->1024 fwd, M=16384 N=1024 K=9216) via " + dense,
+                "frac": achieved_tf / pk["bf16_burst"], "traffic": traffic,
+                "kernel": "conv_tc_kernel<256,0> (RPN 3x3 1024->1024 fwd, M=16384 N=1024 K=9216, TF32: ceiling = 0.5 of the bf16 peak) via " + dense,
                 "peak_source": pk["source"] + ", dense bf16 burst",
                 "step_frac_of_flop_roofline": (2.0 * 1000.0 / ms_step) * TFLOP_PER_IMAGE / pk["bf16_sustained"]}
 

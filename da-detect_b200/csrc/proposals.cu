@@ -102,14 +102,28 @@ __global__ void __launch_bounds__(kTopkThreads) rpn_topk_decode_kernel(
     const int shift = 24 - 8 * pass;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < num_anchors; i += blockDim.x) {
-      // objectness logits share their leading bytes, so nearly every lane hits the same bin in the first passes:
-      // aggregate equal bins inside the warp and issue ONE shared-memory atomic per distinct bin
-      const uint32_t key = float_to_ordered(lg[i]);
-      const bool in = (key & prefix_mask) == prefix;
-      const uint32_t bin = in ? ((key >> shift) & 0xFF) : 0xFFFFFFFFu;
-      const unsigned peers = __match_any_sync(__activemask(), bin);
-      if (in && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+    // objectness logits share their leading bytes, so nearly every lane hits the same bin in the first passes:
+    // aggregate equal bins inside the warp and issue ONE shared-memory atomic per distinct bin.  Four logits per
+    // thread and iteration (one 128-bit load) keep enough loads in flight for a single CTA.
+    const bool vec = (num_anchors & 3) == 0 && (reinterpret_cast<uintptr_t>(lg) & 15) == 0;
+#pragma unroll 2
+    for (int i = threadIdx.x * 4; i < num_anchors; i += blockDim.x * 4) {
+      float v[4];
+      if (vec) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(lg + i));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = i + e < num_anchors ? lg[i + e] : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t key = float_to_ordered(v[e]);
+        const bool in = i + e < num_anchors && (key & prefix_mask) == prefix;
+        const uint32_t bin = in ? ((key >> shift) & 0xFF) : 0xFFFFFFFFu;
+        const unsigned peers = __match_any_sync(__activemask(), bin);
+        if (in && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -66,9 +66,28 @@ __device__ __forceinline__ int warp_totals_exclusive(int my_warp_total, int* sm3
   return __shfl_sync(0xffffffffu, incl - v, wid);
 }
 
-// One CTA per image.  Every warp owns a CONTIGUOUS slice of the candidates (lanes interleaved inside it, so the
-// loads are coalesced and the index order inside a warp is the ballot order); ordering across warps needs one
-// scan of 32 warp totals per phase instead of a block-wide rank per 1024 candidates.
+// Four consecutive candidates starting at i (i % 4 == 0): class (0 pos / 1 neg / 2 ignored or out of range) and
+// ordered key.  128-bit loads when the rows are 16-byte aligned.
+__device__ __forceinline__ void load4(const int* __restrict__ labels, const float* __restrict__ keys, int i, int n,
+                                      bool vec, int (&c)[4], uint32_t (&k)[4]) {
+  if (vec && i + 3 < n) {
+    const int4 l = __ldg(reinterpret_cast<const int4*>(labels + i));
+    const float4 f = __ldg(reinterpret_cast<const float4*>(keys + i));
+    c[0] = cls_of(l.x); c[1] = cls_of(l.y); c[2] = cls_of(l.z); c[3] = cls_of(l.w);
+    k[0] = ordered_key(f.x); k[1] = ordered_key(f.y); k[2] = ordered_key(f.z); k[3] = ordered_key(f.w);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool ok = i + e < n;
+      c[e] = ok ? cls_of(labels[i + e]) : 2;
+      k[e] = ok ? ordered_key(keys[i + e]) : 0u;
+    }
+  }
+}
+
+// One CTA per image.  Every warp owns a CONTIGUOUS slice of the candidates, walked 128 at a time (lane l holds
+// candidates 4l..4l+3 of the step: coalesced 128-bit loads, and (lane, element) order IS index order); ordering
+// across warps needs one scan of 32 warp totals per phase instead of a block-wide rank per 1024 candidates.
 __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
     const int* __restrict__ labels, const int* __restrict__ n_dev, const float* __restrict__ keys, int n_cap,
     int batch, int max_pos, int64_t* __restrict__ sel_idx, int* __restrict__ counts) {
@@ -82,20 +101,24 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
   keys += (size_t)img * n_cap;
   sel_idx += (size_t)img * batch;
   const int n = n_dev ? min(n_dev[img], n_cap) : n_cap;
+  const bool vec = (n_cap & 3) == 0 && ((reinterpret_cast<uintptr_t>(labels) | reinterpret_cast<uintptr_t>(keys)) & 15) == 0;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nwarps = blockDim.x >> 5;
-  const int per_warp = ((n + nwarps - 1) / nwarps + 31) & ~31;       // slice length, multiple of 32
+  const int per_warp = ((n + nwarps - 1) / nwarps + 127) & ~127;     // slice length, multiple of 128
   const int w_begin = min(wid * per_warp, n), w_end = min(w_begin + per_warp, n);
+  const int step = blockDim.x * 4;
 
   // ---- population of the two classes
   if (tid < 2) s_cnt[tid] = 0;
   __syncthreads();
   {
     int c0 = 0, c1 = 0;
-    for (int i = tid; i < n; i += blockDim.x) {
-      const int c = cls_of(labels[i]);
-      c0 += c == 0;
-      c1 += c == 1;
+#pragma unroll 2
+    for (int i = tid * 4; i < n; i += step) {
+      int c[4]; uint32_t k[4];
+      load4(labels, keys, i, n, vec, c, k);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { c0 += c[e] == 0; c1 += c[e] == 1; }
     }
     for (int o = 16; o > 0; o >>= 1) {
       c0 += __shfl_xor_sync(0xffffffffu, c0, o);
@@ -116,12 +139,13 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
     const int shift = 24 - 8 * pass;
     for (int i = tid; i < 512; i += blockDim.x) (&hist[0][0])[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += blockDim.x) {
-      const int c = cls_of(labels[i]);
-      if (c < 2) {
-        const uint32_t key = ordered_key(keys[i]);
-        if ((key & mask) == prefix[c]) atomicAdd(&hist[c][(key >> shift) & 0xFF], 1);
-      }
+#pragma unroll 2
+    for (int i = tid * 4; i < n; i += step) {
+      int c[4]; uint32_t k[4];
+      load4(labels, keys, i, n, vec, c, k);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c[e] < 2 && (k[e] & mask) == prefix[c[e]]) atomicAdd(&hist[c[e]][(k[e] >> shift) & 0xFF], 1);
     }
     __syncthreads();
     if (tid < 2) {
@@ -146,9 +170,12 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
 
   // ---- phase A: ties (key == prefix) per warp slice and class -> tie rank base of every warp
   int eq_w[2] = {0, 0};
-  for (int i = w_begin + lane; i < w_end; i += 32) {
-    const int c = cls_of(labels[i]);
-    if (c < 2 && want[c] > 0 && ordered_key(keys[i]) == prefix[c]) eq_w[c] += 1;
+  for (int i = w_begin + lane * 4; i < w_end; i += 128) {
+    int c[4]; uint32_t k[4];
+    load4(labels, keys, i, w_end, vec, c, k);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (c[e] < 2 && want[c[e]] > 0 && k[e] == prefix[c[e]]) eq_w[c[e]] += 1;
   }
   for (int o = 16; o > 0; o >>= 1) {
     eq_w[0] += __shfl_xor_sync(0xffffffffu, eq_w[0], o);
@@ -162,36 +189,70 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
   // ---- phase B: number of selected candidates per warp slice -> output base of every warp
   // ---- phase C: write them in index order.  (B and C walk the slice identically; `write` switches.)
   int out_base = 0, total = 0;
+  const unsigned below = (1u << lane) - 1u;
   for (int write = 0; write < 2; ++write) {
     int ties[2] = {tie_base[0], tie_base[1]};
     int taken = 0;
-    for (int i0 = w_begin; i0 < w_end; i0 += 32) {
-      const int i = i0 + lane;
-      int c = 2;
-      bool lt = false, eq = false;
-      if (i < w_end) {
-        c = cls_of(labels[i]);
-        if (c < 2 && want[c] > 0) {
-          const uint32_t key = ordered_key(keys[i]);
-          lt = key < prefix[c];
-          eq = key == prefix[c];
+    for (int i0 = w_begin; i0 < w_end; i0 += 128) {
+      const int i = i0 + lane * 4;
+      int c[4]; uint32_t k[4];
+      load4(labels, keys, i, w_end, vec, c, k);
+      bool lt[4], eq[4];
+      int eqc[2] = {0, 0};                       // ties of each class among this lane's four
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool live = c[e] < 2 && want[c[e] & 1] > 0;
+        lt[e] = live && k[e] < prefix[c[e] & 1];
+        eq[e] = live && k[e] == prefix[c[e] & 1];
+      }
+      // tie ranks: ties of lower lanes first, then this lane's earlier elements
+      int lane_eq[2] = {0, 0};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { lane_eq[0] += eq[e] && c[e] == 0; lane_eq[1] += eq[e] && c[e] == 1; }
+      int pre[2] = {lane_eq[0], lane_eq[1]};     // inclusive scan over lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t0 = __shfl_up_sync(0xffffffffu, pre[0], o), t1 = __shfl_up_sync(0xffffffffu, pre[1], o);
+        if (lane >= o) { pre[0] += t0; pre[1] += t1; }
+      }
+      const int tot0 = __shfl_sync(0xffffffffu, pre[0], 31), tot1 = __shfl_sync(0xffffffffu, pre[1], 31);
+      int rank[2] = {ties[0] + pre[0] - lane_eq[0], ties[1] + pre[1] - lane_eq[1]};
+      bool take[4];
+      int my_take = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        take[e] = lt[e];
+        if (eq[e]) {
+          const int cc = c[e] & 1;
+          take[e] = rank[cc] + eqc[cc] < need[cc];
+          eqc[cc] += 1;
+        }
+        my_take += take[e];
+      }
+      ties[0] += tot0;
+      ties[1] += tot1;
+      int tpre = my_take;                        // inclusive scan of the take counts over lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, tpre, o);
+        if (lane >= o) tpre += t;
+      }
+      const int ttot = __shfl_sync(0xffffffffu, tpre, 31);
+      if (write) {
+        int slot = out_base + taken + tpre - my_take;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (take[e]) {
+            if (slot < batch) sel_idx[slot] = (int64_t)(i + e);
+            ++slot;
+          }
         }
       }
-      const unsigned e0 = __ballot_sync(0xffffffffu, eq && c == 0), e1 = __ballot_sync(0xffffffffu, eq && c == 1);
-      const unsigned below = (1u << lane) - 1u;
-      const bool take = lt || (eq && c == 0 && ties[0] + __popc(e0 & below) < need[0]) ||
-                        (eq && c == 1 && ties[1] + __popc(e1 & below) < need[1]);
-      ties[0] += __popc(e0);
-      ties[1] += __popc(e1);
-      const unsigned tk = __ballot_sync(0xffffffffu, take);
-      if (write && take) {
-        const int slot = out_base + taken + __popc(tk & below);
-        if (slot < batch) sel_idx[slot] = (int64_t)i;
-      }
-      taken += __popc(tk);
+      taken += ttot;
     }
     if (!write) out_base = warp_totals_exclusive(taken, sm32, total);
   }
+  (void)below;
   total = min(total, batch);
   for (int r = total + tid; r < batch; r += blockDim.x) sel_idx[r] = 0;   // padding rows point at candidate 0
   if (tid == 0) {

@@ -1,1 +1,2 @@
 from .trainer import FlatSGDTrainer, WarmupMultiStepLR, WarmupCosineLR
+from .prefetch import DevicePrefetcher

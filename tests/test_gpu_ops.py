@@ -127,7 +127,7 @@ def test_nms_batched_ragged_counts_match_single_image():
 
 @pytest.mark.parametrize("n_cap,n,batch,max_pos,p_pos,p_neg,int_keys", [
     (5000, 4321, 256, 64, 0.1, 0.6, False), (122880, 122880, 256, 128, 0.0005, 0.9, False),
-    (600, 600, 256, 128, 0.02, 0.1, False), (300, 150, 256, 64, 0.3, 0.3, True), (64, 64, 16, 4, 0.0, 0.5, True)])
+    (600, 600, 256, 128, 0.02, 0.1, False), (300, 150, 256, 64, 0.3, 0.3, True), (64, 64, 16, 4, 0.0, 0.5, True), (301, 301, 64, 16, 0.2, 0.5, True)])
 def test_balanced_sample_matches_reference_semantics(n_cap, n, batch, max_pos, p_pos, p_neg, int_keys):
     """Device sampler == BalancedPositiveNegativeSampler with `keys` standing for the random permutation:
     min(#pos, max_pos) positives and min(#neg, batch - num_pos) negatives with the smallest keys (ties -> lower
