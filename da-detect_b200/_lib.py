@@ -46,6 +46,7 @@ _SIGS = {
     "dd_maxpool3x3s2": (_I, "ppiiiip"),
     "dd_avgpool_forward": (_I, "ppiiip"),
     "dd_avgpool_backward": (_I, "ppiiip"),
+    "dd_avgpool_relu_backward": (_I, "pppiiip"),
     "dd_relu_backward": (_I, "pppqp"),
     "dd_grl_backward": (_I, "pfpqip"),
     "dd_grl_backward_dev": (_I, "pppqip"),

@@ -58,6 +58,23 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ gy, float* __restri
   }
 }
 
+// gx[k, i, c] = act[k, i, c] > 0 ? gy[k, c] / HW : 0   (AvgPool2d backward fused with the ReLU mask of its input)
+__global__ void avgpool_relu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ act,
+                                        float* __restrict__ gx, int K, int HW, int C4) {
+  const long long total = (long long)K * HW * C4;
+  const float inv = 1.0f / (float)HW;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(t % C4);
+    const long long k = t / ((long long)HW * C4);
+    const float4 g = dd::ldg4(gy + (k * C4 + c4) * 4), a = dd::ldg4(act + t * 4);
+    float4 o;
+    o.x = a.x > 0.f ? g.x * inv : 0.f; o.y = a.y > 0.f ? g.y * inv : 0.f;
+    o.z = a.z > 0.f ? g.z * inv : 0.f; o.w = a.w > 0.f ? g.w * inv : 0.f;
+    *reinterpret_cast<float4*>(gx + t * 4) = o;
+  }
+}
+
 __global__ void relu_bwd_kernel(const float* __restrict__ g, const float* __restrict__ act, float* __restrict__ out,
                                 long long n4, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -158,6 +175,16 @@ extern "C" int dd_avgpool_backward(const float* gy, float* gx, int K, int HW, in
   DD_CHECK_ARG(K >= 0 && HW > 0 && C > 0);
   if (K == 0) return 0;
   avgpool_bwd_kernel<<<dd::grid_for((long long)K * HW * C, 256), 256, 0, dd::S(stream)>>>(gy, gx, K, HW, C);
+  DD_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dd_avgpool_relu_backward(const float* gy, const float* act, float* gx, int K, int HW, int C,
+                                        void* stream) {
+  DD_CHECK_ARG(K >= 0 && HW > 0 && C > 0 && C % 4 == 0);
+  if (K == 0) return 0;
+  avgpool_relu_bwd_kernel<<<dd::grid_for((long long)K * HW * (C / 4), 256), 256, 0, dd::S(stream)>>>(gy, act, gx, K,
+                                                                                                  HW, C / 4);
   DD_LAUNCHED();
   return 0;
 }

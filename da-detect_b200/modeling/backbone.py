@@ -93,11 +93,11 @@ class Stage(nn.Sequential):
 
     fused = True
 
-    def forward(self, x, first_stride_override=None, input_is_relu=False, grad_premasked=False):
+    def forward(self, x, first_stride_override=None, input_is_relu=False, grad_premasked=False, pool_output=False):
         if not self.fused:
             for i, blk in enumerate(self):
                 x = blk(x, stride_override=first_stride_override if i == 0 else None)
-            return x
+            return ops.avgpool_hw(x) if pool_output else x
         blocks, strides = [], []
         for i, blk in enumerate(self):
             d = {}
@@ -109,7 +109,7 @@ class Stage(nn.Sequential):
                 d["wd"], d["sd"], d["bd"] = blk.downsample[0].weight, sc, bi
             blocks.append(d)
             strides.append(first_stride_override if (i == 0 and first_stride_override is not None) else blk.stride)
-        return ops.bottleneck_stage(x, blocks, strides, input_is_relu, grad_premasked)
+        return ops.bottleneck_stage(x, blocks, strides, input_is_relu, grad_premasked, pool_output)
 
 
 def make_stage(cin, mid, cout, blocks, first_stride):
@@ -192,8 +192,10 @@ class ResNetHead(nn.Module):
         self.layer4 = make_stage(cout // 2, mid, cout, 3, 2)
         self.out_channels = cout
 
-    def forward(self, x, input_is_even_bins):
-        return self.layer4(x, first_stride_override=1 if input_is_even_bins else None)
+    def forward(self, x, input_is_even_bins, pooled=False):
+        """pooled: return the 7x7 average [K,C] (what the predictors and the DA instance head consume) — its
+        backward is then fused with the ReLU mask of the res5 output."""
+        return self.layer4(x, first_stride_override=1 if input_is_even_bins else None, pool_output=pooled)
 
 
 def build_backbone(cfg):

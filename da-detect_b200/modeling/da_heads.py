@@ -49,6 +49,14 @@ class DAInsHead(nn.Module):
         nn.init.constant_(self.fc3_da.bias, 0)
         self.rng = rng
 
+    def skip_draws(self, x, row_valid=None):
+        """Consume the two dropout draws of a pass that is not evaluated — only a replaying random source cares
+        (the oracle recorded them); the default source draws nothing."""
+        if self.training and self.rng.replay:
+            shape = (x.shape[0], self.fc1_da.weight.shape[0])
+            self.rng.dropout_keep(shape, x.device, row_valid)
+            self.rng.dropout_keep((x.shape[0], self.fc2_da.weight.shape[0]), x.device, row_valid)
+
     def forward(self, x, row_valid=None):
         x = ops.linear(x, self.fc1_da.weight, self.fc1_da.bias, relu=True)
         if self.training:
@@ -113,17 +121,25 @@ class DomainAdaptationModule(_Base):
             return {}
         D = self.cfg.MODEL.DA_HEADS
         feat = img_features[0]
-        img_g = ops.gradient_scalar(feat, -1.0 * D.DA_IMG_GRL_WEIGHT)
-        ins_g = ops.gradient_scalar(pooled_ins, -1.0 * D.DA_INS_GRL_WEIGHT)
-        img_c = ops.gradient_scalar(feat, 1.0 * D.DA_IMG_GRL_WEIGHT)
-        ins_c = ops.gradient_scalar(pooled_ins, 1.0 * D.DA_INS_GRL_WEIGHT)
-        da_img = self.imghead(img_g)
-        da_ins = self.inshead(ins_g, row_valid)
-        da_img_c = self.imghead(img_c)
-        da_ins_c = self.inshead(ins_c, row_valid)
-        l_img = da_img_loss(da_img, targets, seg)
-        l_ins = da_ins_loss(da_ins, dom, row_valid)
-        l_cst = ops.consistency_loss(da_img_c.reshape(da_img_c.shape[0], -1), da_ins_c.reshape(-1), n_src, row_valid)
+        # The reference evaluates all four head passes and all three losses and then drops the ones whose weight
+        # is 0 (da_heads.py:417-436); a dropped term has no effect on the loss dict or on any gradient, so its
+        # passes are skipped here.  The instance head's dropout draws are still consumed (RNG-stream parity).
+        need_img, need_ins, need_cst = self.img_weight > 0, self.ins_weight > 0, self.cst_weight > 0
+        l_img = l_ins = l_cst = None
+        if need_img:
+            da_img = self.imghead(ops.gradient_scalar(feat, -1.0 * D.DA_IMG_GRL_WEIGHT))
+            l_img = da_img_loss(da_img, targets, seg)
+        if need_ins:
+            da_ins = self.inshead(ops.gradient_scalar(pooled_ins, -1.0 * D.DA_INS_GRL_WEIGHT), row_valid)
+            l_ins = da_ins_loss(da_ins, dom, row_valid)
+        else:
+            self.inshead.skip_draws(pooled_ins, row_valid)
+        if need_cst:
+            da_img_c = self.imghead(ops.gradient_scalar(feat, 1.0 * D.DA_IMG_GRL_WEIGHT))
+            da_ins_c = self.inshead(ops.gradient_scalar(pooled_ins, 1.0 * D.DA_INS_GRL_WEIGHT), row_valid)
+            l_cst = ops.consistency_loss(da_img_c.reshape(da_img_c.shape[0], -1), da_ins_c.reshape(-1), n_src, row_valid)
+        else:
+            self.inshead.skip_draws(pooled_ins, row_valid)
         losses = {}
         if self.img_weight > 0:
             losses["loss_da_image"] = self.img_weight * l_img

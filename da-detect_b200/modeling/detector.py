@@ -47,8 +47,7 @@ class _BoxBranch(nn.Module):
     def forward(self, feat, rois):
         x = ops.roi_align(feat, rois, self.fe.pooler.scale, self.fe.pooler.output_size, self.fe.pooler.sampling_ratio,
                           2 if self.fe.even_bins else 1)
-        x = self.fe.head(x, self.fe.even_bins)
-        pooled = ops.avgpool_hw(x)
+        pooled = self.fe.head(x, self.fe.even_bins, pooled=True)
         cls, box = self.predictor(pooled)
         return pooled, cls, box
 

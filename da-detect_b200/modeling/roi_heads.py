@@ -233,7 +233,7 @@ class ROIBoxHead(nn.Module):
             fe = self.feature_extractor
             x = ops.roi_align(features[0], st["rois"], fe.pooler.scale, fe.pooler.output_size,
                               fe.pooler.sampling_ratio, 2 if fe.even_bins else 1)
-            pooled = ops.avgpool_hw(fe.head(x, fe.even_bins))
+            pooled = fe.head(x, fe.even_bins, pooled=True)
             class_logits, box_regression = self.predictor(pooled)
         loss_classifier, loss_box_reg = self.loss_evaluator.loss_static(class_logits, box_regression)
         # detached: a kept reference into the autograd graph would pin its AccumulateGrad nodes across steps

@@ -272,7 +272,7 @@ class _BottleneckStage(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, meta, *tensors):
-        strides, has_down, input_is_relu, grad_premasked = meta
+        strides, has_down, input_is_relu, grad_premasked, pool_output = meta
         x = _chk(x, name="x")
         need_graph = x.requires_grad or any(t.requires_grad for t in tensors)
         saved, per_block = [], []
@@ -300,16 +300,26 @@ class _BottleneckStage(torch.autograd.Function):
             ctx.n_saved = len(saved)
             ctx.meta = meta
             ctx.param_refs = tensors
+        if pool_output:                       # nn.AvgPool2d over the whole map: [K,h,w,C] -> [K,C]
+            k, h, w, c = cur.shape
+            pooled = torch.empty((k, c), dtype=torch.float32, device=cur.device)
+            _lib.call("dd_avgpool_forward", _ptr(cur), _ptr(pooled), k, h * w, c, _stream())
+            return pooled
         return cur
 
     @staticmethod
     def backward(ctx, g):
-        strides, has_down, input_is_relu, grad_premasked = ctx.meta
+        strides, has_down, input_is_relu, grad_premasked, pool_output = ctx.meta
         all_saved = ctx.saved_tensors
         acts, tensors = all_saved[:ctx.n_saved], all_saved[ctx.n_saved:]
         y_last = acts[-1]
         g = _chk(g, name="grad")
-        g_out = g if grad_premasked else relu_backward_raw(g, y_last)
+        if pool_output:                       # pooling backward and the last ReLU mask in one pass
+            k, h, w, c = y_last.shape
+            g_out = torch.empty_like(y_last)
+            _lib.call("dd_avgpool_relu_backward", _ptr(g), _ptr(y_last), _ptr(g_out), k, h * w, c, _stream())
+        else:
+            g_out = g if grad_premasked else relu_backward_raw(g, y_last)
         grads = [None] * len(tensors)
         # tensor offsets of each block
         offs, k = [], 0
@@ -356,15 +366,17 @@ class _BottleneckStage(torch.autograd.Function):
         return (gx, None) + tuple(grads)
 
 
-def bottleneck_stage(x, blocks, strides, input_is_relu=False, grad_premasked=False):
-    """blocks: list of dicts with w1,s1,b1,w2,s2,b2,w3,s3,b3 and optionally wd,sd,bd (tensors)."""
+def bottleneck_stage(x, blocks, strides, input_is_relu=False, grad_premasked=False, pool_output=False):
+    """blocks: list of dicts with w1,s1,b1,w2,s2,b2,w3,s3,b3 and optionally wd,sd,bd (tensors).
+    pool_output: return the spatial average [K,C] of the stage output (the box head's AvgPool2d(7))."""
     tensors, has_down = [], []
     for b in blocks:
         tensors.extend([b["w1"], b["s1"], b["b1"], b["w2"], b["s2"], b["b2"], b["w3"], b["s3"], b["b3"]])
         has_down.append("wd" in b)
         if "wd" in b:
             tensors.extend([b["wd"], b["sd"], b["bd"]])
-    meta = (tuple(int(s) for s in strides), tuple(has_down), bool(input_is_relu), bool(grad_premasked))
+    meta = (tuple(int(s) for s in strides), tuple(has_down), bool(input_is_relu), bool(grad_premasked),
+            bool(pool_output))
     return _BottleneckStage.apply(x, meta, *tensors)
 
 

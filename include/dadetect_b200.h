@@ -174,6 +174,9 @@ int dd_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, void* 
 /* nn.AvgPool2d(7) on [K,HW,C] -> [K,C] and its backward. */
 int dd_avgpool_forward(const float* x, float* y, int K, int HW, int C, void* stream);
 int dd_avgpool_backward(const float* gy, float* gx, int K, int HW, int C, void* stream);
+/* AvgPool2d backward fused with the ReLU mask of the pooled map: gx[k,i,c] = act[k,i,c] > 0 ? gy[k,c] / HW : 0
+ * (the 7x7 average of the res5 output feeds the predictors; its gradient enters res5 through that ReLU). */
+int dd_avgpool_relu_backward(const float* gy, const float* act, float* gx, int K, int HW, int C, void* stream);
 /* out = g * (act > 0 ? 1 : 0); ReLU backward applied to a gradient that fans in from several consumers. */
 int dd_relu_backward(const float* g, const float* act, float* out, long long n, void* stream);
 /* GradientScalarLayer backward (layers/gradient_scalar_layer.py:11-13): out = w * g (no clone);

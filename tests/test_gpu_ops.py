@@ -368,8 +368,9 @@ def test_conv_autograd_function_and_linear():
 
 
 @pytest.mark.parametrize("impl", ["simt", "tcgen05"])
-@pytest.mark.parametrize("first_stride,in_relu,premasked", [(2, True, True), (1, False, False)])
-def test_fused_stage_matches_per_layer_autograd(impl, first_stride, in_relu, premasked):
+@pytest.mark.parametrize("first_stride,in_relu,premasked,pool", [(2, True, True, False), (1, False, False, False),
+                                                                 (1, False, False, True)])
+def test_fused_stage_matches_per_layer_autograd(impl, first_stride, in_relu, premasked, pool):
     """ops.bottleneck_stage (explicit backward, masks and fan-in adds in dgrad epilogues) against the same
     blocks run layer by layer through conv_bn_act + autograd."""
     from dadetect_b200.modeling.backbone import make_stage
@@ -386,12 +387,12 @@ def test_fused_stage_matches_per_layer_autograd(impl, first_stride, in_relu, pre
         x0 = torch.randn(2, 12, 20, 32, device=DEV)
         if in_relu:
             x0 = x0.relu()
-        go = torch.randn(2, 12 // first_stride, 20 // first_stride, 64, device=DEV)
+        go = torch.randn((2, 64) if pool else (2, 12 // first_stride, 20 // first_stride, 64), device=DEV)
         res = []
         for fused in (False, True):
             stage.fused = fused
             x = x0.clone().requires_grad_(True)
-            y = stage(x, input_is_relu=in_relu, grad_premasked=premasked)
+            y = stage(x, input_is_relu=in_relu, grad_premasked=premasked, pool_output=pool)
             g = go * (y > 0) if premasked else go          # a pre-masked upstream gradient
             grads = torch.autograd.grad(y, [x] + list(stage.parameters()), g)
             gx = grads[0] * (x0 > 0) if (in_relu and not fused) else grads[0]
