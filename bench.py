@@ -190,6 +190,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:                                   # run (and pin host memory) on the CPUs next to this GPU
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", init_method="env://")
     assert world == args.gpus, "launch with torchrun --nproc-per-node {} for --gpus {}".format(args.gpus, args.gpus)

@@ -353,6 +353,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // Each warp owns TMEM lanes / tile rows [32q, 32q+32) end to end (its own staging slices, its own TMA
     // stores), so the chunk loop needs only __syncwarp.  EPI selects the compiled side-input handling.
     constexpr bool kExtra = (EPI & EPI_EXTRA) != 0, kMask = (EPI & EPI_MASK) != 0, kScalar = (EPI & EPI_SCALAR) != 0;
+    constexpr bool kAhead = !kScalar && (kExtra != kMask);     // exactly one side input: prefetch it a chunk ahead
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;                 // tile row owned in the TMEM -> smem pass
     const int pc = lane & 7;                             // re-mapped pass: 16-byte column group of the chunk,
@@ -390,11 +391,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int colbase = n_tile * BN + pc * 4;
       float sc[4], bi[4];                                // per-channel scale / bias, fetched one chunk ahead
       load_scale_bias(p, colbase, sc, bi);
-      mbar_wait(tmem_full_bar + acc, aph);
-      tc_fence_after();
       const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 
-      auto process = [&](const uint32_t (&r)[32], int ch) {
+      // side reads (residual / addend and ReLU mask) of chunk `ch`, all in flight at once; issued ONE CHUNK AHEAD
+      // of their use when a single side input is present (two register sets), else right before use
+      auto issue_side = [&](int ch, float4 (&ex)[8], float4 (&mk)[8]) {
+        const int col = colbase + ch * 32;
+        const bool col_ok = col < p.Cout;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = pix[i] >= 0 && col_ok;
+          const size_t off = ok ? (size_t)pix[i] * p.ldc + col : 0;
+          if (kExtra) ex[i] = ok ? dd::ldg4(p.extra + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kMask) mk[i] = ok ? dd::ldg4(p.mask + off) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+      };
+
+      auto process = [&](const uint32_t (&r)[32], int ch, float4 (&ex)[8], float4 (&mk)[8]) {
         const uint32_t stg = my_stage + (chunk_ctr & 1) * L::kStagingBytes;
         if (!kScalar) {
           if (lane == 0) tma_store_wait_read<1>();       // the store that last read this slice has drained
@@ -407,16 +420,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ---- re-mapped pass: lane = (column group pc, rows pr + 4 i)
         const int col = colbase + ch * 32;
         const bool col_ok = col < p.Cout;
-        float4 ex[8], mk[8];
-        if (!kScalar) {                                  // all side reads of the chunk in flight at once
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool ok = pix[i] >= 0 && col_ok;
-            const size_t off = ok ? (size_t)pix[i] * p.ldc + col : 0;
-            if (kExtra) ex[i] = ok ? dd::ldg4(p.extra + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kMask) mk[i] = ok ? dd::ldg4(p.mask + off) : make_float4(1.f, 1.f, 1.f, 1.f);
-          }
-        }
+        if (!kScalar && !kAhead && (kExtra || kMask)) issue_side(ch, ex, mk);
         float scn[4], bin[4];
         if (ch + 1 < n_chunks) load_scale_bias(p, col + 32, scn, bin);
         __syncwarp();
@@ -465,16 +469,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       };
 
       uint32_t ra[32], rb[32];
+      float4 exa[8], mka[8], exb[kAhead ? 8 : 1], mkb[kAhead ? 8 : 1];
+      if (kAhead) issue_side(0, exa, mka);             // does not depend on the accumulator: before the wait
+      mbar_wait(tmem_full_bar + acc, aph);
+      tc_fence_after();
       tmem_ld32_nowait(tm, ra);
 #pragma unroll 1
       for (int ch = 0; ch < n_chunks; ch += 2) {
         tmem_ld_wait();
-        if (ch + 1 < n_chunks) tmem_ld32_nowait(tm + (uint32_t)((ch + 1) * 32), rb);   // moves while ra is processed
-        process(ra, ch);
+        if (ch + 1 < n_chunks) {
+          tmem_ld32_nowait(tm + (uint32_t)((ch + 1) * 32), rb);   // moves while ra is processed
+          if constexpr (kAhead) issue_side(ch + 1, exb, mkb);
+        }
+        process(ra, ch, exa, mka);
         if (ch + 1 < n_chunks) {
           tmem_ld_wait();
-          if (ch + 2 < n_chunks) tmem_ld32_nowait(tm + (uint32_t)((ch + 2) * 32), ra);
-          process(rb, ch + 1);
+          if (ch + 2 < n_chunks) {
+            tmem_ld32_nowait(tm + (uint32_t)((ch + 2) * 32), ra);
+            if (kAhead) issue_side(ch + 2, exa, mka);
+          }
+          if constexpr (kAhead) process(rb, ch + 1, exb, mkb);
+          else process(rb, ch + 1, exa, mka);
         }
       }
       // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
