@@ -33,9 +33,10 @@ _SIGS = {
     "dd_match": (_I, "pipiffipppp"),
     "dd_box_encode": (_I, "pippiffffipp"),
     "dd_box_decode": (_I, "ppiiffffpp"),
-    "dd_conv2d_forward": (_I, "ppppppiiiiiiiiiiip"),
+    "dd_conv2d_forward_workspace_bytes": (_Z, "iiiii"),
+    "dd_conv2d_forward": (_I, "ppppppiiiiiiiiiiipp"),
     "dd_stem_workspace_bytes": (_Z, "iiii"),
-    "dd_stem_conv7x7s2_forward": (_I, "pppppiiiiipp"),
+    "dd_stem_conv7x7s2_forward": (_I, "pppppiiiiiipp"),
     "dd_conv2d_dgrad_workspace_bytes": (_Z, "iiii"),
     "dd_conv2d_dgrad": (_I, "ppppppiiiiiiiiiipip"),
     "dd_conv2d_wgrad_workspace_bytes": (_Z, "iiiiiiiii"),

@@ -33,6 +33,7 @@ constexpr int BKB = 128;           // bytes of K per stage row (one 128B swizzle
 constexpr int BKE = 32;            // elements of K per stage
 constexpr int UMMA_K = 8;          // tf32: 32 bytes per MMA K step
 constexpr int NUM_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int NUM_THREADS_X3 = 320;   // + warps 6..9: operand splitter of the 3xTF32 mode
 
 struct TcParams {
   // epilogue
@@ -48,6 +49,7 @@ struct TcParams {
   int tiles_h, tiles_w;   // ceil(OH/th), ceil(OW/tw)
   int m_tiles, n_tiles;   // persistent tile space: t -> (n_tile = t % n_tiles, m_tile = t / n_tiles)
   int tma_store;          // 1: staged chunks leave through a TMA tensor store; 0: guarded scalar stores
+  int b_lo_row;           // X3: row offset of the low-part plane inside the prepared B matrix
   int stem;               // 1: A is the 5-D overlapping-window view of the padded NHWC4 image (7x7/2 stem)
   int prefetch_side;      // 1: map_e / map_m are valid and the producer prefetches extra / mask tiles to L2
   // where a row lands in the output tensor: out[((n*out_H + h*os)*out_W + w*os)*ldc + co]
@@ -180,12 +182,14 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BN>
+// X3 = 3xTF32 ("fp32-grade") mode: every operand is split into a TF32-exact high part and a TF32-exact low part,
+// D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi; a stage then holds four tiles [A_hi | A_lo | B_hi | B_lo].
+template <int BN, bool X3>
 struct SmemLayout {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = X3 ? (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kABytes = BM * BKB;      // 16 KB
   static constexpr int kBBytes = BN * BKB;      // 8 / 16 / 32 KB
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = (X3 ? 2 : 1) * (kABytes + kBBytes);
   static constexpr int kStagingBytes = BM * 128;                 // one 128-row x 32-column fp32 chunk
   static constexpr int kStagingOff = kStages * kStageBytes;      // 2 staging buffers (1024-aligned)
   static constexpr int kRowOff = kStagingOff + 2 * kStagingBytes;  // int32 pixel index per tile row
@@ -249,12 +253,12 @@ enum { EPI_EXTRA = 1, EPI_MASK = 2, EPI_SCALAR = 4 };
 // Epilogue per 32-column chunk: tcgen05.ld (thread = one tile row) -> 128B-swizzled smem staging ->
 // re-mapped pass (8 threads per row => coalesced 128-bit reads of residual / mask, per-channel scale + bias,
 // ReLU) -> one TMA tensor store of the [rows x 32 ch] box, which also clips the tile against the tensor edges.
-template <int BN, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int EPI, bool X3>
+__global__ void __launch_bounds__(X3 ? NUM_THREADS_X3 : NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_e,
                const __grid_constant__ CUtensorMap map_m, const TcParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, X3>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + L::kStagingOff;
@@ -263,7 +267,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty_bar = full_bar + L::kStages;
   uint64_t* tmem_full_bar = empty_bar + L::kStages;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* split_bar = tmem_empty_bar + 2;             // [kStages], X3 only: operand tiles split into hi / lo
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split_bar + L::kStages);
+  constexpr int kAOff2 = X3 ? L::kABytes : 0;           // A_lo sits right after A_hi
+  constexpr int kBOff = (X3 ? 2 : 1) * L::kABytes;      // B (hi) tile offset inside a stage
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_iters = p.taps * p.cblocks;
@@ -275,9 +282,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (p.tma_store) tma_prefetch_desc(&map_c);
     for (int s = 0; s < L::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, 128); }
+    if (X3) for (int s = 0; s < L::kStages; ++s) mbar_init(split_bar + s, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  // TMEM: 2 x BN columns (two tile accumulators, ping-pong) — or, in 3xTF32 mode, all 512 columns as EIGHT
+  // 64-column partial accumulators of ONE tile.  The tensor core's fp32 accumulator rounds toward zero on every
+  // accumulation step, a bias that grows with the length of the accumulation chain (measured ~1e-5 relative after
+  // 432 steps); slots 0..6 take the main products A_hi*B_hi round-robin over the K iterations (chain / 7), slot 7
+  // takes the two cross products (2^-11 of the magnitude, their bias is negligible), and the epilogue adds the
+  // slots with round-to-nearest fp32 adds.
+  constexpr int kTmemCols = X3 ? 512 : 2 * BN;
+  constexpr int kMainSlots = 7;
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -309,11 +325,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int tap = kit / p.cblocks, cb = kit - tap * p.cblocks;
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
           uint8_t* sa = smem + s * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
-          mbar_expect_tx(full_bar + s, L::kStageBytes);
+          uint8_t* sb = sa + kBOff;
+          mbar_expect_tx(full_bar + s, L::kABytes + (X3 ? 2 : 1) * L::kBBytes);
           if (p.stem) tma_load_5d(&map_a, full_bar + s, sa, 0, ow0, oh0 + (tap >> 1), tap & 1, n0);
           else tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
           tma_load_2d(&map_b, full_bar + s, sb, tap * p.Cin + cb * BKE, n_tile * BN);
+          if (X3) tma_load_2d(&map_b, full_bar + s, sb + L::kBBytes, tap * p.Cin + cb * BKE, p.b_lo_row + n_tile * BN);
         }
       }
     }
@@ -323,24 +340,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t it = 0;
     int local = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-      const int acc = local & 1;
-      const uint32_t aph = (local >> 1) & 1;
+      const int acc = X3 ? 0 : (local & 1);
+      const uint32_t aph = X3 ? (local & 1) : ((local >> 1) & 1);
       mbar_wait(tmem_empty_bar + acc, aph ^ 1);            // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
       for (int kit = 0; kit < k_iters; ++kit, ++it) {
         const int s = it % L::kStages;
         const uint32_t ph = (it / L::kStages) & 1;
-        mbar_wait(full_bar + s, ph);
+        mbar_wait((X3 ? split_bar : full_bar) + s, ph);         // X3: wait for the splitter, which waited for TMA
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-          const uint32_t b_addr = a_addr + L::kABytes;
+          const uint32_t b_addr = a_addr + kBOff;
 #pragma unroll
           for (int k = 0; k < BKE / UMMA_K; ++k) {
             const uint64_t ad = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
             const uint64_t bd = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
-            umma_tf32(tmem_d, ad, bd, idesc, (kit | k) ? 1u : 0u);
+            if (X3) {
+              const uint64_t adl = make_kmajor_sw128_desc(a_addr + kAOff2 + k * UMMA_K * 4);
+              const uint64_t bdl = make_kmajor_sw128_desc(b_addr + L::kBBytes + k * UMMA_K * 4);
+              const uint32_t d_small = tmem_base + (uint32_t)(kMainSlots * 64);
+              const uint32_t d_main = tmem_base + (uint32_t)((kit % kMainSlots) * 64);
+              umma_tf32(d_small, adl, bd, idesc, (kit | k) ? 1u : 0u);
+              umma_tf32(d_small, ad, bdl, idesc, 1u);
+              umma_tf32(d_main, ad, bd, idesc, (kit >= kMainSlots || k > 0) ? 1u : 0u);
+            } else {
+              umma_tf32(tmem_d, ad, bd, idesc, (kit | k) ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar + s);                              // frees the smem stage when these MMAs retire
           if (kit == k_iters - 1) umma_commit(tmem_full_bar + acc);  // accumulator complete
@@ -348,12 +375,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __syncwarp();
       }
     }
+  } else if (X3 && warp >= 6) {
+    // ================================ operand splitter (warps 6..9, 3xTF32 mode) ================================
+    // A tile rows are fp32 activations: rewrite each element in place as its TF32-exact high part (low 13 mantissa
+    // bits cleared) and store the TF32-exact part of the remainder next to it.  Both parts are exactly
+    // representable in TF32, so the result does not depend on how the tensor core converts fp32 bit patterns.
+    const int rs = threadIdx.x - 192;                    // one 128-byte tile row per thread
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int kit = 0; kit < k_iters; ++kit, ++it) {
+        const int s = it % L::kStages;
+        const uint32_t ph = (it / L::kStages) & 1;
+        mbar_wait(full_bar + s, ph);
+        const uint32_t a_hi = smem_u32(smem + s * L::kStageBytes) + rs * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[4];
+          lds128(a_hi + j * 16, v);
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hi[e] = __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u);
+            lo[e] = __uint_as_float(__float_as_uint(v[e] - hi[e]) & 0xFFFFE000u);
+          }
+          sts128(a_hi + j * 16, hi[0], hi[1], hi[2], hi[3]);
+          sts128(a_hi + kAOff2 + j * 16, lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_async_smem();                               // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(split_bar + s);
+      }
+    }
   } else {
     // ================================ epilogue (warps 2..5) ================================
     // Each warp owns TMEM lanes / tile rows [32q, 32q+32) end to end (its own staging slices, its own TMA
     // stores), so the chunk loop needs only __syncwarp.  EPI selects the compiled side-input handling.
     constexpr bool kExtra = (EPI & EPI_EXTRA) != 0, kMask = (EPI & EPI_MASK) != 0, kScalar = (EPI & EPI_SCALAR) != 0;
-    constexpr bool kAhead = !kScalar && (kExtra != kMask);     // exactly one side input: prefetch it a chunk ahead
+    constexpr bool kAhead = !X3 && !kScalar && (kExtra != kMask);   // exactly one side input: prefetch it a chunk ahead
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;                 // tile row owned in the TMEM -> smem pass
     const int pc = lane & 7;                             // re-mapped pass: 16-byte column group of the chunk,
@@ -369,8 +426,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t chunk_ctr = 0;
     int local = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-      const int acc = local & 1;
-      const uint32_t aph = (local >> 1) & 1;
+      const int acc = X3 ? 0 : (local & 1);
+      const uint32_t aph = X3 ? (local & 1) : ((local >> 1) & 1);
       const int n_tile = t % p.n_tiles;
       int mt = t / p.n_tiles;
       const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
@@ -473,6 +530,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (kAhead) issue_side(0, exa, mka);             // does not depend on the accumulator: before the wait
       mbar_wait(tmem_full_bar + acc, aph);
       tc_fence_after();
+      if constexpr (X3) {
+        // add the partial accumulators of the tile (cross-term slot + the main slots that were used)
+        const int n_main = k_iters < kMainSlots ? k_iters : kMainSlots;
+#pragma unroll 1
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          tmem_ld32(tm + (uint32_t)(kMainSlots * 64 + ch * 32), ra);
+#pragma unroll 1
+          for (int a = 0; a < n_main; ++a) {
+            tmem_ld32(tm + (uint32_t)(a * 64 + ch * 32), rb);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+          }
+          if (ch == n_chunks - 1) {
+            tc_fence_before();
+            mbar_arrive(tmem_empty_bar + acc);
+          }
+          process(ra, ch, exa, mka);
+        }
+        continue;
+      }
       tmem_ld32_nowait(tm, ra);
 #pragma unroll 1
       for (int ch = 0; ch < n_chunks; ch += 2) {
@@ -502,7 +579,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -662,8 +739,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
 
 // W'[ci][KH-1-kh][KW-1-kw][co] = scale[co] * W[co][kh][kw][ci]  (dgrad as a forward conv over GY).
 // One 32x32 smem-tiled transpose per (tap, co block, ci block): coalesced on both sides.
+// lo_off > 0 (3xTF32 mode): wt receives the TF32-exact high parts and wt + lo_off the low parts.
 __global__ void weight_flip_transpose_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                             float* __restrict__ wt, int Cout, int Cin, int taps) {
+                                             float* __restrict__ wt, int Cout, int Cin, int taps, long long lo_off) {
   __shared__ float tile[32][33];
   const int tap = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8
@@ -682,7 +760,17 @@ __global__ void weight_flip_transpose_kernel(const float* __restrict__ w, const 
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int ci = ci0 + ty + j, co = co0 + tx;
-    if (co < Cout && ci < Cin) wt[((size_t)ci * taps + tflip) * Cout + co] = tile[tx][ty + j];
+    if (co < Cout && ci < Cin) {
+      const float v = tile[tx][ty + j];
+      const size_t o = ((size_t)ci * taps + tflip) * Cout + co;
+      if (lo_off > 0) {
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        wt[o] = hi;
+        wt[o + lo_off] = __uint_as_float(__float_as_uint(v - hi) & 0xFFFFE000u);
+      } else {
+        wt[o] = v;
+      }
+    }
   }
 }
 
@@ -732,32 +820,59 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
   return 0;
 }
 
-template <int BN, int EPI>
-int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
+template <int BN, int EPI, bool X3>
+int launch_tc3(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
                const CUtensorMap& mm, const TcParams& p, cudaStream_t s) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, X3>;
   static bool configured = false;
   if (!configured) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, EPI, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < dd::kNumSMs ? total : dd::kNumSMs;
-  conv_tc_kernel<BN, EPI><<<grid, NUM_THREADS, L::kTotal, s>>>(ma, mb, mc, me, mm, p);
+  conv_tc_kernel<BN, EPI, X3><<<grid, X3 ? NUM_THREADS_X3 : NUM_THREADS, L::kTotal, s>>>(ma, mb, mc, me, mm, p);
   DD_LAUNCHED();
   return 0;
 }
 
+template <int BN, int EPI>
+int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
+               const CUtensorMap& mm, const TcParams& p, bool x3, cudaStream_t s) {
+  if constexpr (BN == 64) {
+    if (x3) return launch_tc3<64, EPI, true>(ma, mb, mc, me, mm, p, s);
+  }
+  return launch_tc3<BN, EPI, false>(ma, mb, mc, me, mm, p, s);
+}
+
 template <int BN>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
-              const CUtensorMap& mm, const TcParams& p, cudaStream_t s) {
-  if (!p.tma_store) return launch_tc2<BN, EPI_SCALAR>(ma, mb, mc, me, mm, p, s);
+              const CUtensorMap& mm, const TcParams& p, bool x3, cudaStream_t s) {
+  if (!p.tma_store) return launch_tc2<BN, EPI_SCALAR>(ma, mb, mc, me, mm, p, x3, s);
   const int epi = (p.extra ? EPI_EXTRA : 0) | (p.mask ? EPI_MASK : 0);
   switch (epi) {
-    case 0: return launch_tc2<BN, 0>(ma, mb, mc, me, mm, p, s);
-    case EPI_EXTRA: return launch_tc2<BN, EPI_EXTRA>(ma, mb, mc, me, mm, p, s);
-    case EPI_MASK: return launch_tc2<BN, EPI_MASK>(ma, mb, mc, me, mm, p, s);
-    default: return launch_tc2<BN, EPI_EXTRA | EPI_MASK>(ma, mb, mc, me, mm, p, s);
+    case 0: return launch_tc2<BN, 0>(ma, mb, mc, me, mm, p, x3, s);
+    case EPI_EXTRA: return launch_tc2<BN, EPI_EXTRA>(ma, mb, mc, me, mm, p, x3, s);
+    case EPI_MASK: return launch_tc2<BN, EPI_MASK>(ma, mb, mc, me, mm, p, x3, s);
+    default: return launch_tc2<BN, EPI_EXTRA | EPI_MASK>(ma, mb, mc, me, mm, p, x3, s);
+  }
+}
+
+// 3xTF32 always runs 64-column tiles: its 512 TMEM columns hold 8 partial accumulators of one tile (see the kernel)
+int tc_bn_for(int ncols, bool x3) { return x3 ? 64 : ((ncols % 256 == 0) ? 256 : (ncols > 64 ? 128 : 64)); }
+// rows of one plane of a prepared (hi / lo split) B matrix: the column count rounded up to whole 64-column tiles
+int tc_rows_pad(int ncols) { return (ncols + 63) / 64 * 64; }
+
+// out[r][k] = hi(w[r][k]), out[rows_pad + r][k] = lo(w[r][k]); rows in [rows, rows_pad) are zero in both planes
+__global__ void split_hi_lo_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int rows_pad,
+                                   long long K) {
+  const long long total = (long long)rows_pad * K;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / K;
+    const float v = r < rows ? w[t] : 0.f;
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    out[t] = hi;
+    out[total + t] = __uint_as_float(__float_as_uint(v - hi) & 0xFFFFE000u);
   }
 }
 
@@ -765,8 +880,9 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
 //   A: [N, AH, AW, Cin] NHWC fp32 read with pixel stride `as` (as > 1 only for 1x1 taps: the TMA view simply
 //      has doubled strides, nothing is gathered), B: [ncols, taps*Cin] fp32, output rows enumerate (N, OH, OW)
 //   and land at out[((n*out_H + oh*os)*out_W + ow*os)*ldc + col].
+// x3: b is the PREPARED matrix [2 * tc_rows_pad(ncols)][taps*Cin] (hi plane, lo plane) and the 3xTF32 kernel runs.
 int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const float* b, int ncols, int KH, int KW,
-                 int pad, int OH, int OW, TcParams p, cudaStream_t s) {
+                 int pad, int OH, int OW, TcParams p, bool x3, cudaStream_t s) {
   const bool flat = KH == 1 && KW == 1 && pad == 0 && as == 1 && p.os == 1 && OH == AH && OW == AW &&
                     p.out_H == OH && p.out_W == OW;
   if (flat) {                               // 1x1 stride 1: pixels are one dense axis, no tile padding at all
@@ -786,8 +902,9 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
   const int tiles_n = (N + p.tn - 1) / p.tn;
   p.taps = KH * KW; p.KW = KW; p.pad = pad; p.Cin = Cin; p.cblocks = Cin / BKE; p.Cout = ncols;
   p.m_tiles = tiles_n * p.tiles_h * p.tiles_w;
-  const int BN = (ncols % 256 == 0) ? 256 : (ncols > 64 ? 128 : 64);
+  const int BN = tc_bn_for(ncols, x3);
   p.n_tiles = (ncols + BN - 1) / BN;
+  p.b_lo_row = x3 ? tc_rows_pad(ncols) : 0;
   DD_CHECK_ARG((long long)p.m_tiles * p.n_tiles < (1ll << 31));
   const uintptr_t align_bits = reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.extra) |
                                reinterpret_cast<uintptr_t>(p.mask);
@@ -803,7 +920,7 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
   }
   {
     const cuuint64_t K = (cuuint64_t)KH * KW * Cin;
-    cuuint64_t dims[2] = {K, (cuuint64_t)ncols};
+    cuuint64_t dims[2] = {K, (cuuint64_t)(x3 ? 2 * tc_rows_pad(ncols) : ncols)};
     cuuint64_t strides[1] = {K * 4};
     cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)(BN < 256 ? BN : 256)};
     if (encode_map(&mb, b, 2, dims, strides, box)) return -1;
@@ -832,9 +949,9 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
     if (p.mask && encode_map(&mm, p.mask, 4, dims, strides, box)) return -1;
     p.prefetch_side = 1;
   }
-  if (BN == 256) return launch_tc<256>(ma, mb, mc, me, mm, p, s);
-  if (BN == 128) return launch_tc<128>(ma, mb, mc, me, mm, p, s);
-  return launch_tc<64>(ma, mb, mc, me, mm, p, s);
+  if (BN == 256) return launch_tc<256>(ma, mb, mc, me, mm, p, x3, s);
+  if (BN == 128) return launch_tc<128>(ma, mb, mc, me, mm, p, x3, s);
+  return launch_tc<64>(ma, mb, mc, me, mm, p, x3, s);
 }
 
 
@@ -886,12 +1003,14 @@ __global__ void stem_weight_kernel(const float* __restrict__ w, float* __restric
 }  // namespace
 
 extern "C" size_t dd_stem_workspace_bytes(int N, int H, int W, int Cout) {
-  return sizeof(float) * ((size_t)N * (H + 6) * (W + 8) * 4 + (size_t)Cout * 7 * 32) + 256;
+  (void)Cout;   // padded image + packed weights + their hi / lo planes (64 rows each) for the 3xTF32 mode
+  return sizeof(float) * ((size_t)N * (H + 6) * (W + 8) * 4 + 64 + (size_t)3 * 64 * 7 * 32) + 256;
 }
 
 extern "C" int dd_stem_conv7x7s2_forward(const float* x_nchw, const float* w_ohwi, const float* scale,
                                          const float* bias, float* y, int N, int H, int W, int Cout, int act,
-                                         void* workspace, void* stream) {
+                                         int impl, void* workspace, void* stream) {
+  const bool x3 = impl == DD_IMPL_TCGEN05_X3;
   DD_CHECK_ARG(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && Cout > 0 && Cout % 4 == 0 && Cout <= 64);
   DD_CHECK_ARG(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
                (reinterpret_cast<uintptr_t>(y) & 15) == 0);
@@ -903,6 +1022,13 @@ extern "C" int dd_stem_conv7x7s2_forward(const float* x_nchw, const float* w_ohw
   DD_LAUNCHED();
   stem_weight_kernel<<<(Cout * 7 * 32 + 255) / 256, 256, 0, s>>>(w_ohwi, w2, Cout);
   DD_LAUNCHED();
+  const float* bmat = w2;
+  if (x3) {
+    float* w3 = w2 + 64 * 7 * 32;
+    split_hi_lo_kernel<<<dd::grid_for(64ll * 224, 256), 256, 0, s>>>(w2, w3, Cout, 64, 224);
+    DD_LAUNCHED();
+    bmat = w3;
+  }
 
   TcParams p = {};
   p.out = y; p.scale = scale; p.bias = bias; p.relu = act == DD_ACT_RELU;
@@ -913,6 +1039,7 @@ extern "C" int dd_stem_conv7x7s2_forward(const float* x_nchw, const float* w_ohw
   p.tma_store = 1; p.stem = 1;
   p.out_H = OH; p.out_W = OW; p.os = 1; p.ldc = Cout; p.Cout = Cout;
   p.taps = 7; p.KW = 1; p.pad = 0; p.cblocks = 1; p.Cin = 32;
+  p.b_lo_row = x3 ? 64 : 0;
   CUtensorMap ma, mb, mc;
   {
     // (32 floats of the window, ow, row pair, row parity, n)
@@ -922,10 +1049,10 @@ extern "C" int dd_stem_conv7x7s2_forward(const float* x_nchw, const float* w_ohw
     if (encode_map(&ma, P, 5, dims, strides, box)) return -1;
   }
   {
-    cuuint64_t dims[2] = {224, (cuuint64_t)Cout};
+    cuuint64_t dims[2] = {224, (cuuint64_t)(x3 ? 128 : Cout)};
     cuuint64_t strides[1] = {224 * 4};
     cuuint32_t box[2] = {32, 64};
-    if (encode_map(&mb, w2, 2, dims, strides, box)) return -1;
+    if (encode_map(&mb, bmat, 2, dims, strides, box)) return -1;
   }
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
@@ -933,13 +1060,14 @@ extern "C" int dd_stem_conv7x7s2_forward(const float* x_nchw, const float* w_ohw
     cuuint32_t box[4] = {32, 16, 2, 1};
     if (encode_map(&mc, y, 4, dims, strides, box)) return -1;
   }
-  return launch_tc<64>(ma, mb, mc, ma, ma, p, s);
+  return launch_tc<64>(ma, mb, mc, ma, ma, p, x3, s);
 }
 
 namespace {
 }  // namespace
 
 extern "C" int dd_tcgen05_built(void) { return 1; }
+int tc_rows_pad_public(int ncols) { return (ncols + 63) / 64 * 64; }
 
 // mode: 0 forward, 1 dgrad, 2 wgrad
 bool dd_tc_supports(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
@@ -963,22 +1091,33 @@ bool dd_tc_supports(int mode, int N, int H, int W, int Cin, int Cout, int KH, in
 
 int dd_tc_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias, const float* residual,
                          float* y, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                         int act, cudaStream_t s) {
+                         int act, bool x3, float* ws, cudaStream_t s) {
   const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
   TcParams p = {};
   p.out = y; p.scale = scale; p.bias = bias; p.extra = residual; p.mask = nullptr; p.relu = act == DD_ACT_RELU;
   p.out_H = OH; p.out_W = OW; p.os = 1; p.ldc = Cout;
+  const float* b = w;
+  if (x3) {                                  // split the weights into TF32-exact hi / lo planes
+    DD_CHECK_ARG(ws != nullptr);
+    const long long K = (long long)KH * KW * Cin;
+    const int rp = tc_rows_pad(Cout);
+    split_hi_lo_kernel<<<dd::grid_for((long long)rp * K, 256), 256, 0, s>>>(w, ws, Cout, rp, K);
+    DD_LAUNCHED();
+    b = ws;
+  }
   // strided 1x1: the TMA view of x addresses every stride-th pixel directly
-  return tc_conv_core(x, N, H, W, Cin, stride, w, Cout, KH, KW, pad, OH, OW, p, s);
+  return tc_conv_core(x, N, H, W, Cin, stride, b, Cout, KH, KW, pad, OH, OW, p, x3, s);
 }
 
 int dd_tc_conv2d_dgrad(const float* gy, const float* w, const float* scale, const float* addend, const float* mask_act,
                        float* gx, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                       float* wt, int prepared, cudaStream_t s) {
+                       float* wt, int prepared, bool x3, cudaStream_t s) {
   const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
   if (!prepared) {
+    const long long plane = (long long)tc_rows_pad(Cin) * KH * KW * Cout;
+    if (x3 && tc_rows_pad(Cin) != Cin) DD_CUDA(cudaMemsetAsync(wt, 0, sizeof(float) * 2 * plane, s));   // pad rows
     dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, KH * KW);
-    weight_flip_transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(w, scale, wt, Cout, Cin, KH * KW);
+    weight_flip_transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(w, scale, wt, Cout, Cin, KH * KW, x3 ? plane : 0);
     DD_LAUNCHED();
   }
   TcParams p = {};
@@ -988,14 +1127,14 @@ int dd_tc_conv2d_dgrad(const float* gy, const float* w, const float* scale, cons
   if (stride == 1) {
     p.os = 1;
     // gx[n,h,w,ci] = sum_{kh',kw',co} gy[n, h + kh' - pad', w + kw' - pad', co] * W'[ci, kh', kw', co], pad' = KH-1-pad
-    rc = tc_conv_core(gy, N, OH, OW, Cout, 1, wt, Cin, KH, KW, KH - 1 - pad, H, W, p, s);
+    rc = tc_conv_core(gy, N, OH, OW, Cout, 1, wt, Cin, KH, KW, KH - 1 - pad, H, W, p, x3, s);
   } else {
     // 1x1 stride s: rows enumerate gy's pixels, each lands on (oh*s, ow*s); everything else is addend/0
     const long long n = (long long)N * H * W * Cin;
     fill_kernel<<<dd::grid_for(n, 256), 256, 0, s>>>(addend, mask_act, gx, n);
     DD_LAUNCHED();
     p.os = stride;
-    rc = tc_conv_core(gy, N, OH, OW, Cout, 1, wt, Cin, 1, 1, 0, OH, OW, p, s);
+    rc = tc_conv_core(gy, N, OH, OW, Cout, 1, wt, Cin, 1, 1, 0, OH, OW, p, x3, s);
   }
   return rc;
 }

@@ -91,7 +91,7 @@ class RPNHead(nn.Module):
     def forward(self, feat):
         t = ops.conv_bn_act(feat, self.conv.weight, None, self.conv.bias, pad=1, relu=True)
         a, a4 = self.cls_logits.weight.shape[0], self.bbox_pred.weight.shape[0]
-        if ops.get_default_impl() == ops.IMPL_TCGEN05:
+        if ops.get_default_impl() in (ops.IMPL_TCGEN05, ops.IMPL_TCGEN05_X3):
             # Both 1x1 predictors as ONE tensor-core GEMM: their 15 + 60 output channels are stacked and padded
             # to 96 (a multiple of the 32-channel K block), so that the data- and weight-gradient GEMMs (K = Cout,
             # M = Cout) are tensor-core shaped too; the pad rows are zero and receive zero gradient.

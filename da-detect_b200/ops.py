@@ -19,11 +19,13 @@ from . import _lib
 
 IMPL_SIMT = 0
 IMPL_TCGEN05 = 1
+IMPL_TCGEN05_X3 = 2          # 3xTF32 on the tensor cores: fp32-grade forward / data-gradient products
 _default_impl = IMPL_SIMT
 
 
 def set_default_impl(impl):
-    """Select the dense-tier arm used by conv2d/linear: IMPL_SIMT (fp32) or IMPL_TCGEN05 (TF32)."""
+    """Select the dense-tier arm used by conv2d/linear: IMPL_SIMT (fp32 FMA), IMPL_TCGEN05 (TF32 tensor cores)
+    or IMPL_TCGEN05_X3 (3xTF32 tensor cores, fp32-grade)."""
     global _default_impl
     _default_impl = int(impl)
 
@@ -116,9 +118,13 @@ def conv2d_forward_raw(x, w_ohwi, scale, bias, residual, kh, kw, stride, pad, re
     oh = (h + 2 * pad - kh) // stride + 1
     ow = (wd + 2 * pad - kw) // stride + 1
     y = torch.empty((n, oh, ow, cout), dtype=torch.float32, device=x.device)
+    impl = _default_impl if impl is None else impl
+    ws = None
+    if impl == IMPL_TCGEN05_X3:
+        nbytes = _lib.load().dd_conv2d_forward_workspace_bytes(cin, cout, kh, kw, impl)
+        ws = torch.empty(max(int(nbytes) // 4, 4), dtype=torch.float32, device=x.device)
     _lib.call("dd_conv2d_forward", _ptr(x), _ptr(w_ohwi), _ptr(scale), _ptr(bias), _ptr(residual), _ptr(y),
-              n, h, wd, cin, cout, kh, kw, stride, pad, 1 if relu else 0,
-              _default_impl if impl is None else impl, _stream())
+              n, h, wd, cin, cout, kh, kw, stride, pad, 1 if relu else 0, impl, _ptr(ws), _stream())
     return y
 
 
@@ -193,12 +199,12 @@ def stem_conv7x7s2(x_nchw, weight, scale, bias, relu=True):
     y = torch.empty((n, h // 2, w // 2, cout), dtype=torch.float32, device=x.device)
     ws = _workspace(_lib.load().dd_stem_workspace_bytes(n, h, w, cout), x.device, "stem")
     _lib.call("dd_stem_conv7x7s2_forward", _ptr(x), _ptr(weight_ohwi(weight.detach())), _ptr(scale), _ptr(bias),
-              _ptr(y), n, h, w, cout, 1 if relu else 0, _ptr(ws), _stream())
+              _ptr(y), n, h, w, cout, 1 if relu else 0, _default_impl, _ptr(ws), _stream())
     return y
 
 
 def stem_tc_supported(x_nchw, weight):
-    return (_default_impl == IMPL_TCGEN05 and x_nchw.shape[1] == 3 and x_nchw.shape[2] % 2 == 0
+    return (_default_impl in (IMPL_TCGEN05, IMPL_TCGEN05_X3) and x_nchw.shape[1] == 3 and x_nchw.shape[2] % 2 == 0
             and x_nchw.shape[3] % 2 == 0 and tuple(weight.shape[1:]) == (3, 7, 7) and weight.shape[0] % 4 == 0
             and weight.shape[0] <= 64 and not weight.requires_grad)
 

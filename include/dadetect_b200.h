@@ -132,6 +132,9 @@ int dd_balanced_sample(const int* labels, const int* n_dev, const float* keys, i
 /* impl: 0 = fp32 SIMT tiles (bit-faithful fp32 accumulate), 1 = tcgen05 TF32 (TMA-staged, TMEM accum). */
 #define DD_IMPL_SIMT 0
 #define DD_IMPL_TCGEN05 1
+/* 2 = tcgen05 "3xTF32": every operand is split into TF32-exact high and low parts inside the kernel and
+ * D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi — fp32-grade products on the tensor cores (forward and data gradient). */
+#define DD_IMPL_TCGEN05_X3 2
 #define DD_ACT_NONE 0
 #define DD_ACT_RELU 1
 
@@ -140,14 +143,18 @@ int dd_balanced_sample(const int* labels, const int* n_dev, const float* keys, i
  * NULL.  x [N,H,W,Cin], w [Cout,KH,KW,Cin], y [N,OH,OW,Cout], OH = (H+2p-KH)/s+1. */
 int dd_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias,
                       const float* residual, float* y, int N, int H, int W, int Cin, int Cout, int KH, int KW,
-                      int stride, int pad, int act, int impl, void* stream);
+                      int stride, int pad, int act, int impl, void* workspace, void* stream);
+/* workspace: dd_conv2d_forward_workspace_bytes(...) bytes (0 unless impl == DD_IMPL_TCGEN05_X3: the hi / lo
+ * planes of the weights), 16-byte aligned; may be NULL when 0. */
+size_t dd_conv2d_forward_workspace_bytes(int Cin, int Cout, int KH, int KW, int impl);
 /* The ResNet stem (BaseStem, resnet.py:317-336: 7x7 stride-2 pad-3 conv of the 3-channel image + FrozenBN
  * + ReLU) on the tensor cores, reading the reference's NCHW image directly: x_nchw [N,3,H,W] (H, W even),
  * w [Cout,7,7,3] (OHWI), y [N,H/2,W/2,Cout] NHWC, Cout <= 64.  workspace: dd_stem_workspace_bytes(...) bytes,
  * 256-byte aligned (zero-haloed NHWC4 copy of the image + re-packed weights). */
 size_t dd_stem_workspace_bytes(int N, int H, int W, int Cout);
 int dd_stem_conv7x7s2_forward(const float* x_nchw, const float* w_ohwi, const float* scale, const float* bias,
-                              float* y, int N, int H, int W, int Cout, int act, void* workspace, void* stream);
+                              float* y, int N, int H, int W, int Cout, int act, int impl, void* workspace,
+                              void* stream);
 /* gx = conv_transpose(gy, w * scale[co]) (+ addend) (* (mask_act > 0) if mask_act).  gx [N,H,W,Cin]
  * is fully written (positions a strided conv never read receive addend or 0).
  * workspace: dd_conv2d_dgrad_workspace_bytes(...) bytes (16-byte aligned) — the tcgen05 arm keeps the

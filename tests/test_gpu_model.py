@@ -49,8 +49,11 @@ def scenario(name):
 # Tolerances per dense-tier arm.  simt = fp32 FMA (the parity arm: 1e-4 on losses, BASELINE north_star);
 # tcgen05 = TF32 operands / fp32 accumulate (10-bit mantissa inputs): losses within 2e-3, gradients within 3e-2
 # globally — the documented cost of feeding fp32 storage straight to the tensor cores.
+# tcgen05x3 = 3xTF32 forward / data-gradient on the tensor cores: losses at the fp32 tolerance (1e-4) with its OWN
+# hard decisions; its weight gradients still run as TF32, hence the TF32 gradient tolerances.
 TOL = {"simt": dict(loss=1e-4, grad_tensor=1e-2, grad_global=2e-3),
-       "tcgen05": dict(loss=2e-3, grad_tensor=2.5e-1, grad_global=3e-2)}
+       "tcgen05": dict(loss=2e-3, grad_tensor=2.5e-1, grad_global=3e-2),
+       "tcgen05x3": dict(loss=1e-4, grad_tensor=2.5e-1, grad_global=3e-2)}
 
 
 @pytest.fixture(autouse=True)
@@ -62,12 +65,12 @@ def _restore_impl():
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("dense", ["simt", "tcgen05"])
+@pytest.mark.parametrize("dense", ["simt", "tcgen05", "tcgen05x3"])
 @pytest.mark.parametrize("name", sorted(SCENARIOS))
 def test_training_step_matches_oracle(name, dense):
     from dadetect_b200 import ops
     from dadetect_b200.utils.random_source import ReplaySource
-    ops.set_default_impl(ops.IMPL_TCGEN05 if dense == "tcgen05" else ops.IMPL_SIMT)
+    ops.set_default_impl({"simt": ops.IMPL_SIMT, "tcgen05": ops.IMPL_TCGEN05, "tcgen05x3": ops.IMPL_TCGEN05_X3}[dense])
     tol = TOL[dense]
     cfg, sd, images, targets, hw = scenario(name)
     torch.manual_seed(77)
@@ -102,7 +105,7 @@ def test_training_step_matches_oracle(name, dense):
     # index-exact tier: the sampled ROIs are the same boxes with the same labels
     box = model.roi_heads.box
     ref_samples = aux["samples"] if "samples" in aux else None
-    exact = dense == "simt"      # TF32 logits may legitimately reorder near-tied proposals
+    exact = dense != "tcgen05"   # TF32 logits may legitimately reorder near-tied proposals
     if exact and ref_samples is not None and not cfg.MODEL.DA_HEADS.ALIGNMENT:
         static = model.static_shapes and not cfg.MODEL.DA_HEADS.TRIPLET_USE
         sampled = box.loss_evaluator.static_proposals() if static else box.loss_evaluator._proposals
@@ -129,7 +132,7 @@ def test_training_step_matches_oracle(name, dense):
         # the triplet terms are differences of two nearly equal feature distances (d(a,p) - d(a,n)), which
         # amplifies the TF32 operand rounding ~10x: 1e-2 for those keys on the tcgen05 arm
         t_k = 1e-2 if (dense == "tcgen05" and k.startswith("triplet")) else tol["loss"]
-        assert abs(g - w) <= t_k * max(abs(w), 0.05 if dense == "tcgen05" else 1e-3), (k, g, w)
+        assert abs(g - w) <= t_k * max(abs(w), 1e-3 if dense == "simt" else 0.05), (k, g, w)
     sum(got.values()).backward()
     named = dict(model.named_parameters())
     worst, num, den = [], 0.0, 0.0

@@ -633,3 +633,44 @@ def test_conv_tcgen05_arm(case):
     close(gx.permute(0, 3, 1, 2).cpu(), (gx_want + addend) * (act > 0), "dgrad")
     gw = o.conv2d_wgrad_raw(gpre, xd, sd, cout, k, k, stride, pad, impl=o.IMPL_TCGEN05)
     close(gw.permute(0, 3, 1, 2).cpu(), gw_want, "wgrad")
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_x3_arm_is_fp32_grade(case):
+    """3xTF32 on the tensor cores (operands split into TF32-exact hi / lo parts in the kernel): forward and data
+    gradient agree with the fp64 reference to 5e-6 of the rms magnitude — 100x tighter than TF32 (5e-4..1e-3).
+    The tensor core's accumulator rounds toward zero on every accumulation step (a bias that grows with the chain
+    length: 1e-5 at K = 1152 with a single accumulator), so the kernel spreads a tile over 8 partial accumulators
+    in TMEM and adds them with round-to-nearest in the epilogue."""
+    n, h, w, cin, cout, k, stride, pad = case
+    o = ops()
+    g = torch.Generator().manual_seed(sum(case) + 2)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    scale = 0.5 + torch.rand(cout, generator=g)
+    bias = torch.randn(cout, generator=g) * 0.1
+    xr = x.clone().double().requires_grad_(True)
+    y0 = F.conv2d(xr, wt.double(), stride=stride, padding=pad) * scale.double().view(1, -1, 1, 1) + bias.double().view(1, -1, 1, 1)
+    res = torch.randn(y0.shape, generator=g)
+    want = F.relu(y0 + res.double())
+    go = torch.randn(want.shape, generator=g)
+    (gx_want,) = torch.autograd.grad(want, (xr,), go.double())
+
+    def close(got, ref, what):
+        err = got.double() - ref
+        rms = float(ref.pow(2).mean().sqrt())
+        assert float(err.pow(2).mean().sqrt()) <= 5e-6 * rms, (what, float(err.pow(2).mean().sqrt()), rms)
+        assert float(err.abs().max()) <= 1e-4 * max(rms, 1e-6), (what, float(err.abs().max()), rms)
+
+    xd = _to_nhwc(x).to(DEV)
+    wd = wt.permute(0, 2, 3, 1).contiguous().to(DEV)
+    sd, bd, rd = scale.to(DEV), bias.to(DEV), _to_nhwc(res).to(DEV)
+    got = o.conv2d_forward_raw(xd, wd, sd, bd, rd, k, k, stride, pad, True, impl=o.IMPL_TCGEN05_X3)
+    close(got.permute(0, 3, 1, 2).cpu(), want.detach(), "forward")
+    gpre = _to_nhwc((go.double() * (want > 0)).float()).to(DEV)
+    addend = torch.randn(x.shape, generator=g)
+    act = torch.randn(x.shape, generator=g)
+    gx = o.conv2d_dgrad_raw(gpre, wd, sd, tuple(xd.shape), k, k, stride, pad, addend=_to_nhwc(addend).to(DEV),
+                            mask_act=_to_nhwc(act).to(DEV), impl=o.IMPL_TCGEN05_X3)
+    close(gx.permute(0, 3, 1, 2).cpu(), (gx_want.detach() + addend.double()) * (act > 0), "dgrad")
