@@ -163,6 +163,18 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 // Shared-memory matrix descriptor, K-major, 128B swizzle (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
@@ -285,14 +297,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (X3) for (int s = 0; s < L::kStages; ++s) mbar_init(split_bar + s, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // TMEM: 2 x BN columns (two tile accumulators, ping-pong) — or, in 3xTF32 mode, all 512 columns as EIGHT
-  // 64-column partial accumulators of ONE tile.  The tensor core's fp32 accumulator rounds toward zero on every
-  // accumulation step, a bias that grows with the length of the accumulation chain (measured ~1e-5 relative after
-  // 432 steps); slots 0..6 take the main products A_hi*B_hi round-robin over the K iterations (chain / 7), slot 7
-  // takes the two cross products (2^-11 of the magnitude, their bias is negligible), and the epilogue adds the
-  // slots with round-to-nearest fp32 adds.
-  constexpr int kTmemCols = X3 ? 512 : 2 * BN;
-  constexpr int kMainSlots = 7;
+  // TMEM: 2 x BN columns (two tile accumulators, ping-pong).  3xTF32 mode: [M | P0 | P1], BN columns each.
+  // The tensor core's fp32 accumulator rounds toward zero on every accumulation step, a bias that grows with the
+  // length of the accumulation chain (measured ~1e-5 relative after 432 steps).  So the MMA warp accumulates only
+  // kGroup K-iterations (96 steps) into a partial slot P0/P1 (ping-pong), and the epilogue warps fold every
+  // finished partial into the running sum M with round-to-nearest fp32 adds (tcgen05.ld / add / tcgen05.st) while
+  // the MMA warp fills the other slot.  M never sees a tensor-core accumulation; the last partial of a tile is
+  // added on the fly by the epilogue proper.
+  constexpr int kGroup = 8;
+  constexpr int kTmemCols = X3 ? (BN <= 64 ? 256 : 512) : 2 * BN;
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -339,16 +352,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
     uint32_t it = 0;
     int local = 0;
+    if constexpr (X3) {
+      uint32_t grp = 0;                                      // partial-slot groups, counted across tiles
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int g0 = 0; g0 < k_iters; g0 += kGroup, ++grp) {
+          const int pp = grp & 1;
+          mbar_wait(tmem_empty_bar + pp, ((grp >> 1) & 1) ^ 1);    // the folding warps have drained this slot
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)((1 + pp) * BN);
+          const int g1 = min(g0 + kGroup, k_iters);
+          for (int kit = g0; kit < g1; ++kit, ++it) {
+            const int s = it % L::kStages;
+            const uint32_t ph = (it / L::kStages) & 1;
+            mbar_wait(split_bar + s, ph);                    // the splitter (which waited for TMA) is done
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+              const uint32_t b_addr = a_addr + kBOff;
+#pragma unroll
+              for (int k = 0; k < BKE / UMMA_K; ++k) {
+                const uint64_t ad = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
+                const uint64_t bd = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
+                const uint64_t adl = make_kmajor_sw128_desc(a_addr + kAOff2 + k * UMMA_K * 4);
+                const uint64_t bdl = make_kmajor_sw128_desc(b_addr + L::kBBytes + k * UMMA_K * 4);
+                umma_tf32(d, adl, bd, idesc, (kit > g0 || k > 0) ? 1u : 0u);      // small terms first
+                umma_tf32(d, ad, bdl, idesc, 1u);
+                umma_tf32(d, ad, bd, idesc, 1u);
+              }
+              umma_commit(empty_bar + s);
+              if (kit == g1 - 1) umma_commit(tmem_full_bar + pp);                 // partial complete
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else {
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-      const int acc = X3 ? 0 : (local & 1);
-      const uint32_t aph = X3 ? (local & 1) : ((local >> 1) & 1);
+      const int acc = local & 1;
+      const uint32_t aph = (local >> 1) & 1;
       mbar_wait(tmem_empty_bar + acc, aph ^ 1);            // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
       for (int kit = 0; kit < k_iters; ++kit, ++it) {
         const int s = it % L::kStages;
         const uint32_t ph = (it / L::kStages) & 1;
-        mbar_wait((X3 ? split_bar : full_bar) + s, ph);         // X3: wait for the splitter, which waited for TMA
+        mbar_wait(full_bar + s, ph);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
@@ -357,23 +405,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < BKE / UMMA_K; ++k) {
             const uint64_t ad = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
             const uint64_t bd = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
-            if (X3) {
-              const uint64_t adl = make_kmajor_sw128_desc(a_addr + kAOff2 + k * UMMA_K * 4);
-              const uint64_t bdl = make_kmajor_sw128_desc(b_addr + L::kBBytes + k * UMMA_K * 4);
-              const uint32_t d_small = tmem_base + (uint32_t)(kMainSlots * 64);
-              const uint32_t d_main = tmem_base + (uint32_t)((kit % kMainSlots) * 64);
-              umma_tf32(d_small, adl, bd, idesc, (kit | k) ? 1u : 0u);
-              umma_tf32(d_small, ad, bdl, idesc, 1u);
-              umma_tf32(d_main, ad, bd, idesc, (kit >= kMainSlots || k > 0) ? 1u : 0u);
-            } else {
-              umma_tf32(tmem_d, ad, bd, idesc, (kit | k) ? 1u : 0u);
-            }
+            umma_tf32(tmem_d, ad, bd, idesc, (kit | k) ? 1u : 0u);
           }
           umma_commit(empty_bar + s);                              // frees the smem stage when these MMAs retire
           if (kit == k_iters - 1) umma_commit(tmem_full_bar + acc);  // accumulator complete
         }
         __syncwarp();
       }
+    }
     }
   } else if (X3 && warp >= 6) {
     // ================================ operand splitter (warps 6..9, 3xTF32 mode) ================================
@@ -424,10 +463,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t st_sw = lane & 7;
     const float lo = p.relu ? 0.f : -INFINITY;
     uint32_t chunk_ctr = 0;
+    uint32_t x3_grp = 0;                                   // 3xTF32: partial-slot groups, counted across tiles
     int local = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
       const int acc = X3 ? 0 : (local & 1);
-      const uint32_t aph = X3 ? (local & 1) : ((local >> 1) & 1);
+      const uint32_t aph = (local >> 1) & 1;
       const int n_tile = t % p.n_tiles;
       int mt = t / p.n_tiles;
       const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
@@ -528,28 +568,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t ra[32], rb[32];
       float4 exa[8], mka[8], exb[kAhead ? 8 : 1], mkb[kAhead ? 8 : 1];
       if (kAhead) issue_side(0, exa, mka);             // does not depend on the accumulator: before the wait
-      mbar_wait(tmem_full_bar + acc, aph);
-      tc_fence_after();
       if constexpr (X3) {
-        // add the partial accumulators of the tile (cross-term slot + the main slots that were used)
-        const int n_main = k_iters < kMainSlots ? k_iters : kMainSlots;
+        // fold the finished partial slots into M (round-to-nearest adds); the last partial of the tile is added
+        // on the fly in the chunk loop below.  tm = TMEM address of M for this warp's lanes.
+        const int n_groups = (k_iters + kGroup - 1) / kGroup;
+        for (int g = 0; g < n_groups; ++g, ++x3_grp) {
+          const int pp = x3_grp & 1;
+          mbar_wait(tmem_full_bar + pp, (x3_grp >> 1) & 1);
+          tc_fence_after();
+          const uint32_t tp = tm + (uint32_t)((1 + pp) * BN);
+          if (g < n_groups - 1) {
 #pragma unroll 1
-        for (int ch = 0; ch < n_chunks; ++ch) {
-          tmem_ld32(tm + (uint32_t)(kMainSlots * 64 + ch * 32), ra);
-#pragma unroll 1
-          for (int a = 0; a < n_main; ++a) {
-            tmem_ld32(tm + (uint32_t)(a * 64 + ch * 32), rb);
+            for (int ch = 0; ch < n_chunks; ++ch) {
+              tmem_ld32(tp + (uint32_t)(ch * 32), ra);
+              if (g > 0) {
+                tmem_ld32(tm + (uint32_t)(ch * 32), rb);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+                for (int j = 0; j < 32; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+              }
+              tmem_st32(tm + (uint32_t)(ch * 32), ra);
+            }
+          } else {
+#pragma unroll 1
+            for (int ch = 0; ch < n_chunks; ++ch) {
+              tmem_ld32(tp + (uint32_t)(ch * 32), ra);
+              if (g > 0) {
+                tmem_ld32(tm + (uint32_t)(ch * 32), rb);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+              }
+              if (ch == n_chunks - 1) {                  // slot fully read: hand it back before the slow part
+                tc_fence_before();
+                mbar_arrive(tmem_empty_bar + pp);
+              }
+              process(ra, ch, exa, mka);
+            }
+            continue;
           }
-          if (ch == n_chunks - 1) {
-            tc_fence_before();
-            mbar_arrive(tmem_empty_bar + acc);
-          }
-          process(ra, ch, exa, mka);
+          tc_fence_before();
+          mbar_arrive(tmem_empty_bar + pp);
         }
         continue;
       }
+      mbar_wait(tmem_full_bar + acc, aph);
+      tc_fence_after();
       tmem_ld32_nowait(tm, ra);
 #pragma unroll 1
       for (int ch = 0; ch < n_chunks; ch += 2) {
@@ -839,8 +901,8 @@ int launch_tc3(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
 template <int BN, int EPI>
 int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
                const CUtensorMap& mm, const TcParams& p, bool x3, cudaStream_t s) {
-  if constexpr (BN == 64) {
-    if (x3) return launch_tc3<64, EPI, true>(ma, mb, mc, me, mm, p, s);
+  if constexpr (BN <= 128) {
+    if (x3) return launch_tc3<BN, EPI, true>(ma, mb, mc, me, mm, p, s);
   }
   return launch_tc3<BN, EPI, false>(ma, mb, mc, me, mm, p, s);
 }
@@ -858,10 +920,13 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
   }
 }
 
-// 3xTF32 always runs 64-column tiles: its 512 TMEM columns hold 8 partial accumulators of one tile (see the kernel)
-int tc_bn_for(int ncols, bool x3) { return x3 ? 64 : ((ncols % 256 == 0) ? 256 : (ncols > 64 ? 128 : 64)); }
-// rows of one plane of a prepared (hi / lo split) B matrix: the column count rounded up to whole 64-column tiles
-int tc_rows_pad(int ncols) { return (ncols + 63) / 64 * 64; }
+// 3xTF32 runs tiles of at most 128 columns: TMEM holds the running sum and two partial slots of a tile
+int tc_bn_for(int ncols, bool x3) {
+  if (x3) return ncols > 64 ? 128 : 64;
+  return (ncols % 256 == 0) ? 256 : (ncols > 64 ? 128 : 64);
+}
+// rows of one plane of a prepared (hi / lo split) B matrix: the column count rounded up to whole 3xTF32 tiles
+int tc_rows_pad(int ncols) { return ncols > 64 ? (ncols + 127) / 128 * 128 : 64; }
 
 // out[r][k] = hi(w[r][k]), out[rows_pad + r][k] = lo(w[r][k]); rows in [rows, rows_pad) are zero in both planes
 __global__ void split_hi_lo_kernel(const float* __restrict__ w, float* __restrict__ out, int rows, int rows_pad,
@@ -1067,7 +1132,7 @@ namespace {
 }  // namespace
 
 extern "C" int dd_tcgen05_built(void) { return 1; }
-int tc_rows_pad_public(int ncols) { return (ncols + 63) / 64 * 64; }
+int tc_rows_pad_public(int ncols) { return ncols > 64 ? (ncols + 127) / 128 * 128 : 64; }
 
 // mode: 0 forward, 1 dgrad, 2 wgrad
 bool dd_tc_supports(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
