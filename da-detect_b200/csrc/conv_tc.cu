@@ -419,26 +419,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // A tile rows are fp32 activations: rewrite each element in place as its TF32-exact high part (low 13 mantissa
     // bits cleared) and store the TF32-exact part of the remainder next to it.  Both parts are exactly
     // representable in TF32, so the result does not depend on how the tensor core converts fp32 bit patterns.
-    const int rs = threadIdx.x - 192;                    // one 128-byte tile row per thread
-    uint32_t it = 0;
+    const int rs = threadIdx.x - 192;                    // 0..127; consecutive threads take consecutive 16-byte
+    uint32_t it = 0;                                     // chunks of the tile (element-wise work: conflict-free)
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       for (int kit = 0; kit < k_iters; ++kit, ++it) {
         const int s = it % L::kStages;
         const uint32_t ph = (it / L::kStages) & 1;
         mbar_wait(full_bar + s, ph);
-        const uint32_t a_hi = smem_u32(smem + s * L::kStageBytes) + rs * 128;
+        const uint32_t a_hi = smem_u32(smem + s * L::kStageBytes) + rs * 16;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float v[4];
-          lds128(a_hi + j * 16, v);
+          lds128(a_hi + j * 2048, v);
           float hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             hi[e] = __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u);
             lo[e] = __uint_as_float(__float_as_uint(v[e] - hi[e]) & 0xFFFFE000u);
           }
-          sts128(a_hi + j * 16, hi[0], hi[1], hi[2], hi[3]);
-          sts128(a_hi + kAOff2 + j * 16, lo[0], lo[1], lo[2], lo[3]);
+          sts128(a_hi + j * 2048, hi[0], hi[1], hi[2], hi[3]);
+          sts128(a_hi + kAOff2 + j * 2048, lo[0], lo[1], lo[2], lo[3]);
         }
         fence_async_smem();                               // generic-proxy writes -> visible to the tensor core
         mbar_arrive(split_bar + s);

@@ -2,7 +2,7 @@
 512 ROIs) through the C-ABI conv entry points — forward, dgrad, wgrad — and print ms, TFLOP/s and the
 algorithmic HBM GB/s of each, plus the per-step total weighted by how often the shape occurs.
 
-  python tools/layer_bench.py [simt|tc] [filter-substring]
+  python tools/layer_bench.py [simt|tc|x3] [filter-substring]
 """
 import os
 import sys
@@ -57,7 +57,8 @@ def timed(fn, iters=10, warm=2):
 
 
 def main():
-    impl = o.IMPL_TCGEN05 if (len(sys.argv) < 2 or sys.argv[1] != "simt") else o.IMPL_SIMT
+    arm = sys.argv[1] if len(sys.argv) > 1 else "tc"
+    impl = {"simt": o.IMPL_SIMT, "x3": o.IMPL_TCGEN05_X3}.get(arm, o.IMPL_TCGEN05)
     filt = sys.argv[2] if len(sys.argv) > 2 else ""
     dev = "cuda"
     tot = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
