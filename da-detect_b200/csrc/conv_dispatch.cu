@@ -16,7 +16,7 @@ int dd_tc_conv2d_dgrad(const float*, const float*, const float*, const float*, c
                        int, int, int, int, int, int, float*, int, bool, cudaStream_t);
 int tc_rows_pad_public(int ncols);
 int dd_tc_conv2d_wgrad(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int,
-                       int, void*, cudaStream_t);
+                       int, void*, bool, cudaStream_t);
 bool dd_tc_supports(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
 
 static bool is_tc(int impl) { return impl == DD_IMPL_TCGEN05 || impl == DD_IMPL_TCGEN05_X3; }
@@ -69,7 +69,7 @@ extern "C" int dd_conv2d_wgrad(const float* gy, const float* x, const float* sca
   DD_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0);
   if (is_tc(impl) && dd_tc_supports(2, N, H, W, Cin, Cout, KH, KW, stride, pad))
     return dd_tc_conv2d_wgrad(gy, x, scale, gw, N, H, W, Cin, Cout, KH, KW, stride, pad, accumulate, workspace,
-                              dd::S(stream));
+                              impl == DD_IMPL_TCGEN05_X3, dd::S(stream));
   return dd_simt_conv2d_wgrad(gy, x, scale, gw, N, H, W, Cin, Cout, KH, KW, stride, pad, accumulate, workspace,
                               dd::S(stream));
 }

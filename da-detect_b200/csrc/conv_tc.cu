@@ -686,26 +686,31 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int m, int n) {
   return make_idesc_tf32(m, n) | (1u << 15) | (1u << 16);
 }
 
-template <int BN>
+// X3 (3xTF32): a stage holds [A_hi | A_lo | B_hi | B_lo]; both operands are activations and are split in the kernel.
+template <int BN, bool X3>
 struct WgradSmem {
-  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kStages = X3 ? (BN >= 128 ? 3 : 4) : (BN == 256 ? 4 : 6);
   static constexpr int kABytes = 4 * WG_BOX_BYTES;            // 128 co
   static constexpr int kBBytes = (BN / 32) * WG_BOX_BYTES;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = (X3 ? 2 : 1) * (kABytes + kBBytes);
   static constexpr int kTotal = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, bool X3>
+__global__ void __launch_bounds__(X3 ? NUM_THREADS_X3 : NUM_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_x,
                 const TcWgradParams p) {
-  using L = WgradSmem<BN>;
+  using L = WgradSmem<BN, X3>;
+  constexpr int kALo = X3 ? L::kABytes : 0;                         // A_lo right after A_hi
+  constexpr int kBOff = (X3 ? 2 : 1) * L::kABytes;                  // B_hi
+  constexpr int kBLo = X3 ? L::kBBytes : 0;                         // B_lo right after B_hi
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kStages * L::kStageBytes);
   uint64_t* empty_bar = full_bar + L::kStages;
   uint64_t* tmem_full_bar = empty_bar + L::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* split_bar = tmem_full_bar + 1;                          // [kStages], X3 only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split_bar + L::kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tap = blockIdx.x / p.ci_tiles, ci_tile = blockIdx.x % p.ci_tiles;
@@ -719,6 +724,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
     tma_prefetch_desc(&map_gy);
     tma_prefetch_desc(&map_x);
     for (int s = 0; s < L::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    if (X3) for (int s = 0; s < L::kStages; ++s) mbar_init(split_bar + s, 128);
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -739,8 +745,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
         const int bh = pb % p.tiles_h; pb /= p.tiles_h;
         const int n0 = pb * p.tn, oh0 = bh * p.th, ow0 = bw * p.tw;
         uint8_t* sa = smem + s * L::kStageBytes;
-        uint8_t* sb = sa + L::kABytes;
-        mbar_expect_tx(full_bar + s, L::kStageBytes);
+        uint8_t* sb = sa + kBOff;
+        mbar_expect_tx(full_bar + s, L::kABytes + L::kBBytes);
         // 5-D views {32 ch, W, H, N, channel block}: one instruction lands all [32 pix x 32 ch] column blocks
         tma_load_5d(&map_gy, full_bar + s, sa, 0, ow0, oh0, n0, co0 / 32);
         tma_load_5d(&map_x, full_bar + s, sb, 0, ow0 + kw - p.pad, oh0 + kh - p.pad, n0, ci0 / 32);
@@ -751,21 +757,56 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
     for (int it = 0; it < k_iters; ++it) {
       const int s = it % L::kStages;
       const uint32_t ph = (it / L::kStages) & 1;
-      mbar_wait(full_bar + s, ph);
+      mbar_wait((X3 ? split_bar : full_bar) + s, ph);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint32_t b_addr = a_addr + L::kABytes;
+        const uint32_t b_addr = a_addr + kBOff;
 #pragma unroll
         for (int k = 0; k < WG_KPIX / UMMA_K; ++k) {
           const uint64_t ad = make_mnmajor_sw128_desc(a_addr + k * 1024);
           const uint64_t bd = make_mnmajor_sw128_desc(b_addr + k * 1024);
-          umma_tf32(tmem_base, ad, bd, idesc, (it | k) ? 1u : 0u);
+          if (X3) {                                         // small terms first
+            const uint64_t adl = make_mnmajor_sw128_desc(a_addr + kALo + k * 1024);
+            const uint64_t bdl = make_mnmajor_sw128_desc(b_addr + kBLo + k * 1024);
+            umma_tf32(tmem_base, adl, bd, idesc, (it | k) ? 1u : 0u);
+            umma_tf32(tmem_base, ad, bdl, idesc, 1u);
+            umma_tf32(tmem_base, ad, bd, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, ad, bd, idesc, (it | k) ? 1u : 0u);
+          }
         }
         umma_commit(empty_bar + s);
         if (it == k_iters - 1) umma_commit(tmem_full_bar);
       }
       __syncwarp();
+    }
+  } else if (X3 && warp >= 6) {
+    // operand splitter (3xTF32): both landed tiles -> TF32-exact high parts in place, low parts next to them
+    const int rs = threadIdx.x - 192;
+    for (int it = 0; it < k_iters; ++it) {
+      const int s = it % L::kStages;
+      const uint32_t ph = (it / L::kStages) & 1;
+      mbar_wait(full_bar + s, ph);
+      const uint32_t base = smem_u32(smem + s * L::kStageBytes) + rs * 16;
+#pragma unroll 4
+      for (int j = 0; j < (L::kABytes + L::kBBytes) / 2048; ++j) {
+        const bool is_b = j * 2048 >= L::kABytes;
+        const uint32_t hi_addr = base + (is_b ? kBOff + (j * 2048 - L::kABytes) : j * 2048);
+        const uint32_t lo_addr = hi_addr + (is_b ? kBLo : kALo);
+        float v[4];
+        lds128(hi_addr, v);
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          hi[e] = __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u);
+          lo[e] = __uint_as_float(__float_as_uint(v[e] - hi[e]) & 0xFFFFE000u);
+        }
+        sts128(hi_addr, hi[0], hi[1], hi[2], hi[3]);
+        sts128(lo_addr, lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_async_smem();
+      mbar_arrive(split_bar + s);
     }
   } else {
     // epilogue: BN scale, then fp32 vector reductions straight into gw (split-K partial sums meet in L2; no
@@ -1020,15 +1061,15 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
 }
 
 
-template <int BN>
+template <int BN, bool X3>
 int launch_wgrad(const CUtensorMap& mg, const CUtensorMap& mx, const TcWgradParams& p, dim3 grid, cudaStream_t s) {
-  using L = WgradSmem<BN>;
+  using L = WgradSmem<BN, X3>;
   static bool configured = false;
   if (!configured) {
-    DD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    DD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  wgrad_tc_kernel<BN><<<grid, NUM_THREADS, L::kTotal, s>>>(mg, mx, p);
+  wgrad_tc_kernel<BN, X3><<<grid, X3 ? NUM_THREADS_X3 : NUM_THREADS, L::kTotal, s>>>(mg, mx, p);
   DD_LAUNCHED();
   return 0;
 }
@@ -1205,7 +1246,8 @@ int dd_tc_conv2d_dgrad(const float* gy, const float* w, const float* scale, cons
 }
 
 int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, float* gw, int N, int H, int W, int Cin,
-                       int Cout, int KH, int KW, int stride, int pad, int accumulate, void* workspace, cudaStream_t s) {
+                       int Cout, int KH, int KW, int stride, int pad, int accumulate, void* workspace, bool x3,
+                       cudaStream_t s) {
   (void)workspace;
   const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
   DD_CHECK_ARG((reinterpret_cast<uintptr_t>(gw) & 15) == 0);
@@ -1232,13 +1274,16 @@ int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, floa
   p.tiles_w = (PW + p.tw - 1) / p.tw;
   p.tiles_h = (PH + p.th - 1) / p.th;
   p.pix_blocks = ((PN + p.tn - 1) / p.tn) * p.tiles_h * p.tiles_w;
-  const int BN = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : 32));
+  const int BN = (Cin % 256 == 0 && !x3) ? 256 : (Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : 32));
   p.ci_tiles = (Cin + BN - 1) / BN;
   const int co_tiles = (Cout + BM - 1) / BM;
   // split the pixel range so that about two waves of CTAs exist and every CTA still runs >= 8 K-iterations
   const int tiles = co_tiles * p.ci_tiles * p.taps;
   int splits = (2 * dd::kNumSMs + tiles - 1) / tiles;
   if (splits > (p.pix_blocks + 7) / 8) splits = (p.pix_blocks + 7) / 8;
+  // 3xTF32: the tensor core's accumulator rounds toward zero at every step, so a CTA accumulates at most 64 pixel
+  // blocks (768 steps, ~2e-5 bias) before its partial sum joins the others through round-to-nearest adds in L2
+  if (x3 && splits < (p.pix_blocks + 63) / 64) splits = (p.pix_blocks + 63) / 64;
   if (splits < 1) splits = 1;
   p.blocks_per_split = (p.pix_blocks + splits - 1) / splits;
   splits = (p.pix_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
@@ -1259,9 +1304,13 @@ int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, floa
   }
   dim3 grid(p.ci_tiles * p.taps, co_tiles, splits);
   int rc;
-  if (BN == 256) rc = launch_wgrad<256>(mg, mx, p, grid, s);
-  else if (BN == 128) rc = launch_wgrad<128>(mg, mx, p, grid, s);
-  else if (BN == 64) rc = launch_wgrad<64>(mg, mx, p, grid, s);
-  else rc = launch_wgrad<32>(mg, mx, p, grid, s);
+  if (x3) {
+    if (BN == 128) rc = launch_wgrad<128, true>(mg, mx, p, grid, s);
+    else if (BN == 64) rc = launch_wgrad<64, true>(mg, mx, p, grid, s);
+    else rc = launch_wgrad<32, true>(mg, mx, p, grid, s);
+  } else if (BN == 256) rc = launch_wgrad<256, false>(mg, mx, p, grid, s);
+  else if (BN == 128) rc = launch_wgrad<128, false>(mg, mx, p, grid, s);
+  else if (BN == 64) rc = launch_wgrad<64, false>(mg, mx, p, grid, s);
+  else rc = launch_wgrad<32, false>(mg, mx, p, grid, s);
   return rc;
 }

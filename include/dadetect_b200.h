@@ -133,7 +133,8 @@ int dd_balanced_sample(const int* labels, const int* n_dev, const float* keys, i
 #define DD_IMPL_SIMT 0
 #define DD_IMPL_TCGEN05 1
 /* 2 = tcgen05 "3xTF32": every operand is split into TF32-exact high and low parts inside the kernel and
- * D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi — fp32-grade products on the tensor cores (forward and data gradient). */
+ * D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi — fp32-grade products on the tensor cores (forward, data and weight
+ * gradient). */
 #define DD_IMPL_TCGEN05_X3 2
 #define DD_ACT_NONE 0
 #define DD_ACT_RELU 1

@@ -674,3 +674,8 @@ def test_conv_tcgen05_x3_arm_is_fp32_grade(case):
     gx = o.conv2d_dgrad_raw(gpre, wd, sd, tuple(xd.shape), k, k, stride, pad, addend=_to_nhwc(addend).to(DEV),
                             mask_act=_to_nhwc(act).to(DEV), impl=o.IMPL_TCGEN05_X3)
     close(gx.permute(0, 3, 1, 2).cpu(), (gx_want.detach() + addend.double()) * (act > 0), "dgrad")
+    wr = wt.clone().double().requires_grad_(True)
+    y1 = F.conv2d(x.double(), wr, stride=stride, padding=pad) * scale.double().view(1, -1, 1, 1)
+    (gw_want,) = torch.autograd.grad(y1, (wr,), (go.double() * (want > 0)))
+    gw = o.conv2d_wgrad_raw(gpre, xd, sd, cout, k, k, stride, pad, impl=o.IMPL_TCGEN05_X3)
+    close(gw.permute(0, 3, 1, 2).cpu(), gw_want, "wgrad")
