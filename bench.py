@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dense", default=os.environ.get("DADETECT_DENSE", "auto"), choices=["auto", "simt", "tcgen05", "tcgen05x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-x3", action="store_true", help="skip the extra measurement of the fp32-grade (3xTF32) arm")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly (no whole-step CUDA graph)")
     args = ap.parse_args()
     if os.environ.get("DD_BENCH_WATCHDOG"):          # developer aid: dump all stacks and exit if the run stalls
@@ -261,7 +262,7 @@ def main():
 
     def step_resident(s):
         img, tg = resident[s % n_host]
-        last_losses["d"] = trainer.step(img, tg)
+        last_losses["d"] = trainer.step(img, tg)          # `trainer` is re-bound for the fp32-grade arm below
 
     loss_host = torch.empty(16, dtype=torch.float32).pin_memory()
 
@@ -338,6 +339,28 @@ def main():
         "gpu_launches": launches,
         "roofline": roofline,
     }
+    # ---- the fp32-grade tensor-core arm (3xTF32: losses AND gradients within the fp32 tolerances of the oracle,
+    # tests/test_gpu_model.py) on the same workload, reported beside the default TF32 arm
+    if dense == "tcgen05" and not args.no_x3:
+        import gc
+        trainer.step_graphs = None
+        trainer = model = None
+        prefetch = None
+        gc.collect()
+        torch.cuda.empty_cache()
+        ops.set_default_impl(ops.IMPL_TCGEN05_X3)
+        model3 = build_detection_model(cfg).to(dev)
+        model3.load_state_dict(make_state_dict(shapes), strict=False)
+        model3.train()
+        trainer = FlatSGDTrainer(model3, cfg, world_size=world)
+        if not args.no_graphs:
+            trainer.enable_step_graph(True)
+        for s_ in range(4):
+            step_resident(s_)
+        ms3 = timed(step_resident, max(4, args.steps // 2))
+        line["fp32_grade_arm"] = {"dense_impl": "tcgen05x3", "dtype": "tf32x3 (operands split hi/lo, fp32-grade)",
+                                  "value": images_per_step * 1000.0 / ms3, "unit": "images/s", "ms_per_step": ms3,
+                                  "parity": "losses and gradients within the fp32 tolerances (1e-4 on losses) of the CPU oracle"}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg)
