@@ -279,5 +279,49 @@ def main():
     print("fixture bytes:", sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)))
 
 
+
+
+# ----------------------------------------------------------------------------- eval-mode golden (BASELINE configs[0])
+EVAL_YAML = "e2e_faster_rcnn_R_50_C4_1x.yaml"
+EVAL_HW = (800, 800)
+EVAL_SCALE = {"roi_heads.box.predictor.cls_score.weight": 40.0, "roi_heads.box.predictor.bbox_pred.weight": 40.0}
+
+
+def eval_state_dict(shapes):
+    """make_state_dict with the predictor weights amplified: with the stock std 0.01 / 0.001 initialisers every
+    class score sits at 1/81 and no detection would pass SCORE_THRESH — nothing would be tested."""
+    sd = make_state_dict(shapes)
+    for k, f in EVAL_SCALE.items():
+        sd[k] = sd[k] * f
+    return sd
+
+
+def make_eval():
+    """The reference's OWN eval-mode forward (RPNPostProcessor test mode + box_head PostProcessor) on CPU for the
+    plain R-50-C4 Faster R-CNN YAML (81 classes, DA off) on 2 synthetic 800x800 images — the one configuration the
+    unpatched reference model can run end to end on CPU (BASELINE.json configs[0])."""
+    cfg = rh.reference_cfg(EVAL_YAML, [])
+    sd = eval_state_dict(orc.param_shapes(cfg))
+    model = rh.build_reference_model(cfg, sd)
+    model.eval()
+    images, _ = make_batch(2, EVAL_HW[0], EVAL_HW[1], num_classes=81, boxes_per_image=1, seed=4242)
+    with torch.no_grad():
+        out = model(images)
+    fx = dict(yaml=EVAL_YAML, height=EVAL_HW[0], width=EVAL_HW[1], seed=4242, scale=EVAL_SCALE, nms="cpu_ge",
+              detections=[dict(boxes=o.bbox.clone(), scores=o.get_field("scores").clone(),
+                               labels=o.get_field("labels").clone()) for o in out])
+    torch.save(fx, os.path.join(OUT, "eval_faster_rcnn_c4.pt"))
+    return fx
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "eval":       # only the eval-mode fixture
+        assert rh.available(), "reference not mounted"
+        torch.set_num_threads(os.cpu_count())
+        fx = make_eval()
+        for d in fx["detections"]:
+            print(len(d["scores"]), "detections; labels", sorted(set(d["labels"].tolist()))[:12], "scores",
+                  [round(float(v), 4) for v in d["scores"][:6]])
+    else:
+        main()
+        make_eval()

@@ -236,3 +236,40 @@ def test_whole_step_graph_matches_eager_training():
             assert abs(a[k] - b[k]) <= 2e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
     rel = float((p0 - p1).norm() / p0.norm())
     assert rel < 1e-5, rel
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("dense", ["simt", "tcgen05x3"])
+def test_eval_mode_matches_real_reference_golden(dense):
+    """BASELINE configs[0]: plain R-50-C4 Faster R-CNN (81 classes, DA off), eval mode, 2 synthetic 800x800 images.
+    The golden detections come from the REAL reference model run on CPU (oracle/make_golden.py eval); this is the
+    one configuration the reference can run end to end without a GPU.  RPN test-mode post-processing, ROIAlign,
+    res5, softmax, per-class decode + NMS(0.5) and the top-100 cut all run on our kernels."""
+    from dadetect_b200 import ops
+    from dadetect_b200.config import get_cfg_defaults
+    from dadetect_b200.utils.synthetic import make_batch, make_state_dict
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "eval_faster_rcnn_c4.pt"), weights_only=False)
+    ops.set_default_impl(ops.IMPL_SIMT if dense == "simt" else ops.IMPL_TCGEN05_X3)
+    cfg = get_cfg_defaults()
+    cfg.merge_from_file(os.path.join(ROOT, "configs", fx["yaml"]))
+    sd = make_state_dict(orc.param_shapes(cfg))
+    for k, f in fx["scale"].items():
+        sd[k] = sd[k] * f
+    images, _ = make_batch(2, fx["height"], fx["width"], num_classes=81, boxes_per_image=1, seed=fx["seed"])
+    dev = torch.device("cuda")
+    model = build(cfg, sd, dev)
+    model.eval()
+    with torch.no_grad():
+        out = model(images.to(dev))
+    assert len(out) == len(fx["detections"])
+    for got, want in zip(out, fx["detections"]):
+        gb, gs, gl = got.bbox.cpu(), got.get_field("scores").cpu(), got.get_field("labels").cpu()
+        wb, ws, wl = want["boxes"], want["scores"], want["labels"]
+        assert abs(len(gs) - len(ws)) <= 2
+        # match every reference detection to one of ours: same class, same box, same score.  The top-100 cut is
+        # a threshold on nearly equal scores, so a couple of detections at the cut may differ.
+        matched = 0
+        for i in range(len(ws)):
+            cand = (gl == wl[i]) & ((gb - wb[i]).abs().max(dim=1)[0] < 0.05) & ((gs - ws[i]).abs() < 2e-4)
+            matched += int(cand.any())
+        assert matched >= len(ws) - 3, (matched, len(ws))
