@@ -658,7 +658,7 @@ struct TcWgradParams {
   int Cout, Cin, taps, KW, pad;
   int tn, th, tw;          // pixel block = tn*th*tw == 32
   int tiles_h, tiles_w, pix_blocks, blocks_per_split;
-  int ci_tiles;
+  int ci_tiles, co_tiles, splits;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -696,6 +696,9 @@ struct WgradSmem {
   static constexpr int kTotal = kStages * kStageBytes + 1024 + 256;
 };
 
+// Persistent: grid = min(#work items, #SMs); a work item = (filter tap, ci tile, co tile, pixel split); the items
+// are walked in a static round-robin by every role.  Two TMEM accumulators (ping-pong) let the L2 reductions of
+// item i overlap the main loop of item i+1; the TMA producer runs ahead across items through the smem ring.
 template <int BN, bool X3>
 __global__ void __launch_bounds__(X3 ? NUM_THREADS_X3 : NUM_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_x,
@@ -704,31 +707,40 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
   constexpr int kALo = X3 ? L::kABytes : 0;                         // A_lo right after A_hi
   constexpr int kBOff = (X3 ? 2 : 1) * L::kABytes;                  // B_hi
   constexpr int kBLo = X3 ? L::kBBytes : 0;                         // B_lo right after B_hi
+  constexpr int kAccCols = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kStages * L::kStageBytes);
   uint64_t* empty_bar = full_bar + L::kStages;
-  uint64_t* tmem_full_bar = empty_bar + L::kStages;
-  uint64_t* split_bar = tmem_full_bar + 1;                          // [kStages], X3 only
+  uint64_t* tmem_full_bar = empty_bar + L::kStages;                 // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                     // [2]
+  uint64_t* split_bar = tmem_empty_bar + 2;                         // [kStages], X3 only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split_bar + L::kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tap = blockIdx.x / p.ci_tiles, ci_tile = blockIdx.x % p.ci_tiles;
-  const int co0 = blockIdx.y * BM, ci0 = ci_tile * BN;
-  const int kh = tap / p.KW, kw = tap % p.KW;
-  const int pb_begin = blockIdx.z * p.blocks_per_split;
-  const int pb_end = min(p.pix_blocks, pb_begin + p.blocks_per_split);
-  const int k_iters = max(pb_end - pb_begin, 0);
+  const int total_items = p.taps * p.ci_tiles * p.co_tiles * p.splits;
+
+  // item -> (tap, ci tile, co tile, split): consecutive items share the pixel range (L2 reuse of gy / x tiles)
+  auto decode = [&](int w, int& tap, int& ci0, int& co0, int& pb_begin, int& k_iters) {
+    const int xi = w % (p.taps * p.ci_tiles); w /= (p.taps * p.ci_tiles);
+    const int co_tile = w % p.co_tiles;
+    const int split = w / p.co_tiles;
+    tap = xi / p.ci_tiles;
+    ci0 = (xi % p.ci_tiles) * BN;
+    co0 = co_tile * BM;
+    pb_begin = split * p.blocks_per_split;
+    k_iters = max(min(p.pix_blocks, pb_begin + p.blocks_per_split) - pb_begin, 0);
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_gy);
     tma_prefetch_desc(&map_x);
     for (int s = 0; s < L::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     if (X3) for (int s = 0; s < L::kStages; ++s) mbar_init(split_bar + s, 128);
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * kAccCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -736,93 +748,126 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % L::kStages;
-        const uint32_t ph = (it / L::kStages) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        int pb = pb_begin + it;
-        const int bw = pb % p.tiles_w; pb /= p.tiles_w;
-        const int bh = pb % p.tiles_h; pb /= p.tiles_h;
-        const int n0 = pb * p.tn, oh0 = bh * p.th, ow0 = bw * p.tw;
-        uint8_t* sa = smem + s * L::kStageBytes;
-        uint8_t* sb = sa + kBOff;
-        mbar_expect_tx(full_bar + s, L::kABytes + L::kBBytes);
-        // 5-D views {32 ch, W, H, N, channel block}: one instruction lands all [32 pix x 32 ch] column blocks
-        tma_load_5d(&map_gy, full_bar + s, sa, 0, ow0, oh0, n0, co0 / 32);
-        tma_load_5d(&map_x, full_bar + s, sb, 0, ow0 + kw - p.pad, oh0 + kh - p.pad, n0, ci0 / 32);
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        int tap, ci0, co0, pb_begin, k_iters;
+        decode(w, tap, ci0, co0, pb_begin, k_iters);
+        const int kh = tap / p.KW, kw = tap % p.KW;
+        for (int kit = 0; kit < k_iters; ++kit, ++it) {
+          const int s = it % L::kStages;
+          const uint32_t ph = (it / L::kStages) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          int pb = pb_begin + kit;
+          const int bw = pb % p.tiles_w; pb /= p.tiles_w;
+          const int bh = pb % p.tiles_h; pb /= p.tiles_h;
+          const int n0 = pb * p.tn, oh0 = bh * p.th, ow0 = bw * p.tw;
+          uint8_t* sa = smem + s * L::kStageBytes;
+          uint8_t* sb = sa + kBOff;
+          mbar_expect_tx(full_bar + s, L::kABytes + L::kBBytes);
+          // 5-D views {32 ch, W, H, N, channel block}: one instruction lands all [32 pix x 32 ch] column blocks
+          tma_load_5d(&map_gy, full_bar + s, sa, 0, ow0, oh0, n0, co0 / 32);
+          tma_load_5d(&map_x, full_bar + s, sb, 0, ow0 + kw - p.pad, oh0 + kh - p.pad, n0, ci0 / 32);
+        }
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_tf32_mn(BM, BN);
-    for (int it = 0; it < k_iters; ++it) {
-      const int s = it % L::kStages;
-      const uint32_t ph = (it / L::kStages) & 1;
-      mbar_wait((X3 ? split_bar : full_bar) + s, ph);
+    uint32_t it = 0;
+    int local = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      int tap, ci0, co0, pb_begin, k_iters;
+      decode(w, tap, ci0, co0, pb_begin, k_iters);
+      if (k_iters == 0) continue;                         // (empty split: nothing to accumulate or reduce)
+      const int acc = local & 1;
+      mbar_wait(tmem_empty_bar + acc, ((local >> 1) & 1) ^ 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-        const uint32_t b_addr = a_addr + kBOff;
+      const uint32_t d = tmem_base + (uint32_t)(acc * kAccCols);
+      for (int kit = 0; kit < k_iters; ++kit, ++it) {
+        const int s = it % L::kStages;
+        const uint32_t ph = (it / L::kStages) & 1;
+        mbar_wait((X3 ? split_bar : full_bar) + s, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+          const uint32_t b_addr = a_addr + kBOff;
 #pragma unroll
-        for (int k = 0; k < WG_KPIX / UMMA_K; ++k) {
-          const uint64_t ad = make_mnmajor_sw128_desc(a_addr + k * 1024);
-          const uint64_t bd = make_mnmajor_sw128_desc(b_addr + k * 1024);
-          if (X3) {                                         // small terms first
-            const uint64_t adl = make_mnmajor_sw128_desc(a_addr + kALo + k * 1024);
-            const uint64_t bdl = make_mnmajor_sw128_desc(b_addr + kBLo + k * 1024);
-            umma_tf32(tmem_base, adl, bd, idesc, (it | k) ? 1u : 0u);
-            umma_tf32(tmem_base, ad, bdl, idesc, 1u);
-            umma_tf32(tmem_base, ad, bd, idesc, 1u);
-          } else {
-            umma_tf32(tmem_base, ad, bd, idesc, (it | k) ? 1u : 0u);
+          for (int k = 0; k < WG_KPIX / UMMA_K; ++k) {
+            const uint64_t ad = make_mnmajor_sw128_desc(a_addr + k * 1024);
+            const uint64_t bd = make_mnmajor_sw128_desc(b_addr + k * 1024);
+            if (X3) {                                         // small terms first
+              const uint64_t adl = make_mnmajor_sw128_desc(a_addr + kALo + k * 1024);
+              const uint64_t bdl = make_mnmajor_sw128_desc(b_addr + kBLo + k * 1024);
+              umma_tf32(d, adl, bd, idesc, (kit | k) ? 1u : 0u);
+              umma_tf32(d, ad, bdl, idesc, 1u);
+              umma_tf32(d, ad, bd, idesc, 1u);
+            } else {
+              umma_tf32(d, ad, bd, idesc, (kit | k) ? 1u : 0u);
+            }
           }
+          umma_commit(empty_bar + s);
+          if (kit == k_iters - 1) umma_commit(tmem_full_bar + acc);
         }
-        umma_commit(empty_bar + s);
-        if (it == k_iters - 1) umma_commit(tmem_full_bar);
+        __syncwarp();
       }
-      __syncwarp();
+      ++local;
     }
   } else if (X3 && warp >= 6) {
     // operand splitter (3xTF32): both landed tiles -> TF32-exact high parts in place, low parts next to them
     const int rs = threadIdx.x - 192;
-    for (int it = 0; it < k_iters; ++it) {
-      const int s = it % L::kStages;
-      const uint32_t ph = (it / L::kStages) & 1;
-      mbar_wait(full_bar + s, ph);
-      const uint32_t base = smem_u32(smem + s * L::kStageBytes) + rs * 16;
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      int tap, ci0, co0, pb_begin, k_iters;
+      decode(w, tap, ci0, co0, pb_begin, k_iters);
+      for (int kit = 0; kit < k_iters; ++kit, ++it) {
+        const int s = it % L::kStages;
+        const uint32_t ph = (it / L::kStages) & 1;
+        mbar_wait(full_bar + s, ph);
+        const uint32_t base = smem_u32(smem + s * L::kStageBytes) + rs * 16;
 #pragma unroll 4
-      for (int j = 0; j < (L::kABytes + L::kBBytes) / 2048; ++j) {
-        const bool is_b = j * 2048 >= L::kABytes;
-        const uint32_t hi_addr = base + (is_b ? kBOff + (j * 2048 - L::kABytes) : j * 2048);
-        const uint32_t lo_addr = hi_addr + (is_b ? kBLo : kALo);
-        float v[4];
-        lds128(hi_addr, v);
-        float hi[4], lo[4];
+        for (int j = 0; j < (L::kABytes + L::kBBytes) / 2048; ++j) {
+          const bool is_b = j * 2048 >= L::kABytes;
+          const uint32_t hi_addr = base + (is_b ? kBOff + (j * 2048 - L::kABytes) : j * 2048);
+          const uint32_t lo_addr = hi_addr + (is_b ? kBLo : kALo);
+          float v[4];
+          lds128(hi_addr, v);
+          float hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          hi[e] = __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u);
-          lo[e] = __uint_as_float(__float_as_uint(v[e] - hi[e]) & 0xFFFFE000u);
+          for (int e = 0; e < 4; ++e) {
+            hi[e] = __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u);
+            lo[e] = __uint_as_float(__float_as_uint(v[e] - hi[e]) & 0xFFFFE000u);
+          }
+          sts128(hi_addr, hi[0], hi[1], hi[2], hi[3]);
+          sts128(lo_addr, lo[0], lo[1], lo[2], lo[3]);
         }
-        sts128(hi_addr, hi[0], hi[1], hi[2], hi[3]);
-        sts128(lo_addr, lo[0], lo[1], lo[2], lo[3]);
+        fence_async_smem();
+        mbar_arrive(split_bar + s);
       }
-      fence_async_smem();
-      mbar_arrive(split_bar + s);
     }
   } else {
     // epilogue: BN scale, then fp32 vector reductions straight into gw (split-K partial sums meet in L2; no
     // partial buffers, no reduce pass)
     const int quarter = warp & 3;
-    const int co = co0 + quarter * 32 + lane;
     const size_t ldp = (size_t)p.taps * p.Cin;
-    float* dst_row = p.gw + (size_t)co * ldp + (size_t)tap * p.Cin + ci0;
-    const float sc = (p.scale && co < p.Cout) ? __ldg(p.scale + co) : 1.f;
-    if (k_iters > 0) {
-      mbar_wait(tmem_full_bar, 0);
+    int local = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      int tap, ci0, co0, pb_begin, k_iters;
+      decode(w, tap, ci0, co0, pb_begin, k_iters);
+      if (k_iters == 0) continue;
+      const int acc = local & 1;
+      const int co = co0 + quarter * 32 + lane;
+      float* dst_row = p.gw + (size_t)co * ldp + (size_t)tap * p.Cin + ci0;
+      const float sc = (p.scale && co < p.Cout) ? __ldg(p.scale + co) : 1.f;
+      mbar_wait(tmem_full_bar + acc, (local >> 1) & 1);
       tc_fence_after();
+      const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kAccCols);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld32(tm + (uint32_t)c0, r);
+        if (c0 + 32 >= BN) {                              // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tmem_empty_bar + acc);
+        }
         if (co < p.Cout && ci0 + c0 < p.Cin) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
@@ -830,13 +875,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
                        __uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
         }
       }
+      ++local;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * kAccCols);
   }
 }
 
@@ -1277,10 +1323,21 @@ int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, floa
   const int BN = (Cin % 256 == 0 && !x3) ? 256 : (Cin % 128 == 0 ? 128 : (Cin % 64 == 0 ? 64 : 32));
   p.ci_tiles = (Cin + BN - 1) / BN;
   const int co_tiles = (Cout + BM - 1) / BM;
-  // split the pixel range so that about two waves of CTAs exist and every CTA still runs >= 8 K-iterations
+  // split the pixel range so that the persistent CTAs see whole rounds of work items (items = tiles x splits as
+  // close as possible to a multiple of the SM count, 2-4 rounds) and every item still runs >= 8 K-iterations
   const int tiles = co_tiles * p.ci_tiles * p.taps;
-  int splits = (2 * dd::kNumSMs + tiles - 1) / tiles;
-  if (splits > (p.pix_blocks + 7) / 8) splits = (p.pix_blocks + 7) / 8;
+  int splits = 1;
+  {
+    const int max_splits = (p.pix_blocks + 7) / 8;
+    double best = -1.0;
+    for (int cand = 1; cand <= max_splits && (long long)cand * tiles <= 6ll * dd::kNumSMs; ++cand) {
+      const long long items = (long long)cand * tiles;
+      const long long rounds = (items + dd::kNumSMs - 1) / dd::kNumSMs;
+      double eff = (double)items / (double)(rounds * dd::kNumSMs);
+      if (rounds < 2) eff *= 0.9;                       // one round: no overlap of reductions with the next item
+      if (eff > best + 1e-9) { best = eff; splits = cand; }
+    }
+  }
   // 3xTF32: the tensor core's accumulator rounds toward zero at every step, so a CTA accumulates at most 64 pixel
   // blocks (768 steps, ~2e-5 bias) before its partial sum joins the others through round-to-nearest adds in L2
   if (x3 && splits < (p.pix_blocks + 63) / 64) splits = (p.pix_blocks + 63) / 64;
@@ -1302,7 +1359,10 @@ int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, floa
     cuuint32_t box[5] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn, (cuuint32_t)(BN / 32)};
     if (encode_map(&mx, x, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
   }
-  dim3 grid(p.ci_tiles * p.taps, co_tiles, splits);
+  p.co_tiles = co_tiles; p.splits = splits;
+  const long long items = (long long)p.ci_tiles * p.taps * co_tiles * splits;
+  DD_CHECK_ARG(items < (1ll << 31));
+  dim3 grid((unsigned)(items < dd::kNumSMs ? items : dd::kNumSMs));
   int rc;
   if (x3) {
     if (BN == 128) rc = launch_wgrad<128, true>(mg, mx, p, grid, s);
