@@ -1,18 +1,22 @@
-"""Extract the judged metrics from an .ncu-rep (ncu --set full) into a small text table.
-usage: python tools/ncu_extract.py gpurun_out/prof.ncu-rep > profiles/xxx.txt"""
-import csv, io, subprocess, sys
-raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, data = rows[0], rows[1], rows[2:]
-keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__cycles_active",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active",
-        "sm__inst_executed_pipe_tensor", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
-        "launch__occupancy_limit", "smsp__cycles_active.avg", "sm__pipe_fma_cycles_active"]
-cols = [i for i, h in enumerate(hdr) if any(k in h for k in keys)]
-name_i = hdr.index("Kernel Name")
-for r in data:
-    print("== " + r[name_i][:110])
-    for i in cols:
-        print("   %-95s %s %s" % (hdr[i][:95], r[i], units[i]))
+"""Summarise the first kernel of an `ncu --set full` report: duration, DRAM traffic, tensor-pipe activity, launch shape.
+
+  python tools/ncu_extract.py report.ncu-rep [header text ...] > profiles/xyz.txt
+"""
+import csv
+import subprocess
+import sys
+
+KEYS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.avg.per_second", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "lts__t_bytes.sum"]
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units, vals = rows[0], rows[1], rows[2]
+for line in sys.argv[2:]:
+    print("# " + line)
+for h, u, v in zip(hdr, units, vals):
+    if h in KEYS:
+        print("%-72s %-16s %s" % (h, u, v))
