@@ -273,3 +273,55 @@ def test_eval_mode_matches_real_reference_golden(dense):
             cand = (gl == wl[i]) & ((gb - wb[i]).abs().max(dim=1)[0] < 0.05) & ((gs - ws[i]).abs() < 2e-4)
             matched += int(cand.any())
         assert matched >= len(ws) - 3, (matched, len(ws))
+
+
+@pytest.mark.timeout(1200)
+@pytest.mark.parametrize("dense", ["simt", "tcgen05x3"])
+def test_three_sgd_iterations_match_oracle(dense):
+    """Row a16 (the loop tail): three consecutive iterations of do_da_train (engine/trainer.py:196-242) — forward,
+    backward, SGD with momentum 0.9, weight decay on weights only, bias lr x2 (solver/build.py:7-20) — on the GPU
+    through FlatSGDTrainer against the CPU oracle + torch.optim.SGD with the reference's parameter groups, the
+    oracle's random draws replayed every iteration.  Losses must stay within 1e-4 / 2e-4 / 4e-4 (errors compound
+    through the updated weights); the final parameters must agree."""
+    from dadetect_b200 import ops
+    from dadetect_b200.engine import FlatSGDTrainer
+    from dadetect_b200.utils.random_source import ReplaySource
+    ops.set_default_impl(ops.IMPL_SIMT if dense == "simt" else ops.IMPL_TCGEN05_X3)
+    cfg, sd, images, targets, hw = scenario("da_img_ins_cst")
+    cfg.merge_from_list(["SOLVER.BASE_LR", 0.002])
+    S = cfg.SOLVER
+    # ---- oracle side
+    P = {k: v.clone().requires_grad_(orc.is_trainable(k)) for k, v in sd.items()}
+    groups = []
+    for k, p in P.items():
+        if not p.requires_grad:
+            continue
+        bias = "bias" in k
+        groups.append({"params": [p], "lr": S.BASE_LR * (S.BIAS_LR_FACTOR if bias else 1.0),
+                       "weight_decay": S.WEIGHT_DECAY_BIAS if bias else S.WEIGHT_DECAY})
+    opt = torch.optim.SGD(groups, S.BASE_LR, momentum=S.MOMENTUM)
+    # ---- GPU side
+    dev = torch.device("cuda")
+    model = build(cfg, sd, dev)
+    trainer = FlatSGDTrainer(model, cfg, world_size=1)
+    torch.manual_seed(31)
+    for it, tol in enumerate((1e-4, 2e-4, 4e-4)):
+        imgs = images + 0.5 * it                              # a different batch every iteration
+        rec = orc.RecordingHooks()
+        want = orc.forward_train(P, cfg, imgs, targets, hooks=rec, nms_strict=True)
+        opt.zero_grad()
+        sum(want.values()).backward()
+        opt.step()
+        model.set_random_source(ReplaySource(rec.perms, rec.masks))
+        got = trainer.step(imgs.to(dev), to_boxlists(targets, hw, dev))
+        for k in want:
+            g, w = float(got[k]), float(want[k])
+            assert abs(g - w) <= tol * max(abs(w), 0.05), (it, k, g, w)
+    named = dict(model.named_parameters())
+    num = den = 0.0
+    for k, p in P.items():
+        if p.requires_grad:
+            a, b = named[k].detach().cpu().double(), p.detach().double()
+            num += float((a - b).pow(2).sum())
+            den += float((b - sd[k].double()).pow(2).sum())      # relative to how far the weights moved
+    assert (num / max(den, 1e-30)) ** 0.5 < 2e-2, (num, den)
