@@ -153,8 +153,10 @@ class FlatSGDTrainer(object):
         from ..structures import BoxList, cache_source_flags, is_source_image
         from ..structures.image_list import ImageList
         tensors = images.tensors if isinstance(images, ImageList) else images
-        if not torch.is_tensor(tensors) or self.model.da_heads_triplet or not self.model.roi_heads:
-            return None                  # triplet modes still read sizes on the host: eager path
+        if not torch.is_tensor(tensors) or not self.model.roi_heads:
+            return None
+        if self.model.da_heads_triplet and self.model.da_heads_triplet.host_reads_needed():
+            return None                  # an adaptive margin below its maximum reads the previous loss on the host
         cache_source_flags(targets)
         key = (tuple(tensors.shape),) + tuple((len(t), bool(is_source_image(t)), tuple(t.size)) for t in targets)
         ent = self.step_graphs.get(key)

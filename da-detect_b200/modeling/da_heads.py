@@ -184,7 +184,16 @@ class DomainAdaptationModule_triplet(_Base):
             return ops.adv_grl_weight(loss, ADV_BCE, lam, lam_adv, D.DA_ADV_GRL_THRESHOLD)
         return torch.full((1,), -1.0 * lam, dtype=torch.float32, device=loss.device)
 
-    def forward(self, img_features, pooled_ins, dom, n_src, pooled_set, img_fea_set, targets):
+    def host_reads_needed(self):
+        """The adaptive image margin consults the previous step's loss on the host while it is below its maximum
+        (da_heads.py:236-252); with the stock YAML values (margin == max margin) it never does."""
+        D = self.cfg.MODEL.DA_HEADS
+        return self.triplet_img_weight > 0 and int(D.TRIPLET_MARGIN_IMG) != int(D.TRIPLET_MAX_MARGIN)
+
+    def forward(self, img_features, pooled_ins, dom, n_src, pooled_set, img_fea_set, targets, row_valid=None, seg=None,
+                set_valid=None):
+        """row_valid / set_valid: validity of the fixed-capacity ROI slots of `pooled_ins` / of each member of
+        `pooled_set`; seg: cached per-image domain labels (all optional, supplied by the sync-free path)."""
         if not self.training:
             return {}
         D = self.cfg.MODEL.DA_HEADS
@@ -194,7 +203,16 @@ class DomainAdaptationModule_triplet(_Base):
             s, p, n = pooled_set
             self.margin_ins = self._margin(self.margin_ins, self.prev_ins, False, 0.001, D.TRIPLET_MAX_MARGIN,
                                            D.TRIPLET_MARGIN_INS)
-            l = ops.triplet_margin_loss(s, p, n, self.margin_ins, s.shape[0], s.shape[1], 1)
+            if set_valid is not None:
+                # slots that hold no ROI: anchor = positive and a far-away negative put the hinge at exactly zero
+                # (no loss, no gradient); the mean is rescaled to the rows that exist
+                v = (set_valid[0] & set_valid[1] & set_valid[2]).bool().unsqueeze(1)
+                zero = torch.zeros_like(s[:1])
+                s, p, n = torch.where(v, s, zero), torch.where(v, p, zero), torch.where(v, n, zero + 1.0e3)
+                l = ops.triplet_margin_loss(s, p, n, self.margin_ins, s.shape[0], s.shape[1], 1)
+                l = l * (float(s.shape[0]) / v.sum().to(torch.float32))
+            else:
+                l = ops.triplet_margin_loss(s, p, n, self.margin_ins, s.shape[0], s.shape[1], 1)
             losses["triplet_loss_instance"] = self.triplet_ins_weight * l
             self.prev_ins = l.detach()
         if self.triplet_img_weight > 0:                       # Domainlevel_Img_component
@@ -208,19 +226,19 @@ class DomainAdaptationModule_triplet(_Base):
         if self.img_weight > 0:                               # DA_Img_component
             wdev = torch.empty(1, dtype=torch.float32, device=feat.device)
             da_img = self.imghead(ops.gradient_scalar_dev(feat, wdev))
-            l_img = da_img_loss(da_img, targets)
+            l_img = da_img_loss(da_img, targets, seg)
             wdev.copy_(self._grl_weight(l_img, D.DA_IMG_GRL_WEIGHT, D.DA_IMG_advGRL_WEIGHT))
             losses["loss_da_image"] = self.img_weight * l_img
         if self.ins_weight > 0:                               # DA_Ins_component
             with torch.no_grad():
-                cur = da_ins_loss(self.inshead(pooled_ins.detach()), dom)
+                cur = da_ins_loss(self.inshead(pooled_ins.detach(), row_valid), dom, row_valid)
             w_ins = self._grl_weight(cur, D.DA_INS_GRL_WEIGHT, D.DA_INS_advGRL_WEIGHT)
-            da_ins = self.inshead(ops.gradient_scalar_dev(pooled_ins, w_ins))
-            losses["loss_da_instance"] = self.ins_weight * da_ins_loss(da_ins, dom)
+            da_ins = self.inshead(ops.gradient_scalar_dev(pooled_ins, w_ins), row_valid)
+            losses["loss_da_instance"] = self.ins_weight * da_ins_loss(da_ins, dom, row_valid)
         if self.cst_weight > 0:                               # Consistency_component
             img_c = self.imghead(ops.gradient_scalar(feat, 1.0 * D.DA_IMG_GRL_WEIGHT))
-            ins_c = self.inshead(ops.gradient_scalar(pooled_ins, 1.0 * D.DA_INS_GRL_WEIGHT))
-            l_cst = ops.consistency_loss(img_c.reshape(img_c.shape[0], -1), ins_c.reshape(-1), n_src)
+            ins_c = self.inshead(ops.gradient_scalar(pooled_ins, 1.0 * D.DA_INS_GRL_WEIGHT), row_valid)
+            l_cst = ops.consistency_loss(img_c.reshape(img_c.shape[0], -1), ins_c.reshape(-1), n_src, row_valid)
             losses["loss_da_consistency"] = self.cst_weight * l_cst
         return losses
 

@@ -120,12 +120,31 @@ class GeneralizedRCNN(nn.Module):
         props, proposal_losses = self.rpn.forward_static(images, features, targets, (logits, deltas), meta)
         losses = {}
         box = self.roi_heads.box
+        B = box.loss_evaluator.batch
+        if self.da_heads_triplet:
+            # generalized_rcnn.py:88-122 — exactly one image per domain per rank: [source, target, auxiliary]
+            ori_features, ori_targets = [feat[0:2]], targets[0:2]
+            detector_losses, pooled, dom, row_valid = box.forward_static(ori_features, props.slice(0, 2), ori_targets)
+            pooled_set, set_valid = [0, 0, 0], None
+            if self.Aligned:                             # :109-114 — all three with the TARGET image's proposals
+                pooled_set, set_valid = [], []
+                p1 = props.slice(1, 2)
+                for i in range(3):
+                    _, pooled_i, _, valid_i = box.forward_static([feat[i:i + 1]], p1, [targets[i]])
+                    pooled_set.append(pooled_i)
+                    set_valid.append(valid_i)
+            img_set = [feat[0:1], feat[1:2], feat[2:3]]
+            da_losses = self.da_heads_triplet(ori_features, pooled, dom, B, pooled_set, img_set, ori_targets,
+                                              row_valid=row_valid, seg=meta["seg"][0:2], set_valid=set_valid)
+            losses.update(detector_losses)
+            losses.update(proposal_losses)
+            losses.update(da_losses)
+            return losses
         detector_losses, pooled, dom, row_valid = box.forward_static(features, props, targets)
         losses.update(detector_losses)
         losses.update(proposal_losses)
         if self.da_heads:
-            losses.update(self.da_heads(features, pooled, dom, box.loss_evaluator.batch, targets, row_valid=row_valid,
-                                        seg=meta["seg"]))
+            losses.update(self.da_heads(features, pooled, dom, B, targets, row_valid=row_valid, seg=meta["seg"]))
         return losses
 
     def enable_cuda_graphs(self, flag=True):
@@ -152,7 +171,7 @@ class GeneralizedRCNN(nn.Module):
         with section("trunk_fwd"):
             x = ops._chk(images.tensors, name="images")            # NCHW; the stem consumes it directly
             feat, logits, deltas = self.segments.run("trunk", lambda: _Trunk(self.backbone, self.rpn.head), (x,))
-        if self.training and self.static_shapes and self.roi_heads and not self.da_heads_triplet:
+        if self.training and self.static_shapes and self.roi_heads:
             return self._forward_static(images, targets, feat, logits, deltas)
         features = [feat]
         with section("rpn_proposals_and_loss"):

@@ -113,6 +113,10 @@ class ProposalBatch(object):
     def __init__(self, boxes, objectness, count, size):
         self.boxes, self.objectness, self.count, self.size = boxes, objectness, count, size
 
+    def slice(self, a, b):
+        """Images [a, b) of the batch (views)."""
+        return ProposalBatch(self.boxes[a:b], self.objectness[a:b], self.count[a:b], self.size)
+
     def to_boxlists(self):
         """list[BoxList] like RPNPostProcessor returns (reads the counts on the host)."""
         out = []

@@ -107,7 +107,7 @@ def test_training_step_matches_oracle(name, dense):
     ref_samples = aux["samples"] if "samples" in aux else None
     exact = dense != "tcgen05"   # TF32 logits may legitimately reorder near-tied proposals
     if exact and ref_samples is not None and not cfg.MODEL.DA_HEADS.ALIGNMENT:
-        static = model.static_shapes and not cfg.MODEL.DA_HEADS.TRIPLET_USE
+        static = model.static_shapes
         sampled = box.loss_evaluator.static_proposals() if static else box.loss_evaluator._proposals
         assert len(sampled) == len(ref_samples)
         for p, s in zip(sampled, ref_samples):
