@@ -208,12 +208,13 @@ def test_cuda_graph_segments_match_eager():
 
 
 @pytest.mark.timeout(900)
-def test_whole_step_graph_matches_eager_training():
+@pytest.mark.parametrize("name", ["da_img_ins_cst", "triplet_aligned_advgrl"])
+def test_whole_step_graph_matches_eager_training(name):
     """FlatSGDTrainer.enable_step_graph: three SGD steps replayed from ONE captured CUDA graph (zero_grad, forward,
     backward, SGD with the learning rate read on the device) == the same three steps launched eagerly."""
     from dadetect_b200.engine import FlatSGDTrainer
     from dadetect_b200.utils.random_source import HashSource
-    cfg, sd, images, targets, hw = scenario("da_img_ins_cst")
+    cfg, sd, images, targets, hw = scenario(name)
     dev = torch.device("cuda")
     out = []
     for graph in (False, True):
