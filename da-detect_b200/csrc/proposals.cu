@@ -106,23 +106,32 @@ __global__ void __launch_bounds__(kTopkThreads) rpn_topk_decode_kernel(
     // aggregate equal bins inside the warp and issue ONE shared-memory atomic per distinct bin.  Four logits per
     // thread and iteration (one 128-bit load) keep enough loads in flight for a single CTA.
     const bool vec = (num_anchors & 3) == 0 && (reinterpret_cast<uintptr_t>(lg) & 15) == 0;
-#pragma unroll 2
-    for (int i = threadIdx.x * 4; i < num_anchors; i += blockDim.x * 4) {
-      float v[4];
-      if (vec) {
-        const float4 f = __ldg(reinterpret_cast<const float4*>(lg + i));
-        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-      } else {
+    constexpr int kUn = 4;                          // 128-bit loads in flight per thread
+    const int step = blockDim.x * 4;
+    for (int i0 = threadIdx.x * 4; i0 < num_anchors; i0 += step * kUn) {
+      float v[kUn][4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = i + e < num_anchors ? lg[i + e] : 0.f;
+      for (int u = 0; u < kUn; ++u) {
+        const int i = i0 + u * step;
+        if (vec && i < num_anchors) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(lg + i));
+          v[u][0] = f.x; v[u][1] = f.y; v[u][2] = f.z; v[u][3] = f.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[u][e] = i + e < num_anchors ? lg[i + e] : 0.f;
+        }
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t key = float_to_ordered(v[e]);
-        const bool in = i + e < num_anchors && (key & prefix_mask) == prefix;
-        const uint32_t bin = in ? ((key >> shift) & 0xFF) : 0xFFFFFFFFu;
-        const unsigned peers = __match_any_sync(__activemask(), bin);
-        if (in && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+      for (int u = 0; u < kUn; ++u) {
+        const int i = i0 + u * step;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t key = float_to_ordered(v[u][e]);
+          const bool in = i + e < num_anchors && (key & prefix_mask) == prefix;
+          const uint32_t bin = in ? ((key >> shift) & 0xFF) : 0xFFFFFFFFu;
+          const unsigned peers = __match_any_sync(__activemask(), bin);
+          if (in && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+        }
       }
     }
     __syncthreads();

@@ -15,6 +15,7 @@
 namespace {
 
 constexpr int kThreads = 1024;
+constexpr int kUn = 4;            // load pairs kept in flight per thread in the streaming sweeps
 
 __global__ void __launch_bounds__(256) proposals_gather_kernel(
     const float4* __restrict__ boxes, const float* __restrict__ scores, const int64_t* __restrict__ keep,
@@ -113,12 +114,15 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
   __syncthreads();
   {
     int c0 = 0, c1 = 0;
-#pragma unroll 2
-    for (int i = tid * 4; i < n; i += step) {
-      int c[4]; uint32_t k[4];
-      load4(labels, keys, i, n, vec, c, k);
+    // kUn independent 128-bit load pairs per thread in flight: one CTA has to cover the L2 latency by itself
+    for (int i0 = tid * 4; i0 < n; i0 += step * kUn) {
+      int c[kUn][4]; uint32_t k[kUn][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { c0 += c[e] == 0; c1 += c[e] == 1; }
+      for (int u = 0; u < kUn; ++u) load4(labels, keys, i0 + u * step, n, vec, c[u], k[u]);
+#pragma unroll
+      for (int u = 0; u < kUn; ++u)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { c0 += c[u][e] == 0; c1 += c[u][e] == 1; }
     }
     for (int o = 16; o > 0; o >>= 1) {
       c0 += __shfl_xor_sync(0xffffffffu, c0, o);
@@ -139,13 +143,16 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
     const int shift = 24 - 8 * pass;
     for (int i = tid; i < 512; i += blockDim.x) (&hist[0][0])[i] = 0;
     __syncthreads();
-#pragma unroll 2
-    for (int i = tid * 4; i < n; i += step) {
-      int c[4]; uint32_t k[4];
-      load4(labels, keys, i, n, vec, c, k);
+    for (int i0 = tid * 4; i0 < n; i0 += step * kUn) {
+      int c[kUn][4]; uint32_t k[kUn][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (c[e] < 2 && (k[e] & mask) == prefix[c[e]]) atomicAdd(&hist[c[e]][(k[e] >> shift) & 0xFF], 1);
+      for (int u = 0; u < kUn; ++u) load4(labels, keys, i0 + u * step, n, vec, c[u], k[u]);
+#pragma unroll
+      for (int u = 0; u < kUn; ++u)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c[u][e] < 2 && (k[u][e] & mask) == prefix[c[u][e]])
+            atomicAdd(&hist[c[u][e]][(k[u][e] >> shift) & 0xFF], 1);
     }
     __syncthreads();
     if (tid < 2) {
@@ -170,12 +177,15 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
 
   // ---- phase A: ties (key == prefix) per warp slice and class -> tie rank base of every warp
   int eq_w[2] = {0, 0};
-  for (int i = w_begin + lane * 4; i < w_end; i += 128) {
-    int c[4]; uint32_t k[4];
-    load4(labels, keys, i, w_end, vec, c, k);
+  for (int i0 = w_begin + lane * 4; i0 < w_end; i0 += 128 * kUn) {
+    int c[kUn][4]; uint32_t k[kUn][4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (c[e] < 2 && want[c[e]] > 0 && k[e] == prefix[c[e]]) eq_w[c[e]] += 1;
+    for (int u = 0; u < kUn; ++u) load4(labels, keys, i0 + u * 128, w_end, vec, c[u], k[u]);
+#pragma unroll
+    for (int u = 0; u < kUn; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c[u][e] < 2 && want[c[u][e]] > 0 && k[u][e] == prefix[c[u][e]]) eq_w[c[u][e]] += 1;
   }
   for (int o = 16; o > 0; o >>= 1) {
     eq_w[0] += __shfl_xor_sync(0xffffffffu, eq_w[0], o);
@@ -193,10 +203,14 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
   for (int write = 0; write < 2; ++write) {
     int ties[2] = {tie_base[0], tie_base[1]};
     int taken = 0;
+    int cn[4]; uint32_t kn[4];                       // the next step's candidates are loaded while this one is ranked
+    load4(labels, keys, w_begin + lane * 4, w_end, vec, cn, kn);
     for (int i0 = w_begin; i0 < w_end; i0 += 128) {
       const int i = i0 + lane * 4;
       int c[4]; uint32_t k[4];
-      load4(labels, keys, i, w_end, vec, c, k);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { c[e] = cn[e]; k[e] = kn[e]; }
+      load4(labels, keys, i + 128, w_end, vec, cn, kn);
       bool lt[4], eq[4];
       int eqc[2] = {0, 0};                       // ties of each class among this lane's four
 #pragma unroll
