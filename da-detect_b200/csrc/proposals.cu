@@ -224,17 +224,6 @@ __global__ void __launch_bounds__(kTopkThreads) rpn_topk_decode_kernel(
 }
 
 // ----------------------------------------------------------------------------- NMS
-__device__ __forceinline__ float iou_plus1(const float4 a, const float4 b) {
-  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
-  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
-  const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
-  const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
-  const float inter = __fmul_rn(width, height);
-  const float sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
-  const float sb = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
-  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
-}
-
 // mask[i][cb] bit j: box (cb*64+j) is suppressed by box i (j > i only).  Upper triangle only.
 // Batched over images (blockIdx.z): image g has n = n_dev ? n_dev[g] : n_cap boxes at boxes + g * n_cap and its own
 // [n_cap x cb_cap] mask.
@@ -256,8 +245,27 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__
     const float4 me = boxes[i];
     unsigned long long bits = 0ull;
     const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-    for (int j = start; j < col_size; ++j)
-      if (iou_plus1(me, cols[j]) > thresh) bits |= 1ull << j;
+    const float my_area = __fmul_rn(__fadd_rn(__fsub_rn(me.z, me.x), 1.f), __fadd_rn(__fsub_rn(me.w, me.y), 1.f));
+    for (int j = start; j < col_size; ++j) {
+      // Reference predicate: inter / (sa + sb - inter) > thresh with an IEEE division (nms.cu:13-24).  The division
+      // is only executed inside a +-1e-6 band around the threshold; outside it the comparison inter vs
+      // thresh * union decides with a margin ~16x the rounding error of the quotient, so the result is identical.
+      const float4 b = cols[j];
+      const float left = fmaxf(me.x, b.x), right = fminf(me.z, b.z);
+      const float top = fmaxf(me.y, b.y), bottom = fminf(me.w, b.w);
+      const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+      const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+      const float inter = __fmul_rn(width, height);
+      const float sb = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+      const float uni = __fsub_rn(__fadd_rn(my_area, sb), inter);
+      const float tu = thresh * uni;
+      bool over;
+      if (!(uni > 0.f) || !(thresh > 0.f)) over = __fdiv_rn(inter, uni) > thresh;   // degenerate boxes: as written
+      else if (inter > tu * 1.000001f) over = true;
+      else if (inter < tu * 0.999999f) over = false;
+      else over = __fdiv_rn(inter, uni) > thresh;
+      if (over) bits |= 1ull << j;
+    }
     mask[(size_t)i * cb_cap + cb] = bits;
   }
 }
