@@ -83,13 +83,18 @@ def _chk(t, dtype=torch.float32, name="tensor"):
 
 
 _workspaces = {}
+_retired = []          # outgrown scratch buffers: a captured CUDA graph may still hold their addresses
 
 
 def _workspace(nbytes, device, tag="ws"):
-    """Grow-only scratch buffer per (device, tag); reused across calls on the same stream."""
+    """Grow-only scratch buffer per (device, tag); reused across calls on the same stream.  A buffer that is
+    outgrown is retired, not freed: kernels recorded into a CUDA graph keep using the address they were
+    captured with."""
     key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _retired.append(buf)
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
