@@ -70,8 +70,8 @@ class AnchorGenerator(nn.Module):
     def grid(self, fh, fw, img_w, img_h):
         cell = next(iter(self.cell_anchors))
         key = (fh, fw, img_w, img_h, cell.device, cell._version)
-        if key not in self._cache:
-            self._cache = {key: ops.anchor_grid(cell, fh, fw, self.stride, img_w, img_h, self.straddle_thresh)}
+        if key not in self._cache:       # entries are kept: a captured step graph holds the address of its grid
+            self._cache[key] = ops.anchor_grid(cell, fh, fw, self.stride, img_w, img_h, self.straddle_thresh)
         return self._cache[key]
 
 
