@@ -39,6 +39,7 @@ _SIGS = {
     "dd_stem_conv7x7s2_forward": (_I, "pppppiiiiiipp"),
     "dd_conv2d_dgrad_workspace_bytes": (_Z, "iiii"),
     "dd_conv2d_dgrad": (_I, "ppppppiiiiiiiiiipip"),
+    "dd_conv2d_dgrad_prepare_batch": (_I, "ipppppppip"),
     "dd_conv2d_wgrad_workspace_bytes": (_Z, "iiiiiiiii"),
     "dd_conv2d_wgrad": (_I, "ppppiiiiiiiiiiipp"),
     "dd_bias_grad": (_I, "ppiiip"),

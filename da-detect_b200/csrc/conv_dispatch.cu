@@ -15,6 +15,8 @@ int dd_tc_conv2d_forward(const float*, const float*, const float*, const float*,
 int dd_tc_conv2d_dgrad(const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
                        int, int, int, int, int, int, float*, int, bool, cudaStream_t);
 int tc_rows_pad_public(int ncols);
+int dd_tc_dgrad_prepare_batch(int, const float* const*, const float* const*, float* const*, const int*, const int*,
+                              const int*, const int*, bool, cudaStream_t);
 int dd_tc_conv2d_wgrad(const float*, const float*, const float*, float*, int, int, int, int, int, int, int, int, int,
                        int, void*, bool, cudaStream_t);
 bool dd_tc_supports(int mode, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
@@ -43,6 +45,18 @@ extern "C" int dd_conv2d_forward(const float* x, const float* w, const float* sc
 extern "C" size_t dd_conv2d_dgrad_workspace_bytes(int Cin, int Cout, int KH, int KW) {
   // W' [Cin rows, padded to whole tiles][taps*Cout], twice (hi / lo planes of the 3xTF32 mode)
   return sizeof(float) * 2 * (size_t)tc_rows_pad_public(Cin) * Cout * KH * KW;
+}
+
+extern "C" int dd_conv2d_dgrad_prepare_batch(int n, const float* const* w, const float* const* scale,
+                                             void* const* workspaces, const int* Cin, const int* Cout, const int* KH,
+                                             const int* KW, int impl, void* stream) {
+  DD_CHECK_ARG(n >= 0);
+  if (n == 0 || !is_tc(impl)) return 0;               // the SIMT arm consumes the weights as they are
+  for (int i = 0; i < n; ++i)
+    DD_CHECK_ARG(w[i] != nullptr && workspaces[i] != nullptr && (reinterpret_cast<uintptr_t>(workspaces[i]) & 15) == 0 &&
+                 Cin[i] > 0 && Cout[i] > 0 && KH[i] > 0 && KW[i] > 0);
+  return dd_tc_dgrad_prepare_batch(n, w, scale, reinterpret_cast<float* const*>(workspaces), Cin, Cout, KH, KW,
+                                   impl == DD_IMPL_TCGEN05_X3, dd::S(stream));
 }
 
 extern "C" int dd_conv2d_dgrad(const float* gy, const float* w, const float* scale, const float* addend,

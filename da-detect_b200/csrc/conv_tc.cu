@@ -923,6 +923,55 @@ __global__ void weight_flip_transpose_kernel(const float* __restrict__ w, const 
   }
 }
 
+// The same for up to 16 layers in ONE launch (a ResNet stage prepares all its dgrad weights at once): blockIdx.x
+// walks the concatenated tile lists of the entries.
+struct PrepEntry {
+  const float* w; const float* scale; float* wt;
+  int Cout, Cin, taps, tile_begin;
+  long long lo_off;
+};
+struct PrepBatch { PrepEntry e[16]; int n; };
+
+__global__ void weight_flip_transpose_batch_kernel(const PrepBatch b) {
+  __shared__ float tile[32][33];
+  int k = 0;
+  while (k + 1 < b.n && (int)blockIdx.x >= b.e[k + 1].tile_begin) ++k;
+  const PrepEntry& E = b.e[k];
+  int t = blockIdx.x - E.tile_begin;
+  const int ci_blocks = (E.Cin + 31) / 32, co_blocks = (E.Cout + 31) / 32;
+  const int ci0 = (t % ci_blocks) * 32; t /= ci_blocks;
+  const int co0 = (t % co_blocks) * 32;
+  const int tap = t / co_blocks;
+  const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int co = co0 + ty + j, ci = ci0 + tx;
+    float v = 0.f;
+    if (co < E.Cout && ci < E.Cin) {
+      v = E.w[((size_t)co * E.taps + tap) * E.Cin + ci];
+      if (E.scale) v *= __ldg(E.scale + co);
+    }
+    tile[ty + j][tx] = v;
+  }
+  __syncthreads();
+  const int tflip = E.taps - 1 - tap;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int ci = ci0 + ty + j, co = co0 + tx;
+    if (co < E.Cout && ci < E.Cin) {
+      const float v = tile[tx][ty + j];
+      const size_t o = ((size_t)ci * E.taps + tflip) * E.Cout + co;
+      if (E.lo_off > 0) {
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        E.wt[o] = hi;
+        E.wt[o + E.lo_off] = __uint_as_float(__float_as_uint(v - hi) & 0xFFFFE000u);
+      } else {
+        E.wt[o] = v;
+      }
+    }
+  }
+}
+
 __global__ void fill_kernel(const float* __restrict__ addend, const float* __restrict__ mask, float* __restrict__ gx,
                             long long n) {
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -1222,6 +1271,29 @@ namespace {
 }  // namespace
 
 extern "C" int dd_tcgen05_built(void) { return 1; }
+
+// Prepare the dgrad weights W' of n layers (what dd_conv2d_dgrad does per call when prepared == 0) in one launch per
+// 16 layers.  ws[i] must hold dd_conv2d_dgrad_workspace_bytes(Cin[i], Cout[i], KH[i], KW[i]) bytes.
+int dd_tc_dgrad_prepare_batch(int n, const float* const* w, const float* const* scale, float* const* ws,
+                              const int* Cin, const int* Cout, const int* KH, const int* KW, bool x3, cudaStream_t s) {
+  for (int base = 0; base < n; base += 16) {
+    PrepBatch b = {};
+    b.n = n - base < 16 ? n - base : 16;
+    int tiles = 0;
+    for (int i = 0; i < b.n; ++i) {
+      const int j = base + i, taps = KH[j] * KW[j];
+      const long long plane = (long long)tc_rows_pad(Cin[j]) * taps * Cout[j];
+      if (x3 && tc_rows_pad(Cin[j]) != Cin[j]) DD_CUDA(cudaMemsetAsync(ws[j], 0, sizeof(float) * 2 * plane, s));
+      b.e[i].w = w[j]; b.e[i].scale = scale[j]; b.e[i].wt = ws[j];
+      b.e[i].Cout = Cout[j]; b.e[i].Cin = Cin[j]; b.e[i].taps = taps; b.e[i].tile_begin = tiles;
+      b.e[i].lo_off = x3 ? plane : 0;
+      tiles += ((Cin[j] + 31) / 32) * ((Cout[j] + 31) / 32) * taps;
+    }
+    weight_flip_transpose_batch_kernel<<<tiles, dim3(32, 8), 0, s>>>(b);
+    DD_LAUNCHED();
+  }
+  return 0;
+}
 int tc_rows_pad_public(int ncols) { return ncols > 64 ? (ncols + 127) / 128 * 128 : 64; }
 
 // mode: 0 forward, 1 dgrad, 2 wgrad

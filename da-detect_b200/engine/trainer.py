@@ -105,6 +105,8 @@ class FlatSGDTrainer(object):
         self.step_graphs = None          # signature -> captured whole-step CUDA graph (enable_step_graph)
         self.graph_launches = 0          # kernels of ours replayed through step graphs so far
         self.graph_stream = None
+        self.graph_pool = None           # one memory pool shared by all step graphs (their replays never overlap)
+        self.max_step_graphs = 16        # signatures kept; the least recently used graph is dropped beyond that
 
     def enable_step_graph(self, flag=True):
         """Capture zero_grad + forward + backward + all-reduce + SGD of one iteration into ONE CUDA graph per
@@ -159,8 +161,12 @@ class FlatSGDTrainer(object):
             return None                  # an adaptive margin below its maximum reads the previous loss on the host
         cache_source_flags(targets)
         key = (tuple(tensors.shape),) + tuple((len(t), bool(is_source_image(t)), tuple(t.size)) for t in targets)
-        ent = self.step_graphs.get(key)
+        ent = self.step_graphs.pop(key, None)
+        if ent is not None:
+            self.step_graphs[key] = ent          # most recently used last
         if ent is None:
+            while len(self.step_graphs) >= self.max_step_graphs:
+                self.step_graphs.pop(next(iter(self.step_graphs)))
             st_targets = []
             for t in targets:
                 b = BoxList(t.convert("xyxy").bbox.to(torch.float32).clone(), t.size, mode="xyxy")
@@ -193,8 +199,10 @@ class FlatSGDTrainer(object):
             if ent["graph"] is None:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
+                if self.graph_pool is None:
+                    self.graph_pool = torch.cuda.graph_pool_handle()
                 before = _lib.launch_count()
-                with torch.cuda.graph(g, stream=self.graph_stream):
+                with torch.cuda.graph(g, pool=self.graph_pool, stream=self.graph_stream):
                     ld = self._eager_step(ent["images"], ent["targets"], dev_lr=True)
                     ent["losses"] = {k: v.detach() for k, v in ld.items()}
                     del ld

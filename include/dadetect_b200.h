@@ -165,6 +165,11 @@ size_t dd_conv2d_dgrad_workspace_bytes(int Cin, int Cout, int KH, int KW);
 int dd_conv2d_dgrad(const float* gy, const float* w, const float* scale, const float* addend,
                     const float* mask_act, float* gx, int N, int H, int W, int Cin, int Cout, int KH, int KW,
                     int stride, int pad, int impl, void* workspace, int prepared, void* stream);
+/* Prepare the dgrad workspaces of n layers at once (one launch per 16 layers instead of one per layer); layer i
+ * then calls dd_conv2d_dgrad with workspaces[i] and prepared = 1.  A no-op for the SIMT arm. */
+int dd_conv2d_dgrad_prepare_batch(int n, const float* const* w, const float* const* scale, void* const* workspaces,
+                                  const int* Cin, const int* Cout, const int* KH, const int* KW, int impl,
+                                  void* stream);
 /* gw[co,kh,kw,ci] (+)= scale[co] * sum_{n,oh,ow} gy[n,oh,ow,co] * x[n,oh*s+kh-p,ow*s+kw-p,ci].
  * workspace: dd_conv2d_wgrad_workspace_bytes(...) (split-K partials). */
 size_t dd_conv2d_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);

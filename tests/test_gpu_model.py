@@ -326,3 +326,33 @@ def test_three_sgd_iterations_match_oracle(dense):
             num += float((a - b).pow(2).sum())
             den += float((b - sd[k].double()).pow(2).sum())      # relative to how far the weights moved
     assert (num / max(den, 1e-30)) ** 0.5 < 2e-2, (num, den)
+
+
+@pytest.mark.timeout(900)
+def test_step_graphs_of_two_batch_signatures_share_one_pool():
+    """Real data has a varying number of GT boxes per image: every signature gets its own captured graph, all
+    graphs share one memory pool, and alternating between them keeps matching the eager trainer."""
+    from dadetect_b200.engine import FlatSGDTrainer
+    from dadetect_b200.utils.random_source import HashSource
+    from dadetect_b200.utils.synthetic import make_batch
+    cfg, sd, images, targets, hw = scenario("da_img_only")
+    _, targets_b = make_batch(2, hw[0], hw[1], num_classes=cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES, boxes_per_image=3, seed=7)
+    dev = torch.device("cuda")
+    out = []
+    for graph in (False, True):
+        model = build(cfg, sd, dev)
+        model.set_random_source(HashSource())
+        trainer = FlatSGDTrainer(model, cfg, world_size=1)
+        if graph:
+            trainer.enable_step_graph(True)
+        losses = []
+        for it in range(6):
+            tg = to_boxlists(targets if it % 2 == 0 else targets_b, hw, dev)
+            ld = trainer.step(images.to(dev) + 0.01 * it, tg)
+            losses.append({k: float(v) for k, v in ld.items()})
+        if graph:
+            assert len(trainer.step_graphs) == 2 and all(e["graph"] is not None for e in trainer.step_graphs.values())
+        out.append(losses)
+    for a, b in zip(*out):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 3e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
