@@ -152,6 +152,29 @@ def dgrad_workspace(cin, cout, kh, kw, device):
     return torch.empty(max(int(nbytes) // 4, 4), dtype=torch.float32, device=device)
 
 
+def dgrad_prepare_batch(layers, device, impl=None):
+    """Prepare the dgrad weights W' of several layers with one launch per 16 layers (a ResNet stage does all of its
+    layers up front).  layers: list of (w_ohwi, scale | None); returns one prepared workspace per layer, or a list of
+    None on the SIMT arm (which consumes the weights as they are)."""
+    impl = _default_impl if impl is None else impl
+    n = len(layers)
+    if impl == IMPL_SIMT or n == 0:
+        return [None] * n
+    dims = []
+    for w, _ in layers:
+        if w.dim() == 4:
+            dims.append((w.shape[3], w.shape[0], w.shape[1], w.shape[2]))      # OHWI -> (Cin, Cout, KH, KW)
+        else:
+            dims.append((w.shape[1], w.shape[0], 1, 1))
+    wss = [dgrad_workspace(ci, co, kh, kw, device) for ci, co, kh, kw in dims]
+    vp, ip = ctypes.c_void_p * n, ctypes.c_int * n
+    _lib.call("dd_conv2d_dgrad_prepare_batch", n, vp(*[w.data_ptr() for w, _ in layers]),
+              vp(*[None if s is None else s.data_ptr() for _, s in layers]), vp(*[t.data_ptr() for t in wss]),
+              ip(*[d[0] for d in dims]), ip(*[d[1] for d in dims]), ip(*[d[2] for d in dims]),
+              ip(*[d[3] for d in dims]), impl, _stream())
+    return wss
+
+
 def conv2d_wgrad_raw(gy, x, scale, cout, kh, kw, stride, pad, out=None, accumulate=False, impl=None):
     n, h, wd, cin = x.shape
     if out is None:
@@ -339,20 +362,29 @@ class _BottleneckStage(torch.autograd.Function):
             k += 12 if has_down[bi] else 9
         need_x = ctx.needs_input_grad[0]
         gx = None
+        # the dgrad weights of every layer of the stage, prepared by one launch (per 16 layers)
+        ohwi, todo = {}, []
+        for bi in range(len(strides)):
+            o = offs[bi]
+            for j in (0, 3, 6) + ((9,) if has_down[bi] else ()):
+                ohwi[o + j] = weight_ohwi(tensors[o + j])
+                if j in (3, 6) or bi > 0 or need_x:
+                    todo.append(o + j)
+        prep = dict(zip(todo, dgrad_prepare_batch([(ohwi[i], tensors[i + 1]) for i in todo], g_out.device)))
         for bi in reversed(range(len(strides))):
             o = offs[bi]
             w1, s1, _, w2, s2, _, w3, s3, _ = tensors[o:o + 9]
             x_in, y1, y2 = acts[3 * bi:3 * bi + 3]
             stride = strides[bi]
             first = bi == 0
-            w1o, w2o, w3o = weight_ohwi(w1), weight_ohwi(w2), weight_ohwi(w3)
+            w1o, w2o, w3o = ohwi[o], ohwi[o + 3], ohwi[o + 6]
             refs = ctx.param_refs
             if ctx.needs_input_grad[2 + o + 6]:
                 grads[o + 6] = _wgrad_into(refs[o + 6], g_out, y2, s3, w3o.shape[0], 1, 1, 1, 0)
-            g2 = conv2d_dgrad_raw(g_out, w3o, s3, tuple(y2.shape), 1, 1, 1, 0, mask_act=y2)
+            g2 = conv2d_dgrad_raw(g_out, w3o, s3, tuple(y2.shape), 1, 1, 1, 0, mask_act=y2, prepared_ws=prep[o + 6])
             if ctx.needs_input_grad[2 + o + 3]:
                 grads[o + 3] = _wgrad_into(refs[o + 3], g2, y1, s2, w2o.shape[0], 3, 3, 1, 1)
-            g1 = conv2d_dgrad_raw(g2, w2o, s2, tuple(y1.shape), 3, 3, 1, 1, mask_act=y1)
+            g1 = conv2d_dgrad_raw(g2, w2o, s2, tuple(y1.shape), 3, 3, 1, 1, mask_act=y1, prepared_ws=prep[o + 3])
             del g2
             if ctx.needs_input_grad[2 + o]:
                 grads[o] = _wgrad_into(refs[o], g1, x_in, s1, w1o.shape[0], 1, 1, stride, 0)
@@ -360,17 +392,18 @@ class _BottleneckStage(torch.autograd.Function):
             if has_down[bi]:
                 wd, sd = tensors[o + 9], tensors[o + 10]
                 if ctx.needs_input_grad[2 + o + 9]:
-                    wdo = weight_ohwi(wd)
-                    grads[o + 9] = _wgrad_into(refs[o + 9], g_out, x_in, sd, wdo.shape[0], 1, 1, stride, 0)
+                    grads[o + 9] = _wgrad_into(refs[o + 9], g_out, x_in, sd, ohwi[o + 9].shape[0], 1, 1, stride, 0)
             if first and not need_x:
                 break
             # data gradient of the block input: conv1 path + residual path, masked by the producer's ReLU
             mask = x_in if (not first or input_is_relu) else None
             if wd is not None:
-                t = conv2d_dgrad_raw(g_out, weight_ohwi(wd), sd, tuple(x_in.shape), 1, 1, stride, 0)
+                t = conv2d_dgrad_raw(g_out, ohwi[o + 9], sd, tuple(x_in.shape), 1, 1, stride, 0,
+                                     prepared_ws=prep[o + 9])
             else:
                 t = g_out
-            g_out = conv2d_dgrad_raw(g1, w1o, s1, tuple(x_in.shape), 1, 1, stride, 0, addend=t, mask_act=mask)
+            g_out = conv2d_dgrad_raw(g1, w1o, s1, tuple(x_in.shape), 1, 1, stride, 0, addend=t, mask_act=mask,
+                                     prepared_ws=prep[o])
             del g1, t
             if first:
                 gx = g_out

@@ -679,3 +679,26 @@ def test_conv_tcgen05_x3_arm_is_fp32_grade(case):
     (gw_want,) = torch.autograd.grad(y1, (wr,), (go.double() * (want > 0)))
     gw = o.conv2d_wgrad_raw(gpre, xd, sd, cout, k, k, stride, pad, impl=o.IMPL_TCGEN05_X3)
     close(gw.permute(0, 3, 1, 2).cpu(), gw_want, "wgrad")
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "tcgen05x3"])
+def test_dgrad_batched_weight_preparation_is_bit_identical(impl):
+    """dd_conv2d_dgrad_prepare_batch (one launch for a whole stage's layers) followed by prepared dgrad calls gives
+    exactly what the per-call preparation gives — 18 layers, i.e. two launches, scale present and absent."""
+    o = ops()
+    code = o.IMPL_TCGEN05 if impl == "tcgen05" else o.IMPL_TCGEN05_X3
+    g = torch.Generator().manual_seed(5)
+    shapes = [(64, 32, 1), (32, 64, 3), (128, 32, 1), (40, 24, 3), (256, 64, 1), (32, 96, 1)] * 3
+    layers, gys = [], []
+    for i, (cout, cin, k) in enumerate(shapes):
+        w = (torch.randn(cout, k, k, cin, generator=g) / (cin * k * k) ** 0.5).to(DEV)
+        s = (0.5 + torch.rand(cout, generator=g)).to(DEV) if i % 2 == 0 else None
+        layers.append((w, s))
+        gys.append(torch.randn(2, 9, 13, cout, generator=g).to(DEV))
+    prepared = o.dgrad_prepare_batch(layers, torch.device(DEV), impl=code)
+    assert len(prepared) == len(layers) and all(p is not None for p in prepared)
+    for (w, s), gy, ws, (cout, cin, k) in zip(layers, gys, prepared, shapes):
+        a = o.conv2d_dgrad_raw(gy, w, s, (2, 9, 13, cin), k, k, 1, k // 2, impl=code)
+        b = o.conv2d_dgrad_raw(gy, w, s, (2, 9, 13, cin), k, k, 1, k // 2, impl=code, prepared_ws=ws)
+        assert torch.equal(a, b), (cout, cin, k)
+    assert o.dgrad_prepare_batch(layers[:2], torch.device(DEV), impl=o.IMPL_SIMT) == [None, None]
