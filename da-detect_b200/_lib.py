@@ -64,6 +64,9 @@ _SIGS = {
     "dd_sgd_momentum_dev": (_I, "pppqpffffp"),
     "dd_triplet_margin_loss": (_I, "pppqiqfppppp"),
     "dd_sgd_momentum": (_I, "pppqffffip"),
+    "dd_resample_ksize": (_I, "ii"),
+    "dd_resample_coeffs": (_I, "iipp"),
+    "dd_preprocess_image": (_I, "piiiqppippiiiiipppiip"),
 }
 _CT = {"p": _P, "i": _I, "f": _F, "q": _Q}
 

@@ -248,6 +248,27 @@ int dd_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr,
 int dd_sgd_momentum_dev(float* p, const float* g, float* buf, long long n, const float* lr_dev, float lr_factor,
                         float momentum, float wd, float grad_scale, void* stream);
 
+/* ---------------------------------------------------------------- input pipeline */
+
+/* Pillow's bilinear resampling coefficients for one axis (Resample.c precompute_coeffs + normalize_coeffs_8bpc,
+ * the arithmetic behind torchvision F.resize on a PIL image — data/transforms/transforms.py:65-69).  HOST
+ * functions, no CUDA work: h_bounds int[out_size][2] = (first source index, count), h_kk int[out_size][ksize]
+ * fixed-point weights with 22 fractional bits.  dd_resample_ksize returns ksize (-1 on bad sizes). */
+int dd_resample_ksize(int in_size, int out_size);
+int dd_resample_coeffs(int in_size, int out_size, int* h_bounds, int* h_kk);
+/* One sample of Compose([Resize, RandomHorizontalFlip, ToTensor, Normalize]) (data/transforms/build.py:22-31,
+ * transforms.py:35-98) fused with the zero padding of to_image_list (structures/image_list.py:66-88), one launch:
+ * src uint8 [src_h][src_w] RGB pixels of pixel_stride (3 or 4) bytes, rows row_stride bytes apart (device memory)
+ * -> dst float [3][Hp][Wp], the image's slot of the batch tensor: rows < out_h / columns < out_w hold the resized
+ * (two integer passes, horizontal first, uint8 intermediate: bit-exact Pillow), optionally mirrored image as
+ * ((u8 / 255) [* 255, channels reversed when to_bgr255] - mean) / std in correctly rounded fp32 steps, the rest
+ * zeros.  xbounds/xk/ybounds/yk: DEVICE copies of dd_resample_coeffs(src_w, out_w) / (src_h, out_h);
+ * h_mean / h_std: 3 host floats each, in output-plane order. */
+int dd_preprocess_image(const uint8_t* src, int src_h, int src_w, int pixel_stride, long long row_stride,
+                        const int* xbounds, const int* xk, int xksize, const int* ybounds, const int* yk, int yksize,
+                        int out_h, int out_w, int flip, int to_bgr255, const float* h_mean, const float* h_std,
+                        float* dst, int Hp, int Wp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

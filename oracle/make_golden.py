@@ -314,8 +314,71 @@ def make_eval():
     return fx
 
 
+# ----------------------------------------------------------------------------- input pipeline golden
+PREPROCESS_CASES = [
+    # (name, cfg opts, [(h, w) of the decoded images], random seed)
+    ("down_2to1", ["INPUT.MIN_SIZE_TRAIN", (40,), "INPUT.MAX_SIZE_TRAIN", 80, "DATALOADER.SIZE_DIVISIBILITY", 32],
+     [(70, 140), (70, 140)], 3),
+    ("multi_scale_ragged", ["INPUT.MIN_SIZE_TRAIN", (30, 44, 52), "INPUT.MAX_SIZE_TRAIN", 90,
+                            "DATALOADER.SIZE_DIVISIBILITY", 16], [(61, 97), (97, 61), (50, 50)], 11),
+    ("upsample_no_divisor", ["INPUT.MIN_SIZE_TRAIN", (64,), "INPUT.MAX_SIZE_TRAIN", 200,
+                             "DATALOADER.SIZE_DIVISIBILITY", 0], [(24, 37), (31, 29)], 5),
+    ("identity_size", ["INPUT.MIN_SIZE_TRAIN", (48,), "INPUT.MAX_SIZE_TRAIN", 96, "DATALOADER.SIZE_DIVISIBILITY", 32],
+     [(48, 96), (48, 80)], 8),
+    ("max_size_rule_rgb", ["INPUT.MIN_SIZE_TRAIN", (60,), "INPUT.MAX_SIZE_TRAIN", 100, "INPUT.TO_BGR255", False,
+                           "INPUT.PIXEL_MEAN", [0.485, 0.456, 0.406], "INPUT.PIXEL_STD", [0.229, 0.224, 0.225],
+                           "DATALOADER.SIZE_DIVISIBILITY", 32], [(45, 130), (130, 45)], 21),
+]
+
+
+def make_preprocess():
+    """The reference's OWN build_transforms(cfg, is_train=True) chain (PIL resize, flip, ToTensor, Normalize) and
+    BatchCollator on synthetic decoded images + BoxLists, Python `random` seeded per case."""
+    import random
+    from PIL import Image
+    rh.install()
+    # `maskrcnn_benchmark/data/__init__.py` pulls in the dataset catalogue (pycocotools, torch._six: both absent
+    # here); register the package by path so that only the two modules under test are executed.
+    import types
+    pkg = types.ModuleType("maskrcnn_benchmark.data")
+    pkg.__path__ = [os.path.join(rh.REF, "maskrcnn_benchmark", "data")]
+    sys.modules.setdefault("maskrcnn_benchmark.data", pkg)
+    from maskrcnn_benchmark.data.transforms import build_transforms
+    from maskrcnn_benchmark.data.collate_batch import BatchCollator
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    cases = {}
+    for name, opts, sizes, seed in PREPROCESS_CASES:
+        cfg = rh.reference_cfg("da_faster_rcnn/e2e_da_faster_rcnn_R_50_C4_cityscapes_to_foggy_cityscapes.yaml", opts)
+        g = torch.Generator().manual_seed(seed)
+        raws, boxes = [], []
+        for (h, w) in sizes:
+            raws.append(torch.randint(0, 256, (h, w, 3), generator=g, dtype=torch.uint8))
+            x1 = torch.rand(5, generator=g) * (w - 8)
+            y1 = torch.rand(5, generator=g) * (h - 8)
+            boxes.append(torch.stack([x1, y1, x1 + 2 + torch.rand(5, generator=g) * 5,
+                                      y1 + 2 + torch.rand(5, generator=g) * 5], 1))
+        tf = build_transforms(cfg, is_train=True)
+        random.seed(seed)
+        samples = []
+        for i, (raw, bx) in enumerate(zip(raws, boxes)):
+            t = BoxList(bx.clone(), (raw.shape[1], raw.shape[0]), mode="xyxy")
+            t.add_field("labels", torch.arange(1, 6))
+            img, t = tf(Image.fromarray(raw.numpy(), mode="RGB"), t)
+            samples.append((img, t, i))
+        images, targets, ids = BatchCollator(cfg.DATALOADER.SIZE_DIVISIBILITY)(samples)
+        cases[name] = dict(opts=opts, seed=seed, raw=raws, boxes=boxes, batch=images.tensors.clone(),
+                           image_sizes=[tuple(int(v) for v in s) for s in images.image_sizes],
+                           target_boxes=[t.bbox.clone() for t in targets], target_sizes=[t.size for t in targets])
+    torch.save(cases, os.path.join(OUT, "preprocess_ref.pt"))
+    return cases
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "eval":       # only the eval-mode fixture
+    if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+        assert rh.available(), "reference not mounted"
+        for k, c in make_preprocess().items():
+            print(k, tuple(c["batch"].shape), c["image_sizes"])
+    elif len(sys.argv) > 1 and sys.argv[1] == "eval":       # only the eval-mode fixture
         assert rh.available(), "reference not mounted"
         torch.set_num_threads(os.cpu_count())
         fx = make_eval()
@@ -325,3 +388,4 @@ if __name__ == "__main__":
     else:
         main()
         make_eval()
+        make_preprocess()
