@@ -64,6 +64,13 @@ _SIGS = {
     "dd_sgd_momentum_dev": (_I, "pppqpffffp"),
     "dd_triplet_margin_loss": (_I, "pppqiqfppppp"),
     "dd_sgd_momentum": (_I, "pppqffffip"),
+    "dd_upsample2x_forward": (_I, "ppiiiip"),
+    "dd_upsample2x_backward": (_I, "ppiiiip"),
+    "dd_subsample2_forward": (_I, "ppiiiip"),
+    "dd_subsample2_backward": (_I, "ppiiiip"),
+    "dd_fpn_level_map": (_I, "piiififpp"),
+    "dd_roi_align_level_forward": (_I, "pppipiiiiifiiip"),
+    "dd_roi_align_level_backward": (_I, "pppipiiiiifiiip"),
     "dd_resample_ksize": (_I, "ii"),
     "dd_resample_coeffs": (_I, "iipp"),
     "dd_preprocess_image": (_I, "piiiqppippiiiiipppiip"),

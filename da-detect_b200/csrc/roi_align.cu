@@ -66,8 +66,10 @@ __device__ __forceinline__ float sample_coord(float start, int p, float bin, int
 __global__ void __launch_bounds__(256) roi_align_fwd_nhwc(const float* __restrict__ feat,
                                                           const float* __restrict__ rois, float* __restrict__ out,
                                                           int H, int W, int C, float scale, int PH, int PW,
-                                                          int sampling_ratio, int bin_step, int OPW) {
+                                                          int sampling_ratio, int bin_step, int OPW,
+                                                          const int* __restrict__ roi_level, int level) {
   const int k = blockIdx.y;
+  if (roi_level != nullptr && __ldg(roi_level + k) != level) return;   // multi-level pooling: not this map's ROI
   const int ob = blockIdx.x;
   const int ph = (ob / OPW) * bin_step, pw = (ob % OPW) * bin_step;
   const RoiGeom g = roi_geom(rois + 5 * k, scale, PH, PW, sampling_ratio);
@@ -105,8 +107,10 @@ __device__ __forceinline__ void red_add4(float* addr, float4 v) {
 __global__ void __launch_bounds__(256) roi_align_bwd_nhwc(const float* __restrict__ gout,
                                                           const float* __restrict__ rois, float* __restrict__ gfeat,
                                                           int H, int W, int C, float scale, int PH, int PW,
-                                                          int sampling_ratio, int bin_step, int OPW) {
+                                                          int sampling_ratio, int bin_step, int OPW,
+                                                          const int* __restrict__ roi_level, int level) {
   const int k = blockIdx.y;
+  if (roi_level != nullptr && __ldg(roi_level + k) != level) return;   // multi-level pooling: not this map's ROI
   const int ob = blockIdx.x;
   const int ph = (ob / OPW) * bin_step, pw = (ob % OPW) * bin_step;
   const RoiGeom g = roi_geom(rois + 5 * k, scale, PH, PW, sampling_ratio);
@@ -134,8 +138,10 @@ __global__ void __launch_bounds__(256) roi_align_bwd_nhwc(const float* __restric
 // Scalar-channel variants for C % 4 != 0 (tests with odd channel counts; never on the R-50 path).
 __global__ void roi_align_fwd_nhwc_c1(const float* __restrict__ feat, const float* __restrict__ rois,
                                       float* __restrict__ out, int H, int W, int C, float scale, int PH, int PW,
-                                      int sampling_ratio, int bin_step, int OPW) {
+                                      int sampling_ratio, int bin_step, int OPW, const int* __restrict__ roi_level,
+                                      int level) {
   const int k = blockIdx.y, ob = blockIdx.x;
+  if (roi_level != nullptr && __ldg(roi_level + k) != level) return;
   const int ph = (ob / OPW) * bin_step, pw = (ob % OPW) * bin_step;
   const RoiGeom g = roi_geom(rois + 5 * k, scale, PH, PW, sampling_ratio);
   const float inv_count = 1.0f / (float)(g.grid_h * g.grid_w);
@@ -158,8 +164,10 @@ __global__ void roi_align_fwd_nhwc_c1(const float* __restrict__ feat, const floa
 
 __global__ void roi_align_bwd_nhwc_c1(const float* __restrict__ gout, const float* __restrict__ rois,
                                       float* __restrict__ gfeat, int H, int W, int C, float scale, int PH, int PW,
-                                      int sampling_ratio, int bin_step, int OPW) {
+                                      int sampling_ratio, int bin_step, int OPW, const int* __restrict__ roi_level,
+                                      int level) {
   const int k = blockIdx.y, ob = blockIdx.x;
+  if (roi_level != nullptr && __ldg(roi_level + k) != level) return;
   const int ph = (ob / OPW) * bin_step, pw = (ob % OPW) * bin_step;
   const RoiGeom g = roi_geom(rois + 5 * k, scale, PH, PW, sampling_ratio);
   const float count = (float)(g.grid_h * g.grid_w);
@@ -213,9 +221,11 @@ extern "C" int dd_nhwc_to_nchw(const float* x, float* y, int N, int C, int H, in
   return transpose_launch(x, y, N, H * W, C, dd::S(stream));
 }
 
-extern "C" int dd_roi_align_forward(const float* feat, const float* rois, float* out, int N, int H, int W, int C,
-                                    int K, float spatial_scale, int PH, int PW, int sampling_ratio, int bin_step,
-                                    void* stream) {
+namespace {
+
+int roi_align_launch(bool fwd, const float* a, const float* rois, float* b, int N, int H, int W, int C, int K,
+                     float spatial_scale, int PH, int PW, int sampling_ratio, int bin_step, const int* roi_level,
+                     int level, cudaStream_t s) {
   DD_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && K >= 0 && PH > 0 && PW > 0 && bin_step >= 1);
   if (K == 0) return 0;
   const int OPH = (PH + bin_step - 1) / bin_step, OPW = (PW + bin_step - 1) / bin_step;
@@ -223,34 +233,78 @@ extern "C" int dd_roi_align_forward(const float* feat, const float* rois, float*
   dim3 grid(OPH * OPW, K);
   if (C % 4 == 0) {
     int threads = C / 4 < 256 ? ((C / 4 + 31) / 32) * 32 : 256;
-    roi_align_fwd_nhwc<<<grid, threads, 0, dd::S(stream)>>>(feat, rois, out, H, W, C, spatial_scale, PH, PW,
-                                                            sampling_ratio, bin_step, OPW);
+    if (fwd)
+      roi_align_fwd_nhwc<<<grid, threads, 0, s>>>(a, rois, b, H, W, C, spatial_scale, PH, PW, sampling_ratio,
+                                                  bin_step, OPW, roi_level, level);
+    else
+      roi_align_bwd_nhwc<<<grid, threads, 0, s>>>(a, rois, b, H, W, C, spatial_scale, PH, PW, sampling_ratio,
+                                                  bin_step, OPW, roi_level, level);
   } else {
-    roi_align_fwd_nhwc_c1<<<grid, 128, 0, dd::S(stream)>>>(feat, rois, out, H, W, C, spatial_scale, PH, PW,
-                                                           sampling_ratio, bin_step, OPW);
+    if (fwd)
+      roi_align_fwd_nhwc_c1<<<grid, 128, 0, s>>>(a, rois, b, H, W, C, spatial_scale, PH, PW, sampling_ratio,
+                                                 bin_step, OPW, roi_level, level);
+    else
+      roi_align_bwd_nhwc_c1<<<grid, 128, 0, s>>>(a, rois, b, H, W, C, spatial_scale, PH, PW, sampling_ratio,
+                                                 bin_step, OPW, roi_level, level);
   }
   DD_LAUNCHED();
   return 0;
 }
 
+// LevelMapper (poolers.py:11-42): floor(lvl0 + log2(sqrt(area) / s0 + eps)) clamped to [k_min, k_max], minus k_min;
+// area with the +1 convention (bounding_box.py:227-230).  Correctly rounded fp32 steps, like the torch expression.
+__global__ void fpn_level_map_kernel(const float* __restrict__ rois, int K, int k_min, int k_max, float s0, int lvl0,
+                                     float eps, int* __restrict__ levels) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const float* r = rois + 5 * k;
+  const float w = __fadd_rn(__fsub_rn(r[3], r[1]), 1.0f), h = __fadd_rn(__fsub_rn(r[4], r[2]), 1.0f);
+  const float s = __fsqrt_rn(__fmul_rn(w, h));
+  float t = floorf(__fadd_rn((float)lvl0, log2f(__fadd_rn(__fdiv_rn(s, s0), eps))));
+  t = fminf(fmaxf(t, (float)k_min), (float)k_max);        // NaN (negative area) -> k_min, like torch.clamp's min first
+  levels[k] = (int)t - k_min;
+}
+
+}  // namespace
+
+extern "C" int dd_roi_align_forward(const float* feat, const float* rois, float* out, int N, int H, int W, int C,
+                                    int K, float spatial_scale, int PH, int PW, int sampling_ratio, int bin_step,
+                                    void* stream) {
+  return roi_align_launch(true, feat, rois, out, N, H, W, C, K, spatial_scale, PH, PW, sampling_ratio, bin_step,
+                          nullptr, 0, dd::S(stream));
+}
+
 extern "C" int dd_roi_align_backward(const float* grad_out, const float* rois, float* grad_feat, int N, int H,
                                      int W, int C, int K, float spatial_scale, int PH, int PW, int sampling_ratio,
                                      int bin_step, void* stream) {
-  DD_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && K >= 0 && PH > 0 && PW > 0 && bin_step >= 1);
+  return roi_align_launch(false, grad_out, rois, grad_feat, N, H, W, C, K, spatial_scale, PH, PW, sampling_ratio,
+                          bin_step, nullptr, 0, dd::S(stream));
+}
+
+extern "C" int dd_fpn_level_map(const float* rois, int K, int k_min, int k_max, float canonical_scale,
+                                int canonical_level, float eps, int* levels, void* stream) {
+  DD_CHECK_ARG(K >= 0 && k_min <= k_max && canonical_scale > 0.f);
   if (K == 0) return 0;
-  const int OPH = (PH + bin_step - 1) / bin_step, OPW = (PW + bin_step - 1) / bin_step;
-  DD_CHECK_ARG(K <= 65535);
-  dim3 grid(OPH * OPW, K);
-  if (C % 4 == 0) {
-    int threads = C / 4 < 256 ? ((C / 4 + 31) / 32) * 32 : 256;
-    roi_align_bwd_nhwc<<<grid, threads, 0, dd::S(stream)>>>(grad_out, rois, grad_feat, H, W, C, spatial_scale, PH,
-                                                            PW, sampling_ratio, bin_step, OPW);
-  } else {
-    roi_align_bwd_nhwc_c1<<<grid, 128, 0, dd::S(stream)>>>(grad_out, rois, grad_feat, H, W, C, spatial_scale, PH,
-                                                           PW, sampling_ratio, bin_step, OPW);
-  }
+  fpn_level_map_kernel<<<(K + 255) / 256, 256, 0, dd::S(stream)>>>(rois, K, k_min, k_max, canonical_scale,
+                                                                     canonical_level, eps, levels);
   DD_LAUNCHED();
   return 0;
+}
+
+extern "C" int dd_roi_align_level_forward(const float* feat, const float* rois, const int* roi_level, int level,
+                                          float* out, int N, int H, int W, int C, int K, float spatial_scale,
+                                          int PH, int PW, int sampling_ratio, void* stream) {
+  DD_CHECK_ARG(roi_level != nullptr);
+  return roi_align_launch(true, feat, rois, out, N, H, W, C, K, spatial_scale, PH, PW, sampling_ratio, 1, roi_level,
+                          level, dd::S(stream));
+}
+
+extern "C" int dd_roi_align_level_backward(const float* grad_out, const float* rois, const int* roi_level, int level,
+                                           float* grad_feat, int N, int H, int W, int C, int K, float spatial_scale,
+                                           int PH, int PW, int sampling_ratio, void* stream) {
+  DD_CHECK_ARG(roi_level != nullptr);
+  return roi_align_launch(false, grad_out, rois, grad_feat, N, H, W, C, K, spatial_scale, PH, PW, sampling_ratio, 1,
+                          roi_level, level, dd::S(stream));
 }
 
 extern "C" int dd_roi_align_forward_nchw(const float* feat, const float* rois, float* out, int N, int C, int H,

@@ -14,7 +14,8 @@ from torch import nn
 
 from .. import ops
 
-STAGE_BLOCKS = {"R-50-C4": (3, 4, 6), "R-101-C4": (3, 4, 23)}
+STAGE_BLOCKS = {"R-50-C4": (3, 4, 6), "R-101-C4": (3, 4, 23),
+                "R-50-FPN": (3, 4, 6, 3), "R-101-FPN": (3, 4, 23, 3), "R-152-FPN": (3, 8, 36, 3)}      # resnet.py:41-77
 
 
 class FrozenBatchNorm2d(nn.Module):
@@ -139,7 +140,8 @@ class Stem(nn.Module):
 
 
 class ResNetC4(nn.Module):
-    """ResNet.forward for the *-C4 bodies: NCHW image in, returns [res4 feature map] (NHWC)."""
+    """ResNet.forward (resnet.py:138-145): NCHW image in, NHWC maps out.  *-C4 bodies return [res4]; *-FPN bodies
+    return [res2, res3, res4, res5] (every stage has return_features, resnet.py:60-66)."""
 
     def __init__(self, cfg):
         super().__init__()
@@ -160,6 +162,7 @@ class ResNetC4(nn.Module):
             self.stages.append(name)
             cin = cout
         self.out_channels = cin
+        self.return_all = body.endswith("-FPN")
         self._freeze(cfg.MODEL.BACKBONE.FREEZE_CONV_BODY_AT)
 
     def _freeze(self, freeze_at):
@@ -171,6 +174,13 @@ class ResNetC4(nn.Module):
 
     def forward(self, x):
         x = self.stem(x)
+        if self.return_all:
+            # every stage output also feeds an FPN lateral conv, so no ReLU mask may be deferred across a boundary
+            outs = []
+            for name in self.stages:
+                x = getattr(self, name)(x)
+                outs.append(x)
+            return outs
         last = len(self.stages) - 1
         for i, name in enumerate(self.stages):
             # every stage output is a ReLU output consumed only by the next stage, so the mask (x > 0) of the
@@ -198,7 +208,53 @@ class ResNetHead(nn.Module):
         return self.layer4(x, first_stride_override=1 if input_is_even_bins else None, pool_output=pooled)
 
 
+class FPN(nn.Module):
+    """Feature pyramid (modeling/backbone/fpn.py:8-85) over [C2..C5]: 1x1 laterals ``fpn_inner{i}``, 3x3 outputs
+    ``fpn_layer{i}`` (conv_with_kaiming_uniform: bias, no norm, no ReLU — make_layers.py:97-122), nearest 2x
+    top-down path, LastLevelMaxPool for P6.  The lateral add rides in the lateral conv's epilogue (the up-sampled
+    coarser map is its residual input)."""
+
+    def __init__(self, in_channels_list, out_channels):
+        super().__init__()
+        self.inner_blocks, self.layer_blocks = [], []
+        for idx, cin in enumerate(in_channels_list, 1):
+            inner, layer = "fpn_inner{}".format(idx), "fpn_layer{}".format(idx)
+            self.add_module(inner, Conv2dParams(cin, out_channels, 1, bias=True))
+            self.add_module(layer, Conv2dParams(out_channels, out_channels, 3, 1, 1, bias=True))
+            self.inner_blocks.append(inner)
+            self.layer_blocks.append(layer)
+
+    def forward(self, feats):
+        def conv(name, x, residual=None, pad=0):
+            m = getattr(self, name)
+            return ops.conv_bn_act(x, m.weight, None, m.bias, residual=residual, pad=pad)
+
+        last_inner = conv(self.inner_blocks[-1], feats[-1])
+        results = [conv(self.layer_blocks[-1], last_inner, pad=1)]
+        for feat, inner, layer in zip(feats[:-1][::-1], self.inner_blocks[:-1][::-1], self.layer_blocks[:-1][::-1]):
+            n, h, w, _ = feat.shape
+            if (h, w) != (2 * last_inner.shape[1], 2 * last_inner.shape[2]):
+                raise RuntimeError("FPN: a {}x{} map cannot take the 2x up-sampled {}x{} map — pad the images to a "
+                                   "multiple of 32 (DATALOADER.SIZE_DIVISIBILITY)".format(
+                                       h, w, last_inner.shape[1], last_inner.shape[2]))
+            last_inner = conv(inner, feat, residual=ops.upsample2x(last_inner))     # fpn.py:62-67
+            results.insert(0, conv(layer, last_inner, pad=1))
+        results.append(ops.subsample2(results[-1]))                                  # LastLevelMaxPool
+        return results
+
+
+class _BodyFPN(nn.Sequential):
+    def forward(self, x):
+        return self.fpn(self.body(x))
+
+
 def build_backbone(cfg):
-    """build_backbone (backbone.py:68-73): nn.Sequential(OrderedDict([('body', ResNet)]))."""
-    model = nn.Sequential(OrderedDict([("body", ResNetC4(cfg))]))
-    return model
+    """build_backbone (backbone.py:11-18,21-43,68-73): nn.Sequential(OrderedDict([('body', ResNet)(, ('fpn', FPN))]))."""
+    body = ResNetC4(cfg)
+    if cfg.MODEL.BACKBONE.CONV_BODY.endswith("-FPN"):
+        if cfg.MODEL.FPN.USE_GN or cfg.MODEL.FPN.USE_RELU:
+            raise NotImplementedError("FPN.USE_GN / FPN.USE_RELU are not used by any DA config")
+        c2 = cfg.MODEL.RESNETS.RES2_OUT_CHANNELS
+        fpn = FPN([c2, c2 * 2, c2 * 4, c2 * 8], cfg.MODEL.BACKBONE.OUT_CHANNELS)
+        return _BodyFPN(OrderedDict([("body", body), ("fpn", fpn)]))
+    return nn.Sequential(OrderedDict([("body", body)]))

@@ -87,7 +87,13 @@ class GeneralizedRCNN(nn.Module):
         self.da_heads_triplet = build_da_heads_triplet(cfg, self.rng) if self.triplet_use else False
         self.Aligned = cfg.MODEL.DA_HEADS.ALIGNMENT
         self.size_divisible = cfg.DATALOADER.SIZE_DIVISIBILITY
-        self.static_shapes = True
+        # FPN: multi-level features, host-driven control flow.  The reference ships no working
+        # FPN + DA combination (da_heads.py:368-370 sizes the heads for C4), so none is invented here.
+        self.fpn = cfg.MODEL.BACKBONE.CONV_BODY.endswith("-FPN")
+        if self.fpn and (self.da_heads or self.da_heads_triplet):
+            raise NotImplementedError("domain-adaptation heads on an FPN backbone: the reference's own combination "
+                                      "is broken (SURVEY §9.9); set MODEL.DOMAIN_ADAPTATION_ON False")
+        self.static_shapes = not self.fpn
         self.__dict__["_meta_cache"] = {}
 
     def enable_static_shapes(self, flag=True):
@@ -168,14 +174,19 @@ class GeneralizedRCNN(nn.Module):
         images = to_image_list(images)
         if targets is not None:
             cache_source_flags(targets)
-        with section("trunk_fwd"):
-            x = ops._chk(images.tensors, name="images")            # NCHW; the stem consumes it directly
-            feat, logits, deltas = self.segments.run("trunk", lambda: _Trunk(self.backbone, self.rpn.head), (x,))
-        if self.training and self.static_shapes and self.roi_heads:
-            return self._forward_static(images, targets, feat, logits, deltas)
-        features = [feat]
-        with section("rpn_proposals_and_loss"):
-            proposals, proposal_losses = self.rpn(images, features, targets, head_out=(logits, deltas))
+        if self.fpn:
+            x = ops._chk(images.tensors, name="images")
+            features = self.backbone(x)
+            proposals, proposal_losses = self.rpn(images, features, targets)
+        else:
+            with section("trunk_fwd"):
+                x = ops._chk(images.tensors, name="images")        # NCHW; the stem consumes it directly
+                feat, logits, deltas = self.segments.run("trunk", lambda: _Trunk(self.backbone, self.rpn.head), (x,))
+            if self.training and self.static_shapes and self.roi_heads:
+                return self._forward_static(images, targets, feat, logits, deltas)
+            features = [feat]
+            with section("rpn_proposals_and_loss"):
+                proposals, proposal_losses = self.rpn(images, features, targets, head_out=(logits, deltas))
         da_losses = {}
         if self.roi_heads:
             if self.training:

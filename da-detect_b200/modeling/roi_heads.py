@@ -60,6 +60,68 @@ class ResNet50Conv5ROIFeatureExtractor(nn.Module):
         return self.head(x, self.even_bins)
 
 
+class MultiLevelPooler(nn.Module):
+    """Pooler over FPN levels (poolers.py:45-121): LevelMapper + one ROIAlign per level, written straight into the
+    rows of one output tensor by ops.roi_align_levels (no nonzero / index_put round trips)."""
+
+    def __init__(self, output_size, scales, sampling_ratio):
+        super().__init__()
+        self.output_size = int(output_size)
+        self.scales = tuple(float(s) for s in scales)
+        self.sampling_ratio = int(sampling_ratio)
+
+    def forward(self, feats, boxes):
+        rois = Pooler.convert_to_roi_format(boxes)
+        out, self.last_levels = ops.roi_align_levels(list(feats[:len(self.scales)]), rois, self.scales,
+                                                     self.output_size, self.sampling_ratio)
+        return out
+
+
+class FPN2MLPFeatureExtractor(nn.Module):
+    """roi_box_feature_extractors.py:48-79: multi-level 7x7 ROIAlign -> fc6 -> ReLU -> fc7 -> ReLU.  The reference
+    flattens its NCHW ROI map as (C, h, w); ours is NHWC, so fc6's columns are re-ordered to (h, w, C) on the fly —
+    the parameter keeps the reference's [1024, C*49] shape and column order (checkpoint compatible)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        B = cfg.MODEL.ROI_BOX_HEAD
+        if B.USE_GN:
+            raise NotImplementedError("ROI_BOX_HEAD.USE_GN is not used by any DA config")
+        self.pooler = MultiLevelPooler(B.POOLER_RESOLUTION, B.POOLER_SCALES, B.POOLER_SAMPLING_RATIO)
+        self.channels, self.resolution = cfg.MODEL.BACKBONE.OUT_CHANNELS, B.POOLER_RESOLUTION
+        self.fc6 = nn.Linear(self.channels * self.resolution ** 2, B.MLP_HEAD_DIM)
+        self.fc7 = nn.Linear(B.MLP_HEAD_DIM, B.MLP_HEAD_DIM)
+        for fc in (self.fc6, self.fc7):                      # make_fc (make_layers.py:83-94)
+            nn.init.kaiming_uniform_(fc.weight, a=1)
+            nn.init.constant_(fc.bias, 0)
+        self.even_bins = False
+
+    def forward(self, feats, proposals):
+        x = self.pooler(feats, proposals)                    # [K, r, r, C]
+        k, r, c = x.shape[0], self.resolution, self.channels
+        w6 = self.fc6.weight.view(-1, c, r * r).permute(0, 2, 1).reshape(-1, r * r * c)
+        x = ops.linear(x.reshape(k, r * r * c), w6, self.fc6.bias, relu=True)
+        return ops.linear(x, self.fc7.weight, self.fc7.bias, relu=True)
+
+
+class FPNPredictor(nn.Module):
+    """roi_box_predictors.py:37-57."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        rep, nc = cfg.MODEL.ROI_BOX_HEAD.MLP_HEAD_DIM, cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES
+        self.cls_score = nn.Linear(rep, nc)
+        self.bbox_pred = nn.Linear(rep, (2 if cfg.MODEL.CLS_AGNOSTIC_BBOX_REG else nc) * 4)
+        nn.init.normal_(self.cls_score.weight, std=0.01)
+        nn.init.normal_(self.bbox_pred.weight, std=0.001)
+        for l in (self.cls_score, self.bbox_pred):
+            nn.init.constant_(l.bias, 0)
+
+    def forward(self, x):
+        return (ops.linear(x, self.cls_score.weight, self.cls_score.bias),
+                ops.linear(x, self.bbox_pred.weight, self.bbox_pred.bias))
+
+
 class FastRCNNPredictor(nn.Module):
     def __init__(self, cfg):
         super().__init__()
@@ -213,10 +275,16 @@ class FastRCNNLossComputation(object):
 class ROIBoxHead(nn.Module):
     def __init__(self, cfg, rng):
         super().__init__()
-        if cfg.MODEL.ROI_BOX_HEAD.FEATURE_EXTRACTOR != "ResNet50Conv5ROIFeatureExtractor":
-            raise NotImplementedError("only the C4 res5 box head is on the accelerated path")
-        self.feature_extractor = ResNet50Conv5ROIFeatureExtractor(cfg)
-        self.predictor = FastRCNNPredictor(cfg)
+        fe, pred = cfg.MODEL.ROI_BOX_HEAD.FEATURE_EXTRACTOR, cfg.MODEL.ROI_BOX_HEAD.PREDICTOR
+        self.mlp_head = fe == "FPN2MLPFeatureExtractor"
+        if self.mlp_head and pred == "FPNPredictor":
+            self.feature_extractor = FPN2MLPFeatureExtractor(cfg)
+            self.predictor = FPNPredictor(cfg)
+        elif fe == "ResNet50Conv5ROIFeatureExtractor" and pred == "FastRCNNPredictor":
+            self.feature_extractor = ResNet50Conv5ROIFeatureExtractor(cfg)
+            self.predictor = FastRCNNPredictor(cfg)
+        else:
+            raise NotImplementedError("box head {} + {} is outside the accelerated path".format(fe, pred))
         self.loss_evaluator = FastRCNNLossComputation(cfg, rng)
         self.cfg = cfg.clone()
 
@@ -248,7 +316,10 @@ class ROIBoxHead(nn.Module):
             with section("  box_subsample"):
                 proposals = self.loss_evaluator.subsample(proposals, targets)
         segments = self.__dict__.get("segments")
-        if segments is not None and self.training:
+        if self.mlp_head:                                     # FPN: the extractor output IS the [K,1024] vector
+            x = pooled = self.feature_extractor(features, proposals)
+            class_logits, box_regression = self.predictor(pooled)
+        elif segments is not None and self.training:
             from .detector import _BoxBranch
             rois = Pooler.convert_to_roi_format(proposals)
             pooled, class_logits, box_regression = segments.run(

@@ -58,20 +58,31 @@ class AnchorGenerator(nn.Module):
     arange/meshgrid/stack every iteration."""
 
     def __init__(self, sizes, aspect_ratios, stride, straddle_thresh):
+        """stride: one int (single level: all `sizes` at every location) or a tuple of strides, one per entry of
+        `sizes` (FPN: one anchor size per level, anchor_generator.py:47-66)."""
         super().__init__()
-        self.stride = int(stride)
         self.straddle_thresh = int(straddle_thresh)
-        self.cell_anchors = BufferList([generate_cell_anchors(self.stride, sizes, aspect_ratios)])
+        if isinstance(stride, (tuple, list)) and len(stride) > 1:
+            if len(stride) != len(sizes):
+                raise RuntimeError("FPN should have #anchor_strides == #sizes")
+            self.strides = tuple(int(s) for s in stride)
+            cells = [generate_cell_anchors(st, sz if isinstance(sz, (tuple, list)) else (sz,), aspect_ratios)
+                     for st, sz in zip(self.strides, sizes)]
+        else:
+            self.strides = (int(stride[0] if isinstance(stride, (tuple, list)) else stride),)
+            cells = [generate_cell_anchors(self.strides[0], sizes, aspect_ratios)]
+        self.stride = self.strides[0]
+        self.cell_anchors = BufferList(cells)
         self._cache = {}
 
     def num_anchors_per_location(self):
         return [len(c) for c in self.cell_anchors]
 
-    def grid(self, fh, fw, img_w, img_h):
-        cell = next(iter(self.cell_anchors))
-        key = (fh, fw, img_w, img_h, cell.device, cell._version)
+    def grid(self, fh, fw, img_w, img_h, level=0):
+        cell = list(self.cell_anchors)[level]
+        key = (level, fh, fw, img_w, img_h, cell.device, cell._version)
         if key not in self._cache:       # entries are kept: a captured step graph holds the address of its grid
-            self._cache[key] = ops.anchor_grid(cell, fh, fw, self.stride, img_w, img_h, self.straddle_thresh)
+            self._cache[key] = ops.anchor_grid(cell, fh, fw, self.strides[level], img_w, img_h, self.straddle_thresh)
         return self._cache[key]
 
 
@@ -132,9 +143,14 @@ class RPNModule(nn.Module):
         super().__init__()
         self.cfg = cfg.clone()
         R = cfg.MODEL.RPN
-        if R.USE_FPN or len(R.ANCHOR_STRIDE) != 1:
-            raise NotImplementedError("multi-level RPN (FPN) is a 'next' row (SURVEY §8f)")
-        self.anchor_generator = AnchorGenerator(R.ANCHOR_SIZES, R.ASPECT_RATIOS, R.ANCHOR_STRIDE[0], R.STRADDLE_THRESH)
+        self.fpn = bool(R.USE_FPN)
+        if self.fpn != (len(R.ANCHOR_STRIDE) > 1):           # make_anchor_generator's asserts (anchor_generator.py:133-138)
+            raise AssertionError("USE_FPN needs one ANCHOR_STRIDE per ANCHOR_SIZE; non-FPN a single ANCHOR_STRIDE")
+        if R.RPN_HEAD != "SingleConvRPNHead":
+            raise NotImplementedError("RPN head {} is outside the accelerated path".format(R.RPN_HEAD))
+        self.anchor_generator = AnchorGenerator(R.ANCHOR_SIZES, R.ASPECT_RATIOS,
+                                                tuple(R.ANCHOR_STRIDE) if self.fpn else R.ANCHOR_STRIDE[0],
+                                                R.STRADDLE_THRESH)
         self.head = RPNHead(cfg.MODEL.BACKBONE.OUT_CHANNELS, self.anchor_generator.num_anchors_per_location()[0])
         self.rng = rng
         self.proposal_hook = None
@@ -291,7 +307,77 @@ class RPNModule(nn.Module):
         obj_loss, box_loss = self.losses_static(anchors, vis, logits, deltas, targets)
         return props, {"loss_objectness": obj_loss, "loss_rpn_box_reg": box_loss}
 
+    # ---- FPN: per-level post-processing + select_over_all_levels (rpn/inference.py:126-181) ----------
+    @torch.no_grad()
+    def proposals_fpn(self, grids, outs, image_sizes, targets):
+        R = self.cfg.MODEL.RPN
+        train = self.training
+        pre = R.PRE_NMS_TOP_N_TRAIN if train else R.PRE_NMS_TOP_N_TEST
+        post = R.POST_NMS_TOP_N_TRAIN if train else R.POST_NMS_TOP_N_TEST
+        fpn_post = R.FPN_POST_NMS_TOP_N_TRAIN if train else R.FPN_POST_NMS_TOP_N_TEST
+        sizes = set((int(h), int(w)) for h, w in image_sizes)
+        if len(sizes) != 1:
+            raise NotImplementedError("images of different un-padded sizes in one batch")
+        ih, iw = sizes.pop()
+        n = outs[0][0].shape[0]
+        boxes_i, scores_i = [[] for _ in range(n)], [[] for _ in range(n)]
+        for (anchors, _), (logits, deltas) in zip(grids, outs):
+            _, fh, fw, a = logits.shape
+            k = min(pre, fh * fw * a)
+            boxes, scores, _, valid = ops.rpn_topk_decode(logits.detach(), deltas.detach(), anchors, k, iw, ih,
+                                                          R.MIN_SIZE)
+            keep, cnt = ops.nms_sorted_batched(boxes, valid, R.NMS_THRESH, min(post, k))
+            for i, c in enumerate(cnt.tolist()):             # one host read per level
+                sel = keep[i, :c]
+                boxes_i[i].append(boxes[i][sel])
+                scores_i[i].append(scores[i][sel])
+        boxes_i = [torch.cat(b) for b in boxes_i]
+        scores_i = [torch.cat(s) for s in scores_i]
+        if train:            # :160-171 — ONE top-k over the proposals of the whole batch (the reference's known quirk)
+            allsc = torch.cat(scores_i)
+            _, top = torch.topk(allsc, min(fpn_post, allsc.numel()), dim=0, sorted=True)
+            mask = torch.zeros_like(allsc, dtype=torch.bool)
+            mask[top] = True
+            picks = [torch.nonzero(m).squeeze(1) for m in mask.split([len(s) for s in scores_i])]
+        else:                # :172-180 — per image, returned in descending objectness order
+            picks = [torch.topk(s, min(fpn_post, s.numel()), dim=0, sorted=True)[1] for s in scores_i]
+        out = []
+        for i, pk in enumerate(picks):
+            bl = BoxList(boxes_i[i][pk], (iw, ih), mode="xyxy")
+            bl.add_field("objectness", scores_i[i][pk])
+            out.append(bl)
+        if train and targets is not None:
+            for i, t in enumerate(targets):
+                if is_source_image(t):
+                    gt = t.bbox.to(out[i].bbox.dtype)
+                    bl = BoxList(torch.cat([out[i].bbox, gt]), out[i].size, mode="xyxy")
+                    bl.add_field("objectness", torch.cat([out[i].get_field("objectness"),
+                                                          torch.ones(len(gt), device=gt.device)]))
+                    out[i] = bl
+        return out
+
+    def forward_fpn(self, images, features, targets=None):
+        outs = [self.head(f) for f in features]              # the same head on every level (rpn.py:39-46)
+        ih, iw = images.image_sizes[0]
+        grids = [self.anchor_generator.grid(f.shape[1], f.shape[2], int(iw), int(ih), level=l)
+                 for l, f in enumerate(features)]
+        boxes = self.proposals_fpn(grids, outs, images.image_sizes, targets)
+        if self.proposal_hook is not None:
+            boxes = self.proposal_hook(boxes)
+        if not self.training:
+            return boxes, {}
+        # concat_box_prediction_layers (rpn/utils.py:17-45): per image, the levels one after the other
+        n = outs[0][0].shape[0]
+        obj = torch.cat([lg.reshape(n, -1) for lg, _ in outs], dim=1)
+        reg = torch.cat([dl.reshape(n, -1, 4) for _, dl in outs], dim=1)
+        anchors = torch.cat([g[0] for g in grids], dim=0)
+        vis = torch.cat([g[1] for g in grids], dim=0)
+        obj_loss, box_loss = self.losses(anchors, vis, obj, reg, targets)
+        return boxes, {"loss_objectness": obj_loss, "loss_rpn_box_reg": box_loss}
+
     def forward(self, images, features, targets=None, head_out=None):
+        if self.fpn:
+            return self.forward_fpn(images, features, targets)
         feat = features[0]
         logits, deltas = head_out if head_out is not None else self.head(feat)
         n, fh, fw, _ = feat.shape

@@ -486,6 +486,103 @@ def roi_align(feat, rois, spatial_scale, pooled, sampling_ratio, bin_step=1):
     return _RoIAlign.apply(feat, rois, spatial_scale, pooled, sampling_ratio, bin_step)
 
 
+class _RoIAlignLevels(torch.autograd.Function):
+    """Multi-level Pooler.forward (poolers.py:104-121): LevelMapper on the device, then one launch per level over
+    all ROIs (a ROI is pooled only from its own level's map) — no nonzero / index_put, no host read."""
+
+    @staticmethod
+    def forward(ctx, rois, scales, pooled, sampling_ratio, k_min, k_max, *feats):
+        rois = _chk(rois, name="rois")
+        feats = [_chk(f, name="feat") for f in feats]
+        k = rois.shape[0]
+        c = feats[0].shape[3]
+        levels = torch.empty((max(k, 1),), dtype=torch.int32, device=rois.device)
+        _lib.call("dd_fpn_level_map", _ptr(rois), k, int(k_min), int(k_max), 224.0, 4, 1e-6, _ptr(levels), _stream())
+        out = torch.empty((k, pooled, pooled, c), dtype=torch.float32, device=rois.device)
+        for lvl, (f, sc) in enumerate(zip(feats, scales)):
+            n, h, w, _ = f.shape
+            _lib.call("dd_roi_align_level_forward", _ptr(f), _ptr(rois), _ptr(levels), lvl, _ptr(out), n, h, w, c, k,
+                      float(sc), pooled, pooled, int(sampling_ratio), _stream())
+        ctx.save_for_backward(rois, levels)
+        ctx.meta = ([tuple(f.shape) for f in feats], tuple(float(sc) for sc in scales), pooled, int(sampling_ratio))
+        ctx.mark_non_differentiable(levels)
+        return out, levels
+
+    @staticmethod
+    def backward(ctx, g, _glevels):
+        rois, levels = ctx.saved_tensors
+        shapes, scales, pooled, sr = ctx.meta
+        g = _chk(g, name="grad")
+        k = rois.shape[0]
+        grads = []
+        for lvl, (shape, sc) in enumerate(zip(shapes, scales)):
+            if not ctx.needs_input_grad[6 + lvl]:
+                grads.append(None)
+                continue
+            n, h, w, c = shape
+            gf = torch.zeros(shape, dtype=torch.float32, device=g.device)
+            _lib.call("dd_roi_align_level_backward", _ptr(g), _ptr(rois), _ptr(levels), lvl, _ptr(gf), n, h, w, c, k,
+                      sc, pooled, pooled, sr, _stream())
+            grads.append(gf)
+        return (None, None, None, None, None, None) + tuple(grads)
+
+
+def roi_align_levels(feats, rois, scales, pooled, sampling_ratio):
+    """feats: list of NHWC maps (finest first), scales their spatial scales -> (out [K,pooled,pooled,C], levels int32
+    [K]); level range from the scales as in Pooler.__init__ (poolers.py:71-73)."""
+    import math
+    k_min, k_max = -math.log2(scales[0]), -math.log2(scales[-1])
+    return _RoIAlignLevels.apply(rois, tuple(scales), int(pooled), int(sampling_ratio), int(k_min), int(k_max), *feats)
+
+
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x, name="x")
+        n, h, w, c = x.shape
+        y = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.float32, device=x.device)
+        _lib.call("dd_upsample2x_forward", _ptr(x), _ptr(y), n, h, w, c, _stream())
+        ctx.shape = (n, h, w, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, h, w, c = ctx.shape
+        gy = _chk(gy, name="grad")
+        gx = torch.empty(ctx.shape, dtype=torch.float32, device=gy.device)
+        _lib.call("dd_upsample2x_backward", _ptr(gy), _ptr(gx), n, h, w, c, _stream())
+        return gx
+
+
+def upsample2x(x):
+    """F.interpolate(x, scale_factor=2, mode="nearest") on NHWC (fpn.py:62)."""
+    return _Upsample2x.apply(x)
+
+
+class _Subsample2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x, name="x")
+        n, h, w, c = x.shape
+        y = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.float32, device=x.device)
+        _lib.call("dd_subsample2_forward", _ptr(x), _ptr(y), n, h, w, c, _stream())
+        ctx.shape = (n, h, w, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, h, w, c = ctx.shape
+        gy = _chk(gy, name="grad")
+        gx = torch.empty(ctx.shape, dtype=torch.float32, device=gy.device)
+        _lib.call("dd_subsample2_backward", _ptr(gy), _ptr(gx), n, h, w, c, _stream())
+        return gx
+
+
+def subsample2(x):
+    """LastLevelMaxPool: F.max_pool2d(x, 1, 2, 0) on NHWC (fpn.py:80-82)."""
+    return _Subsample2.apply(x)
+
+
 class _GradientScalar(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight):

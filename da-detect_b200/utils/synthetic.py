@@ -52,7 +52,7 @@ def make_state_dict(shapes, seed=100, random_bn=True):
     for name in sorted(shapes):
         shape = tuple(shapes[name])
         g = _gen(seed * 1000003 + zlib.crc32(name.encode()))
-        if name.endswith("cell_anchors.0"):
+        if ".cell_anchors." in name:
             continue
         leaf = name.rsplit(".", 1)[-1]
         is_bn = ".bn" in name or ".downsample.1." in name

@@ -248,6 +248,31 @@ int dd_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr,
 int dd_sgd_momentum_dev(float* p, const float* g, float* buf, long long n, const float* lr_dev, float lr_factor,
                         float momentum, float wd, float grad_scale, void* stream);
 
+/* ---------------------------------------------------------------- FPN */
+
+/* F.interpolate(x, scale_factor=2, mode="nearest") (modeling/backbone/fpn.py:62): x [N,H,W,C] -> y [N,2H,2W,C];
+ * backward: gx [N,H,W,C] = 2x2 block sums of gy [N,2H,2W,C].  C % 4 == 0, 16-byte aligned pointers. */
+int dd_upsample2x_forward(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int dd_upsample2x_backward(const float* gy, float* gx, int N, int H, int W, int C, void* stream);
+/* LastLevelMaxPool = F.max_pool2d(x, 1, 2, 0) (fpn.py:80-82): x [N,H,W,C] -> y [N,(H-1)/2+1,(W-1)/2+1,C]; backward
+ * writes EVERY element of gx [N,H,W,C] (gy at the even pixels, zeros elsewhere). */
+int dd_subsample2_forward(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int dd_subsample2_backward(const float* gy, float* gx, int N, int H, int W, int C, void* stream);
+/* LevelMapper (modeling/poolers.py:11-42): levels[k] = clamp(floor(canonical_level + log2(sqrt(area_k) /
+ * canonical_scale + eps)), k_min, k_max) - k_min for rois [K,5] = (batch_idx, x1, y1, x2, y2), +1 areas. */
+int dd_fpn_level_map(const float* rois, int K, int k_min, int k_max, float canonical_scale, int canonical_level,
+                     float eps, int* levels, void* stream);
+/* Multi-level Pooler.forward (poolers.py:104-121) without index lists: one call per feature level over ALL K rois;
+ * only rois with roi_level[k] == level are pooled from this map, into their own rows of out [K,PH,PW,C] (the other
+ * rows are left untouched — after the calls for every level each row has been written exactly once).  Backward
+ * likewise scatters only those rois' gradients into this level's grad_feat (zero-filled by the caller). */
+int dd_roi_align_level_forward(const float* feat, const float* rois, const int* roi_level, int level, float* out,
+                               int N, int H, int W, int C, int K, float spatial_scale, int PH, int PW,
+                               int sampling_ratio, void* stream);
+int dd_roi_align_level_backward(const float* grad_out, const float* rois, const int* roi_level, int level,
+                                float* grad_feat, int N, int H, int W, int C, int K, float spatial_scale, int PH,
+                                int PW, int sampling_ratio, void* stream);
+
 /* ---------------------------------------------------------------- input pipeline */
 
 /* Pillow's bilinear resampling coefficients for one axis (Resample.c precompute_coeffs + normalize_coeffs_8bpc,

@@ -314,6 +314,61 @@ def make_eval():
     return fx
 
 
+# ----------------------------------------------------------------------------- FPN eval-mode golden (BASELINE configs[4])
+FPN_YAML = "e2e_faster_rcnn_R_101_FPN_1x.yaml"
+FPN_HW = (480, 640)
+# fewer pre-NMS candidates per level and a cut at 1500, so that proposals of every pyramid level survive the
+# select_over_all_levels top-k (with the YAML's 1000/1000 the random-weight model keeps P2/P3 boxes only and the
+# LevelMapper would see one level)
+FPN_OPTS = ["MODEL.RPN.PRE_NMS_TOP_N_TEST", 500, "MODEL.RPN.FPN_POST_NMS_TOP_N_TEST", 1200]
+FPN_SCALE = {"roi_heads.box.predictor.cls_score.weight": 12.0, "roi_heads.box.predictor.bbox_pred.weight": 40.0}
+
+
+def tensor_probe(t):
+    """Small fingerprint of a big activation: moments + the first channels at three pixels."""
+    t = t.detach().float()
+    n, c, h, w = t.shape
+    return dict(shape=(n, c, h, w), mean=float(t.double().mean()), absmean=float(t.double().abs().mean()),
+                corner=t[:, :8, 0, 0].clone(), centre=t[:, :8, h // 2, w // 2].clone(), last=t[:, :8, h - 1, w - 1].clone())
+
+
+def make_fpn_eval():
+    """The reference's OWN eval-mode forward of the R-101-FPN Faster R-CNN YAML on CPU (2 synthetic 256x320 images,
+    81 classes): FPN top-down path, 5-level RPN + select_over_all_levels (test branch), LevelMapper pooling,
+    FPN2MLP head, PostProcessor.  Records the detections plus probes of the pyramid and the RPN proposals."""
+    import contextlib
+    import io
+    cfg = rh.reference_cfg(FPN_YAML, FPN_OPTS)
+    rh.install()
+    from maskrcnn_benchmark.modeling.detector import build_detection_model
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = build_detection_model(cfg)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    sd = make_state_dict(shapes)
+    for k, f in FPN_SCALE.items():
+        sd[k] = sd[k] * f
+    missing = model.load_state_dict(sd, strict=False)
+    assert all("cell_anchors" in k for k in missing.missing_keys) and not missing.unexpected_keys
+    model.eval()
+    images, _ = make_batch(2, FPN_HW[0], FPN_HW[1], num_classes=81, boxes_per_image=1, seed=777)
+    rec = {}
+    h1 = model.backbone.register_forward_hook(lambda m, i, o: rec.__setitem__("pyramid", [tensor_probe(t) for t in o]))
+    h2 = model.rpn.register_forward_hook(lambda m, i, o: rec.__setitem__(
+        "proposals", [dict(boxes=b.bbox.clone(), objectness=b.get_field("objectness").clone()) for b in o[0]]))
+    h3 = model.roi_heads.box.feature_extractor.pooler.register_forward_hook(
+        lambda m, i, o: rec.__setitem__("levels", m.map_levels(i[1]).to(torch.int64)))
+    with torch.no_grad():
+        out = model(images)
+    for h in (h1, h2, h3):
+        h.remove()
+    fx = dict(yaml=FPN_YAML, opts=FPN_OPTS, height=FPN_HW[0], width=FPN_HW[1], seed=777, scale=FPN_SCALE, nms="cpu_ge",
+              shapes=shapes, pyramid=rec["pyramid"], proposals=rec["proposals"], levels=rec["levels"],
+              detections=[dict(boxes=o.bbox.clone(), scores=o.get_field("scores").clone(),
+                               labels=o.get_field("labels").clone()) for o in out])
+    torch.save(fx, os.path.join(OUT, "eval_faster_rcnn_r101_fpn.pt"))
+    return fx
+
+
 # ----------------------------------------------------------------------------- input pipeline golden (SURVEY §8 f-4)
 PREPROCESS_CASES = [
     # (name, cfg opts, [(h, w) of the decoded images], random seed)
@@ -374,7 +429,16 @@ def make_preprocess():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "preprocess":
+    if len(sys.argv) > 1 and sys.argv[1] == "fpn":
+        assert rh.available(), "reference not mounted"
+        torch.set_num_threads(os.cpu_count())
+        fx = make_fpn_eval()
+        print("pyramid", [(p["shape"], round(p["absmean"], 4)) for p in fx["pyramid"]])
+        print("proposals", [len(p["objectness"]) for p in fx["proposals"]], "levels", torch.bincount(fx["levels"]).tolist())
+        for d in fx["detections"]:
+            print(len(d["scores"]), "detections; labels", sorted(set(d["labels"].tolist()))[:12], "scores",
+                  [round(float(v), 4) for v in d["scores"][:6]])
+    elif len(sys.argv) > 1 and sys.argv[1] == "preprocess":
         assert rh.available(), "reference not mounted"
         for k, c in make_preprocess().items():
             print(k, tuple(c["batch"].shape), c["image_sizes"])
@@ -388,4 +452,5 @@ if __name__ == "__main__":
     else:
         main()
         make_eval()
+        make_fpn_eval()
         make_preprocess()
