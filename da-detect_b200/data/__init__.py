@@ -1,1 +1,2 @@
-from .transforms import DeviceTransform, DeviceBatchCollator, build_transforms, get_size, resample_coeffs
+from .transforms import (DeviceBatchCollator, DeviceBatchCollatorTriplet, DeviceTransform, build_transforms, get_size,
+                         resample_coeffs)

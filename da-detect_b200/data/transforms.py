@@ -163,15 +163,41 @@ class DeviceBatchCollator(object):
             targets.append(sample[1] if len(sample) > 1 else None)
             ids.append(sample[2] if len(sample) > 2 else None)
         plans = [self.transform.plan((im.shape[1], im.shape[0])) for im in images]
+        images, new_targets = self.collate_planned(images, targets, plans)
+        return images, new_targets, tuple(ids)
+
+    def collate_planned(self, images, targets, plans, slot_base=0):
+        """One padded device batch from raw images whose (output size, flip) decisions are already made."""
         hp = max(p[0][0] for p in plans)
         wp = max(p[0][1] for p in plans)
         if self.size_divisible > 0:
             hp = int(math.ceil(hp / self.size_divisible) * self.size_divisible)
             wp = int(math.ceil(wp / self.size_divisible) * self.size_divisible)
         out = torch.empty((len(images), 3, hp, wp), dtype=torch.float32, device=self.transform.device)
-        self.h2d_bytes = 0
+        if slot_base == 0:
+            self.h2d_bytes = 0
         new_targets = []
         for i, (im, tg, (out_hw, flip)) in enumerate(zip(images, targets, plans)):
-            self.transform.run(self._to_device(i, im), out_hw, flip, out[i])
+            self.transform.run(self._to_device(slot_base + i, im), out_hw, flip, out[i])
             new_targets.append(self.transform.transform_target(tg, out_hw, flip))
-        return ImageList(out, [torch.Size(p[0]) for p in plans]), tuple(new_targets), tuple(ids)
+        return ImageList(out, [torch.Size(p[0]) for p in plans]), tuple(new_targets)
+
+
+class DeviceBatchCollatorTriplet(DeviceBatchCollator):
+    """BatchCollator_triplet (data/collate_batch.py:14-36): samples are 9-tuples (image, target, image_p, target_p,
+    image_n, target_n, idx1, idx2, idx3) — source, target-domain and auxiliary-domain views; three padded device
+    batches come back in the reference's tuple order.  The reference transforms the three images of a sample one after
+    the other inside the dataset, so the random draws are made sample by sample in (image, image_p, image_n) order."""
+
+    def plan_batch(self, batch):
+        return [[self.transform.plan((s[j].shape[1], s[j].shape[0])) for j in (0, 2, 4)] for s in batch]
+
+    def __call__(self, batch):
+        plans = self.plan_batch(batch)
+        n = len(batch)
+        out = []
+        for v, j in enumerate((0, 2, 4)):
+            imgs, tgs = self.collate_planned([s[j] for s in batch], [s[j + 1] for s in batch],
+                                             [plans[i][v] for i in range(n)], slot_base=v * n)
+            out.extend([imgs, tgs])
+        return tuple(out) + tuple(tuple(s[k] for s in batch) for k in (6, 7, 8))

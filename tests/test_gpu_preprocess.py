@@ -120,3 +120,28 @@ def test_pipeline_feeds_the_model():
         assert torch.isfinite(total)
     finally:
         ops.set_default_impl(ops.IMPL_SIMT)
+
+
+def test_triplet_collator_equals_three_planned_batches():
+    """DeviceBatchCollatorTriplet returns the reference's 9-tuple; each of its three batches equals the oracle's
+    transform of the same raw images under the same (size, flip) decisions."""
+    from dadetect_b200.data import DeviceBatchCollatorTriplet, build_transforms
+    cfg = cfg_for(["INPUT.MIN_SIZE_TRAIN", (40, 52), "INPUT.MAX_SIZE_TRAIN", 90, "DATALOADER.SIZE_DIVISIBILITY", 32])
+    coll = DeviceBatchCollatorTriplet(build_transforms(cfg, True, DEV), 32)
+    g = torch.Generator().manual_seed(12)
+    batch = []
+    for i in range(2):
+        imgs = [torch.randint(0, 256, (70, 140, 3), generator=g, dtype=torch.uint8) for _ in range(3)]
+        batch.append((imgs[0], None, imgs[1], None, imgs[2], None, "a%d" % i, "b%d" % i, "c%d" % i))
+    random.seed(3)
+    plans = coll.plan_batch(batch)
+    random.seed(3)
+    out = coll(batch)
+    assert len(out) == 9 and out[6] == ("a0", "a1") and out[8] == ("c0", "c1")
+    for v in range(3):
+        tensors = [pr.transform_image(batch[i][2 * v].numpy(), plans[i][v][0], plans[i][v][1], cfg.INPUT.PIXEL_MEAN,
+                                      cfg.INPUT.PIXEL_STD, cfg.INPUT.TO_BGR255) for i in range(2)]
+        want, sizes = pr.collate(tensors, 32)
+        assert np.array_equal(out[2 * v].tensors.cpu().numpy(), want)
+        assert [tuple(s) for s in out[2 * v].image_sizes] == sizes
+    assert coll.h2d_bytes == 6 * 70 * 140 * 3

@@ -108,3 +108,26 @@ def test_eval_transform_never_flips_and_rejects_host_images():
         assert out_hw == (600, 1200) and flip is False
     with pytest.raises(RuntimeError):                                       # no CPU path for the arithmetic
         tf.run(torch.zeros((4, 4, 3), dtype=torch.uint8), (4, 4), False, torch.zeros((3, 4, 4)))
+
+
+def test_triplet_collator_draws_sample_by_sample():
+    """BatchCollator_triplet's datasets transform (image, image_p, image_n) of one sample before the next sample:
+    the plans of the device collator must consume Python's `random` in exactly that order."""
+    from dadetect_b200.data import DeviceBatchCollatorTriplet, build_transforms
+    cfg = cfg_for(["INPUT.MIN_SIZE_TRAIN", (30, 44, 52), "INPUT.MAX_SIZE_TRAIN", 90])
+    coll = DeviceBatchCollatorTriplet(build_transforms(cfg, True, device="cpu"), 32)
+    shapes = [(61, 97), (97, 61), (50, 50)]
+    batch = [tuple(x for j in range(3) for x in (torch.zeros(shapes[(i + j) % 3] + (3,), dtype=torch.uint8), None))
+             + (i, i, i) for i in range(2)]
+    random.seed(5)
+    plans = coll.plan_batch(batch)
+    random.seed(5)
+    want = []
+    for i in range(2):
+        row = []
+        for j in range(3):
+            h, w = shapes[(i + j) % 3]
+            size = random.choice((30, 44, 52))
+            row.append((pr.get_size((w, h), size, 90), random.random() < 0.5))
+        want.append(row)
+    assert plans == want
