@@ -155,6 +155,8 @@ class RPNModule(nn.Module):
         self.rng = rng
         self.proposal_hook = None
         self.keep_debug = False       # tests: keep label / sample index tensors of the last step (host reads)
+        self.overlap_loss = True      # sync-free path: RPN loss chain on a side stream beside the proposal chain
+        self.__dict__["_side"] = None
 
     def set_proposal_hook(self, fn):
         """fn(list[BoxList]) -> list[BoxList], called on the proposals of every forward (None = off).
@@ -301,10 +303,24 @@ class RPNModule(nn.Module):
         n, fh, fw, _ = feat.shape
         ih, iw = images.image_sizes[0]
         anchors, vis = self.anchor_generator.grid(fh, fw, int(iw), int(ih))
-        props = self.proposals_static(anchors, logits.detach(), deltas.detach(), images.image_sizes, meta)
+        if self.overlap_loss:
+            # The proposal chain (top-k, NMS, gather: one or two CTAs per image, ~1.2 ms) and the RPN loss chain
+            # (match, sampler, encode, losses: ~0.45 ms, also a few CTAs) are independent: the loss chain runs on a
+            # side stream beside the proposals and joins before the box head.  Inside a step graph the fork / join
+            # become graph edges.  The random draws keep their order (RPN sampler before box-head sampler).
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=feat.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                obj_loss, box_loss = self.losses_static(anchors, vis, logits, deltas, targets)
+            props = self.proposals_static(anchors, logits.detach(), deltas.detach(), images.image_sizes, meta)
+            main.wait_stream(self._side)
+        else:
+            props = self.proposals_static(anchors, logits.detach(), deltas.detach(), images.image_sizes, meta)
+            obj_loss, box_loss = self.losses_static(anchors, vis, logits, deltas, targets)
         if self.proposal_hook is not None:
             props = self.proposal_hook(props)
-        obj_loss, box_loss = self.losses_static(anchors, vis, logits, deltas, targets)
         return props, {"loss_objectness": obj_loss, "loss_rpn_box_reg": box_loss}
 
     # ---- FPN: per-level post-processing + select_over_all_levels (rpn/inference.py:126-181) ----------
