@@ -57,3 +57,35 @@ def test_golden_exercises_every_pyramid_level(fx):
     assert torch.bincount(fx["levels"], minlength=4).min() > 0
     assert [p["shape"][2:] for p in fx["pyramid"]] == [(120, 160), (60, 80), (30, 40), (15, 20), (8, 10)]
     assert all(len(p["objectness"]) == 1200 for p in fx["proposals"])      # the select_over_all_levels cut is active
+
+
+@pytest.mark.timeout(600)
+def test_fpn_oracle_matches_real_reference_golden(fx):
+    """oracle/fpn_ref.py (the CPU restatement of the FPN eval path) against the recorded outputs of the REAL
+    reference R-101-FPN model: pyramid probes bit-level close, identical per-ROI levels, the same proposals and the
+    same detections.  nms_strict=False: the golden was made with the reference's CPU NMS (>=)."""
+    import fpn_ref
+    from dadetect_b200.utils.synthetic import make_batch, make_state_dict
+    cfg = fpn_cfg(fx["opts"])
+    P = make_state_dict(fx["shapes"])
+    for k, f in fx["scale"].items():
+        P[k] = P[k] * f
+    images, _ = make_batch(2, fx["height"], fx["width"], num_classes=81, boxes_per_image=1, seed=fx["seed"])
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        out = fpn_ref.forward_eval_fpn(P, cfg, images, nms_strict=False)
+    for t, want in zip(out["pyramid"], fx["pyramid"]):
+        n, c, h, w = want["shape"]
+        assert tuple(t.shape) == (n, c, h, w)
+        for name, (y, x) in (("corner", (0, 0)), ("centre", (h // 2, w // 2)), ("last", (h - 1, w - 1))):
+            torch.testing.assert_close(t[:, :8, y, x], want[name], atol=1e-5, rtol=1e-5)
+    for (gb, gs), want in zip(out["proposals"], fx["proposals"]):
+        assert len(gs) == len(want["objectness"])
+        torch.testing.assert_close(gs, want["objectness"], atol=1e-6, rtol=0)
+        torch.testing.assert_close(gb, want["boxes"], atol=1e-3, rtol=0)
+    assert torch.equal(out["levels"], fx["levels"])
+    for got, want in zip(out["detections"], fx["detections"]):
+        assert len(got["scores"]) == len(want["scores"])
+        assert torch.equal(got["labels"], want["labels"])
+        torch.testing.assert_close(got["scores"], want["scores"], atol=1e-6, rtol=0)
+        torch.testing.assert_close(got["boxes"], want["boxes"], atol=1e-3, rtol=0)
