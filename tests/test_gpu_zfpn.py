@@ -234,3 +234,52 @@ def test_fpn_training_step_runs_and_reaches_every_trainable_parameter():
     missing = [k for k, p in model.named_parameters() if p.requires_grad and p.grad is None]
     assert not missing, missing[:8]
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+@pytest.mark.timeout(600)
+def test_fpn_training_proposals_match_oracle():
+    """Training-mode RPN over five levels: PRE/POST_NMS_TOP_N_TRAIN per level, then select_over_all_levels' ONE
+    top-k over the whole batch (rpn/inference.py:160-171) and the GT boxes appended for source images — against
+    oracle/fpn_ref.py (pinned to the real reference by tests/test_fpn_cpu.py) on the fp32 arm."""
+    import fpn_ref
+    from dadetect_b200 import ops
+    from dadetect_b200.modeling import build_detection_model
+    from dadetect_b200.structures import BoxList
+    from dadetect_b200.utils.synthetic import make_batch, make_state_dict
+    ops.set_default_impl(ops.IMPL_SIMT)
+    cfg = fpn_cfg(["MODEL.BACKBONE.CONV_BODY", "R-50-FPN", "MODEL.ROI_BOX_HEAD.NUM_CLASSES", 9,
+                   "MODEL.RPN.FPN_POST_NMS_TOP_N_TRAIN", 1500])
+    model = build_detection_model(cfg).to(DEV)
+    sd = make_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    sd["rpn.head.cls_logits.weight"] = sd["rpn.head.cls_logits.weight"] * 20.0      # spread the objectness scores
+    model.load_state_dict(sd, strict=False)
+    model.train()
+    H, W = 256, 320
+    images, targets = make_batch(2, H, W, num_classes=9, boxes_per_image=5, seed=21)
+    tg = []
+    for t in targets:
+        b = BoxList(t["boxes"].to(DEV), (W, H), mode="xyxy")
+        b.add_field("labels", t["labels"].to(DEV))
+        b.add_field("is_source", torch.full((len(t["labels"]),), bool(t["is_source"]), dtype=torch.bool, device=DEV))
+        tg.append(b)
+    seen = {}
+    model.rpn.set_proposal_hook(lambda boxes: seen.setdefault("p", boxes) or boxes)
+    with torch.no_grad():
+        model(images.to(DEV), tg)
+    with torch.no_grad():
+        pyramid = fpn_ref.fpn_forward(fpn_ref.resnet_body_all_stages(images, sd, "R-50-FPN"), sd)
+        want = fpn_ref.rpn_fpn_proposals(pyramid, sd, cfg, [(H, W)] * 2, training=True, nms_strict=True)
+    total = 0
+    for i, (got, (wb, ws)) in enumerate(zip(seen["p"], want)):
+        if targets[i]["is_source"]:                          # add_gt_proposals (rpn/inference.py:51-74)
+            wb = torch.cat([wb, targets[i]["boxes"]])
+            ws = torch.cat([ws, torch.ones(len(targets[i]["boxes"]))])
+        gb, gs = got.bbox.cpu(), got.get_field("objectness").cpu()
+        total += len(gs)
+        assert abs(len(gs) - len(ws)) <= 3, (i, len(gs), len(ws))
+        d = torch.cdist(wb.double(), gb.double(), p=float("inf"))
+        assert int((d.min(dim=1)[0] < 0.05).sum()) >= len(wb) - 4, i
+        m = min(len(gs), len(ws)) - 4
+        torch.testing.assert_close(torch.sort(gs, descending=True)[0][:m], torch.sort(ws, descending=True)[0][:m],
+                                   atol=2e-5, rtol=0)
+    assert abs(total - (1500 + 5)) <= 1                      # the cut is over the BATCH, plus the source image's GT
