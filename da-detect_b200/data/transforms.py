@@ -138,7 +138,8 @@ class DeviceBatchCollator(object):
     def __init__(self, transform, size_divisible=0):
         self.transform = transform
         self.size_divisible = int(size_divisible)
-        self._pinned = {}
+        self._pinned = {}                       # slot -> pinned staging buffer (grow-only)
+        self._copied = {}                       # slot -> event recorded after the H2D copy out of that buffer
         self.h2d_bytes = 0                      # bytes copied host -> device by the last call
 
     def _to_device(self, slot, img):
@@ -147,6 +148,9 @@ class DeviceBatchCollator(object):
         if img.is_cuda:
             return img
         img = img.contiguous()
+        busy = self._copied.get(slot)
+        if busy is not None:
+            busy.synchronize()                   # the previous batch's DMA out of this staging buffer has finished
         pin = self._pinned.get(slot)
         if pin is None or pin.numel() < img.numel():
             pin = torch.empty(img.numel(), dtype=torch.uint8).pin_memory()
@@ -154,7 +158,11 @@ class DeviceBatchCollator(object):
         stage = pin[: img.numel()].view(img.shape)
         stage.copy_(img)
         self.h2d_bytes += img.numel()
-        return stage.to(self.transform.device, non_blocking=True)
+        dev = stage.to(self.transform.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._copied[slot] = ev
+        return dev
 
     def __call__(self, batch):
         images, targets, ids = [], [], []
