@@ -157,6 +157,8 @@ class FlatSGDTrainer(object):
         tensors = images.tensors if isinstance(images, ImageList) else images
         if not torch.is_tensor(tensors) or not self.model.roi_heads:
             return None
+        if not getattr(self.model, "static_shapes", False):
+            return None                  # host-driven control flow (FPN, enable_static_shapes(False)) reads sizes
         if self.model.da_heads_triplet and self.model.da_heads_triplet.host_reads_needed():
             return None                  # an adaptive margin below its maximum reads the previous loss on the host
         cache_source_flags(targets)
