@@ -6,7 +6,6 @@ Module/parameter names mirror the reference so its checkpoints load unchanged
 ``....bn{1,2,3}.{weight,bias,running_mean,running_var}``, ``....downsample.{0.weight,1.*}``.
 Each Conv2d + FrozenBatchNorm2d (+ residual add) (+ ReLU) group of the reference is ONE kernel here.
 """
-import math
 from collections import OrderedDict
 
 import torch

@@ -210,7 +210,6 @@ def test_fpn_training_step_runs_and_reaches_every_trainable_parameter():
     the same kernels).  No parity claim here — only that forward + backward run, losses are finite and every
     trainable parameter of the pyramid, the shared RPN head and the MLP box head receives a gradient."""
     from dadetect_b200 import ops
-    from dadetect_b200.config import get_cfg_defaults
     from dadetect_b200.modeling import build_detection_model
     from dadetect_b200.structures import BoxList
     from dadetect_b200.utils.synthetic import make_batch
