@@ -1,8 +1,9 @@
 """Region proposal network: head convs, on-device proposal generation, RPN losses.
 
-Mirrors maskrcnn_benchmark/modeling/rpn/{rpn,anchor_generator,inference,loss}.py for the
-single-level (C4) case; state-dict names ``rpn.head.{conv,cls_logits,bbox_pred}.{weight,bias}``
-and the buffer ``rpn.anchor_generator.cell_anchors.0`` are preserved.
+Mirrors maskrcnn_benchmark/modeling/rpn/{rpn,anchor_generator,inference,loss}.py: the single-level (C4) case on
+the sync-free path, the multi-level (FPN) case with the reference's host-driven control flow; state-dict names
+``rpn.head.{conv,cls_logits,bbox_pred}.{weight,bias}`` and the buffers ``rpn.anchor_generator.cell_anchors.{i}``
+are preserved.
 """
 import numpy as np
 import torch
@@ -53,7 +54,7 @@ class BufferList(nn.Module):
 
 
 class AnchorGenerator(nn.Module):
-    """Single-level AnchorGenerator (anchor_generator.py:34-125).  The grid and its visibility mask are
+    """AnchorGenerator (anchor_generator.py:34-125), single- or multi-level.  The grid and its visibility mask are
     produced by one kernel and cached per (feature size, image size) instead of being rebuilt from
     arange/meshgrid/stack every iteration."""
 
