@@ -87,13 +87,17 @@ def test_flip_is_the_mirror_and_resize_commutes_with_it():
     assert torch.equal(c, b)
 
 
-def test_pipeline_feeds_the_model():
-    """Raw uint8 samples -> DeviceBatchCollator -> GeneralizedRCNN.forward in training mode: finite losses."""
+@pytest.mark.parametrize("min_size,max_size,padded", [(96, 192, (96, 192)), (90, 180, (96, 192))])
+def test_pipeline_feeds_the_model(min_size, max_size, padded):
+    """Raw uint8 samples -> DeviceBatchCollator -> GeneralizedRCNN.forward in training mode: finite losses.  The
+    second case is the real-data situation of the DA YAMLs (600x1200 padded to 608x1216): the un-padded image size
+    (anchor visibility, clipping) differs from the size of the batch tensor (feature-map extent)."""
     from dadetect_b200 import ops
     from dadetect_b200.data import DeviceBatchCollator, build_transforms
     from dadetect_b200.modeling import build_detection_model
     from dadetect_b200.structures import BoxList
-    cfg = cfg_for(["INPUT.MIN_SIZE_TRAIN", (96,), "INPUT.MAX_SIZE_TRAIN", 192, "DATALOADER.SIZE_DIVISIBILITY", 32])
+    cfg = cfg_for(["INPUT.MIN_SIZE_TRAIN", (min_size,), "INPUT.MAX_SIZE_TRAIN", max_size,
+                   "DATALOADER.SIZE_DIVISIBILITY", 32])
     ops.set_default_impl(ops.IMPL_TCGEN05)
     try:
         torch.manual_seed(3)
@@ -113,7 +117,8 @@ def test_pipeline_feeds_the_model():
             samples.append((raw, t, i))
         random.seed(1)
         images, targets, _ = collate(samples)
-        assert tuple(images.tensors.shape) == (2, 3, 96, 192)
+        assert tuple(images.tensors.shape) == (2, 3) + padded
+        assert [tuple(s) for s in images.image_sizes] == [(min_size, max_size)] * 2
         losses = model(images, [t.to(DEV) for t in targets])
         total = sum(losses.values())
         total.backward()
