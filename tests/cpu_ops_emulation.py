@@ -1,0 +1,108 @@
+"""TEST INFRASTRUCTURE ONLY — torch-CPU stand-ins for the kernel-calling functions of dadetect_b200.ops, installed
+by the `cpu_ops` fixture (monkeypatch, undone after the test) so that the PYTHON control flow of the model code
+(FPN pyramid wiring, multi-level RPN selection, level mapping, head plumbing, post-processing) can be exercised in
+the `-m "not gpu"` suite.  Nothing here ships: the product has no CPU path (ops raise on CPU tensors), and the
+arithmetic of every stand-in comes from torch / the oracle, never from the product."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import da_frcnn_ref as orc
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def conv_bn_act(x, weight, scale=None, bias=None, residual=None, stride=1, pad=0, relu=False):
+    w = weight if weight.dim() == 4 else weight[:, :, None, None]
+    y = F.conv2d(nchw(x), w.contiguous(), stride=stride, padding=pad)
+    if scale is not None:
+        y = y * scale.view(1, -1, 1, 1)
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1)
+    y = nhwc(y)
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y
+
+
+def linear(x, weight, bias=None, relu=False):
+    y = F.linear(x, weight, bias)
+    return F.relu(y) if relu else y
+
+
+def bottleneck_stage(x, blocks, strides, input_is_relu=False, grad_premasked=False, pool_output=False):
+    for b, s in zip(blocks, strides):
+        y = conv_bn_act(x, b["w1"], b["s1"], b["b1"], stride=s, relu=True)
+        y = conv_bn_act(y, b["w2"], b["s2"], b["b2"], pad=1, relu=True)
+        idt = conv_bn_act(x, b["wd"], b["sd"], b["bd"], stride=s) if "wd" in b else x
+        x = conv_bn_act(y, b["w3"], b["s3"], b["b3"], residual=idt, relu=True)
+    return x.mean(dim=(1, 2)) if pool_output else x
+
+
+def anchor_grid(cell, fh, fw, stride, img_w, img_h, straddle):
+    a = orc.grid_anchors(fh, fw, stride, cell)
+    return a, orc.anchor_visibility(a, img_w, img_h, straddle).to(torch.uint8)
+
+
+def rpn_topk_decode(logits, deltas, anchors, k, img_w, img_h, min_size):
+    n = logits.shape[0]
+    obj = logits.reshape(n, -1).sigmoid()
+    reg = deltas.reshape(n, -1, 4)
+    sc, idx = obj.topk(k, dim=1, sorted=True)
+    boxes, scores, valid = torch.zeros(n, k, 4), torch.zeros(n, k), torch.zeros(n, dtype=torch.int32)
+    for i in range(n):
+        bx = orc.clip_boxes(orc.box_decode(reg[i][idx[i]], anchors[idx[i]], (1.0, 1.0, 1.0, 1.0)), img_w, img_h)
+        keep = ((bx[:, 2] - bx[:, 0] + 1) >= min_size) & ((bx[:, 3] - bx[:, 1] + 1) >= min_size)
+        m = int(keep.sum())
+        boxes[i, :m], scores[i, :m], valid[i] = bx[keep], sc[i][keep], m
+    return boxes, scores, idx.to(torch.int32), valid
+
+
+def nms_sorted_batched(boxes, valid, thresh, max_keep):
+    n = boxes.shape[0]
+    keep, cnt = torch.zeros(n, max_keep, dtype=torch.int64), torch.zeros(n, dtype=torch.int32)
+    for i in range(n):
+        v = int(valid[i])
+        k = orc.nms(boxes[i, :v], torch.arange(v, 0, -1).float(), thresh, strict=True)[:max_keep]
+        keep[i, :len(k)], cnt[i] = k, len(k)
+    return keep, cnt
+
+
+def roi_align_levels(feats, rois, scales, pooled, sampling_ratio):
+    import fpn_ref
+    out, lv = fpn_ref.multilevel_pool([nchw(f) for f in feats], rois, scales, pooled, sampling_ratio)
+    return nhwc(out), lv.to(torch.int32)
+
+
+def roi_align(feat, rois, scale, pooled, sampling_ratio, bin_step=1):
+    return nhwc(orc.roi_align(nchw(feat), rois, scale, pooled, pooled, sampling_ratio))[:, ::bin_step, ::bin_step]
+
+
+STAND_INS = dict(
+    _chk=lambda t, dtype=torch.float32, name="tensor": t,
+    conv_bn_act=conv_bn_act, linear=linear, bottleneck_stage=bottleneck_stage,
+    stem_tc_supported=lambda x, w: False, nchw_to_nhwc=nhwc,
+    maxpool3x3s2=lambda x: nhwc(F.max_pool2d(nchw(x), 3, 2, 1)),
+    upsample2x=lambda x: nhwc(F.interpolate(nchw(x), scale_factor=2, mode="nearest")),
+    subsample2=lambda x: nhwc(F.max_pool2d(nchw(x), 1, 2, 0)),
+    avgpool_hw=lambda x: x.mean(dim=(1, 2)),
+    anchor_grid=anchor_grid, rpn_topk_decode=rpn_topk_decode, nms_sorted_batched=nms_sorted_batched,
+    nms=lambda boxes, scores, thresh: orc.nms(boxes, scores, thresh, strict=True),
+    box_decode=lambda codes, boxes, weights: orc.box_decode(codes, boxes, weights),
+    roi_align_levels=roi_align_levels, roi_align=roi_align,
+)
+
+
+@pytest.fixture
+def cpu_ops(monkeypatch):
+    from dadetect_b200 import ops
+    for name, fn in STAND_INS.items():
+        assert hasattr(ops, name), name                 # a renamed op must not silently lose its stand-in
+        monkeypatch.setattr(ops, name, fn)
+    return ops

@@ -89,3 +89,55 @@ def test_fpn_oracle_matches_real_reference_golden(fx):
         assert torch.equal(got["labels"], want["labels"])
         torch.testing.assert_close(got["scores"], want["scores"], atol=1e-6, rtol=0)
         torch.testing.assert_close(got["boxes"], want["boxes"], atol=1e-3, rtol=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The PYTHON control flow of the product's FPN path (modeling/backbone.py::FPN, rpn.py::proposals_fpn / forward_fpn,
+# roi_heads.py::MultiLevelPooler / FPN2MLPFeatureExtractor / FPNPredictor, inference.py) with the kernels replaced by
+# torch stand-ins (tests/cpu_ops_emulation.py): wiring, ordering and selection logic are checked on CPU every round;
+# the kernels themselves are checked on the GPU (tests/test_gpu_zfpn.py).
+from cpu_ops_emulation import cpu_ops  # noqa: E402,F401  (pytest fixture)
+
+
+@pytest.mark.timeout(900)
+def test_product_fpn_eval_control_flow_matches_real_reference_golden(fx, cpu_ops):
+    from dadetect_b200.modeling import build_detection_model
+    from dadetect_b200.utils.synthetic import make_batch, make_state_dict
+    cfg = fpn_cfg(fx["opts"])
+    sd = make_state_dict(fx["shapes"])
+    for k, f in fx["scale"].items():
+        sd[k] = sd[k] * f
+    images, _ = make_batch(2, fx["height"], fx["width"], num_classes=81, boxes_per_image=1, seed=fx["seed"])
+    model = build_detection_model(cfg)
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all("cell_anchors" in k for k in missing.missing_keys)
+    model.eval()
+    seen = {}
+    model.rpn.set_proposal_hook(lambda boxes: seen.setdefault("p", boxes) or boxes)
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        out = model(images)
+    for got, want in zip(seen["p"], fx["proposals"]):
+        assert len(got) == len(want["objectness"])
+        torch.testing.assert_close(got.get_field("objectness"), want["objectness"], atol=1e-6, rtol=0)
+        d = torch.cdist(want["boxes"].double(), got.bbox.double(), p=float("inf"))      # equal scores may swap places
+        assert int((d.min(dim=1)[0] < 1e-2).sum()) >= len(want["boxes"]) - 2
+    lv = model.roi_heads.box.feature_extractor.pooler.last_levels.to(torch.int64)
+    assert int((torch.bincount(lv, minlength=4) - torch.bincount(fx["levels"], minlength=4)).abs().sum()) <= 2
+    for got, want in zip(out, fx["detections"]):
+        assert abs(len(got) - len(want["scores"])) <= 1          # product NMS is strict >, the golden's is >=
+        gb, gs, gl = got.bbox, got.get_field("scores"), got.get_field("labels")
+        hits = 0
+        for i in range(len(want["scores"])):
+            hits += int(((gl == want["labels"][i]) & ((gb - want["boxes"][i]).abs().max(dim=1)[0] < 1e-2)
+                         & ((gs - want["scores"][i]).abs() < 1e-5)).any())
+        assert hits >= len(want["scores"]) - 1
+
+
+def test_ops_refuse_cpu_tensors_without_the_stand_ins():
+    """The stand-ins above are a test fixture; the product itself has no CPU path."""
+    from dadetect_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.upsample2x(torch.zeros(1, 2, 2, 4))
+    with pytest.raises(RuntimeError):
+        ops.roi_align_levels([torch.zeros(1, 4, 4, 4)], torch.zeros(1, 5), (0.25,), 7, 2)
