@@ -84,6 +84,83 @@ def roi_align(feat, rois, scale, pooled, sampling_ratio, bin_step=1):
     return nhwc(orc.roi_align(nchw(feat), rois, scale, pooled, pooled, sampling_ratio))[:, ::bin_step, ::bin_step]
 
 
+# ---- training path (host-driven control flow)
+class _Grl(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.w = w
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        w = ctx.w
+        return g * (float(w) if not torch.is_tensor(w) else w.reshape(()).to(g.dtype)), None   # a device weight is read NOW
+
+
+def match(gt, pred, high, low, allow_low_quality):
+    if gt.shape[0] == 0 or pred.shape[0] == 0:
+        raise ValueError("No ground-truth or proposal boxes available for one of the images during training")
+    q = orc.box_iou(gt, pred)
+    return orc.matcher(q, high, low, allow_low_quality), q.max(dim=0)[0]
+
+
+def box_encode(gt, pred, matches, weights, wrap_negative=False):
+    idx = torch.where(matches < 0, matches + gt.shape[0] if wrap_negative else torch.zeros_like(matches), matches)
+    return orc.box_encode(gt[idx.clamp(min=0)], pred, weights)
+
+
+def bce_with_logits_mean(x, targets=None, seg_labels=None, seg_len=0):
+    if targets is None:
+        targets = seg_labels.to(torch.float32).repeat_interleave(int(seg_len)).view_as(x)
+    return F.binary_cross_entropy_with_logits(x, targets.view_as(x))
+
+
+def smooth_l1_sum(x, t, beta, divisor):
+    n = (x - t).abs()
+    return torch.where(n < beta, 0.5 * n * n / beta, n - 0.5 * beta).sum() / divisor
+
+
+def softmax_ce_mean(logits, labels, row_mask):
+    m = row_mask.bool()
+    return F.cross_entropy(logits[m], labels[m])
+
+
+def box_reg_loss(box_reg, reg_targets, labels, row_mask):
+    m = row_mask.bool()                                            # box_head/loss.py:205-219
+    pos = torch.nonzero(m & (labels > 0)).squeeze(1)
+    cols = 4 * labels[pos][:, None] + torch.arange(4)
+    return smooth_l1_sum(box_reg[pos[:, None], cols], reg_targets[pos], 1.0, float(m.sum()))
+
+
+def consistency_loss(img_logits, ins_logits, n_src, row_valid=None):
+    assert row_valid is None
+    k = ins_logits.numel()
+    dom = torch.arange(k) < int(n_src)
+    return orc.consistency_loss(img_logits.sigmoid(), ins_logits.sigmoid().reshape(-1, 1), dom)
+
+
+def triplet_margin_loss(a, p, n, margin, rows, d, inner):
+    def rows_of(t):
+        return t.reshape(-1, d, inner).permute(0, 2, 1).reshape(rows, d)
+    return F.triplet_margin_loss(rows_of(a), rows_of(p), rows_of(n), margin=float(margin), p=2)
+
+
+def adv_grl_weight(loss, bce, lam, lam_adv, threshold, out=None):
+    w = torch.tensor([orc.adv_grl_weight(loss.detach(), lam, lam_adv, threshold)], dtype=torch.float32)
+    if out is not None:
+        out.copy_(w)
+        return out
+    return w
+
+
+TRAINING_STAND_INS = dict(
+    gradient_scalar=lambda x, w: _Grl.apply(x, w), gradient_scalar_dev=lambda x, wdev: _Grl.apply(x, wdev),
+    dropout_with_mask=lambda x, keep: x * keep * 2.0, match=match, box_encode=box_encode,
+    bce_with_logits_mean=bce_with_logits_mean, smooth_l1_sum=smooth_l1_sum, softmax_ce_mean=softmax_ce_mean,
+    box_reg_loss=box_reg_loss, consistency_loss=consistency_loss, triplet_margin_loss=triplet_margin_loss,
+    adv_grl_weight=adv_grl_weight,
+)
+
 STAND_INS = dict(
     _chk=lambda t, dtype=torch.float32, name="tensor": t,
     conv_bn_act=conv_bn_act, linear=linear, bottleneck_stage=bottleneck_stage,
@@ -102,7 +179,7 @@ STAND_INS = dict(
 @pytest.fixture
 def cpu_ops(monkeypatch):
     from dadetect_b200 import ops
-    for name, fn in STAND_INS.items():
+    for name, fn in list(STAND_INS.items()) + list(TRAINING_STAND_INS.items()):
         assert hasattr(ops, name), name                 # a renamed op must not silently lose its stand-in
         monkeypatch.setattr(ops, name, fn)
     return ops

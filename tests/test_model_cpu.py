@@ -1,0 +1,77 @@
+"""CPU: the PYTHON orchestration of the training path (modeling/detector.py, rpn.py, roi_heads.py, da_heads.py on
+the host-driven control flow) against the CPU oracle, with the kernels replaced by torch stand-ins
+(tests/cpu_ops_emulation.py — a test fixture; the product has no CPU path).  What this pins every round without a
+GPU: call order, loss-dict keys and weights, GRL signs, which tensors feed which head, sampler / RNG draw order
+(the oracle's recorded draws are replayed and must be consumed exactly), de-duplicated passes adding up to the
+reference's gradients.  The kernels themselves are pinned on the GPU (tests/test_gpu_*.py)."""
+import os
+
+import pytest
+import torch
+
+import da_frcnn_ref as orc
+from cpu_ops_emulation import cpu_ops  # noqa: F401  (pytest fixture)
+from make_golden import SCENARIOS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def scenario(name):
+    from dadetect_b200.config import get_cfg_defaults
+    from dadetect_b200.utils.synthetic import make_batch, make_state_dict
+    yaml_name, opts, n, H, W, m = SCENARIOS[name]
+    cfg = get_cfg_defaults()
+    cfg.merge_from_file(os.path.join(ROOT, "configs", yaml_name))
+    cfg.merge_from_list(list(opts))
+    sd = make_state_dict(orc.param_shapes(cfg))
+    images, targets = make_batch(n, H, W, num_classes=cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES, boxes_per_image=m)
+    return cfg, sd, images, targets, (H, W)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("name", ["da_img_ins_cst", "triplet_aligned_advgrl"])
+def test_host_driven_training_step_matches_oracle(name, cpu_ops):
+    from dadetect_b200.modeling import build_detection_model
+    from dadetect_b200.structures import BoxList
+    from dadetect_b200.utils.random_source import ReplaySource
+    torch.set_num_threads(os.cpu_count())
+    cfg, sd, images, targets, (H, W) = scenario(name)
+    torch.manual_seed(77)
+    rec = orc.RecordingHooks()
+    P = {k: v.clone().requires_grad_(orc.is_trainable(k)) for k, v in sd.items()}
+    want = orc.forward_train(P, cfg, images, targets, hooks=rec, nms_strict=True)
+    sum(want.values()).backward()
+
+    model = build_detection_model(cfg)
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all("cell_anchors" in k for k in missing.missing_keys)
+    model.train()
+    model.enable_static_shapes(False)                       # the reference-like control flow (host reads sizes)
+    replay = ReplaySource(rec.perms, rec.masks)
+    model.set_random_source(replay)
+    tg = []
+    for t in targets:
+        b = BoxList(t["boxes"].clone(), (W, H), mode="xyxy")
+        b.add_field("labels", t["labels"].clone())
+        b.add_field("is_source", torch.full((len(t["labels"]),), bool(t["is_source"]), dtype=torch.bool))
+        tg.append(b)
+    got = model(images, tg)
+    assert list(got.keys()) == list(want.keys())
+    assert not replay.perms and not replay.masks            # every recorded draw consumed, in order
+    for k in want:
+        g, w = float(got[k].detach()), float(want[k].detach())
+        assert abs(g - w) <= 2e-5 * max(1.0, abs(w)), (k, g, w)
+    sum(got.values()).backward()
+    params = dict(model.named_parameters())
+    checked = 0
+    for k, p in P.items():
+        if not p.requires_grad:
+            continue
+        if p.grad is None:
+            assert params[k].grad is None or float(params[k].grad.abs().max()) == 0.0, k
+            continue
+        assert params[k].grad is not None, k
+        a, b = params[k].grad.double(), p.grad.double()
+        assert float((a - b).norm()) <= 1e-3 * float(b.norm()) + 1e-9, (k, float((a - b).norm()), float(b.norm()))
+        checked += 1
+    assert checked > 50
