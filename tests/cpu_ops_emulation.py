@@ -153,11 +153,57 @@ def adv_grl_weight(loss, bce, lam, lam_adv, threshold, out=None):
     return w
 
 
+# ---- sync-free (fixed-capacity) path
+def proposals_gather(boxes, scores, keep, keep_count, gt_cat, gt_offsets, append_gt, cap):
+    n, post = boxes.shape[0], keep.shape[1]
+    out_b, out_s = torch.zeros(n, cap, 4), torch.zeros(n, cap)
+    out_c = torch.zeros(n, dtype=torch.int32)
+    for g in range(n):
+        c = min(int(keep_count[g]), post)
+        sel = keep[g, :c]
+        out_b[g, :c], out_s[g, :c] = boxes[g][sel], scores[g][sel]
+        if int(append_gt[g]):
+            a, b = int(gt_offsets[g]), int(gt_offsets[g + 1])
+            out_b[g, c:c + b - a], out_s[g, c:c + b - a] = gt_cat[a:b], 1.0
+            c += b - a
+        out_c[g] = c
+    return out_b, out_s, out_c
+
+
+def balanced_sample(labels, n_dev, keys, batch, max_pos):
+    images, n_cap = labels.shape
+    sel = torch.zeros(images, batch, dtype=torch.int64)
+    cnt = torch.zeros(images, 2, dtype=torch.int32)
+    for g in range(images):
+        n = n_cap if n_dev is None else int(n_dev[g])
+        lab, k = labels[g, :n], keys[g, :n]
+        pos, neg = torch.nonzero(lab >= 1).squeeze(1), torch.nonzero(lab == 0).squeeze(1)
+        npos = min(pos.numel(), max_pos)
+        nneg = min(neg.numel(), batch - npos)
+        p = pos[torch.argsort(k[pos], stable=True)[:npos]]           # smallest keys; ties -> lower index
+        q = neg[torch.argsort(k[neg], stable=True)[:nneg]]
+        chosen = torch.sort(torch.cat([p, q]))[0]
+        sel[g, :chosen.numel()] = chosen
+        cnt[g, 0], cnt[g, 1] = npos, npos + nneg
+    return sel, cnt
+
+
+def consistency_loss_masked(img_logits, ins_logits, n_src, row_valid=None):
+    if row_valid is None:
+        return consistency_loss(img_logits, ins_logits, n_src)
+    means = img_logits.sigmoid().reshape(2, -1).mean(1)
+    k = ins_logits.numel()
+    per_roi = torch.where(torch.arange(k) < int(n_src), means[0], means[1])
+    v = row_valid.bool()
+    return (torch.abs(per_roi - ins_logits.sigmoid().reshape(-1)) * v).sum() / v.sum()
+
+
 TRAINING_STAND_INS = dict(
+    proposals_gather=proposals_gather, balanced_sample=balanced_sample,
     gradient_scalar=lambda x, w: _Grl.apply(x, w), gradient_scalar_dev=lambda x, wdev: _Grl.apply(x, wdev),
     dropout_with_mask=lambda x, keep: x * keep * 2.0, match=match, box_encode=box_encode,
     bce_with_logits_mean=bce_with_logits_mean, smooth_l1_sum=smooth_l1_sum, softmax_ce_mean=softmax_ce_mean,
-    box_reg_loss=box_reg_loss, consistency_loss=consistency_loss, triplet_margin_loss=triplet_margin_loss,
+    box_reg_loss=box_reg_loss, consistency_loss=consistency_loss_masked, triplet_margin_loss=triplet_margin_loss,
     adv_grl_weight=adv_grl_weight,
 )
 

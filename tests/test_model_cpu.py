@@ -29,8 +29,12 @@ def scenario(name):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("name", ["da_img_ins_cst", "triplet_aligned_advgrl"])
-def test_host_driven_training_step_matches_oracle(name, cpu_ops):
+@pytest.mark.parametrize("name,static", [("da_img_ins_cst", False), ("da_img_ins_cst", True),
+                                         ("triplet_aligned_advgrl", True)])
+def test_training_orchestration_matches_oracle(name, static, cpu_ops):
+    """static=False: the reference-like host-driven control flow; static=True: the production sync-free path
+    (fixed-capacity proposal / ROI buffers with validity masks, device sampler on replayed keys) — its second
+    stream is switched off here, streams being a CUDA notion."""
     from dadetect_b200.modeling import build_detection_model
     from dadetect_b200.structures import BoxList
     from dadetect_b200.utils.random_source import ReplaySource
@@ -46,7 +50,8 @@ def test_host_driven_training_step_matches_oracle(name, cpu_ops):
     missing = model.load_state_dict(sd, strict=False)
     assert not missing.unexpected_keys and all("cell_anchors" in k for k in missing.missing_keys)
     model.train()
-    model.enable_static_shapes(False)                       # the reference-like control flow (host reads sizes)
+    model.enable_static_shapes(static)
+    model.rpn.overlap_loss = False
     replay = ReplaySource(rec.perms, rec.masks)
     model.set_random_source(replay)
     tg = []
