@@ -369,6 +369,64 @@ def make_fpn_eval():
     return fx
 
 
+# ----------------------------------------------------------------------------- config surface + structures (boundary B3 / B1)
+def _flatten(node, prefix=""):
+    out = {}
+    for k, v in node.items():
+        if hasattr(v, "items"):
+            out.update(_flatten(v, prefix + k + "."))
+        else:
+            out[prefix + k] = list(v) if isinstance(v, tuple) else v
+    return out
+
+
+def make_boundary():
+    """(1) The reference's config/defaults.py tree merged with each of its DA YAMLs (+ the two plain detectors this
+    repo pins): YAML text and the flattened effective configuration.  (2) BoxList / ImageList behaviour of the real
+    reference classes on seeded inputs (resize, transpose, convert, clip_to_image, area, to_image_list, __add__)."""
+    rh.install()
+    import glob
+    from maskrcnn_benchmark.structures.bounding_box import BoxList
+    from maskrcnn_benchmark.structures.image_list import to_image_list
+    cfgs = {}
+    names = sorted(glob.glob(os.path.join(rh.REF, "configs", "da_faster_rcnn", "*.y*ml")))
+    names += [os.path.join(rh.REF, "configs", n) for n in ("e2e_faster_rcnn_R_50_C4_1x.yaml",
+                                                           "e2e_faster_rcnn_R_101_FPN_1x.yaml")]
+    for path in names:
+        rel = os.path.relpath(path, os.path.join(rh.REF, "configs"))
+        c = rh.reference_cfg(rel, [])
+        flat = _flatten(c)
+        flat["MODEL.DEVICE"] = "cuda"                       # reference_cfg forces cpu for the CPU runs
+        cfgs[rel] = dict(text=open(path).read(), effective=flat)
+    g = torch.Generator().manual_seed(17)
+    x1 = torch.rand(12, generator=g) * 300 - 20
+    y1 = torch.rand(12, generator=g) * 200 - 20
+    boxes = torch.stack([x1, y1, x1 + torch.rand(12, generator=g) * 150, y1 + torch.rand(12, generator=g) * 120], 1)
+    b = BoxList(boxes.clone(), (320, 200), mode="xyxy")
+    b.add_field("labels", torch.arange(12))
+    st = dict(boxes=boxes, size=(320, 200))
+    st["xywh"] = b.convert("xywh").bbox.clone()
+    st["xywh_back"] = b.convert("xywh").convert("xyxy").bbox.clone()
+    st["area"] = b.area().clone()
+    st["resize_same_ratio"] = b.resize((640, 400)).bbox.clone()
+    st["resize_two_ratios"] = b.resize((500, 333)).bbox.clone()
+    st["flip_lr"] = b.transpose(0).bbox.clone()
+    st["flip_tb"] = b.transpose(1).bbox.clone()
+    cl = BoxList(boxes.clone(), (320, 200), mode="xyxy")
+    cl.add_field("labels", torch.arange(12))
+    cl = cl.clip_to_image(remove_empty=True)
+    st["clip_boxes"], st["clip_labels"] = cl.bbox.clone(), cl.get_field("labels").clone()
+    imgs = [torch.rand(3, 37, 53, generator=g), torch.rand(3, 41, 50, generator=g)]
+    il = to_image_list(imgs, 32)
+    il2 = to_image_list([torch.rand(3, 70, 20, generator=g)], 0)
+    both = il + il2
+    st["images"] = imgs + [il2.tensors[0].clone()]
+    st["padded"], st["padded_sizes"] = il.tensors.clone(), [tuple(s) for s in il.image_sizes]
+    st["added"], st["added_sizes"] = both.tensors.clone(), [tuple(s) for s in both.image_sizes]
+    torch.save(dict(configs=cfgs, structures=st), os.path.join(OUT, "boundary_ref.pt"))
+    return cfgs, st
+
+
 # ----------------------------------------------------------------------------- input pipeline golden (SURVEY §8 f-4)
 PREPROCESS_CASES = [
     # (name, cfg opts, [(h, w) of the decoded images], random seed)
@@ -429,7 +487,11 @@ def make_preprocess():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "fpn":
+    if len(sys.argv) > 1 and sys.argv[1] == "boundary":
+        assert rh.available(), "reference not mounted"
+        cfgs, st = make_boundary()
+        print(len(cfgs), "configs;", sorted(cfgs)[:3], "...;", len(next(iter(cfgs.values()))["effective"]), "keys each")
+    elif len(sys.argv) > 1 and sys.argv[1] == "fpn":
         assert rh.available(), "reference not mounted"
         torch.set_num_threads(os.cpu_count())
         fx = make_fpn_eval()
@@ -454,3 +516,4 @@ if __name__ == "__main__":
         make_eval()
         make_fpn_eval()
         make_preprocess()
+        make_boundary()

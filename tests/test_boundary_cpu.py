@@ -1,0 +1,91 @@
+"""CPU: the drop-in boundary's host types against the REAL reference (tests/golden/boundary_ref.pt, made by
+`python oracle/make_golden.py boundary`):
+  B3  every DA YAML of the reference (+ the two plain detectors pinned here) merges UNMODIFIED into this package's
+      default tree and yields exactly the reference's effective configuration (config/defaults.py:21-430);
+  B1  BoxList (structures/bounding_box.py:9-266) and ImageList / to_image_list (structures/image_list.py:9-91)
+      behave like the reference classes on the same seeded inputs."""
+import os
+
+import pytest
+import torch
+
+
+@pytest.fixture(scope="module")
+def fx(golden_dir):
+    return torch.load(os.path.join(golden_dir, "boundary_ref.pt"), weights_only=False)
+
+
+def _flatten(node, prefix=""):
+    out = {}
+    for k, v in node.items():
+        if hasattr(v, "items"):
+            out.update(_flatten(v, prefix + k + "."))
+        else:
+            out[prefix + k] = list(v) if isinstance(v, tuple) else v
+    return out
+
+
+def test_reference_yamls_merge_unmodified_into_identical_effective_configs(fx, tmp_path):
+    from dadetect_b200.config import get_cfg_defaults
+    assert len(fx["configs"]) >= 11
+    for rel, ent in fx["configs"].items():
+        path = tmp_path / os.path.basename(rel)
+        path.write_text(ent["text"])
+        cfg = get_cfg_defaults()
+        cfg.merge_from_file(str(path))
+        ours, want = _flatten(cfg), ent["effective"]
+        assert set(ours) == set(want), (rel, sorted(set(ours) ^ set(want))[:8])
+        # PATHS_CATALOG is the absolute path of a file inside the reference checkout (defaults.py:430)
+        diff = {k: (ours[k], want[k]) for k in want if ours[k] != want[k] and k != "PATHS_CATALOG"}
+        assert not diff, (rel, dict(list(diff.items())[:6]))
+
+
+def test_config_node_rejects_unknown_keys_and_type_mismatches():
+    from dadetect_b200.config import get_cfg_defaults
+    cfg = get_cfg_defaults()
+    with pytest.raises(KeyError):
+        cfg.merge_from_list(["MODEL.DA_HEADS.NO_SUCH_KEY", 1])
+    with pytest.raises(ValueError):
+        cfg.merge_from_list(["MODEL.RPN.NMS_THRESH", "high"])
+    cfg.freeze()
+    with pytest.raises(AttributeError):
+        cfg.MODEL.DEVICE = "cpu"
+
+
+def test_boxlist_matches_reference_class(fx):
+    from dadetect_b200.structures import BoxList
+    st = fx["structures"]
+    b = BoxList(st["boxes"].clone(), st["size"], mode="xyxy")
+    b.add_field("labels", torch.arange(12))
+    assert torch.equal(b.convert("xywh").bbox, st["xywh"])
+    assert torch.equal(b.convert("xywh").convert("xyxy").bbox, st["xywh_back"])
+    assert torch.equal(b.area(), st["area"])
+    assert torch.equal(b.resize((640, 400)).bbox, st["resize_same_ratio"])
+    assert torch.equal(b.resize((500, 333)).bbox, st["resize_two_ratios"])
+    assert torch.equal(b.transpose(0).bbox, st["flip_lr"])
+    assert torch.equal(b.transpose(1).bbox, st["flip_tb"])
+    assert b.resize((640, 400)).size == (640, 400) and torch.equal(b.resize((640, 400)).get_field("labels"), torch.arange(12))
+    cl = BoxList(st["boxes"].clone(), st["size"], mode="xyxy")
+    cl.add_field("labels", torch.arange(12))
+    cl = cl.clip_to_image(remove_empty=True)
+    assert torch.equal(cl.bbox, st["clip_boxes"]) and torch.equal(cl.get_field("labels"), st["clip_labels"])
+    with pytest.raises(ValueError):
+        BoxList(torch.zeros(3, 5), (10, 10))
+    with pytest.raises(ValueError):
+        BoxList(torch.zeros(3, 4), (10, 10), mode="cxcywh")
+
+
+def test_image_list_matches_reference_class(fx):
+    from dadetect_b200.structures import ImageList, to_image_list
+    st = fx["structures"]
+    il = to_image_list(st["images"][:2], 32)
+    assert torch.equal(il.tensors, st["padded"]) and [tuple(s) for s in il.image_sizes] == st["padded_sizes"]
+    il2 = to_image_list([st["images"][2]], 0)
+    both = il + il2
+    assert torch.equal(both.tensors, st["added"]) and [tuple(s) for s in both.image_sizes] == st["added_sizes"]
+    assert to_image_list(il) is il
+    batch = torch.zeros(2, 3, 8, 8)
+    assert to_image_list(batch).tensors is batch
+    with pytest.raises(TypeError):
+        to_image_list(st["images"][0].numpy())
+    assert isinstance(il.to("cpu"), ImageList)
