@@ -80,3 +80,35 @@ def test_training_orchestration_matches_oracle(name, static, cpu_ops):
         assert float((a - b).norm()) <= 1e-3 * float(b.norm()) + 1e-9, (k, float((a - b).norm()), float(b.norm()))
         checked += 1
     assert checked > 50
+
+
+@pytest.mark.timeout(900)
+def test_eval_orchestration_matches_real_reference_golden_c4(cpu_ops):
+    """BASELINE configs[0] (plain R-50-C4 Faster R-CNN, eval mode, 2 x 800x800): the product's eval control flow
+    (test-mode RPN post-processing, box head, PostProcessor) with kernel stand-ins against the detections of the REAL
+    reference model (tests/golden/eval_faster_rcnn_c4.pt)."""
+    from dadetect_b200.config import get_cfg_defaults
+    from dadetect_b200.modeling import build_detection_model
+    from dadetect_b200.utils.synthetic import make_batch, make_state_dict
+    torch.set_num_threads(os.cpu_count())
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "eval_faster_rcnn_c4.pt"), weights_only=False)
+    cfg = get_cfg_defaults()
+    cfg.merge_from_file(os.path.join(ROOT, "configs", fx["yaml"]))
+    sd = make_state_dict(orc.param_shapes(cfg))
+    for k, f in fx["scale"].items():
+        sd[k] = sd[k] * f
+    images, _ = make_batch(2, fx["height"], fx["width"], num_classes=81, boxes_per_image=1, seed=fx["seed"])
+    model = build_detection_model(cfg)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    with torch.no_grad():
+        out = model(images)
+    assert len(out) == len(fx["detections"])
+    for got, want in zip(out, fx["detections"]):
+        gb, gs, gl = got.bbox, got.get_field("scores"), got.get_field("labels")
+        assert abs(len(gs) - len(want["scores"])) <= 2
+        hits = 0
+        for i in range(len(want["scores"])):
+            hits += int(((gl == want["labels"][i]) & ((gb - want["boxes"][i]).abs().max(dim=1)[0] < 0.05)
+                         & ((gs - want["scores"][i]).abs() < 2e-4)).any())
+        assert hits >= len(want["scores"]) - 3, (hits, len(want["scores"]))
