@@ -1,5 +1,6 @@
-"""TEST INFRASTRUCTURE ONLY (oracle) — CPU restatement of the reference's FPN detector path in eval mode
-(BASELINE configs[4], R-101-FPN).  Functional, fp32, NCHW, on top of the helpers of
+"""TEST INFRASTRUCTURE ONLY (oracle) — CPU restatement of the reference's FPN detector path: eval mode (pinned to the
+real reference model) and plain Faster R-CNN training (restated from the reference's loss classes; the reference cannot
+run it, see forward_train_fpn) (BASELINE configs[4], R-101-FPN).  Functional, fp32, NCHW, on top of the helpers of
 oracle/da_frcnn_ref.py.  Only tests/ may import this file; the product path never does.
 
 Follows (reference file:line):
@@ -168,3 +169,67 @@ def forward_eval_fpn(P, cfg, images, nms_strict=True):
     logits, reg = fpn2mlp_head(pooled, P)
     dets = box_postprocess(cfg, logits, reg, [b for b, _ in props], image_sizes, nms_strict=nms_strict)
     return dict(pyramid=pyramid, proposals=props, levels=levels, detections=dets)
+
+
+# --------------------------------------------------------------------------------------------------- training (no DA)
+def rpn_loss_fpn(pyramid, heads, cfg, gt_boxes, is_source_img, image_size, hooks):
+    """RPNLossComputation over five levels (rpn/loss.py:57-143): per image the anchors of all levels are
+    concatenated (cat_boxlist, :119), the predictions are flattened level by level per image
+    (concat_box_prediction_layers, rpn/utils.py:17-45)."""
+    R = cfg.MODEL.RPN
+    ih, iw = image_size
+    anchors, vis = [], []
+    for feat, stride, size in zip(pyramid, R.ANCHOR_STRIDE, R.ANCHOR_SIZES):
+        a = orc.grid_anchors(feat.shape[2], feat.shape[3], stride, orc.cell_anchors(stride, (size,), R.ASPECT_RATIOS))
+        anchors.append(a)
+        vis.append(orc.anchor_visibility(a, iw, ih, R.STRADDLE_THRESH))
+    anchors, vis = torch.cat(anchors), torch.cat(vis)
+    labels, reg_targets = [], []
+    for gt, src in zip(gt_boxes, is_source_img):
+        if not src:
+            continue
+        m = orc.matcher(orc.box_iou(gt, anchors), R.FG_IOU_THRESHOLD, R.BG_IOU_THRESHOLD, True)
+        lab = (m >= 0).to(torch.float32)
+        lab[m == orc.BELOW_LOW] = 0
+        lab[~vis] = -1
+        lab[m == orc.BETWEEN] = -1
+        labels.append(lab)
+        reg_targets.append(orc.box_encode(gt[m.clamp(min=0)], anchors, (1.0, 1.0, 1.0, 1.0)))
+    pos_m, neg_m = orc.balanced_sampler(labels, R.BATCH_SIZE_PER_IMAGE, R.POSITIVE_FRACTION, hooks)
+    pos = torch.nonzero(torch.cat(pos_m)).squeeze(1)
+    neg = torch.nonzero(torch.cat(neg_m)).squeeze(1)
+    sampled = torch.cat([pos, neg])
+    n = pyramid[0].shape[0]
+    obj = torch.cat([orc.permute_and_flatten(lg, n, 1, lg.shape[2], lg.shape[3]) for lg, _ in heads], dim=1).reshape(-1)
+    reg = torch.cat([orc.permute_and_flatten(dl, n, 4, dl.shape[2], dl.shape[3]) for _, dl in heads], dim=1).reshape(-1, 4)
+    labels, reg_targets = torch.cat(labels), torch.cat(reg_targets)
+    box_loss = orc.smooth_l1(reg[pos], reg_targets[pos], 1.0 / 9, False) / sampled.numel()
+    obj_loss = F.binary_cross_entropy_with_logits(obj[sampled], labels[sampled])
+    return obj_loss, box_loss
+
+
+def forward_train_fpn(P, cfg, images, targets, hooks):
+    """GeneralizedRCNN.forward in training mode for an R-*-FPN model WITHOUT DA heads.  The reference leaves
+    `detector_losses` unbound in this configuration; the evident intent — the four Faster R-CNN losses
+    — is restated from the same loss classes the DA path uses (rpn/loss.py, box_head/loss.py), with the FPN-specific
+    proposal selection of rpn/inference.py:154-181 (training branch).  Returns the loss dict."""
+    n, _, ih, iw = images.shape
+    gt_boxes = [t["boxes"] for t in targets]
+    gt_labels = [t["labels"] for t in targets]
+    is_src = [bool(t["is_source"]) for t in targets]
+    pyramid = fpn_forward(resnet_body_all_stages(images, P, cfg.MODEL.BACKBONE.CONV_BODY), P)
+    heads = [orc.rpn_head(f, P) for f in pyramid]
+    with torch.no_grad():
+        props = rpn_fpn_proposals([f.detach() for f in pyramid], {k: v.detach() for k, v in P.items()}, cfg,
+                                  [(ih, iw)] * n, training=True, nms_strict=True)
+        props = [(torch.cat([b, g]), torch.cat([s, torch.ones(len(g))])) if src else (b, s)      # add_gt_proposals
+                 for (b, s), g, src in zip(props, gt_boxes, is_src)]
+    obj_loss, rpn_box_loss = rpn_loss_fpn(pyramid, heads, cfg, gt_boxes, is_src, (ih, iw), hooks)
+    samples = orc.box_head_subsample(props, gt_boxes, gt_labels, is_src, cfg, hooks)
+    B = cfg.MODEL.ROI_BOX_HEAD
+    pooled, _ = multilevel_pool(pyramid[:len(B.POOLER_SCALES)], orc.rois_from(samples), B.POOLER_SCALES,
+                                B.POOLER_RESOLUTION, B.POOLER_SAMPLING_RATIO)
+    cls_logits, box_reg = fpn2mlp_head(pooled, P)
+    cls_loss, box_loss, _ = orc.fastrcnn_loss(cls_logits, box_reg, samples)
+    return dict(loss_classifier=cls_loss, loss_box_reg=box_loss, loss_objectness=obj_loss,
+                loss_rpn_box_reg=rpn_box_loss)

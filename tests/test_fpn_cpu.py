@@ -141,3 +141,63 @@ def test_ops_refuse_cpu_tensors_without_the_stand_ins():
         ops.upsample2x(torch.zeros(1, 2, 2, 4))
     with pytest.raises(RuntimeError):
         ops.roi_align_levels([torch.zeros(1, 4, 4, 4)], torch.zeros(1, 5), (0.25,), 7, 2)
+
+
+@pytest.mark.timeout(900)
+def test_product_fpn_training_orchestration_matches_oracle(cpu_ops):
+    """FPN training (plain Faster R-CNN losses): the product's python path (multi-level RPN loss over concatenated
+    levels, batch-wide proposal cut, GT append, box-head sampling, multi-level pooling, MLP head, losses) with kernel
+    stand-ins against oracle/fpn_ref.py::forward_train_fpn on replayed random draws: losses and gradients."""
+    import da_frcnn_ref as orc
+    import fpn_ref
+    from dadetect_b200.modeling import build_detection_model
+    from dadetect_b200.structures import BoxList
+    from dadetect_b200.utils.random_source import ReplaySource
+    from dadetect_b200.utils.synthetic import make_batch, make_state_dict
+    torch.set_num_threads(os.cpu_count())
+    cfg = fpn_cfg(["MODEL.BACKBONE.CONV_BODY", "R-50-FPN", "MODEL.ROI_BOX_HEAD.NUM_CLASSES", 9,
+                   "MODEL.RPN.FPN_POST_NMS_TOP_N_TRAIN", 600])
+    model = build_detection_model(cfg)
+    sd = make_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    sd["rpn.head.cls_logits.weight"] = sd["rpn.head.cls_logits.weight"] * 20.0
+    model.load_state_dict(sd, strict=False)
+    model.train()
+    H, W = 128, 192
+    images, targets = make_batch(2, H, W, num_classes=9, boxes_per_image=4, seed=33)
+    for t in targets:
+        t["is_source"] = True                               # without DA heads every image is a labelled one
+
+    torch.manual_seed(5)
+    rec = orc.RecordingHooks()
+    frozen = ("backbone.body.stem.", "backbone.body.layer1.")
+    P = {k: v.clone().requires_grad_(v.is_floating_point() and ".bn" not in k and ".downsample.1." not in k
+                                     and not k.startswith(frozen)) for k, v in sd.items()}
+    want = fpn_ref.forward_train_fpn(P, cfg, images, targets, rec)
+    sum(want.values()).backward()
+
+    replay = ReplaySource(rec.perms, rec.masks)
+    model.set_random_source(replay)
+    tg = []
+    for t in targets:
+        b = BoxList(t["boxes"].clone(), (W, H), mode="xyxy")
+        b.add_field("labels", t["labels"].clone())
+        b.add_field("is_source", torch.ones(len(t["labels"]), dtype=torch.bool))
+        tg.append(b)
+    got = model(images, tg)
+    assert set(got) == set(want)
+    assert not replay.perms and not replay.masks
+    for k in want:
+        g, w = float(got[k].detach()), float(want[k].detach())
+        assert abs(g - w) <= 2e-5 * max(1.0, abs(w)), (k, g, w)
+    sum(got.values()).backward()
+    params = dict(model.named_parameters())
+    checked = 0
+    for k, p in params.items():
+        if not p.requires_grad:
+            continue
+        assert P[k].requires_grad, k                        # the same parameters are trainable (FREEZE_CONV_BODY_AT 2)
+        assert p.grad is not None and P[k].grad is not None, k
+        a, b = p.grad.double(), P[k].grad.double()
+        assert float((a - b).norm()) <= 1e-3 * float(b.norm()) + 1e-9, (k, float((a - b).norm()), float(b.norm()))
+        checked += 1
+    assert checked > 60
