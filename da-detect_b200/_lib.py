@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libdadetect_b200.so")
 
 _P, _I, _F, _Q, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_size_t
 
-# name -> (restype, argtypes)   p = pointer, i = int, f = float, q = long long
+# name -> (restype, argtypes)   p = pointer, i = int, f = float, q = long long, d = double
 _SIGS = {
     "dd_last_error": (ctypes.c_char_p, ""),
     "dd_abi_version": (_I, ""),
@@ -30,8 +30,8 @@ _SIGS = {
     "dd_anchor_grid": (_I, "piiiiiiippp"),
     "dd_rpn_topk_workspace_bytes": (_Z, "ii"),
     "dd_rpn_topk_decode": (_I, "pppiiiiiiifpppppp"),
-    "dd_match": (_I, "pipiffipppp"),
-    "dd_box_encode": (_I, "pippiffffipp"),
+    "dd_match": (_I, "pippiffipppp"),
+    "dd_box_encode": (_I, "pipppiffffipp"),
     "dd_box_decode": (_I, "ppiiffffpp"),
     "dd_conv2d_forward_workspace_bytes": (_Z, "iiiii"),
     "dd_conv2d_forward": (_I, "ppppppiiiiiiiiiiipp"),
@@ -59,10 +59,11 @@ _SIGS = {
     "dd_smooth_l1_sum": (_I, "ppqffppp"),
     "dd_box_reg_loss": (_I, "ppppiippp"),
     "dd_consistency_loss": (_I, "pqpiipppppp"),
-    "dd_proposals_gather": (_I, "pppppppiiiipppp"),
+    "dd_proposals_gather": (_I, "ppppppppiiiipppp"),
     "dd_balanced_sample": (_I, "pppiiiippp"),
     "dd_sgd_momentum_dev": (_I, "pppqpffffp"),
-    "dd_triplet_margin_loss": (_I, "pppqiqfppppp"),
+    "dd_triplet_margin_loss": (_I, "pppqiqfpppppp"),
+    "dd_adaptive_margin_update": (_I, "ppdddpp"),
     "dd_sgd_momentum": (_I, "pppqffffip"),
     "dd_upsample2x_forward": (_I, "ppiiiip"),
     "dd_upsample2x_backward": (_I, "ppiiiip"),
@@ -75,7 +76,7 @@ _SIGS = {
     "dd_resample_coeffs": (_I, "iipp"),
     "dd_preprocess_image": (_I, "piiiqppippiiiiipppiip"),
 }
-_CT = {"p": _P, "i": _I, "f": _F, "q": _Q}
+_CT = {"p": _P, "i": _I, "f": _F, "q": _Q, "d": ctypes.c_double}
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGS))
 

@@ -185,9 +185,11 @@ __device__ __forceinline__ size_t tri_addr(long long r, int d, int D, long long 
 // inner > 1: one thread per distance vector (threads along `inner` are coalesced)
 __global__ void __launch_bounds__(256) triplet_strided_kernel(const float* __restrict__ a, const float* __restrict__ p,
                                                               const float* __restrict__ n, long long rows, int D,
-                                                              long long inner, float margin, float inv_rows,
+                                                              long long inner, float margin_host,
+                                                              const float* __restrict__ margin_dev, float inv_rows,
                                                               float* __restrict__ loss, float* __restrict__ ga,
                                                               float* __restrict__ gp, float* __restrict__ gn) {
+  const float margin = margin_dev ? __ldg(margin_dev) : margin_host;
   __shared__ float red[32];
   float acc = 0.f;
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
@@ -222,9 +224,11 @@ __global__ void __launch_bounds__(256) triplet_strided_kernel(const float* __res
 // inner == 1: one warp per row, lanes along D
 __global__ void __launch_bounds__(256) triplet_rows_kernel(const float* __restrict__ a, const float* __restrict__ p,
                                                            const float* __restrict__ n, long long rows, int D,
-                                                           float margin, float inv_rows, float* __restrict__ loss,
+                                                           float margin_host, const float* __restrict__ margin_dev,
+                                                           float inv_rows, float* __restrict__ loss,
                                                            float* __restrict__ ga, float* __restrict__ gp,
                                                            float* __restrict__ gn) {
+  const float margin = margin_dev ? __ldg(margin_dev) : margin_host;
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -316,19 +320,39 @@ extern "C" int dd_consistency_loss(const float* img_logits, long long hw, const 
   return 0;
 }
 
+// The adaptive image-level margin of da_heads/loss.py:182-200 as device state (no host read of the previous loss):
+//   if state == 0: state = margin_cfg;  if prev_loss == 0 and int(state) != int(max_margin): state += lr
+// state is a double like the reference's Python float; margin_out receives the float the loss kernel consumes.
+__global__ void adaptive_margin_kernel(double* state, const float* __restrict__ prev_loss, double margin_cfg, double lr,
+                                       double max_margin, float* margin_out) {
+  double m = *state;
+  if (m == 0.0) m = margin_cfg;
+  if (prev_loss != nullptr && *prev_loss == 0.0f && (long long)m != (long long)max_margin) m += lr;
+  *state = m;
+  *margin_out = (float)m;
+}
+
+extern "C" int dd_adaptive_margin_update(double* state, const float* prev_loss, double margin_cfg, double lr,
+                                         double max_margin, float* margin_out, void* stream) {
+  DD_CHECK_ARG(state != nullptr && margin_out != nullptr);
+  adaptive_margin_kernel<<<1, 1, 0, dd::S(stream)>>>(state, prev_loss, margin_cfg, lr, max_margin, margin_out);
+  DD_LAUNCHED();
+  return 0;
+}
+
 extern "C" int dd_triplet_margin_loss(const float* a, const float* p, const float* n, long long rows, int D,
-                                      long long inner, float margin, float* loss, float* grad_a, float* grad_p,
-                                      float* grad_n, void* stream) {
+                                      long long inner, float margin, const float* margin_dev, float* loss,
+                                      float* grad_a, float* grad_p, float* grad_n, void* stream) {
   DD_CHECK_ARG(rows > 0 && D > 0 && inner >= 1 && rows % inner == 0);
   DD_CHECK_ARG((grad_a == nullptr) == (grad_p == nullptr) && (grad_a == nullptr) == (grad_n == nullptr));
   cudaStream_t s = dd::S(stream);
   DD_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
   const float inv_rows = 1.0f / (float)rows;
   if (inner > 1) {
-    triplet_strided_kernel<<<dd::grid_for(rows, 256, 2), 256, 0, s>>>(a, p, n, rows, D, inner, margin, inv_rows, loss,
+    triplet_strided_kernel<<<dd::grid_for(rows, 256, 2), 256, 0, s>>>(a, p, n, rows, D, inner, margin, margin_dev, inv_rows, loss,
                                                                       grad_a, grad_p, grad_n);
   } else {
-    triplet_rows_kernel<<<dd::grid_for(rows * 32, 256, 2), 256, 0, s>>>(a, p, n, rows, D, margin, inv_rows, loss,
+    triplet_rows_kernel<<<dd::grid_for(rows * 32, 256, 2), 256, 0, s>>>(a, p, n, rows, D, margin, margin_dev, inv_rows, loss,
                                                                         grad_a, grad_p, grad_n);
   }
   DD_LAUNCHED();

@@ -29,12 +29,20 @@ __device__ __forceinline__ float area_plus1(const float4 b) {
 }
 
 // Pass 1: per prediction argmax/max; per GT max (atomicMax on the int view: IoU >= 0).
-__global__ void __launch_bounds__(256) match_pass1(const float4* __restrict__ gt, int M,
+// m_dev (optional): the number of valid GT rows lives on the device (GT padded to the capacity M, so that one
+// captured step graph serves batches with any number of boxes); rows at and beyond it do not exist for the Matcher.
+__device__ __forceinline__ int live_rows(int M, const int32_t* __restrict__ m_dev) {
+  return m_dev ? max(min(__ldg(m_dev), M), 0) : M;
+}
+
+__global__ void __launch_bounds__(256) match_pass1(const float4* __restrict__ gt, int Mcap,
+                                                   const int32_t* __restrict__ m_dev,
                                                    const float4* __restrict__ pred, int N, float high, float low,
                                                    int64_t* __restrict__ matches, int32_t* __restrict__ argmax_out,
                                                    float* __restrict__ vals_out, float* __restrict__ gt_best) {
-  extern __shared__ float4 sgt[];          // M boxes, then M areas
-  float* sarea = reinterpret_cast<float*>(sgt + M);
+  extern __shared__ float4 sgt[];          // Mcap boxes, then Mcap areas
+  float* sarea = reinterpret_cast<float*>(sgt + Mcap);
+  const int M = live_rows(Mcap, m_dev);
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
     const float4 g = gt[i];
     sgt[i] = g;
@@ -70,14 +78,16 @@ __global__ void __launch_bounds__(256) match_pass1(const float4* __restrict__ gt
 
 // Pass 2 (allow_low_quality_matches): a prediction whose IoU with some GT equals that GT's maximum gets
 // its argmax back (matcher.py:92-112).
-__global__ void __launch_bounds__(256) match_pass2(const float4* __restrict__ gt, int M,
+__global__ void __launch_bounds__(256) match_pass2(const float4* __restrict__ gt, int Mcap,
+                                                   const int32_t* __restrict__ m_dev,
                                                    const float4* __restrict__ pred, int N,
                                                    const float* __restrict__ gt_best,
                                                    const int32_t* __restrict__ argmax_in,
                                                    int64_t* __restrict__ matches) {
   extern __shared__ float4 sgt[];
-  float* sarea = reinterpret_cast<float*>(sgt + M);
-  float* sbest = sarea + M;
+  float* sarea = reinterpret_cast<float*>(sgt + Mcap);
+  float* sbest = sarea + Mcap;
+  const int M = live_rows(Mcap, m_dev);
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
     const float4 g = gt[i];
     sgt[i] = g;
@@ -94,11 +104,13 @@ __global__ void __launch_bounds__(256) match_pass2(const float4* __restrict__ gt
   if (restore) matches[j] = argmax_in[j];
 }
 
-__global__ void box_encode_kernel(const float4* __restrict__ gt, int M, const float4* __restrict__ pred,
+__global__ void box_encode_kernel(const float4* __restrict__ gt, int Mcap, const int32_t* __restrict__ m_dev,
+                                  const float4* __restrict__ pred,
                                   const int64_t* __restrict__ matches, int N, float wx, float wy, float ww, float wh,
                                   int wrap_negative, float4* __restrict__ out) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
+  const int M = max(live_rows(Mcap, m_dev), 1);
   long long m = matches[j];
   if (m < 0) m = wrap_negative ? m + M : 0;
   if (m < 0) m = 0;
@@ -139,7 +151,7 @@ __global__ void box_decode_kernel(const float* __restrict__ codes, const float4*
 
 }  // namespace
 
-extern "C" int dd_match(const float* gt, int M, const float* pred, int N, float high, float low,
+extern "C" int dd_match(const float* gt, int M, const int32_t* m_dev, const float* pred, int N, float high, float low,
                         int allow_low_quality, int64_t* matches, float* matched_vals, float* gt_best, void* stream) {
   DD_CHECK_ARG(M > 0 && M <= kMaxGT && N > 0);   // the reference raises on empty GT / proposals (matcher.py:53-62)
   DD_CHECK_ARG(!allow_low_quality || gt_best != nullptr);
@@ -148,12 +160,12 @@ extern "C" int dd_match(const float* gt, int M, const float* pred, int N, float 
   DD_CUDA(cudaMallocAsync(&argmax, sizeof(int32_t) * (size_t)N, s));
   if (allow_low_quality) DD_CUDA(cudaMemsetAsync(gt_best, 0, sizeof(float) * M, s));
   const int blocks = (N + 255) / 256;
-  match_pass1<<<blocks, 256, M * 20, s>>>(reinterpret_cast<const float4*>(gt), M,
+  match_pass1<<<blocks, 256, M * 20, s>>>(reinterpret_cast<const float4*>(gt), M, m_dev,
                                           reinterpret_cast<const float4*>(pred), N, high, low, matches, argmax,
                                           matched_vals, allow_low_quality ? gt_best : nullptr);
   DD_LAUNCHED();
   if (allow_low_quality) {
-    match_pass2<<<blocks, 256, M * 24, s>>>(reinterpret_cast<const float4*>(gt), M,
+    match_pass2<<<blocks, 256, M * 24, s>>>(reinterpret_cast<const float4*>(gt), M, m_dev,
                                             reinterpret_cast<const float4*>(pred), N, gt_best, argmax, matches);
     DD_LAUNCHED();
   }
@@ -161,12 +173,13 @@ extern "C" int dd_match(const float* gt, int M, const float* pred, int N, float 
   return 0;
 }
 
-extern "C" int dd_box_encode(const float* gt, int M, const float* pred, const int64_t* matches, int N, float wx,
+extern "C" int dd_box_encode(const float* gt, int M, const int32_t* m_dev, const float* pred, const int64_t* matches,
+                             int N, float wx,
                              float wy, float ww, float wh, int wrap_negative, float* targets, void* stream) {
   DD_CHECK_ARG(M > 0 && N >= 0);
   if (N == 0) return 0;
   box_encode_kernel<<<(N + 255) / 256, 256, 0, dd::S(stream)>>>(
-      reinterpret_cast<const float4*>(gt), M, reinterpret_cast<const float4*>(pred), matches, N, wx, wy, ww, wh,
+      reinterpret_cast<const float4*>(gt), M, m_dev, reinterpret_cast<const float4*>(pred), matches, N, wx, wy, ww, wh,
       wrap_negative, reinterpret_cast<float4*>(targets));
   DD_LAUNCHED();
   return 0;

@@ -20,11 +20,14 @@ constexpr int kUn = 4;            // load pairs kept in flight per thread in the
 __global__ void __launch_bounds__(256) proposals_gather_kernel(
     const float4* __restrict__ boxes, const float* __restrict__ scores, const int64_t* __restrict__ keep,
     const int* __restrict__ keep_count, const float4* __restrict__ gt, const int* __restrict__ gt_off,
-    const uint8_t* __restrict__ append_gt, int k, int post, int cap, float4* __restrict__ out_boxes,
-    float* __restrict__ out_obj, int* __restrict__ out_count) {
+    const int* __restrict__ gt_counts, const uint8_t* __restrict__ append_gt, int k, int post, int cap,
+    float4* __restrict__ out_boxes, float* __restrict__ out_obj, int* __restrict__ out_count) {
   const int img = blockIdx.x;
   const int nk = min(keep_count[img], post);
-  const int g0 = gt_off[img], ng = append_gt[img] ? gt_off[img + 1] - g0 : 0;
+  const int g0 = gt_off[img];
+  // gt_counts (optional): GT rows padded to a fixed capacity, the live count of each image on the device
+  const int have = gt_counts ? min(max(gt_counts[img], 0), gt_off[img + 1] - g0) : gt_off[img + 1] - g0;
+  const int ng = append_gt[img] ? have : 0;
   const int total = min(nk + ng, cap);
   for (int r = threadIdx.x; r < cap; r += blockDim.x) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -278,13 +281,13 @@ __global__ void __launch_bounds__(kThreads) balanced_sample_kernel(
 }  // namespace
 
 extern "C" int dd_proposals_gather(const float* boxes, const float* scores, const int64_t* keep, const int* keep_count,
-                                   const float* gt, const int* gt_offsets, const uint8_t* append_gt, int N, int k,
-                                   int post, int cap, float* out_boxes, float* out_objectness, int* out_count,
-                                   void* stream) {
+                                   const float* gt, const int* gt_offsets, const int* gt_counts,
+                                   const uint8_t* append_gt, int N, int k, int post, int cap, float* out_boxes,
+                                   float* out_objectness, int* out_count, void* stream) {
   DD_CHECK_ARG(N > 0 && k > 0 && post > 0 && cap >= post);
   proposals_gather_kernel<<<N, 256, 0, dd::S(stream)>>>(
       reinterpret_cast<const float4*>(boxes), scores, keep, keep_count, reinterpret_cast<const float4*>(gt), gt_offsets,
-      append_gt, k, post, cap, reinterpret_cast<float4*>(out_boxes), out_objectness, out_count);
+      gt_counts, append_gt, k, post, cap, reinterpret_cast<float4*>(out_boxes), out_objectness, out_count);
   DD_LAUNCHED();
   return 0;
 }

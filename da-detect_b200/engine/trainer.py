@@ -11,8 +11,10 @@ Differences from the reference (SURVEY §5 "Distributed communication backend", 
   * parameters are views of one flat buffer as well, ordered [weights..., biases...], so the whole SGD
     update (momentum 0.9, weight decay on weights only, bias lr x BIAS_LR_FACTOR — solver/build.py:7-20)
     is two launches of one fused kernel instead of ~170 per-tensor param-group updates;
-  * parameters that receive no gradient in a configuration (e.g. `da_heads.*` in triplet mode) keep a
-    zero slot, which is what DDP(find_unused_parameters) semantics would produce.
+  * parameters no loss of the active configuration depends on (e.g. `da_heads.*` in triplet mode, a DA head
+    whose loss weights are all 0) stay OUTSIDE the flat buffers and are never touched: under the reference's
+    autograd their .grad stays None and torch.optim.SGD skips them — no weight decay, no momentum
+    (`unused_parameter_names`).
 """
 import math
 from bisect import bisect_right
@@ -64,7 +66,34 @@ class WarmupCosineLR(object):
         return self.lr_min + 0.5 * (self.base_lr - self.lr_min) * (1 + math.cos(math.pi * it / self.max_iter))
 
 
+def unused_parameter_names(model):
+    """Names of the trainable parameters that no loss term of the model's configuration depends on.  The reference
+    builds `da_heads` even in triplet mode (generalized_rcnn.py:53) and evaluates heads whose losses are then
+    dropped for a zero weight (da_heads.py:417-436): those parameters never receive a gradient, so SGD never
+    updates them (torch.optim.SGD skips p.grad is None)."""
+    unused = set()
+
+    def heads(mod, prefix):
+        img = mod.img_weight > 0 or mod.cst_weight > 0
+        ins = mod.ins_weight > 0 or mod.cst_weight > 0
+        for n, _ in mod.named_parameters():
+            if (n.startswith("imghead.") and not img) or (n.startswith("inshead.") and not ins):
+                unused.add(prefix + n)
+
+    da, tri = getattr(model, "da_heads", None), getattr(model, "da_heads_triplet", None)
+    if da:
+        if tri:
+            unused.update("da_heads." + n for n, _ in da.named_parameters())
+        else:
+            heads(da, "da_heads.")
+    if tri:
+        heads(tri, "da_heads_triplet.")
+    return unused
+
+
 class FlatSGDTrainer(object):
+    gt_capacity = 128            # GT boxes per image the step graphs are captured for (grows by doubling)
+
     def __init__(self, model, cfg, schedule=None, world_size=None):
         S = cfg.SOLVER
         self.model = model
@@ -74,7 +103,8 @@ class FlatSGDTrainer(object):
         self.schedule = schedule
         self.iteration = 0
         self.world = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
-        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        self.unused = unused_parameter_names(model)
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and n not in self.unused]
         weights = [(n, p) for n, p in named if "bias" not in n]      # solver/build.py:14: `"bias" in key`
         biases = [(n, p) for n, p in named if "bias" in n]
         self.order = weights + biases
@@ -159,31 +189,45 @@ class FlatSGDTrainer(object):
             return None
         if not getattr(self.model, "static_shapes", False):
             return None                  # host-driven control flow (FPN, enable_static_shapes(False)) reads sizes
-        if self.model.da_heads_triplet and self.model.da_heads_triplet.host_reads_needed():
-            return None                  # an adaptive margin below its maximum reads the previous loss on the host
+        # the un-padded (h, w) of every image: anchor visibility and proposal clipping depend on them
+        sizes = tuple((int(h), int(w)) for h, w in (images.image_sizes if isinstance(images, ImageList)
+                                                    else [tensors.shape[-2:]] * tensors.shape[0]))
         cache_source_flags(targets)
-        key = (tuple(tensors.shape),) + tuple((len(t), bool(is_source_image(t)), tuple(t.size)) for t in targets)
+        counts = [len(t) for t in targets]
+        if min(counts) == 0:             # matcher.py:53-62 raises on an image without ground truth
+            raise ValueError("No ground-truth boxes available for one of the images during training")
+        # GT boxes live in fixed-capacity buffers with device-side counts: ONE graph per image shape serves every
+        # batch, whatever the number of boxes per image (real batches differ in it almost every step)
+        cap = int(self.gt_capacity)
+        while cap < max(counts):
+            cap *= 2
+        key = (tuple(tensors.shape), sizes, cap) + tuple((bool(is_source_image(t)), tuple(t.size)) for t in targets)
         ent = self.step_graphs.pop(key, None)
         if ent is not None:
             self.step_graphs[key] = ent          # most recently used last
         if ent is None:
             while len(self.step_graphs) >= self.max_step_graphs:
                 self.step_graphs.pop(next(iter(self.step_graphs)))
+            dev = tensors.device
+            counts_dev = torch.zeros(len(targets), dtype=torch.int32, device=dev)
             st_targets = []
-            for t in targets:
-                b = BoxList(t.convert("xyxy").bbox.to(torch.float32).clone(), t.size, mode="xyxy")
-                b.add_field("labels", t.get_field("labels").clone())
+            for i, t in enumerate(targets):
+                b = BoxList(torch.zeros((cap, 4), dtype=torch.float32, device=dev), t.size, mode="xyxy")
+                b.add_field("labels", torch.zeros((cap,), dtype=t.get_field("labels").dtype, device=dev))
                 b._is_source_image = bool(is_source_image(t))
+                b._gt_count_dev = counts_dev[i:i + 1]
                 st_targets.append(b)
-            ent = dict(images=tensors.clone(), targets=st_targets, graph=None, losses=None, calls=0, launches=0)
+            ent = dict(images=torch.empty_like(tensors), sizes=[torch.Size(s) for s in sizes], targets=st_targets,
+                       counts=counts_dev, graph=None, loss_keys=None, loss_vec=None, calls=0, launches=0)
             self.step_graphs[key] = ent
-        else:
-            ent["images"].copy_(tensors, non_blocking=True)
-            for st, t in zip(ent["targets"], targets):
-                st.bbox.copy_(t.convert("xyxy").bbox, non_blocking=True)
-                st.get_field("labels").copy_(t.get_field("labels"), non_blocking=True)
+        ent["images"].copy_(tensors, non_blocking=True)
+        for st, t, n in zip(ent["targets"], targets, counts):
+            st.bbox[:n].copy_(t.convert("xyxy").bbox, non_blocking=True)
+            st.get_field("labels")[:n].copy_(t.get_field("labels"), non_blocking=True)
+        ent["counts"].copy_(torch.tensor(counts, dtype=torch.int32), non_blocking=True)
         self.lr_dev.fill_(self.lr())
         ent["calls"] += 1
+        batch = ImageList(ent["images"], ent["sizes"])
         # Eager warm-up and capture run on ONE dedicated stream, and nothing returned keeps the autograd graph
         # alive: a stale AccumulateGrad node bound to another stream would invalidate the capture.
         if self.graph_stream is None:
@@ -193,7 +237,7 @@ class FlatSGDTrainer(object):
             # first sight of a signature: one eager step (lazy workspaces, cached constants, kernel attributes)
             self.graph_stream.wait_stream(cur)
             with torch.cuda.stream(self.graph_stream):
-                ld = self._eager_step(ent["images"], ent["targets"], dev_lr=True)
+                ld = self._eager_step(batch, ent["targets"], dev_lr=True)
                 loss_dict = {k: v.detach().clone() for k, v in ld.items()}
                 del ld
             cur.wait_stream(self.graph_stream)
@@ -205,14 +249,17 @@ class FlatSGDTrainer(object):
                     self.graph_pool = torch.cuda.graph_pool_handle()
                 before = _lib.launch_count()
                 with torch.cuda.graph(g, pool=self.graph_pool, stream=self.graph_stream):
-                    ld = self._eager_step(ent["images"], ent["targets"], dev_lr=True)
-                    ent["losses"] = {k: v.detach() for k, v in ld.items()}
+                    ld = self._eager_step(batch, ent["targets"], dev_lr=True)
+                    ent["loss_keys"] = list(ld.keys())
+                    ent["loss_vec"] = torch.stack([v.detach().reshape(()) for v in ld.values()])
                     del ld
                 ent["launches"] = _lib.launch_count() - before
                 ent["graph"] = g
             ent["graph"].replay()
             self.graph_launches += ent["launches"]
-            loss_dict = ent["losses"]
+            # a copy: the graph's own output buffer is overwritten by the next replay of this signature
+            vec = ent["loss_vec"].clone()
+            loss_dict = {k: vec[i] for i, k in enumerate(ent["loss_keys"])}
         self.iteration += 1
         return loss_dict
 

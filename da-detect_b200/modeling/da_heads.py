@@ -161,34 +161,25 @@ class DomainAdaptationModule_triplet(_Base):
         super().__init__(cfg, rng)
         D = cfg.MODEL.DA_HEADS
         self.triplet_img_weight, self.triplet_ins_weight = D.DA_TRIPLET_IMG_WEIGHT, D.DA_TRIPLET_INS_WEIGHT
-        # host-side state of the reference (da_heads.py:107-110, loss.py:128-130); the previous triplet
-        # losses stay on the device and are only read when the adaptive margin can actually move.
-        self.prev_img, self.prev_ins = None, None
-        self.margin_img, self.margin_ins = 0.0, 0.0
+        # State of the reference (da_heads.py:107-113, loss.py:128-130).  The instance margin is not adaptive (a
+        # constant).  The adaptive IMAGE margin and the previous image-triplet loss it consults live on the device
+        # (non-persistent buffers: they are not part of the reference's state dict), so that no configuration reads
+        # a loss on the host and every one of them can be captured into the whole-step graph.
+        self.margin_ins = 0.0
+        self.register_buffer("margin_img_state", torch.zeros(1, dtype=torch.float64), persistent=False)
+        self.register_buffer("margin_img_dev", torch.zeros(1, dtype=torch.float32), persistent=False)
+        self.register_buffer("prev_img", torch.ones(1, dtype=torch.float32), persistent=False)   # triplet_img = [1]
 
-    def _margin(self, current, prev_loss, adaptive, lr, max_margin, margin):
-        if current == 0.0:
-            current = margin
-        if adaptive:
-            if int(current) != int(max_margin):             # only then is the previous loss consulted
-                prev = 1.0 if prev_loss is None else float(prev_loss)
-                if prev == 0.0:
-                    current = current + lr
-        else:
-            current = margin
-        return current
+    @property
+    def margin_img(self):
+        """The current image-level margin (host read; for logging and tests)."""
+        return float(self.margin_img_state)
 
     def _grl_weight(self, loss, lam, lam_adv):
         D = self.cfg.MODEL.DA_HEADS
         if D.DA_ADV_GRL:
             return ops.adv_grl_weight(loss, ADV_BCE, lam, lam_adv, D.DA_ADV_GRL_THRESHOLD)
         return torch.full((1,), -1.0 * lam, dtype=torch.float32, device=loss.device)
-
-    def host_reads_needed(self):
-        """The adaptive image margin consults the previous step's loss on the host while it is below its maximum
-        (da_heads.py:236-252); with the stock YAML values (margin == max margin) it never does."""
-        D = self.cfg.MODEL.DA_HEADS
-        return self.triplet_img_weight > 0 and int(D.TRIPLET_MARGIN_IMG) != int(D.TRIPLET_MAX_MARGIN)
 
     def forward(self, img_features, pooled_ins, dom, n_src, pooled_set, img_fea_set, targets, row_valid=None, seg=None,
                 set_valid=None):
@@ -201,8 +192,7 @@ class DomainAdaptationModule_triplet(_Base):
         losses = {}
         if self.triplet_ins_weight > 0:                       # Domainlevel_Ins_component
             s, p, n = pooled_set
-            self.margin_ins = self._margin(self.margin_ins, self.prev_ins, False, 0.001, D.TRIPLET_MAX_MARGIN,
-                                           D.TRIPLET_MARGIN_INS)
+            self.margin_ins = D.TRIPLET_MARGIN_INS           # adaptive=False (da_heads.py:266, loss.py:214-216)
             if set_valid is not None:
                 # slots that hold no ROI: anchor = positive and a far-away negative put the hinge at exactly zero
                 # (no loss, no gradient); the mean is rescaled to the rows that exist
@@ -214,15 +204,17 @@ class DomainAdaptationModule_triplet(_Base):
             else:
                 l = ops.triplet_margin_loss(s, p, n, self.margin_ins, s.shape[0], s.shape[1], 1)
             losses["triplet_loss_instance"] = self.triplet_ins_weight * l
-            self.prev_ins = l.detach()
         if self.triplet_img_weight > 0:                       # Domainlevel_Img_component
             s, p, n = img_fea_set
-            self.margin_img = self._margin(self.margin_img, self.prev_img, True, 0.001, D.TRIPLET_MAX_MARGIN,
-                                           D.TRIPLET_MARGIN_IMG)
+            # adaptive margin (loss.py:182-200): += 0.001 whenever the previous step's loss was exactly 0 and
+            # int(margin) != int(max margin) — evaluated on the device from the kept previous loss
+            margin = ops.adaptive_margin_update(self.margin_img_state, self.prev_img, D.TRIPLET_MARGIN_IMG, 0.001,
+                                                D.TRIPLET_MAX_MARGIN, out=self.margin_img_dev)
             _, h, w, c = s.shape                              # NHWC [1,h,w,C]: distance over w per (c,h)
-            l = ops.triplet_margin_loss(s, p, n, self.margin_img, h * c, w, c)
+            l = ops.triplet_margin_loss(s, p, n, margin, h * c, w, c)
             losses["triplet_loss_image"] = self.triplet_img_weight * l
-            self.prev_img = l.detach()
+            with torch.no_grad():
+                self.prev_img.copy_(l.detach().reshape(1))
         if self.img_weight > 0:                               # DA_Img_component
             wdev = torch.empty(1, dtype=torch.float32, device=feat.device)
             da_img = self.imghead(ops.gradient_scalar_dev(feat, wdev))

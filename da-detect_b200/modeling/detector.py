@@ -118,6 +118,9 @@ class GeneralizedRCNN(nn.Module):
             self._meta_cache[key] = meta
         meta = dict(meta)
         meta["gt_cat"] = torch.cat([t.convert("xyxy").bbox.to(torch.float32) for t in targets], dim=0)
+        counts = [getattr(t, "_gt_count_dev", None) for t in targets]
+        if all(c is not None for c in counts):       # GT padded to a capacity: the live row counts are on the device
+            meta["gt_counts"] = torch.cat(counts)
         return meta
 
     def _forward_static(self, images, targets, feat, logits, deltas):

@@ -212,7 +212,7 @@ class FastRCNNLossComputation(object):
         labs, ms = [], []
         for i, t in enumerate(targets):
             gt = t.convert("xyxy").bbox
-            m, _ = ops.match(gt, boxes[i], self.high, self.low, False)
+            m, _ = ops.match(gt, boxes[i], self.high, self.low, False, m_dev=getattr(t, "_gt_count_dev", None))
             if is_source_image(t):
                 lab = t.get_field("labels").to(torch.int64)[m.clamp(min=0)]
                 lab = torch.where(m == BELOW_LOW_THRESHOLD, torch.zeros_like(lab), lab)
@@ -232,10 +232,11 @@ class FastRCNNLossComputation(object):
             bx = boxes[i][sel[i]]
             rois.append(torch.cat([torch.full((B, 1), float(i), dtype=bx.dtype, device=dev), bx], dim=1))
             labels.append(torch.where(valid[i], labs[i][sel[i]].to(torch.int64), torch.zeros_like(sel[i])))
-            regs.append(ops.box_encode(t.convert("xyxy").bbox, bx, ms[i][sel[i]], self.weights, wrap_negative=not src))
+            regs.append(ops.box_encode(t.convert("xyxy").bbox, bx, ms[i][sel[i]], self.weights, wrap_negative=not src,
+                                       m_dev=getattr(t, "_gt_count_dev", None)))
             doms.append(torch.full((B,), src, dtype=torch.bool, device=dev))
         st = dict(rois=torch.cat(rois), labels=torch.cat(labels), regression_targets=torch.cat(regs),
-                  domain_labels=torch.cat(doms), valid=valid.reshape(-1), counts=cnt[:, 1], size=props.size,
+                  domain_labels=torch.cat(doms), valid=valid.reshape(-1), counts=cnt[:, 1], sizes=props.sizes,
                   objectness=torch.stack([props.objectness[i][sel[i]] for i in range(n_img)]).reshape(-1))
         self._static = st
         self.rng.consume_da_draws(st["counts"])
@@ -248,7 +249,7 @@ class FastRCNNLossComputation(object):
         out = []
         for i, c in enumerate(st["counts"].tolist()):
             sl = slice(i * B, i * B + c)
-            q = BoxList(st["rois"][sl, 1:], st["size"], mode="xyxy")
+            q = BoxList(st["rois"][sl, 1:], st["sizes"][i], mode="xyxy")
             for f in ("objectness", "labels", "regression_targets", "domain_labels"):
                 q.add_field(f, st[f][sl])
             out.append(q)

@@ -103,7 +103,7 @@ class RPNHead(nn.Module):
     def forward(self, feat):
         t = ops.conv_bn_act(feat, self.conv.weight, None, self.conv.bias, pad=1, relu=True)
         a, a4 = self.cls_logits.weight.shape[0], self.bbox_pred.weight.shape[0]
-        if ops.get_default_impl() in (ops.IMPL_TCGEN05, ops.IMPL_TCGEN05_X3):
+        if ops.get_default_impl() in ops.TC_IMPLS:
             # Both 1x1 predictors as ONE tensor-core GEMM: their 15 + 60 output channels are stacked and padded
             # to 96 (a multiple of the 32-channel K block), so that the data- and weight-gradient GEMMs (K = Cout,
             # M = Cout) are tensor-core shaped too; the pad rows are zero and receive zero gradient.
@@ -120,20 +120,21 @@ class RPNHead(nn.Module):
 
 
 class ProposalBatch(object):
-    """Fixed-capacity proposals of a batch: boxes [N,cap,4], objectness [N,cap], count int32 [N] (device)."""
+    """Fixed-capacity proposals of a batch: boxes [N,cap,4], objectness [N,cap], count int32 [N] (device);
+    sizes: the un-padded (w, h) of every image (host)."""
 
-    def __init__(self, boxes, objectness, count, size):
-        self.boxes, self.objectness, self.count, self.size = boxes, objectness, count, size
+    def __init__(self, boxes, objectness, count, sizes):
+        self.boxes, self.objectness, self.count, self.sizes = boxes, objectness, count, list(sizes)
 
     def slice(self, a, b):
         """Images [a, b) of the batch (views)."""
-        return ProposalBatch(self.boxes[a:b], self.objectness[a:b], self.count[a:b], self.size)
+        return ProposalBatch(self.boxes[a:b], self.objectness[a:b], self.count[a:b], self.sizes[a:b])
 
     def to_boxlists(self):
         """list[BoxList] like RPNPostProcessor returns (reads the counts on the host)."""
         out = []
         for i, c in enumerate(self.count.tolist()):
-            bl = BoxList(self.boxes[i, :c], self.size, mode="xyxy")
+            bl = BoxList(self.boxes[i, :c], self.sizes[i], mode="xyxy")
             bl.add_field("objectness", self.objectness[i, :c])
             out.append(bl)
         return out
@@ -166,6 +167,30 @@ class RPNModule(nn.Module):
         error instead of a flipped near-tie."""
         self.proposal_hook = fn
 
+    @staticmethod
+    def _topk_decode(logits, deltas, anchors, k, image_sizes, min_size):
+        """ops.rpn_topk_decode with every image clipped to ITS un-padded size (rpn/inference.py:101-103 builds one
+        BoxList per image with that image's size; a batch may mix datasets of different sizes, e.g.
+        cityscapes -> kitti).  Equal sizes: one launch for the batch; otherwise one launch per image."""
+        sizes = [(int(h), int(w)) for h, w in image_sizes]
+        if len(set(sizes)) == 1:
+            ih, iw = sizes[0]
+            return ops.rpn_topk_decode(logits, deltas, anchors, k, iw, ih, min_size)
+        parts = [ops.rpn_topk_decode(logits[i:i + 1], deltas[i:i + 1], anchors, k, iw, ih, min_size)
+                 for i, (ih, iw) in enumerate(sizes)]
+        return tuple(torch.cat(t, dim=0) for t in zip(*parts))
+
+    def _anchors_and_visibility(self, fh, fw, image_sizes, level=0):
+        """(anchors [A,4], visibility): the anchor coordinates depend on the feature map only; the visibility mask
+        (anchor_generator.py:98-111) on each image's un-padded size — one mask when all images share a size, else a
+        list with one mask per image."""
+        sizes = [(int(h), int(w)) for h, w in image_sizes]
+        grids = {sz: self.anchor_generator.grid(fh, fw, sz[1], sz[0], level=level) for sz in set(sizes)}
+        anchors = grids[sizes[0]][0]
+        if len(grids) == 1:
+            return anchors, grids[sizes[0]][1]
+        return anchors, [grids[sz][1] for sz in sizes]
+
     # ---- proposals (RPNPostProcessor, rpn/inference.py:76-152) -------------------------------------
     @torch.no_grad()
     def proposals(self, anchors, logits, deltas, image_sizes, targets):
@@ -175,24 +200,21 @@ class RPNModule(nn.Module):
         post = R.POST_NMS_TOP_N_TRAIN if train else R.POST_NMS_TOP_N_TEST
         n, fh, fw, a = logits.shape
         k = min(pre, fh * fw * a)
-        sizes = set((int(h), int(w)) for h, w in image_sizes)
-        if len(sizes) != 1:
-            raise NotImplementedError("images of different un-padded sizes in one batch")
-        ih, iw = sizes.pop()
-        boxes, scores, _, valid = ops.rpn_topk_decode(logits, deltas, anchors, k, iw, ih, R.MIN_SIZE)
+        wh = [(int(w), int(h)) for h, w in image_sizes]
+        boxes, scores, _, valid = self._topk_decode(logits, deltas, anchors, k, image_sizes, R.MIN_SIZE)
         out = []
         if R.NMS_THRESH > 0:
             keep, cnt = ops.nms_sorted_batched(boxes, valid, R.NMS_THRESH, post)     # whole batch, 2 launches
             counts = cnt.tolist()                                                    # the one host read
             for i in range(n):
                 sel = keep[i, : counts[i]]
-                bl = BoxList(boxes[i][sel], (iw, ih), mode="xyxy")
+                bl = BoxList(boxes[i][sel], wh[i], mode="xyxy")
                 bl.add_field("objectness", scores[i][sel])
                 out.append(bl)
         else:
             valid_h = valid.tolist()
             for i in range(n):
-                bl = BoxList(boxes[i, : valid_h[i]], (iw, ih), mode="xyxy")
+                bl = BoxList(boxes[i, : valid_h[i]], wh[i], mode="xyxy")
                 bl.add_field("objectness", scores[i, : valid_h[i]])
                 out.append(bl)
         if train and targets is not None:       # add_gt_proposals: source images only (:51-74)
@@ -207,12 +229,13 @@ class RPNModule(nn.Module):
 
     # ---- losses (RPNLossComputation, rpn/loss.py:57-143) -------------------------------------------
     def losses(self, anchors, visibility, logits, deltas, targets):
+        """visibility: one uint8 [A] mask, or a list with one mask per image (images of different sizes)."""
         R = self.cfg.MODEL.RPN
         labels, reg_targets = [], []
-        vis = visibility.bool()
-        for t in targets:                                   # labels exist for source images only (:66-67)
+        for i, t in enumerate(targets):                     # labels exist for source images only (:66-67)
             if not is_source_image(t):
                 continue
+            vis = (visibility[i] if isinstance(visibility, (list, tuple)) else visibility).bool()
             gt = t.convert("xyxy").bbox
             m, _ = ops.match(gt, anchors, R.FG_IOU_THRESHOLD, R.BG_IOU_THRESHOLD, True)
             lab = (m >= 0).to(torch.float32)
@@ -243,14 +266,12 @@ class RPNModule(nn.Module):
         n, fh, fw, a = logits.shape
         k = min(R.PRE_NMS_TOP_N_TRAIN, fh * fw * a)
         post = min(R.POST_NMS_TOP_N_TRAIN, k)
-        sizes = set((int(h), int(w)) for h, w in image_sizes)
-        if len(sizes) != 1:
-            raise NotImplementedError("images of different un-padded sizes in one batch")
-        ih, iw = sizes.pop()
-        boxes, scores, _, valid = ops.rpn_topk_decode(logits, deltas, anchors, k, iw, ih, R.MIN_SIZE)
+        boxes, scores, _, valid = self._topk_decode(logits, deltas, anchors, k, image_sizes, R.MIN_SIZE)
         keep, cnt = ops.nms_sorted_batched(boxes, valid, R.NMS_THRESH, post)
         return ProposalBatch(*ops.proposals_gather(boxes, scores, keep, cnt, meta["gt_cat"], meta["gt_offsets"],
-                                                   meta["append_gt"], post + meta["max_gt"]), size=(iw, ih))
+                                                   meta["append_gt"], post + meta["max_gt"],
+                                                   gt_counts=meta.get("gt_counts")),
+                             sizes=[(int(w), int(h)) for h, w in image_sizes])
 
     def losses_static(self, anchors, visibility, logits, deltas, targets):
         """RPNLossComputation (rpn/loss.py:57-143) with the sampler on the device.  Per source image the 256
@@ -260,18 +281,19 @@ class RPNModule(nn.Module):
         B = R.BATCH_SIZE_PER_IMAGE
         max_pos = int(B * R.POSITIVE_FRACTION)
         A = anchors.shape[0]
-        vis = visibility.bool()
         obj = logits.reshape(-1)                             # (n, h, w, a) order == permute_and_flatten
         reg = deltas.reshape(-1, 4)
         ar = torch.arange(B, device=obj.device)
         bce_sum = l1_sum = total = None
         dbg = dict(labels=[], pos=[], neg=[]) if self.keep_debug else None
         ordinal = 0
-        for t in targets:                                   # labels exist for source images only (:66-67)
+        for i, t in enumerate(targets):                     # labels exist for source images only (:66-67)
             if not is_source_image(t):
                 continue
+            vis = (visibility[i] if isinstance(visibility, (list, tuple)) else visibility).bool()
             gt = t.convert("xyxy").bbox
-            m, _ = ops.match(gt, anchors, R.FG_IOU_THRESHOLD, R.BG_IOU_THRESHOLD, True)
+            m_dev = getattr(t, "_gt_count_dev", None)        # GT padded to a capacity (signature-free step graph)
+            m, _ = ops.match(gt, anchors, R.FG_IOU_THRESHOLD, R.BG_IOU_THRESHOLD, True, m_dev=m_dev)
             lab = (m >= 0).to(torch.int32)
             lab = torch.where((m == BETWEEN_THRESHOLDS) | ~vis, torch.full_like(lab, -1), lab)
             sel, cnt = ops.balanced_sample(lab.view(1, -1), None, self.rng.sample_keys(lab).view(1, -1), B, max_pos)
@@ -283,7 +305,7 @@ class RPNModule(nn.Module):
             tgt = torch.where(valid, lab_s.to(torch.float32), torch.ones_like(x))
             bce_i = ops.bce_with_logits_mean(x, tgt) * float(B)
             posm = (valid & (lab_s == 1)).to(torch.float32).unsqueeze(1)
-            tg = ops.box_encode(gt, anchors[sel], m[sel], (1.0, 1.0, 1.0, 1.0))
+            tg = ops.box_encode(gt, anchors[sel], m[sel], (1.0, 1.0, 1.0, 1.0), m_dev=m_dev)
             l1_i = ops.smooth_l1_sum(reg[rows] * posm, tg * posm, 1.0 / 9, 1.0)
             bce_sum = bce_i if bce_sum is None else bce_sum + bce_i
             l1_sum = l1_i if l1_sum is None else l1_sum + l1_i
@@ -302,8 +324,7 @@ class RPNModule(nn.Module):
         feat = features[0]
         logits, deltas = head_out
         n, fh, fw, _ = feat.shape
-        ih, iw = images.image_sizes[0]
-        anchors, vis = self.anchor_generator.grid(fh, fw, int(iw), int(ih))
+        anchors, vis = self._anchors_and_visibility(fh, fw, images.image_sizes)
         if self.overlap_loss:
             # The proposal chain (top-k, NMS, gather: one or two CTAs per image, ~1.2 ms) and the RPN loss chain
             # (match, sampler, encode, losses: ~0.45 ms, also a few CTAs) are independent: the loss chain runs on a
@@ -332,17 +353,14 @@ class RPNModule(nn.Module):
         pre = R.PRE_NMS_TOP_N_TRAIN if train else R.PRE_NMS_TOP_N_TEST
         post = R.POST_NMS_TOP_N_TRAIN if train else R.POST_NMS_TOP_N_TEST
         fpn_post = R.FPN_POST_NMS_TOP_N_TRAIN if train else R.FPN_POST_NMS_TOP_N_TEST
-        sizes = set((int(h), int(w)) for h, w in image_sizes)
-        if len(sizes) != 1:
-            raise NotImplementedError("images of different un-padded sizes in one batch")
-        ih, iw = sizes.pop()
+        wh = [(int(w), int(h)) for h, w in image_sizes]
         n = outs[0][0].shape[0]
         boxes_i, scores_i = [[] for _ in range(n)], [[] for _ in range(n)]
         for (anchors, _), (logits, deltas) in zip(grids, outs):
             _, fh, fw, a = logits.shape
             k = min(pre, fh * fw * a)
-            boxes, scores, _, valid = ops.rpn_topk_decode(logits.detach(), deltas.detach(), anchors, k, iw, ih,
-                                                          R.MIN_SIZE)
+            boxes, scores, _, valid = self._topk_decode(logits.detach(), deltas.detach(), anchors, k, image_sizes,
+                                                        R.MIN_SIZE)
             keep, cnt = ops.nms_sorted_batched(boxes, valid, R.NMS_THRESH, min(post, k))
             for i, c in enumerate(cnt.tolist()):             # one host read per level
                 sel = keep[i, :c]
@@ -360,7 +378,7 @@ class RPNModule(nn.Module):
             picks = [torch.topk(s, min(fpn_post, s.numel()), dim=0, sorted=True)[1] for s in scores_i]
         out = []
         for i, pk in enumerate(picks):
-            bl = BoxList(boxes_i[i][pk], (iw, ih), mode="xyxy")
+            bl = BoxList(boxes_i[i][pk], wh[i], mode="xyxy")
             bl.add_field("objectness", scores_i[i][pk])
             out.append(bl)
         if train and targets is not None:
@@ -375,8 +393,7 @@ class RPNModule(nn.Module):
 
     def forward_fpn(self, images, features, targets=None):
         outs = [self.head(f) for f in features]              # the same head on every level (rpn.py:39-46)
-        ih, iw = images.image_sizes[0]
-        grids = [self.anchor_generator.grid(f.shape[1], f.shape[2], int(iw), int(ih), level=l)
+        grids = [self._anchors_and_visibility(f.shape[1], f.shape[2], images.image_sizes, level=l)
                  for l, f in enumerate(features)]
         boxes = self.proposals_fpn(grids, outs, images.image_sizes, targets)
         if self.proposal_hook is not None:
@@ -388,7 +405,10 @@ class RPNModule(nn.Module):
         obj = torch.cat([lg.reshape(n, -1) for lg, _ in outs], dim=1)
         reg = torch.cat([dl.reshape(n, -1, 4) for _, dl in outs], dim=1)
         anchors = torch.cat([g[0] for g in grids], dim=0)
-        vis = torch.cat([g[1] for g in grids], dim=0)
+        if isinstance(grids[0][1], list):                    # images of different sizes: one mask per image
+            vis = [torch.cat([g[1][i] for g in grids], dim=0) for i in range(n)]
+        else:
+            vis = torch.cat([g[1] for g in grids], dim=0)
         obj_loss, box_loss = self.losses(anchors, vis, obj, reg, targets)
         return boxes, {"loss_objectness": obj_loss, "loss_rpn_box_reg": box_loss}
 
@@ -398,8 +418,7 @@ class RPNModule(nn.Module):
         feat = features[0]
         logits, deltas = head_out if head_out is not None else self.head(feat)
         n, fh, fw, _ = feat.shape
-        ih, iw = images.image_sizes[0]
-        anchors, vis = self.anchor_generator.grid(fh, fw, int(iw), int(ih))
+        anchors, vis = self._anchors_and_visibility(fh, fw, images.image_sizes)
         with section("  rpn_proposals"):
             boxes = self.proposals(anchors, logits.detach(), deltas.detach(), images.image_sizes, targets)
             if self.proposal_hook is not None:

@@ -20,12 +20,27 @@ from . import _lib
 IMPL_SIMT = 0
 IMPL_TCGEN05 = 1
 IMPL_TCGEN05_X3 = 2          # 3xTF32 on the tensor cores: fp32-grade forward / data-gradient products
+IMPL_TCGEN05_MIXED = 3       # host-level policy: forward products 3xTF32 (fp32-grade losses and hard decisions),
+                             # data- and weight-gradient products plain TF32 (what cuDNN computes by default)
 _default_impl = IMPL_SIMT
+TC_IMPLS = (IMPL_TCGEN05, IMPL_TCGEN05_X3, IMPL_TCGEN05_MIXED)
+
+
+def fwd_impl(impl=None):
+    """The kernel arm (a DD_IMPL_* value of the C ABI) that forward products run on under `impl`."""
+    impl = _default_impl if impl is None else impl
+    return IMPL_TCGEN05_X3 if impl == IMPL_TCGEN05_MIXED else impl
+
+
+def bwd_impl(impl=None):
+    """The kernel arm that data- and weight-gradient products run on under `impl`."""
+    impl = _default_impl if impl is None else impl
+    return IMPL_TCGEN05 if impl == IMPL_TCGEN05_MIXED else impl
 
 
 def set_default_impl(impl):
-    """Select the dense-tier arm used by conv2d/linear: IMPL_SIMT (fp32 FMA), IMPL_TCGEN05 (TF32 tensor cores)
-    or IMPL_TCGEN05_X3 (3xTF32 tensor cores, fp32-grade)."""
+    """Select the dense-tier arm used by conv2d/linear: IMPL_SIMT (fp32 FMA), IMPL_TCGEN05 (TF32 tensor cores),
+    IMPL_TCGEN05_X3 (3xTF32 tensor cores, fp32-grade) or IMPL_TCGEN05_MIXED (3xTF32 forward, TF32 backward)."""
     global _default_impl
     _default_impl = int(impl)
 
@@ -123,7 +138,7 @@ def conv2d_forward_raw(x, w_ohwi, scale, bias, residual, kh, kw, stride, pad, re
     oh = (h + 2 * pad - kh) // stride + 1
     ow = (wd + 2 * pad - kw) // stride + 1
     y = torch.empty((n, oh, ow, cout), dtype=torch.float32, device=x.device)
-    impl = _default_impl if impl is None else impl
+    impl = fwd_impl(impl)
     ws = None
     if impl == IMPL_TCGEN05_X3:
         nbytes = _lib.load().dd_conv2d_forward_workspace_bytes(cin, cout, kh, kw, impl)
@@ -141,7 +156,7 @@ def conv2d_dgrad_raw(gy, w_ohwi, scale, x_shape, kh, kw, stride, pad, addend=Non
     gx = torch.empty(x_shape, dtype=torch.float32, device=gy.device)
     ws = prepared_ws if prepared_ws is not None else dgrad_workspace(cin, cout, kh, kw, gy.device)
     _lib.call("dd_conv2d_dgrad", _ptr(gy), _ptr(w_ohwi), _ptr(scale), _ptr(addend), _ptr(mask_act), _ptr(gx),
-              n, h, wd, cin, cout, kh, kw, stride, pad, _default_impl if impl is None else impl, _ptr(ws),
+              n, h, wd, cin, cout, kh, kw, stride, pad, bwd_impl(impl), _ptr(ws),
               1 if prepared_ws is not None else 0, _stream())
     return gx
 
@@ -156,7 +171,7 @@ def dgrad_prepare_batch(layers, device, impl=None):
     """Prepare the dgrad weights W' of several layers with one launch per 16 layers (a ResNet stage does all of its
     layers up front).  layers: list of (w_ohwi, scale | None); returns one prepared workspace per layer, or a list of
     None on the SIMT arm (which consumes the weights as they are)."""
-    impl = _default_impl if impl is None else impl
+    impl = bwd_impl(impl)
     n = len(layers)
     if impl == IMPL_SIMT or n == 0:
         return [None] * n
@@ -182,7 +197,7 @@ def conv2d_wgrad_raw(gy, x, scale, cout, kh, kw, stride, pad, out=None, accumula
     nbytes = _lib.load().dd_conv2d_wgrad_workspace_bytes(n, h, wd, cin, cout, kh, kw, stride, pad)
     ws = _workspace(nbytes, x.device, "wgrad")
     _lib.call("dd_conv2d_wgrad", _ptr(gy), _ptr(x), _ptr(scale), _ptr(out), n, h, wd, cin, cout, kh, kw, stride, pad,
-              1 if accumulate else 0, _default_impl if impl is None else impl, _ptr(ws), _stream())
+              1 if accumulate else 0, bwd_impl(impl), _ptr(ws), _stream())
     return out
 
 
@@ -227,12 +242,12 @@ def stem_conv7x7s2(x_nchw, weight, scale, bias, relu=True):
     y = torch.empty((n, h // 2, w // 2, cout), dtype=torch.float32, device=x.device)
     ws = _workspace(_lib.load().dd_stem_workspace_bytes(n, h, w, cout), x.device, "stem")
     _lib.call("dd_stem_conv7x7s2_forward", _ptr(x), _ptr(weight_ohwi(weight.detach())), _ptr(scale), _ptr(bias),
-              _ptr(y), n, h, w, cout, 1 if relu else 0, _default_impl, _ptr(ws), _stream())
+              _ptr(y), n, h, w, cout, 1 if relu else 0, fwd_impl(), _ptr(ws), _stream())
     return y
 
 
 def stem_tc_supported(x_nchw, weight):
-    return (_default_impl in (IMPL_TCGEN05, IMPL_TCGEN05_X3) and x_nchw.shape[1] == 3 and x_nchw.shape[2] % 2 == 0
+    return (_default_impl in TC_IMPLS and x_nchw.shape[1] == 3 and x_nchw.shape[2] % 2 == 0
             and x_nchw.shape[3] % 2 == 0 and tuple(weight.shape[1:]) == (3, 7, 7) and weight.shape[0] % 4 == 0
             and weight.shape[0] <= 64 and not weight.requires_grad)
 
@@ -743,16 +758,30 @@ def consistency_loss(img_logits, ins_logits, n_src, row_valid=None):
     return _finish(loss, (img_logits, ins_logits), (gi, gs))
 
 
+def adaptive_margin_update(state, prev_loss, margin_cfg, lr, max_margin, out=None):
+    """The adaptive triplet margin (da_heads/loss.py:182-200) as device state: `state` double[1] (0 = uninitialised),
+    `prev_loss` the previous step's triplet loss (device float[1] or None) -> float[1] margin for this step."""
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=state.device)
+    _lib.call("dd_adaptive_margin_update", _ptr(_chk(state, torch.float64, "state")),
+              _ptr(_chk(prev_loss, name="prev_loss")), float(margin_cfg), float(lr), float(max_margin), _ptr(out),
+              _stream())
+    return out
+
+
 def triplet_margin_loss(a, p, n, margin, rows, d, inner):
-    """nn.TripletMarginLoss(margin, p=2) with the distance over `d` elements strided by `inner`."""
+    """nn.TripletMarginLoss(margin, p=2) with the distance over `d` elements strided by `inner`.
+    margin: a Python float, or a device float[1] tensor (adaptive margin kept on the device)."""
     ac, pc, nc = _chk(a, name="anchor"), _chk(p, name="positive"), _chk(n, name="negative")
     loss = torch.empty(1, dtype=torch.float32, device=ac.device)
     need = a.requires_grad or p.requires_grad or n.requires_grad
     ga = torch.empty_like(ac) if need else None
     gp = torch.empty_like(pc) if need else None
     gn = torch.empty_like(nc) if need else None
-    _lib.call("dd_triplet_margin_loss", _ptr(ac), _ptr(pc), _ptr(nc), int(rows), int(d), int(inner), float(margin),
-              _ptr(loss), _ptr(ga), _ptr(gp), _ptr(gn), _stream())
+    m_dev = _chk(margin, name="margin") if torch.is_tensor(margin) else None
+    _lib.call("dd_triplet_margin_loss", _ptr(ac), _ptr(pc), _ptr(nc), int(rows), int(d), int(inner),
+              0.0 if m_dev is not None else float(margin), _ptr(m_dev), _ptr(loss), _ptr(ga), _ptr(gp), _ptr(gn),
+              _stream())
     if not need:
         return loss.view(())
     return _ScaledGradLoss.apply(loss, 3, a, p, n, ga, gp, gn)
@@ -821,8 +850,9 @@ def nms(boxes, scores, thresh):
     return keep[: int(count.item())]
 
 
-def match(gt, pred, high, low, allow_low_quality):
-    """Fused boxlist_iou + Matcher: int64 [N] with -1 (below low) / -2 (between) sentinels."""
+def match(gt, pred, high, low, allow_low_quality, m_dev=None):
+    """Fused boxlist_iou + Matcher: int64 [N] with -1 (below low) / -2 (between) sentinels.
+    m_dev (device int32[1], optional): gt is padded to its row capacity and only the first *m_dev rows exist."""
     g = _chk(gt, name="gt")
     p = _chk(pred, name="pred")
     m, n = g.shape[0], p.shape[0]
@@ -833,17 +863,19 @@ def match(gt, pred, high, low, allow_low_quality):
     matches = torch.empty((n,), dtype=torch.int64, device=p.device)
     vals = torch.empty((n,), dtype=torch.float32, device=p.device)
     best = torch.empty((m,), dtype=torch.float32, device=p.device)
-    _lib.call("dd_match", _ptr(g), m, _ptr(p), n, float(high), float(low), 1 if allow_low_quality else 0,
+    _lib.call("dd_match", _ptr(g), m, _ptr(_chk(m_dev, torch.int32, "m_dev")), _ptr(p), n, float(high), float(low),
+              1 if allow_low_quality else 0,
               _ptr(matches), _ptr(vals), _ptr(best), _stream())
     return matches, vals
 
 
-def box_encode(gt, pred, matches, weights, wrap_negative=False):
+def box_encode(gt, pred, matches, weights, wrap_negative=False, m_dev=None):
     g = _chk(gt, name="gt")
     p = _chk(pred, name="pred")
     out = torch.empty((p.shape[0], 4), dtype=torch.float32, device=p.device)
     wx, wy, ww, wh = (float(v) for v in weights)
-    _lib.call("dd_box_encode", _ptr(g), g.shape[0], _ptr(p), _ptr(_chk(matches, torch.int64, "matches")), p.shape[0],
+    _lib.call("dd_box_encode", _ptr(g), g.shape[0], _ptr(_chk(m_dev, torch.int32, "m_dev")), _ptr(p),
+              _ptr(_chk(matches, torch.int64, "matches")), p.shape[0],
               wx, wy, ww, wh, 1 if wrap_negative else 0, _ptr(out), _stream())
     return out
 
@@ -858,9 +890,10 @@ def box_decode(codes, boxes, weights):
     return out
 
 
-def proposals_gather(boxes, scores, keep, keep_count, gt_cat, gt_offsets, append_gt, cap):
+def proposals_gather(boxes, scores, keep, keep_count, gt_cat, gt_offsets, append_gt, cap, gt_counts=None):
     """boxes [N,k,4], scores [N,k], keep int64 [N,post], keep_count int32 [N], gt_cat [G,4], gt_offsets int32 [N+1],
-    append_gt uint8 [N] -> (proposals [N,cap,4], objectness [N,cap], count int32 [N]); no host read."""
+    append_gt uint8 [N] -> (proposals [N,cap,4], objectness [N,cap], count int32 [N]); no host read.
+    gt_counts (device int32 [N], optional): live GT rows per image when the GT boxes are padded to a capacity."""
     n, k = scores.shape
     post = keep.shape[1]
     dev = boxes.device
@@ -870,6 +903,7 @@ def proposals_gather(boxes, scores, keep, keep_count, gt_cat, gt_offsets, append
     _lib.call("dd_proposals_gather", _ptr(_chk(boxes, name="boxes")), _ptr(_chk(scores, name="scores")),
               _ptr(_chk(keep, torch.int64, "keep")), _ptr(_chk(keep_count, torch.int32, "keep_count")),
               _ptr(_chk(gt_cat, name="gt")), _ptr(_chk(gt_offsets, torch.int32, "gt_offsets")),
+              _ptr(_chk(gt_counts, torch.int32, "gt_counts")),
               _ptr(_chk(append_gt, torch.uint8, "append_gt")), n, k, post, int(cap), _ptr(out_b), _ptr(out_s),
               _ptr(out_c), _stream())
     return out_b, out_s, out_c

@@ -97,6 +97,11 @@ class BoxList(object):
 
     def resize(self, size, *args, **kwargs):
         rw, rh = (float(s) / float(o) for s, o in zip(size, self.size))
+        if rw == rh:                     # bounding_box.py:99-108: equal ratios scale the box in its own mode
+            out = BoxList(self.bbox * rw, size, mode=self.mode)
+            for k, v in self.extra_fields.items():
+                out.add_field(k, v if isinstance(v, torch.Tensor) else v.resize(size, *args, **kwargs))
+            return out
         x1, y1, x2, y2 = self._split_into_xyxy()
         out = BoxList(torch.cat((x1 * rw, y1 * rh, x2 * rw, y2 * rh), dim=-1), size, mode="xyxy")
         for k, v in self.extra_fields.items():

@@ -97,14 +97,17 @@ int dd_rpn_topk_decode(const float* logits, const float* deltas, const float* an
 
 /* boxlist_iou + Matcher (structures/boxlist_ops.py:56-91, modeling/matcher.py:42-112) fused: never
  * materialises the [M,N] matrix.  gt [M,4], pred [N,4]; matches int64[N] in {-2,-1,0..M-1};
- * matched_vals float[N] (may be NULL).  gt_best is workspace float[M]. */
-int dd_match(const float* gt, int M, const float* pred, int N, float high, float low, int allow_low_quality,
-             int64_t* matches, float* matched_vals, float* gt_best, void* stream);
+ * matched_vals float[N] (may be NULL).  gt_best is workspace float[M].
+ * m_dev (may be NULL): device int32[1], the number of live GT rows when gt is padded to the capacity M (a
+ * training step captured once as a CUDA graph then serves batches with any number of boxes per image,
+ * data/datasets/coco.py:96-97); rows at and beyond *m_dev do not exist for the Matcher. */
+int dd_match(const float* gt, int M, const int32_t* m_dev, const float* pred, int N, float high, float low,
+             int allow_low_quality, int64_t* matches, float* matched_vals, float* gt_best, void* stream);
 /* BoxCoder.encode (box_coder.py:22-50) of gt[matches[i] clamped at 0] against pred[i];
  * wrap_negative != 0 reproduces the reference's negative-index wrap for target images
- * (box_head/loss.py:47-51). */
-int dd_box_encode(const float* gt, int M, const float* pred, const int64_t* matches, int N, float wx, float wy,
-                  float ww, float wh, int wrap_negative, float* targets, void* stream);
+ * (box_head/loss.py:47-51) — relative to the live row count (*m_dev when given, else M). */
+int dd_box_encode(const float* gt, int M, const int32_t* m_dev, const float* pred, const int64_t* matches, int N,
+                  float wx, float wy, float ww, float wh, int wrap_negative, float* targets, void* stream);
 /* BoxCoder.decode (box_coder.py:52-95) for codes [R, 4*k] against boxes [R,4]. */
 int dd_box_decode(const float* codes, const float* boxes, int R, int k, float wx, float wy, float ww, float wh,
                   float* out, void* stream);
@@ -113,11 +116,13 @@ int dd_box_decode(const float* codes, const float* boxes, int R, int k, float wx
 
 /* RPNPostProcessor tail (rpn/inference.py:116-127 + add_gt_proposals :51-74) without host reads: image g keeps
  * its first min(keep_count[g], post) NMS survivors boxes[g, keep[g, r]] and, when append_gt[g] != 0, is extended
- * with its ground-truth boxes gt[gt_offsets[g] .. gt_offsets[g+1]) (objectness 1).  out_boxes [N, cap, 4],
- * out_objectness [N, cap] (rows beyond out_count[g] are zero). */
+ * with its ground-truth boxes gt[gt_offsets[g] .. gt_offsets[g+1]) (objectness 1) — only the first gt_counts[g]
+ * of them when gt_counts (device int32 [N], may be NULL) is given: GT rows padded to a fixed capacity.
+ * out_boxes [N, cap, 4], out_objectness [N, cap] (rows beyond out_count[g] are zero). */
 int dd_proposals_gather(const float* boxes, const float* scores, const int64_t* keep, const int* keep_count,
-                        const float* gt, const int* gt_offsets, const uint8_t* append_gt, int N, int k, int post,
-                        int cap, float* out_boxes, float* out_objectness, int* out_count, void* stream);
+                        const float* gt, const int* gt_offsets, const int* gt_counts, const uint8_t* append_gt, int N,
+                        int k, int post, int cap, float* out_boxes, float* out_objectness, int* out_count,
+                        void* stream);
 /* BalancedPositiveNegativeSampler (balanced_positive_negative_sampler.py:27-76) per image on the device:
  * labels int32 [images, n_cap] (>= 1 positive, 0 negative, < 0 ignored), image g has n_dev[g] candidates
  * (n_dev NULL: n_cap), keys float [images, n_cap] the random draw.  Chooses min(#pos, max_pos) positives and
@@ -234,9 +239,18 @@ int dd_consistency_loss(const float* img_logits, long long hw, const float* ins_
 /* nn.TripletMarginLoss(margin, p=2) (da_heads/loss.py:198-200): a,p,n [rows, D] with the norm over D
  * computed on rows gathered with element stride `inner` (NHWC feature maps: D = W taken with stride C);
  * see SURVEY §2.3/§9.8.  rows = number of distance vectors.  Layout: element (r, d) of a tensor lives at
- * base[(r / inner) * D * inner + d * inner + (r % inner)].  grads may be NULL. */
+ * base[(r / inner) * D * inner + d * inner + (r % inner)].  grads may be NULL.
+ * margin_dev (may be NULL): the margin is read from device memory instead (the adaptive margin below). */
 int dd_triplet_margin_loss(const float* a, const float* p, const float* n, long long rows, int D, long long inner,
-                           float margin, float* loss, float* grad_a, float* grad_p, float* grad_n, void* stream);
+                           float margin, const float* margin_dev, float* loss, float* grad_a, float* grad_p,
+                           float* grad_n, void* stream);
+/* The adaptive margin of DALossComputation_Component.triplet_img_loss (da_heads/loss.py:182-200) kept on the
+ * device: state (double[1], the reference's Python float; 0 = not yet initialised) becomes margin_cfg when it is
+ * 0 and grows by lr when the PREVIOUS step's triplet loss (prev_loss, device float[1], may be NULL) was exactly 0
+ * and int(state) != int(max_margin); margin_out (float[1]) receives the value the loss kernel consumes.  Replaces
+ * the reference's host read of the previous loss (da_heads.py:325 `.cpu()`), so that the step stays capturable. */
+int dd_adaptive_margin_update(double* state, const float* prev_loss, double margin_cfg, double lr, double max_margin,
+                              float* margin_out, void* stream);
 
 /* ---------------------------------------------------------------- optimiser */
 /* torch.optim.SGD step over a flat segment: g' = g*grad_scale + wd*p; buf = momentum*buf + g'; p -= lr*buf

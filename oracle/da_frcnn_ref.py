@@ -84,6 +84,12 @@ class _RoiAlignRef(torch.autograd.Function):
 
 
 def roi_align(x, rois, scale, ph, pw, sampling_ratio):
+    if x.is_cuda:
+        # "reference graph on the same GPU" timing leg only (bench.py torch_cudnn_baseline): the reference's csrc
+        # CUDA kernels cannot be built (THC removed from torch); torchvision's roi_align(aligned=False)
+        # implements the same ROIAlign arithmetic.  Never used as a parity checker.
+        import torchvision
+        return torchvision.ops.roi_align(x, rois, (int(ph), int(pw)), float(scale), int(sampling_ratio), aligned=False)
     return _RoiAlignRef.apply(x, rois, float(scale), int(ph), int(pw), int(sampling_ratio))
 
 
@@ -93,6 +99,9 @@ def nms(boxes, scores, thresh, strict=True):
     n = boxes.shape[0]
     if n == 0:
         return torch.empty(0, dtype=torch.int64)
+    if boxes.is_cuda:                 # same-GPU timing leg only (see roi_align): stock torchvision NMS
+        import torchvision
+        return torchvision.ops.nms(boxes.float(), scores.float(), float(thresh)).sort()[0]
     boxes = boxes.contiguous().float()
     order = torch.sort(scores.float(), descending=True, stable=True)[1].contiguous()
     keep = torch.empty(n, dtype=torch.int64)
@@ -183,7 +192,7 @@ def grid_anchors(fh, fw, stride, cell):
     yy, xx = torch.meshgrid(sy, sx, indexing="ij")
     xx, yy = xx.reshape(-1), yy.reshape(-1)
     shifts = torch.stack((xx, yy, xx, yy), dim=1)
-    return (shifts.view(-1, 1, 4) + cell.view(1, -1, 4)).reshape(-1, 4)
+    return (shifts.view(-1, 1, 4) + cell.to(shifts.device).view(1, -1, 4)).reshape(-1, 4)
 
 
 def anchor_visibility(anchors, img_w, img_h, straddle):
@@ -397,15 +406,16 @@ def rpn_loss(anchors, visibility, logits, deltas, gt_boxes, is_source_img, cfg, 
     source-first order)."""
     R = cfg.MODEL.RPN
     labels, reg_targets = [], []
-    for gt, src in zip(gt_boxes, is_source_img):
+    for i, (gt, src) in enumerate(zip(gt_boxes, is_source_img)):
         if not src:
             continue
+        vis_i = visibility[i] if isinstance(visibility, (list, tuple)) else visibility
         q = box_iou(gt, anchors)
         m = matcher(q, R.FG_IOU_THRESHOLD, R.BG_IOU_THRESHOLD, True)
         matched = gt[m.clamp(min=0)]
         lab = (m >= 0).to(torch.float32)
         lab[m == BELOW_LOW] = 0
-        lab[~visibility] = -1
+        lab[~vis_i] = -1
         lab[m == BETWEEN] = -1
         labels.append(lab)
         reg_targets.append(box_encode(matched, anchors, (1.0, 1.0, 1.0, 1.0)))
@@ -678,11 +688,15 @@ def da_heads_triplet(feat2, da_ins_feas, dom, ins_set, img_set, is_source_img2, 
 
 
 # --------------------------------------------------------------------------- detector
-def forward_train(P, cfg, images, targets, hooks=None, triplet_state=None, nms_strict=True, aux=None):
+def forward_train(P, cfg, images, targets, hooks=None, triplet_state=None, nms_strict=True, aux=None,
+                  image_sizes=None):
     """GeneralizedRCNN.forward, training (generalized_rcnn.py:61-156).
 
-    images  : float32 [N,3,H,W] already mean-subtracted/padded (ImageList.tensors); all images
-              are taken to be H x W (the synthetic batches of SURVEY §8d are unpadded)
+    images  : float32 [N,3,H,W] already mean-subtracted/padded (ImageList.tensors); without `image_sizes` all
+              images are taken to be H x W (the synthetic batches of SURVEY §8d are unpadded)
+    image_sizes : optional list of un-padded (h, w) per image (ImageList.image_sizes): proposals are clipped to
+              and anchor visibility is evaluated against each image's OWN size (anchor_generator.py:113-125
+              builds one anchor BoxList per image with that image's size; rpn/inference.py:101-103)
     targets : list of dict(boxes f32 [M,4] xyxy, labels int64 [M], is_source bool) in
               [source..., target...(, aux...)] order
     Returns the reference's loss dict (same keys) of 0-d tensors attached to P's autograd graph.
@@ -694,14 +708,16 @@ def forward_train(P, cfg, images, targets, hooks=None, triplet_state=None, nms_s
     gt_boxes = [t["boxes"] for t in targets]
     gt_labels = [t["labels"] for t in targets]
     is_src = [bool(t["is_source"]) for t in targets]
-    image_sizes = [(ih, iw)] * n
+    image_sizes = [(ih, iw)] * n if image_sizes is None else [(int(h), int(w)) for h, w in image_sizes]
 
     feat = backbone_c4(images, P, cfg.MODEL.BACKBONE.CONV_BODY)
     logits, deltas = rpn_head(feat, P)
     fh, fw = feat.shape[-2:]
     cell = cell_anchors(R.ANCHOR_STRIDE[0], R.ANCHOR_SIZES, R.ASPECT_RATIOS)
     anchors = grid_anchors(fh, fw, R.ANCHOR_STRIDE[0], cell)
-    vis = anchor_visibility(anchors, iw, ih, R.STRADDLE_THRESH)
+    vis = [anchor_visibility(anchors, w_i, h_i, R.STRADDLE_THRESH) for h_i, w_i in image_sizes]
+    if len(set(image_sizes)) == 1:
+        vis = vis[0]
     with torch.no_grad():
         props = rpn_proposals(anchors, logits, deltas, image_sizes, R.PRE_NMS_TOP_N_TRAIN,
                               R.POST_NMS_TOP_N_TRAIN, R.NMS_THRESH, R.MIN_SIZE, nms_strict)

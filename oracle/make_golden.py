@@ -410,6 +410,8 @@ def make_boundary():
     st["area"] = b.area().clone()
     st["resize_same_ratio"] = b.resize((640, 400)).bbox.clone()
     st["resize_two_ratios"] = b.resize((500, 333)).bbox.clone()
+    st["resize_same_ratio_xywh"] = b.convert("xywh").resize((640, 400)).bbox.clone()    # scaled in its own mode (:99-108)
+    st["resize_two_ratios_xywh"] = b.convert("xywh").resize((500, 333)).bbox.clone()
     st["flip_lr"] = b.transpose(0).bbox.clone()
     st["flip_tb"] = b.transpose(1).bbox.clone()
     cl = BoxList(boxes.clone(), (320, 200), mode="xyxy")

@@ -97,14 +97,18 @@ class _Grl(torch.autograd.Function):
         return g * (float(w) if not torch.is_tensor(w) else w.reshape(()).to(g.dtype)), None   # a device weight is read NOW
 
 
-def match(gt, pred, high, low, allow_low_quality):
+def match(gt, pred, high, low, allow_low_quality, m_dev=None):
+    if m_dev is not None:                      # GT padded to a capacity: only the first *m_dev rows exist
+        gt = gt[: int(m_dev)]
     if gt.shape[0] == 0 or pred.shape[0] == 0:
         raise ValueError("No ground-truth or proposal boxes available for one of the images during training")
     q = orc.box_iou(gt, pred)
     return orc.matcher(q, high, low, allow_low_quality), q.max(dim=0)[0]
 
 
-def box_encode(gt, pred, matches, weights, wrap_negative=False):
+def box_encode(gt, pred, matches, weights, wrap_negative=False, m_dev=None):
+    if m_dev is not None:
+        gt = gt[: int(m_dev)]
     idx = torch.where(matches < 0, matches + gt.shape[0] if wrap_negative else torch.zeros_like(matches), matches)
     return orc.box_encode(gt[idx.clamp(min=0)], pred, weights)
 
@@ -145,6 +149,16 @@ def triplet_margin_loss(a, p, n, margin, rows, d, inner):
     return F.triplet_margin_loss(rows_of(a), rows_of(p), rows_of(n), margin=float(margin), p=2)
 
 
+def adaptive_margin_update(state, prev_loss, margin_cfg, lr, max_margin, out=None):
+    state.fill_(orc._adaptive_margin(float(state), 1.0 if prev_loss is None else float(prev_loss), True, lr, max_margin,
+                                     margin_cfg))
+    m = state.to(torch.float32)
+    if out is not None:
+        out.copy_(m)
+        return out
+    return m
+
+
 def adv_grl_weight(loss, bce, lam, lam_adv, threshold, out=None):
     w = torch.tensor([orc.adv_grl_weight(loss.detach(), lam, lam_adv, threshold)], dtype=torch.float32)
     if out is not None:
@@ -154,7 +168,7 @@ def adv_grl_weight(loss, bce, lam, lam_adv, threshold, out=None):
 
 
 # ---- sync-free (fixed-capacity) path
-def proposals_gather(boxes, scores, keep, keep_count, gt_cat, gt_offsets, append_gt, cap):
+def proposals_gather(boxes, scores, keep, keep_count, gt_cat, gt_offsets, append_gt, cap, gt_counts=None):
     n, post = boxes.shape[0], keep.shape[1]
     out_b, out_s = torch.zeros(n, cap, 4), torch.zeros(n, cap)
     out_c = torch.zeros(n, dtype=torch.int32)
@@ -164,6 +178,8 @@ def proposals_gather(boxes, scores, keep, keep_count, gt_cat, gt_offsets, append
         out_b[g, :c], out_s[g, :c] = boxes[g][sel], scores[g][sel]
         if int(append_gt[g]):
             a, b = int(gt_offsets[g]), int(gt_offsets[g + 1])
+            if gt_counts is not None:
+                b = a + min(int(gt_counts[g]), b - a)
             out_b[g, c:c + b - a], out_s[g, c:c + b - a] = gt_cat[a:b], 1.0
             c += b - a
         out_c[g] = c
@@ -204,7 +220,7 @@ TRAINING_STAND_INS = dict(
     dropout_with_mask=lambda x, keep: x * keep * 2.0, match=match, box_encode=box_encode,
     bce_with_logits_mean=bce_with_logits_mean, smooth_l1_sum=smooth_l1_sum, softmax_ce_mean=softmax_ce_mean,
     box_reg_loss=box_reg_loss, consistency_loss=consistency_loss_masked, triplet_margin_loss=triplet_margin_loss,
-    adv_grl_weight=adv_grl_weight,
+    adv_grl_weight=adv_grl_weight, adaptive_margin_update=adaptive_margin_update,
 )
 
 STAND_INS = dict(

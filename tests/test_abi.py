@@ -23,6 +23,8 @@ def header_prototypes():
                     sig += "p"
                 elif a.startswith("float"):
                     sig += "f"
+                elif a.startswith("double"):
+                    sig += "d"
                 elif a.startswith("long long"):
                     sig += "q"
                 elif a.startswith("int"):

@@ -62,6 +62,8 @@ def test_boxlist_matches_reference_class(fx):
     assert torch.equal(b.area(), st["area"])
     assert torch.equal(b.resize((640, 400)).bbox, st["resize_same_ratio"])
     assert torch.equal(b.resize((500, 333)).bbox, st["resize_two_ratios"])
+    assert torch.equal(b.convert("xywh").resize((640, 400)).bbox, st["resize_same_ratio_xywh"])
+    assert torch.equal(b.convert("xywh").resize((500, 333)).bbox, st["resize_two_ratios_xywh"])
     assert torch.equal(b.transpose(0).bbox, st["flip_lr"])
     assert torch.equal(b.transpose(1).bbox, st["flip_tb"])
     assert b.resize((640, 400)).size == (640, 400) and torch.equal(b.resize((640, 400)).get_field("labels"), torch.arange(12))

@@ -51,9 +51,20 @@ def scenario(name):
 # globally — the documented cost of feeding fp32 storage straight to the tensor cores.
 # tcgen05x3 = 3xTF32 on the tensor cores (forward, data and weight gradient): the fp32 tolerances, with its OWN
 # hard decisions.
+# mixed = 3xTF32 forward / TF32 backward (the benchmarked arm): losses and hard decisions at the fp32 tolerances
+# (1e-4, its OWN top-k / NMS / sampling decisions); gradients are TF32 products of fp32-grade activations, so they
+# carry the TF32 operand rounding (2^-11 per operand): 1e-2 of the global gradient norm, 2.5e-1 per tensor (the
+# per-tensor bound is dominated by the near-cancelling domain-classifier sums, see below).
 TOL = {"simt": dict(loss=1e-4, grad_tensor=1e-2, grad_global=2e-3),
        "tcgen05": dict(loss=2e-3, grad_tensor=2.5e-1, grad_global=3e-2),
-       "tcgen05x3": dict(loss=1e-4, grad_tensor=1e-2, grad_global=2e-3)}
+       "tcgen05x3": dict(loss=1e-4, grad_tensor=1e-2, grad_global=2e-3),
+       "mixed": dict(loss=1e-4, grad_tensor=2.5e-1, grad_global=1e-2)}
+
+
+def impl_of(dense):
+    from dadetect_b200 import ops
+    return {"simt": ops.IMPL_SIMT, "tcgen05": ops.IMPL_TCGEN05, "tcgen05x3": ops.IMPL_TCGEN05_X3,
+            "mixed": ops.IMPL_TCGEN05_MIXED}[dense]
 
 
 @pytest.fixture(autouse=True)
@@ -65,12 +76,12 @@ def _restore_impl():
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("dense", ["simt", "tcgen05", "tcgen05x3"])
+@pytest.mark.parametrize("dense", ["simt", "tcgen05", "tcgen05x3", "mixed"])
 @pytest.mark.parametrize("name", sorted(SCENARIOS))
 def test_training_step_matches_oracle(name, dense):
     from dadetect_b200 import ops
     from dadetect_b200.utils.random_source import ReplaySource
-    ops.set_default_impl({"simt": ops.IMPL_SIMT, "tcgen05": ops.IMPL_TCGEN05, "tcgen05x3": ops.IMPL_TCGEN05_X3}[dense])
+    ops.set_default_impl(impl_of(dense))
     tol = TOL[dense]
     cfg, sd, images, targets, hw = scenario(name)
     torch.manual_seed(77)
@@ -277,7 +288,7 @@ def test_eval_mode_matches_real_reference_golden(dense):
 
 
 @pytest.mark.timeout(1200)
-@pytest.mark.parametrize("dense", ["simt", "tcgen05x3"])
+@pytest.mark.parametrize("dense", ["simt", "tcgen05x3", "mixed"])
 def test_three_sgd_iterations_match_oracle(dense):
     """Row a16 (the loop tail): three consecutive iterations of do_da_train (engine/trainer.py:196-242) — forward,
     backward, SGD with momentum 0.9, weight decay on weights only, bias lr x2 (solver/build.py:7-20) — on the GPU
@@ -287,7 +298,7 @@ def test_three_sgd_iterations_match_oracle(dense):
     from dadetect_b200 import ops
     from dadetect_b200.engine import FlatSGDTrainer
     from dadetect_b200.utils.random_source import ReplaySource
-    ops.set_default_impl(ops.IMPL_SIMT if dense == "simt" else ops.IMPL_TCGEN05_X3)
+    ops.set_default_impl(impl_of(dense))
     cfg, sd, images, targets, hw = scenario("da_img_ins_cst")
     cfg.merge_from_list(["SOLVER.BASE_LR", 0.002])
     S = cfg.SOLVER
@@ -329,14 +340,21 @@ def test_three_sgd_iterations_match_oracle(dense):
 
 
 @pytest.mark.timeout(900)
-def test_step_graphs_of_two_batch_signatures_share_one_pool():
-    """Real data has a varying number of GT boxes per image: every signature gets its own captured graph, all
-    graphs share one memory pool, and alternating between them keeps matching the eager trainer."""
+def test_one_step_graph_serves_every_gt_count():
+    """Real batches differ in the number of GT boxes per image almost every step (data/datasets/coco.py:96-97).  The
+    trainer keeps the boxes in fixed-capacity buffers with device-side counts, so ONE captured graph per image shape
+    serves them all: six different (source, target) GT-count pairs replay a single graph and match the eager
+    trainer step for step."""
     from dadetect_b200.engine import FlatSGDTrainer
     from dadetect_b200.utils.random_source import HashSource
     from dadetect_b200.utils.synthetic import make_batch
-    cfg, sd, images, targets, hw = scenario("da_img_only")
-    _, targets_b = make_batch(2, hw[0], hw[1], num_classes=cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES, boxes_per_image=3, seed=7)
+    cfg, sd, images, targets, hw = scenario("da_img_ins_cst")
+    nc = cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES
+    variants = []
+    for it, (ms, mt) in enumerate([(4, 4), (1, 7), (9, 2), (3, 3), (12, 1), (2, 11)]):
+        _, ta = make_batch(2, hw[0], hw[1], num_classes=nc, boxes_per_image=ms, seed=100 + it)
+        _, tb = make_batch(2, hw[0], hw[1], num_classes=nc, boxes_per_image=mt, seed=200 + it)
+        variants.append([ta[0], tb[1]])
     dev = torch.device("cuda")
     out = []
     for graph in (False, True):
@@ -346,13 +364,108 @@ def test_step_graphs_of_two_batch_signatures_share_one_pool():
         if graph:
             trainer.enable_step_graph(True)
         losses = []
-        for it in range(6):
-            tg = to_boxlists(targets if it % 2 == 0 else targets_b, hw, dev)
-            ld = trainer.step(images.to(dev) + 0.01 * it, tg)
-            losses.append({k: float(v) for k, v in ld.items()})
+        for rep in range(2):
+            for it, tgt in enumerate(variants):
+                ld = trainer.step(images.to(dev) + 0.01 * it, to_boxlists(tgt, hw, dev))
+                losses.append({k: float(v) for k, v in ld.items()})
         if graph:
-            assert len(trainer.step_graphs) == 2 and all(e["graph"] is not None for e in trainer.step_graphs.values())
+            assert len(trainer.step_graphs) == 1 and trainer.graph_launches > 0
+            assert all(e["graph"] is not None for e in trainer.step_graphs.values())
+        out.append((losses, trainer.flat_param.clone()))
+    (l0, p0), (l1, p1) = out
+    for a, b in zip(l0, l1):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 3e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    assert float((p0 - p1).norm() / p0.norm()) < 1e-5
+
+
+@pytest.mark.timeout(900)
+def test_step_graph_keeps_unpadded_image_sizes():
+    """The stock DA YAMLs pad 600x1200 images to 608x1216 (SIZE_DIVISIBILITY 32).  Anchor visibility and proposal
+    clipping must use the un-padded sizes under the whole-step graph exactly as on the eager path — here two images
+    of different sizes in one padded batch, against the eager trainer AND against the oracle's first step."""
+    from dadetect_b200.engine import FlatSGDTrainer
+    from dadetect_b200.structures import to_image_list
+    from dadetect_b200.utils.random_source import HashSource, ReplaySource
+    from dadetect_b200.utils.synthetic import make_batch
+    cfg, sd, _, _, _ = scenario("da_img_ins_cst")
+    sizes = [(150, 250), (136, 200)]
+    imgs, tg_raw = [], []
+    for i, (h, w) in enumerate(sizes):
+        im, t = make_batch(2, h, w, num_classes=cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES, boxes_per_image=4, seed=40 + i)
+        imgs.append(im[i])
+        tg_raw.append(t[i])
+    il = to_image_list(imgs, 32)
+    assert tuple(il.tensors.shape[-2:]) == (160, 256)
+    dev = torch.device("cuda")
+
+    def boxlists():
+        from dadetect_b200.structures import BoxList
+        out = []
+        for t, (h, w) in zip(tg_raw, sizes):
+            b = BoxList(t["boxes"].to(dev), (w, h), mode="xyxy")
+            b.add_field("labels", t["labels"].to(dev))
+            b.add_field("is_source", torch.full((len(t["labels"]),), bool(t["is_source"]), dtype=torch.bool, device=dev))
+            out.append(b)
+        return out
+
+    # oracle, first step, with recorded draws
+    torch.manual_seed(3)
+    rec = orc.RecordingHooks()
+    with torch.no_grad():
+        want = orc.forward_train({k: v.clone() for k, v in sd.items()}, cfg, il.tensors, tg_raw, hooks=rec,
+                                 nms_strict=True, image_sizes=il.image_sizes)
+    model = build(cfg, sd, dev)
+    model.set_random_source(ReplaySource(rec.perms, rec.masks))
+    got = model(il.to(dev), boxlists())
+    for k in want:
+        assert abs(float(got[k]) - float(want[k])) <= 1e-4 * max(abs(float(want[k])), 0.05), (k, float(got[k]), float(want[k]))
+    del model, got
+    out = []
+    for graph in (False, True):
+        model = build(cfg, sd, dev)
+        model.set_random_source(HashSource())
+        trainer = FlatSGDTrainer(model, cfg, world_size=1)
+        if graph:
+            trainer.enable_step_graph(True)
+        losses = []
+        for it in range(4):
+            ld = trainer.step(il.to(dev), boxlists())
+            losses.append({k: float(v) for k, v in ld.items()})
         out.append(losses)
     for a, b in zip(*out):
         for k in a:
             assert abs(a[k] - b[k]) <= 3e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
+
+
+@pytest.mark.timeout(900)
+def test_adaptive_triplet_margin_on_device_matches_oracle_state():
+    """da_heads/loss.py:182-200: the image-level triplet margin grows by 0.001 whenever the previous step's loss was
+    exactly 0 and int(margin) != int(max margin).  The product keeps the margin and the previous loss on the device
+    (no host read, the step stays one CUDA graph); four steps (one eager, capture, replays) must follow the
+    oracle's host-side TripletState."""
+    from dadetect_b200.engine import FlatSGDTrainer
+    from dadetect_b200.utils.random_source import HashSource
+    cfg, sd, images, targets, hw = scenario("triplet_aligned_advgrl")
+    cfg.merge_from_list(["MODEL.DA_HEADS.TRIPLET_MARGIN_IMG", 0.5, "MODEL.DA_HEADS.TRIPLET_MAX_MARGIN", 3.0,
+                         "SOLVER.BASE_LR", 0.0])
+    dev = torch.device("cuda")
+    model = build(cfg, sd, dev)
+    model.set_random_source(HashSource())       # the image-level triplet term depends on no random draw
+    trainer = FlatSGDTrainer(model, cfg, world_size=1)
+    trainer.enable_step_graph(True)
+    state = orc.TripletState()
+    P = {k: v.clone() for k, v in sd.items()}   # learning rate 0: the weights stay where they are
+    torch.manual_seed(9)
+    margins = []
+    for it in range(4):
+        with torch.no_grad():
+            want = orc.forward_train(P, cfg, images, targets, triplet_state=state, nms_strict=True)
+        got = trainer.step(images.to(dev), to_boxlists(targets, hw, dev))
+        margins.append((model.da_heads_triplet.margin_img, state.margin_img))
+        assert abs(float(got["triplet_loss_image"]) - float(want["triplet_loss_image"])) <= 1e-4, (it, got, want)
+        assert abs(margins[-1][0] - margins[-1][1]) < 1e-12, margins
+    # (the increments themselves — a previous loss of exactly 0 — are exercised at the op level,
+    # tests/test_gpu_ops.py::test_adaptive_margin_update_follows_reference_rule)
+    assert margins[0][1] == 0.5, margins
+    assert len(trainer.step_graphs) == 1 and trainer.graph_launches > 0      # such a config used to fall back to eager

@@ -681,6 +681,129 @@ def test_conv_tcgen05_x3_arm_is_fp32_grade(case):
     close(gw.permute(0, 3, 1, 2).cpu(), gw_want, "wgrad")
 
 
+# The shapes bench.py actually times (BASELINE configs[1..3] at 2 x 1024 x 2048, 512 ROIs): the dominant GEMM
+# (RPN 3x3 1024 -> 1024 on the 64 x 128 map, K = 9216), res5 on 7x7 ROI maps, the memory-bound res2 expansion, the
+# fused 96-column RPN predictor.  Reference: torch fp64 convolution on the same GPU (a stock op used as the checker).
+TC_BENCH_CASES = [
+    (2, 64, 128, 1024, 1024, 3, 1, 1),
+    (512, 7, 7, 512, 2048, 1, 1, 0),
+    (2, 256, 512, 64, 256, 1, 1, 0),
+    (512, 7, 7, 512, 512, 3, 1, 1),
+    (2, 64, 128, 1024, 96, 1, 1, 0),
+    (512, 7, 7, 1024, 512, 1, 1, 0),
+]
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("arm", ["tcgen05", "tcgen05x3"])
+@pytest.mark.parametrize("case", TC_BENCH_CASES)
+def test_conv_tcgen05_at_bench_shapes(case, arm):
+    """Forward (+BN scale/bias, residual, ReLU), data gradient (+addend, ReLU mask) and weight gradient of both
+    tensor-core arms at the full-size shapes of the benchmarked step: TF32 within 2e-3 rms of the fp64 result,
+    3xTF32 within 5e-6 rms (fp32 grade; 1e-5 on the weight gradient, whose chains run over up to 25 088 pixels)."""
+    n, h, w, cin, cout, k, stride, pad = case
+    o = ops()
+    impl = o.IMPL_TCGEN05 if arm == "tcgen05" else o.IMPL_TCGEN05_X3
+    g = torch.Generator(device=DEV).manual_seed(sum(case) + 3)
+    x = torch.randn(n, h, w, cin, generator=g, device=DEV)
+    wt = torch.randn(cout, k, k, cin, generator=g, device=DEV) / (cin * k * k) ** 0.5
+    scale = 0.5 + torch.rand(cout, generator=g, device=DEV)
+    bias = torch.randn(cout, generator=g, device=DEV) * 0.1
+    xr = x.permute(0, 3, 1, 2).double().requires_grad_(True)
+    wr = wt.permute(0, 3, 1, 2).double().requires_grad_(True)
+    y0 = F.conv2d(xr, wr, stride=stride, padding=pad) * scale.double().view(1, -1, 1, 1) + bias.double().view(1, -1, 1, 1)
+    res = torch.randn(n, y0.shape[2], y0.shape[3], cout, generator=g, device=DEV)
+    want = F.relu(y0 + res.permute(0, 3, 1, 2).double())
+    go = torch.randn(res.shape, generator=g, device=DEV)
+    gpre = (go * (want.permute(0, 2, 3, 1) > 0)).contiguous()                        # NHWC fp32, already ReLU-masked
+    gx_want, gw_want = torch.autograd.grad(want, (xr, wr), go.permute(0, 3, 1, 2).double())
+    tol_rms = 2e-3 if arm == "tcgen05" else 5e-6
+
+    def close(got_nhwc, ref_nchw, what, rms_tol):
+        err = got_nhwc.permute(0, 3, 1, 2).double() - ref_nchw
+        rms = float(ref_nchw.pow(2).mean().sqrt())
+        assert float(err.pow(2).mean().sqrt()) <= rms_tol * rms, (what, float(err.pow(2).mean().sqrt()), rms)
+        assert float(err.abs().max()) <= 30 * rms_tol * max(rms, 1e-6), (what, float(err.abs().max()), rms)
+
+    got = o.conv2d_forward_raw(x, wt, scale, bias, res, k, k, stride, pad, True, impl=impl)
+    close(got, want.detach(), "forward", tol_rms)
+    del got, y0
+    addend = torch.randn(x.shape, generator=g, device=DEV)
+    act = torch.randn(x.shape, generator=g, device=DEV)
+    gx = o.conv2d_dgrad_raw(gpre, wt, scale, tuple(x.shape), k, k, stride, pad, addend=addend, mask_act=act, impl=impl)
+    close(gx, (gx_want + addend.permute(0, 3, 1, 2).double()) * (act.permute(0, 3, 1, 2) > 0), "dgrad", tol_rms)
+    del gx, gx_want
+    gw = o.conv2d_wgrad_raw(gpre, x, scale, cout, k, k, stride, pad, impl=impl)
+    # d(want)/d(wr) already carries the BN scale (it multiplies the conv output)
+    close(gw, gw_want, "wgrad", tol_rms if arm == "tcgen05" else 1e-5)
+
+
+def test_match_and_encode_with_padded_gt_and_device_count():
+    """GT boxes padded to a fixed capacity with the live count on the device (signature-free step graph): the
+    Matcher (incl. the low-quality restore, which would otherwise fire on EVERY anchor for an all-zero padding
+    row), the negative-index wrap of the encoder and the GT append of the proposals see only the live rows."""
+    o = ops()
+    g = torch.Generator().manual_seed(77)
+    cap = 32
+    pred = orc.grid_anchors(16, 24, 16, orc.cell_anchors(16, (32, 64, 128, 256, 512), (0.5, 1.0, 2.0)))
+    for m in (1, 5, 32):
+        gt = rand_boxes(g, m, 384, 256, 16.0).floor()
+        padded = torch.zeros(cap, 4)
+        padded[:m] = gt
+        padded[m:] = torch.rand(cap - m, 4, generator=g) * 100          # stale rows of an earlier batch
+        cnt = torch.tensor([m], dtype=torch.int32, device=DEV)
+        iou = orc.box_iou(gt, pred)
+        for hi, lo, lq in ((0.7, 0.3, True), (0.5, 0.5, False)):
+            want = orc.matcher(iou.clone(), hi, lo, lq)
+            got, vals = o.match(padded.to(DEV), pred.to(DEV), hi, lo, lq, m_dev=cnt)
+            assert torch.equal(got.cpu(), want)
+            assert torch.equal(vals.cpu(), iou.max(dim=0)[0])
+        matches = torch.randint(-2, m, (pred.shape[0],), generator=g)
+        want_wrap = orc.box_encode(gt[matches], pred, (10.0, 10.0, 5.0, 5.0))
+        got_wrap = o.box_encode(padded.to(DEV), pred.to(DEV), matches.to(DEV), (10.0, 10.0, 5.0, 5.0),
+                                wrap_negative=True, m_dev=cnt)
+        torch.testing.assert_close(got_wrap.cpu(), want_wrap, atol=1e-5, rtol=1e-5)
+    # proposals_gather with per-image live counts inside fixed-capacity GT rows
+    n, k, post = 2, 40, 8
+    boxes, scores = torch.rand(n, k, 4, generator=g), torch.rand(n, k, generator=g)
+    keep = torch.stack([torch.randperm(k, generator=g)[:post] for _ in range(n)])
+    cnt = torch.tensor([8, 3], dtype=torch.int32)
+    gt = torch.rand(2 * cap, 4, generator=g)
+    offs = torch.tensor([0, cap, 2 * cap], dtype=torch.int32)
+    live = torch.tensor([5, 9], dtype=torch.int32)
+    app = torch.tensor([1, 1], dtype=torch.uint8)
+    ob, os_, oc = o.proposals_gather(boxes.to(DEV), scores.to(DEV), keep.to(DEV), cnt.to(DEV), gt.to(DEV), offs.to(DEV),
+                                     app.to(DEV), post + cap, gt_counts=live.to(DEV))
+    assert oc.cpu().tolist() == [13, 12]
+    for i in range(n):
+        want_b = torch.cat([boxes[i][keep[i, : cnt[i]]], gt[i * cap: i * cap + live[i]]])
+        assert torch.equal(ob[i, : oc[i]].cpu(), want_b)
+        assert float(ob[i, oc[i]:].abs().sum()) == 0.0
+
+
+def test_adaptive_margin_update_follows_reference_rule():
+    """dd_adaptive_margin_update against the reference's host rule (da_heads/loss.py:182-200, restated in
+    oracle._adaptive_margin) over a sequence of previous losses, including the stop at int(margin) == int(max)."""
+    o = ops()
+    for margin_cfg, max_margin in ((0.5, 3.0), (0.998, 1.5), (0.0, 3.0), (1.0, 1.0)):
+        state = torch.zeros(1, dtype=torch.float64, device=DEV)
+        cur = 0.0
+        prevs = [1.0, 0.0, 0.0, 0.3, 0.0, 0.0, 0.0, 2.0, 0.0]
+        for prev in prevs:
+            cur = orc._adaptive_margin(cur, prev, True, 0.001, max_margin, margin_cfg)
+            out = o.adaptive_margin_update(state, torch.tensor([prev], dtype=torch.float32, device=DEV), margin_cfg, 0.001,
+                                           max_margin)
+            assert float(state) == cur, (margin_cfg, max_margin, float(state), cur)
+            assert float(out) == float(torch.tensor(cur, dtype=torch.float32))
+    # and the loss kernel reads the margin from the device
+    g = torch.Generator().manual_seed(3)
+    a, p, n = (torch.randn(64, 48, generator=g).to(DEV) for _ in range(3))
+    m = torch.tensor([0.75], dtype=torch.float32, device=DEV)
+    l_dev = o.triplet_margin_loss(a, p, n, m, 64, 48, 1)
+    l_host = o.triplet_margin_loss(a, p, n, 0.75, 64, 48, 1)
+    assert float(l_dev) == float(l_host)
+
+
 @pytest.mark.parametrize("impl", ["tcgen05", "tcgen05x3"])
 def test_dgrad_batched_weight_preparation_is_bit_identical(impl):
     """dd_conv2d_dgrad_prepare_batch (one launch for a whole stage's layers) followed by prepared dgrad calls gives

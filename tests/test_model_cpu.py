@@ -83,6 +83,58 @@ def test_training_orchestration_matches_oracle(name, static, cpu_ops):
 
 
 @pytest.mark.timeout(900)
+@pytest.mark.parametrize("static", [False, True])
+def test_images_of_different_unpadded_sizes_in_one_batch(static, cpu_ops):
+    """A batch that mixes image sizes (cityscapes -> kitti, multi-scale MIN_SIZE_TRAIN): to_image_list pads to the
+    common size (SIZE_DIVISIBILITY 32), proposals are clipped to and anchor visibility is evaluated against each
+    image's OWN un-padded size (anchor_generator.py:113-125, rpn/inference.py:101-103)."""
+    from dadetect_b200.modeling import build_detection_model
+    from dadetect_b200.structures import BoxList, to_image_list
+    from dadetect_b200.utils.random_source import ReplaySource
+    from dadetect_b200.utils.synthetic import make_batch
+    torch.set_num_threads(os.cpu_count())
+    cfg, sd, _, _, _ = scenario("da_img_ins_cst")
+    sizes = [(150, 250), (136, 200)]                         # (h, w): padded to 160 x 256
+    imgs, tg_raw = [], []
+    for i, (h, w) in enumerate(sizes):
+        im, t = make_batch(2, h, w, num_classes=cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES, boxes_per_image=4, seed=40 + i)
+        imgs.append(im[i])
+        tg_raw.append(t[i])
+    il = to_image_list(imgs, 32)
+    assert tuple(il.tensors.shape[-2:]) == (160, 256)
+    torch.manual_seed(3)
+    rec = orc.RecordingHooks()
+    P = {k: v.clone().requires_grad_(orc.is_trainable(k)) for k, v in sd.items()}
+    with torch.no_grad():
+        want = orc.forward_train(P, cfg, il.tensors, tg_raw, hooks=rec, nms_strict=True, image_sizes=il.image_sizes)
+    model = build_detection_model(cfg)
+    model.load_state_dict(sd, strict=False)
+    model.train()
+    model.enable_static_shapes(static)
+    model.rpn.overlap_loss = False
+    replay = ReplaySource(rec.perms, rec.masks)
+    model.set_random_source(replay)
+    tg = []
+    for t, (h, w) in zip(tg_raw, sizes):
+        b = BoxList(t["boxes"].clone(), (w, h), mode="xyxy")
+        b.add_field("labels", t["labels"].clone())
+        b.add_field("is_source", torch.full((len(t["labels"]),), bool(t["is_source"]), dtype=torch.bool))
+        tg.append(b)
+    got = model(il, tg)
+    assert not replay.perms and not replay.masks
+    for k in want:
+        g, w_ = float(got[k].detach()), float(want[k].detach())
+        assert abs(g - w_) <= 2e-5 * max(1.0, abs(w_)), (k, g, w_)
+    # and the answer does depend on the sizes: with both images taken as 160 x 256 other anchors are visible
+    a0, a1 = {}, {}
+    with torch.no_grad():
+        plain = {k: v.clone() for k, v in sd.items()}
+        orc.forward_train(plain, cfg, il.tensors, tg_raw, nms_strict=True, aux=a0, image_sizes=il.image_sizes)
+        orc.forward_train(plain, cfg, il.tensors, tg_raw, nms_strict=True, aux=a1)
+    assert not torch.equal(a0["rpn_labels"], a1["rpn_labels"])
+
+
+@pytest.mark.timeout(900)
 def test_eval_orchestration_matches_real_reference_golden_c4(cpu_ops):
     """BASELINE configs[0] (plain R-50-C4 Faster R-CNN, eval mode, 2 x 800x800): the product's eval control flow
     (test-mode RPN post-processing, box head, PostProcessor) with kernel stand-ins against the detections of the REAL

@@ -91,3 +91,20 @@ def test_lr_schedules():
     assert c.lr_at(0) == pytest.approx(1e-4)
     assert c.lr_at(33200) < 0.001 and c.lr_at(33200) > 0.0009
     assert c.lr_at(170000) == pytest.approx(1e-6)
+
+
+@pytest.mark.parametrize("name", ["da_img_only", "da_img_ins_cst", "triplet_aligned_advgrl", "triplet_yaml_default"])
+def test_parameters_outside_the_flat_buffers_are_the_ones_the_reference_never_updates(name):
+    """torch.optim.SGD skips parameters whose .grad is None (no weight decay, no momentum).  The set the trainer
+    leaves outside its flat buffers must be exactly the set the REAL reference left without a gradient
+    (tests/golden/scenario_*.pt `params_without_grad`, recorded from the reference's own backward)."""
+    from dadetect_b200.config import get_cfg_defaults
+    from dadetect_b200.engine.trainer import unused_parameter_names
+    from dadetect_b200.modeling import build_detection_model
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fx = torch.load(os.path.join(root, "tests", "golden", "scenario_{}.pt".format(name)), weights_only=False)
+    cfg = get_cfg_defaults()
+    cfg.merge_from_file(os.path.join(root, "configs", fx["yaml"]))
+    cfg.merge_from_list(list(fx["opts"]))
+    model = build_detection_model(cfg)
+    assert sorted(unused_parameter_names(model)) == sorted(fx["params_without_grad"])

@@ -2,7 +2,12 @@
 512 ROIs) through the C-ABI conv entry points — forward, dgrad, wgrad — and print ms, TFLOP/s and the
 algorithmic HBM GB/s of each, plus the per-step total weighted by how often the shape occurs.
 
-  python tools/layer_bench.py [simt|tc|x3] [filter-substring]
+  python tools/layer_bench.py [simt|tc|x3|cudnn|cudnn32] [filter-substring]
+
+`cudnn` / `cudnn32` time the SAME shapes through stock torch (F.conv2d, torch.nn.grad.conv2d_input / conv2d_weight,
+channels_last, cuDNN with TF32 allowed / forbidden): the "reference on the same B200" per-layer baseline of SURVEY
+§8(d).  cuDNN's numbers are the bare convolution — the reference runs FrozenBN, the residual add and the ReLU as
+separate elementwise passes on top, ours are fused into the epilogue and included in the time.
 """
 import os
 import sys
@@ -59,6 +64,12 @@ def timed(fn, iters=10, warm=2):
 def main():
     arm = sys.argv[1] if len(sys.argv) > 1 else "tc"
     impl = {"simt": o.IMPL_SIMT, "x3": o.IMPL_TCGEN05_X3}.get(arm, o.IMPL_TCGEN05)
+    cudnn = arm.startswith("cudnn")
+    if cudnn:
+        torch.backends.cudnn.allow_tf32 = arm == "cudnn"
+        torch.backends.cuda.matmul.allow_tf32 = arm == "cudnn"
+        torch.backends.cudnn.benchmark = True
+    print("# arm:", arm)
     filt = sys.argv[2] if len(sys.argv) > 2 else ""
     dev = "cuda"
     tot = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
@@ -78,13 +89,23 @@ def main():
         flop = 2.0 * n * oh * ow * cout * cin * k * k
         by_f = 4.0 * (n * oh * ow * cin * (1 if stride == 1 else 1) + n * oh * ow * cout * (2 if has_res else 1) + wt.numel())
         by_d = 4.0 * (n * oh * ow * cout + n * h * w * cin + wt.numel())
-        t_f = timed(lambda: o.conv2d_forward_raw(x, wt, sc, bi, res, k, k, stride, pad, relu, impl=impl))
+        if cudnn:
+            xc = x.permute(0, 3, 1, 2)                       # logical NCHW over channels_last storage
+            wc = wt.permute(0, 3, 1, 2)
+            gc = gy.permute(0, 3, 1, 2)
+            t_f = timed(lambda: torch.nn.functional.conv2d(xc, wc, None, stride, pad))
+        else:
+            t_f = timed(lambda: o.conv2d_forward_raw(x, wt, sc, bi, res, k, k, stride, pad, relu, impl=impl))
         line = "%-32s %5d | %8.3f %7.1f %7.0f" % (name, cnt, t_f, flop / t_f / 1e9, by_f / t_f / 1e6)
         tot["fwd"] += t_f * cnt
         totf["fwd"] += flop * cnt
         if train:
-            t_d = timed(lambda: o.conv2d_dgrad_raw(gy, wt, sc, (n, h, w, cin), k, k, stride, pad, impl=impl))
-            t_w = timed(lambda: o.conv2d_wgrad_raw(gy, x, sc, cout, k, k, stride, pad, impl=impl))
+            if cudnn:
+                t_d = timed(lambda: torch.nn.grad.conv2d_input(xc.shape, wc, gc, stride, pad))
+                t_w = timed(lambda: torch.nn.grad.conv2d_weight(xc, wc.shape, gc, stride, pad))
+            else:
+                t_d = timed(lambda: o.conv2d_dgrad_raw(gy, wt, sc, (n, h, w, cin), k, k, stride, pad, impl=impl))
+                t_w = timed(lambda: o.conv2d_wgrad_raw(gy, x, sc, cout, k, k, stride, pad, impl=impl))
             line += " | %8.3f %7.1f %7.0f | %8.3f %7.1f" % (t_d, flop / t_d / 1e9, by_d / t_d / 1e6, t_w, flop / t_w / 1e9)
             tot["dgrad"] += t_d * cnt
             tot["wgrad"] += t_w * cnt
