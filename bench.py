@@ -450,8 +450,14 @@ def main():
             rep = fullsize_parity.run(args.config, dense=dense, with_grads=False)
             bad = fullsize_parity.verdict(rep)
             line["parity_check"] = {"passed": not bad, "failures": bad, "shape": rep["shape"], "dense": dense,
+                                    "method": "tests/fullsize_parity.py: (1) RPN-head arithmetic vs oracle, (2) oracle decision "
+                                              "procedure on the product's own logits == product proposals, (3) downstream of the "
+                                              "proposals vs oracle with replayed draws",
                                     "max_loss_rel": max(v[2] for v in rep["losses"].values()),
                                     "losses": {k: [round(v[0], 7), round(v[1], 7)] for k, v in rep["losses"].items()},
+                                    "arithmetic": rep["arithmetic"], "decisions": rep["decisions"],
+                                    "vs_oracle_proposals": rep["vs_oracle_proposals"],
+                                    "losses_with_own_decisions": rep["losses_with_own_decisions"],
                                     "index_tier": {k: rep[k] for k in rep if k.endswith("_equal") or k == "roi_boxes_moved"},
                                     "oracle_seconds": rep["oracle_s"]}
         if not args.no_torch_baseline:

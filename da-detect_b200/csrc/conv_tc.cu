@@ -23,6 +23,7 @@
 // Reference being replaced: cuDNN/cuBLAS calls behind F.conv2d / F.linear.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -113,6 +114,77 @@ __device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms.  Both CTAs of a pair issue their own TMA loads; the transaction bytes are
+// counted on the LEADER's (even CTA's) barrier: clearing bit 24 of a shared-window address selects the even CTA of
+// the pair (CUTLASS Sm100MmaPeerBitMask).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// wait with acquire at cluster scope: the arrivals may come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of the leader's MMAs: arrives on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -196,17 +268,21 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 
 // X3 = 3xTF32 ("fp32-grade") mode: every operand is split into a TF32-exact high part and a TF32-exact low part,
 // D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi; a stage then holds four tiles [A_hi | A_lo | B_hi | B_lo].
-template <int BN, bool X3>
+// CTA2 = CTA-pair mode (tcgen05 cta_group::2): two CTAs of a cluster compute a 256 x BN tile; each holds its own 128
+// rows of A and HALF of the B tile (BN/2 columns), the tensor cores of both SMs read both halves.
+template <int BN, bool X3, bool CTA2>
 struct SmemLayout {
-  static constexpr int kStages = X3 ? (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
-  static constexpr int kABytes = BM * BKB;      // 16 KB
-  static constexpr int kBBytes = BN * BKB;      // 8 / 16 / 32 KB
+  static constexpr int kABytes = BM * BKB;                       // 16 KB
+  static constexpr int kBBytes = (CTA2 ? BN / 2 : BN) * BKB;     // 4 .. 32 KB
   static constexpr int kStageBytes = (X3 ? 2 : 1) * (kABytes + kBBytes);
+  static constexpr int kFit = (192 * 1024) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kStagingBytes = BM * 128;                 // one 128-row x 32-column fp32 chunk
   static constexpr int kStagingOff = kStages * kStageBytes;      // 2 staging buffers (1024-aligned)
   static constexpr int kRowOff = kStagingOff + 2 * kStagingBytes;  // int32 pixel index per tile row
   static constexpr int kBarOff = kRowOff + BM * 4;
-  static constexpr int kTotal = kBarOff + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int kTotal = kBarOff + 512 /*barriers*/ + 1024 /*alignment slack*/;
+  static_assert(kTotal <= 232448, "shared memory budget");
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -265,12 +341,22 @@ enum { EPI_EXTRA = 1, EPI_MASK = 2, EPI_SCALAR = 4 };
 // Epilogue per 32-column chunk: tcgen05.ld (thread = one tile row) -> 128B-swizzled smem staging ->
 // re-mapped pass (8 threads per row => coalesced 128-bit reads of residual / mask, per-channel scale + bias,
 // ReLU) -> one TMA tensor store of the [rows x 32 ch] box, which also clips the tile against the tensor edges.
-template <int BN, int EPI, bool X3>
+//
+// CTA2 (CTA pair, cluster of 2): the pair walks tiles of 256 pixels x BN columns; CTA r owns pixel tile 2*mp + r (its
+// own A loads, its own 128 TMEM lanes, its own epilogue) and loads columns [r*BN/2, (r+1)*BN/2) of the B tile.  Only
+// the leader (rank 0) issues MMAs (cta_group::2, M = 256): half the B traffic per output and half the B operand
+// reads per SM.  Barrier protocol of the pair:
+//   full      leader's barrier counts the TMA bytes of BOTH CTAs (3xTF32: only the B halves; the A tile of each CTA
+//             lands on that CTA's own barrier, where its splitter warps wait)
+//   split     (3xTF32) leader's barrier, 8 arrivals: the splitter warps of both CTAs (remote arrive for rank 1)
+//   empty     per CTA; the leader's tcgen05.commit is multicast to both
+//   tmem_full per CTA, multicast commit; tmem_empty leader's barrier, 8 arrivals (epilogue warps of both CTAs)
+template <int BN, int EPI, bool X3, bool CTA2>
 __global__ void __launch_bounds__(X3 ? NUM_THREADS_X3 : NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_e,
                const __grid_constant__ CUtensorMap map_m, const TcParams p) {
-  using L = SmemLayout<BN, X3>;
+  using L = SmemLayout<BN, X3, CTA2>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + L::kStagingOff;
@@ -280,21 +366,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + L::kStages;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
   uint64_t* split_bar = tmem_empty_bar + 2;             // [kStages], X3 only: operand tiles split into hi / lo
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split_bar + L::kStages);
+  uint64_t* bfull_bar = split_bar + L::kStages;         // [kStages], X3 && CTA2 only: B halves of both CTAs landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull_bar + L::kStages);
   constexpr int kAOff2 = X3 ? L::kABytes : 0;           // A_lo sits right after A_hi
   constexpr int kBOff = (X3 ? 2 : 1) * L::kABytes;      // B (hi) tile offset inside a stage
+  constexpr int kBRows = CTA2 ? BN / 2 : BN;            // B rows (output columns) this CTA loads
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_iters = p.taps * p.cblocks;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // tile walk: a unit is one CTA (CTA1) or one pair (CTA2)
+  const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_units = CTA2 ? (p.m_tiles + 1) >> 1 : p.m_tiles;
+  const int total_tiles = m_units * p.n_tiles;
+  // this CTA's 128-pixel tile of unit tile t: (n_tile, mt); mt >= m_tiles (odd count, rank 1) is a phantom tile whose
+  // loads are zero-filled and whose stores are clipped away by TMA
+  auto tile_of = [&](int t, int& n_tile, int& n0, int& oh0, int& ow0) {
+    n_tile = t % p.n_tiles;
+    int mt = t / p.n_tiles;
+    if (CTA2) mt = 2 * mt + (int)rank;
+    const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
+    const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
+    n0 = mt * p.tn; oh0 = tile_h * p.th; ow0 = tile_w * p.tw;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (p.tma_store) tma_prefetch_desc(&map_c);
     for (int s = 0; s < L::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, 128); }
-    if (X3) for (int s = 0; s < L::kStages; ++s) mbar_init(split_bar + s, 128);
+    // consumer-side barriers count WARPS (one elected arrive per warp after __syncwarp): a remote arrive is a DSMEM
+    // transaction, and 128 of them per K-iteration made the pair mode a third slower than single CTAs
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, CTA2 ? 8 : 4); }
+    if (X3) for (int s = 0; s < L::kStages; ++s) { mbar_init(split_bar + s, CTA2 ? 8 : 4); mbar_init(bfull_bar + s, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // TMEM: 2 x BN columns (two tile accumulators, ping-pong).  3xTF32 mode: [M | P0 | P1], BN columns each.
@@ -305,10 +411,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // the MMA warp fills the other slot.  M never sees a tensor-core accumulation; the last partial of a tile is
   // added on the fly by the epilogue proper.
   constexpr int kGroup = 8;
-  constexpr int kTmemCols = X3 ? (BN <= 64 ? 256 : 512) : 2 * BN;
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  constexpr int kTmemCols = X3 ? (BN <= 64 ? 256 : 512) : (2 * BN < 32 ? 32 : 2 * BN);
+  if (warp == 1) { if (CTA2) tmem_alloc2(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols); }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();       // barriers of both CTAs initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -316,12 +422,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================================ TMA producer ================================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int n_tile = t % p.n_tiles;
-        int mt = t / p.n_tiles;
-        const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
-        const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
-        const int n0 = mt * p.tn, oh0 = tile_h * p.th, ow0 = tile_w * p.tw;
+      for (int t = unit; t < total_tiles; t += n_units) {
+        int n_tile, n0, oh0, ow0;
+        tile_of(t, n_tile, n0, oh0, ow0);
         if (p.prefetch_side) {
           // pull the tile of the residual / addend / mask tensors towards L2 while the MMAs of this tile run, so
           // the epilogue's side reads are L2 hits
@@ -331,6 +434,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.mask) tma_prefetch_l2_4d(&map_m, n_tile * BN + c, ow0, oh0, n0);
           }
         }
+        const int brow = n_tile * BN + (CTA2 ? (int)rank * kBRows : 0);     // first B row (output column) of this CTA
         for (int kit = 0; kit < k_iters; ++kit, ++it) {
           const int s = it % L::kStages;
           const uint32_t ph = (it / L::kStages) & 1;
@@ -339,32 +443,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
           uint8_t* sa = smem + s * L::kStageBytes;
           uint8_t* sb = sa + kBOff;
-          mbar_expect_tx(full_bar + s, L::kABytes + (X3 ? 2 : 1) * L::kBBytes);
-          if (p.stem) tma_load_5d(&map_a, full_bar + s, sa, 0, ow0, oh0 + (tap >> 1), tap & 1, n0);
-          else tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
-          tma_load_2d(&map_b, full_bar + s, sb, tap * p.Cin + cb * BKE, n_tile * BN);
-          if (X3) tma_load_2d(&map_b, full_bar + s, sb + L::kBBytes, tap * p.Cin + cb * BKE, p.b_lo_row + n_tile * BN);
+          const int kcol = tap * p.Cin + cb * BKE;
+          if constexpr (!CTA2) {
+            mbar_expect_tx(full_bar + s, L::kABytes + (X3 ? 2 : 1) * L::kBBytes);
+            if (p.stem) tma_load_5d(&map_a, full_bar + s, sa, 0, ow0, oh0 + (tap >> 1), tap & 1, n0);
+            else tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
+            tma_load_2d(&map_b, full_bar + s, sb, kcol, brow);
+            if (X3) tma_load_2d(&map_b, full_bar + s, sb + L::kBBytes, kcol, p.b_lo_row + brow);
+          } else if constexpr (!X3) {
+            // one barrier at the leader for the A tiles and B halves of both CTAs
+            if (leader) mbar_expect_tx(full_bar + s, 2 * (L::kABytes + L::kBBytes));
+            tma2_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
+            tma2_load_2d(&map_b, full_bar + s, sb, kcol, brow);
+          } else {
+            // A lands on this CTA's own barrier (its splitter waits there); the B halves on the leader's
+            mbar_expect_tx(full_bar + s, L::kABytes);
+            tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
+            if (leader) mbar_expect_tx(bfull_bar + s, 4 * L::kBBytes);
+            tma2_load_2d(&map_b, bfull_bar + s, sb, kcol, brow);
+            tma2_load_2d(&map_b, bfull_bar + s, sb + L::kBBytes, kcol, p.b_lo_row + brow);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    // ================================ MMA issuer (CTA pair: the leader only) ================================
+    constexpr uint32_t idesc = make_idesc_tf32(CTA2 ? 2 * BM : BM, BN);
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
+      if constexpr (CTA2) umma2_tf32(d, ad, bd, idesc, acc); else umma_tf32(d, ad, bd, idesc, acc);
+    };
+    auto commit = [&](uint64_t* bar) { if constexpr (CTA2) umma_commit2(bar); else umma_commit(bar); };
     uint32_t it = 0;
     int local = 0;
-    if constexpr (X3) {
+    if (!leader) {
+      // the peer's MMA warp only owns its TMEM allocation
+    } else if constexpr (X3) {
       uint32_t grp = 0;                                      // partial-slot groups, counted across tiles
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = unit; t < total_tiles; t += n_units) {
         for (int g0 = 0; g0 < k_iters; g0 += kGroup, ++grp) {
           const int pp = grp & 1;
-          mbar_wait(tmem_empty_bar + pp, ((grp >> 1) & 1) ^ 1);    // the folding warps have drained this slot
+          // the folding warps (of both CTAs) have drained this slot
+          if (CTA2) mbar_wait_cluster(tmem_empty_bar + pp, ((grp >> 1) & 1) ^ 1);
+          else mbar_wait(tmem_empty_bar + pp, ((grp >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)((1 + pp) * BN);
           const int g1 = min(g0 + kGroup, k_iters);
           for (int kit = g0; kit < g1; ++kit, ++it) {
             const int s = it % L::kStages;
             const uint32_t ph = (it / L::kStages) & 1;
-            mbar_wait(split_bar + s, ph);                    // the splitter (which waited for TMA) is done
+            if (CTA2) {                                      // the splitters of both CTAs are done; the B halves landed
+              mbar_wait_cluster(split_bar + s, ph);
+              mbar_wait(bfull_bar + s, ph);
+            } else {
+              mbar_wait(split_bar + s, ph);                  // the splitter (which waited for TMA) is done
+            }
             tc_fence_after();
             if (lane == 0) {
               const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
@@ -375,22 +507,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint64_t bd = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
                 const uint64_t adl = make_kmajor_sw128_desc(a_addr + kAOff2 + k * UMMA_K * 4);
                 const uint64_t bdl = make_kmajor_sw128_desc(b_addr + L::kBBytes + k * UMMA_K * 4);
-                umma_tf32(d, adl, bd, idesc, (kit > g0 || k > 0) ? 1u : 0u);      // small terms first
-                umma_tf32(d, ad, bdl, idesc, 1u);
-                umma_tf32(d, ad, bd, idesc, 1u);
+                mma(d, adl, bd, (kit > g0 || k > 0) ? 1u : 0u);      // small terms first
+                mma(d, ad, bdl, 1u);
+                mma(d, ad, bd, 1u);
               }
-              umma_commit(empty_bar + s);
-              if (kit == g1 - 1) umma_commit(tmem_full_bar + pp);                 // partial complete
+              commit(empty_bar + s);
+              if (kit == g1 - 1) commit(tmem_full_bar + pp);                 // partial complete
             }
             __syncwarp();
           }
         }
       }
     } else {
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+    for (int t = unit; t < total_tiles; t += n_units, ++local) {
       const int acc = local & 1;
       const uint32_t aph = (local >> 1) & 1;
-      mbar_wait(tmem_empty_bar + acc, aph ^ 1);            // epilogue has drained this accumulator
+      // the epilogue (of both CTAs) has drained this accumulator
+      if (CTA2) mbar_wait_cluster(tmem_empty_bar + acc, aph ^ 1); else mbar_wait(tmem_empty_bar + acc, aph ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
       for (int kit = 0; kit < k_iters; ++kit, ++it) {
@@ -405,10 +538,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < BKE / UMMA_K; ++k) {
             const uint64_t ad = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
             const uint64_t bd = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
-            umma_tf32(tmem_d, ad, bd, idesc, (kit | k) ? 1u : 0u);
+            mma(tmem_d, ad, bd, (kit | k) ? 1u : 0u);
           }
-          umma_commit(empty_bar + s);                              // frees the smem stage when these MMAs retire
-          if (kit == k_iters - 1) umma_commit(tmem_full_bar + acc);  // accumulator complete
+          commit(empty_bar + s);                              // frees the smem stage when these MMAs retire
+          if (kit == k_iters - 1) commit(tmem_full_bar + acc);  // accumulator complete
         }
         __syncwarp();
       }
@@ -421,7 +554,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // representable in TF32, so the result does not depend on how the tensor core converts fp32 bit patterns.
     const int rs = threadIdx.x - 192;                    // 0..127; consecutive threads take consecutive 16-byte
     uint32_t it = 0;                                     // chunks of the tile (element-wise work: conflict-free)
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = unit; t < total_tiles; t += n_units) {
       for (int kit = 0; kit < k_iters; ++kit, ++it) {
         const int s = it % L::kStages;
         const uint32_t ph = (it / L::kStages) & 1;
@@ -441,7 +574,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           sts128(a_hi + kAOff2 + j * 2048, lo[0], lo[1], lo[2], lo[3]);
         }
         fence_async_smem();                               // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(split_bar + s);
+        __syncwarp();
+        if (lane == 0) {
+          if (CTA2 && !leader) mbar_arrive_remote(split_bar + s, 0);
+          else mbar_arrive(split_bar + s);
+        }
       }
     }
   } else {
@@ -462,17 +599,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t st_off = lane * 128;                  // TMEM -> smem pass: own row, chunk j at (j ^ (lane & 7)) * 16
     const uint32_t st_sw = lane & 7;
     const float lo = p.relu ? 0.f : -INFINITY;
+    // hand a TMEM accumulator / partial slot back to the (leader's) MMA warp
+    auto release_tmem = [&](uint64_t* bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CTA2 && !leader) mbar_arrive_remote(bar, 0); else mbar_arrive(bar);
+      }
+    };
     uint32_t chunk_ctr = 0;
     uint32_t x3_grp = 0;                                   // 3xTF32: partial-slot groups, counted across tiles
     int local = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+    for (int t = unit; t < total_tiles; t += n_units, ++local) {
       const int acc = X3 ? 0 : (local & 1);
       const uint32_t aph = (local >> 1) & 1;
-      const int n_tile = t % p.n_tiles;
-      int mt = t / p.n_tiles;
-      const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
-      const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
-      const int n0 = mt * p.tn, oh0 = tile_h * p.th, ow0 = tile_w * p.tw;
+      int n_tile, n0, oh0, ow0;
+      tile_of(t, n_tile, n0, oh0, ow0);
       int pix[8];
       if (kExtra || kMask || kScalar) {                  // side reads / scalar stores need the rows' pixel index
         __syncwarp();                                    // lanes are done reading the previous tile's row table
@@ -597,16 +739,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
               }
-              if (ch == n_chunks - 1) {                  // slot fully read: hand it back before the slow part
-                tc_fence_before();
-                mbar_arrive(tmem_empty_bar + pp);
-              }
+              if (ch == n_chunks - 1) release_tmem(tmem_empty_bar + pp);   // slot fully read: hand it back before the slow part
               process(ra, ch, exa, mka);
             }
             continue;
           }
-          tc_fence_before();
-          mbar_arrive(tmem_empty_bar + pp);
+          release_tmem(tmem_empty_bar + pp);
         }
         continue;
       }
@@ -632,16 +770,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
-      tc_fence_before();
-      mbar_arrive(tmem_empty_bar + acc);
+      release_tmem(tmem_empty_bar + acc);
     }
     if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();   // (pair: the peer may still be arriving on our barriers)
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CTA2) tmem_dealloc2(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -1018,41 +1155,82 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
   return 0;
 }
 
-template <int BN, int EPI, bool X3>
-int launch_tc3(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
+// CTA-pair mode switch (default on).  DD_TC_CTA2=0 in the environment (read once) keeps every launch on single CTAs:
+// used to A/B the two modes on the GPU.
+bool tc_cta2_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DD_TC_CTA2");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+bool tc_cta2_forced() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DD_TC_CTA2");
+    on = (e != nullptr && e[0] == '2') ? 1 : 0;
+  }
+  return on == 1;
+}
+
+template <int BN, int EPI, bool X3, bool CTA2>
+int launch_tc4(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
                const CUtensorMap& mm, const TcParams& p, cudaStream_t s) {
-  using L = SmemLayout<BN, X3>;
+  using L = SmemLayout<BN, X3, CTA2>;
   static bool configured = false;
   if (!configured) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, EPI, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, EPI, X3, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < dd::kNumSMs ? total : dd::kNumSMs;
-  conv_tc_kernel<BN, EPI, X3><<<grid, X3 ? NUM_THREADS_X3 : NUM_THREADS, L::kTotal, s>>>(ma, mb, mc, me, mm, p);
+  const int m_units = CTA2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const long long total = (long long)m_units * p.n_tiles;
+  const int max_units = CTA2 ? dd::kNumSMs / 2 : dd::kNumSMs;
+  const int units = total < max_units ? (int)total : max_units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(CTA2 ? 2 * units : units));
+  cfg.blockDim = dim3(X3 ? NUM_THREADS_X3 : NUM_THREADS);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, EPI, X3, CTA2>, ma, mb, mc, me, mm, p));
   DD_LAUNCHED();
   return 0;
 }
 
+template <int BN, int EPI, bool X3>
+int launch_tc3(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
+               const CUtensorMap& mm, const TcParams& p, bool cta2, cudaStream_t s) {
+  if (cta2) return launch_tc4<BN, EPI, X3, true>(ma, mb, mc, me, mm, p, s);
+  return launch_tc4<BN, EPI, X3, false>(ma, mb, mc, me, mm, p, s);
+}
+
 template <int BN, int EPI>
 int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
-               const CUtensorMap& mm, const TcParams& p, bool x3, cudaStream_t s) {
+               const CUtensorMap& mm, const TcParams& p, bool x3, bool cta2, cudaStream_t s) {
   if constexpr (BN <= 128) {
-    if (x3) return launch_tc3<BN, EPI, true>(ma, mb, mc, me, mm, p, s);
+    if (x3) return launch_tc3<BN, EPI, true>(ma, mb, mc, me, mm, p, cta2, s);
   }
-  return launch_tc3<BN, EPI, false>(ma, mb, mc, me, mm, p, s);
+  return launch_tc3<BN, EPI, false>(ma, mb, mc, me, mm, p, cta2, s);
 }
 
 template <int BN>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
-              const CUtensorMap& mm, const TcParams& p, bool x3, cudaStream_t s) {
-  if (!p.tma_store) return launch_tc2<BN, EPI_SCALAR>(ma, mb, mc, me, mm, p, x3, s);
+              const CUtensorMap& mm, const TcParams& p, bool x3, bool cta2, cudaStream_t s) {
+  if (!p.tma_store) return launch_tc2<BN, EPI_SCALAR>(ma, mb, mc, me, mm, p, x3, cta2, s);
   const int epi = (p.extra ? EPI_EXTRA : 0) | (p.mask ? EPI_MASK : 0);
   switch (epi) {
-    case 0: return launch_tc2<BN, 0>(ma, mb, mc, me, mm, p, x3, s);
-    case EPI_EXTRA: return launch_tc2<BN, EPI_EXTRA>(ma, mb, mc, me, mm, p, x3, s);
-    case EPI_MASK: return launch_tc2<BN, EPI_MASK>(ma, mb, mc, me, mm, p, x3, s);
-    default: return launch_tc2<BN, EPI_EXTRA | EPI_MASK>(ma, mb, mc, me, mm, p, x3, s);
+    case 0: return launch_tc2<BN, 0>(ma, mb, mc, me, mm, p, x3, cta2, s);
+    case EPI_EXTRA: return launch_tc2<BN, EPI_EXTRA>(ma, mb, mc, me, mm, p, x3, cta2, s);
+    case EPI_MASK: return launch_tc2<BN, EPI_MASK>(ma, mb, mc, me, mm, p, x3, cta2, s);
+    default: return launch_tc2<BN, EPI_EXTRA | EPI_MASK>(ma, mb, mc, me, mm, p, x3, cta2, s);
   }
 }
 
@@ -1105,6 +1283,14 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
   p.m_tiles = tiles_n * p.tiles_h * p.tiles_w;
   const int BN = tc_bn_for(ncols, x3);
   p.n_tiles = (ncols + BN - 1) / BN;
+  // CTA pairs (256-pixel x BN tiles, half the B traffic per output) whenever there are at least two pixel tiles
+  // and the K loop is long enough to pay for the pair's cluster barriers (measured per layer, TF32: +5..9 % from 18
+  // K-iterations up, -5..25 % on the 2..16-iteration 1x1 layers); DD_TC_CTA2=2 forces pairs everywhere (tests)
+  // The 3xTF32 kernel stays on single CTAs: its stage chain (TMA -> splitter -> MMA) is latency-bound, and the
+  // pair's cross-CTA hops (remote split arrive, cluster-scope wait, multicast commit) lengthen exactly that chain
+  // (measured: RPN 3x3 1.49 ms single, 2.28 ms paired).
+  const bool cta2 = tc_cta2_enabled() && !p.stem && p.m_tiles >= 2 &&
+                    ((!x3 && p.taps * p.cblocks >= 18) || tc_cta2_forced());
   p.b_lo_row = x3 ? tc_rows_pad(ncols) : 0;
   DD_CHECK_ARG((long long)p.m_tiles * p.n_tiles < (1ll << 31));
   const uintptr_t align_bits = reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.extra) |
@@ -1123,7 +1309,7 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
     const cuuint64_t K = (cuuint64_t)KH * KW * Cin;
     cuuint64_t dims[2] = {K, (cuuint64_t)(x3 ? 2 * tc_rows_pad(ncols) : ncols)};
     cuuint64_t strides[1] = {K * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)(BN < 256 ? BN : 256)};
+    cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)(cta2 ? BN / 2 : BN)};    // a CTA of a pair loads half the columns
     if (encode_map(&mb, b, 2, dims, strides, box)) return -1;
   }
   if (p.tma_store) {
@@ -1153,9 +1339,9 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
     // read traffic on res2 conv3, 0.192 -> 0.167 ms without it) and changes nothing when both inputs are present.
     p.prefetch_side = 0;
   }
-  if (BN == 256) return launch_tc<256>(ma, mb, mc, me, mm, p, x3, s);
-  if (BN == 128) return launch_tc<128>(ma, mb, mc, me, mm, p, x3, s);
-  return launch_tc<64>(ma, mb, mc, me, mm, p, x3, s);
+  if (BN == 256) return launch_tc<256>(ma, mb, mc, me, mm, p, x3, cta2, s);
+  if (BN == 128) return launch_tc<128>(ma, mb, mc, me, mm, p, x3, cta2, s);
+  return launch_tc<64>(ma, mb, mc, me, mm, p, x3, cta2, s);
 }
 
 
@@ -1264,7 +1450,7 @@ extern "C" int dd_stem_conv7x7s2_forward(const float* x_nchw, const float* w_ohw
     cuuint32_t box[4] = {32, 16, 2, 1};
     if (encode_map(&mc, y, 4, dims, strides, box)) return -1;
   }
-  return launch_tc<64>(ma, mb, mc, ma, ma, p, x3, s);
+  return launch_tc<64>(ma, mb, mc, ma, ma, p, x3, false, s);
 }
 
 namespace {

@@ -31,7 +31,7 @@ class DAImgHead(nn.Module):
 
     def forward(self, feat):
         t = ops.conv_bn_act(feat, self.conv1_da.weight, None, self.conv1_da.bias, relu=True)
-        return ops.conv_bn_act(t, self.conv2_da.weight, None, self.conv2_da.bias)
+        return ops.fused_heads(t, [self.conv2_da.weight], [self.conv2_da.bias])[0]     # 1 channel, padded to 32
 
 
 class DAInsHead(nn.Module):
@@ -64,7 +64,7 @@ class DAInsHead(nn.Module):
         x = ops.linear(x, self.fc2_da.weight, self.fc2_da.bias, relu=True)
         if self.training:
             x = ops.dropout_with_mask(x, self.rng.dropout_keep(tuple(x.shape), x.device, row_valid))
-        return ops.linear(x, self.fc3_da.weight, self.fc3_da.bias)
+        return ops.fused_heads(x, [self.fc3_da.weight], [self.fc3_da.bias])[0]
 
 
 def _image_domain_labels(targets, device):

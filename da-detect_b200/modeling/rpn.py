@@ -102,20 +102,9 @@ class RPNHead(nn.Module):
 
     def forward(self, feat):
         t = ops.conv_bn_act(feat, self.conv.weight, None, self.conv.bias, pad=1, relu=True)
-        a, a4 = self.cls_logits.weight.shape[0], self.bbox_pred.weight.shape[0]
-        if ops.get_default_impl() in ops.TC_IMPLS:
-            # Both 1x1 predictors as ONE tensor-core GEMM: their 15 + 60 output channels are stacked and padded
-            # to 96 (a multiple of the 32-channel K block), so that the data- and weight-gradient GEMMs (K = Cout,
-            # M = Cout) are tensor-core shaped too; the pad rows are zero and receive zero gradient.
-            cin = self.cls_logits.weight.shape[1]
-            pad = (-(a + a4)) % 32
-            w = torch.cat([self.cls_logits.weight.reshape(a, cin), self.bbox_pred.weight.reshape(a4, cin),
-                           self.cls_logits.weight.new_zeros(pad, cin)], dim=0)
-            b = torch.cat([self.cls_logits.bias, self.bbox_pred.bias, self.cls_logits.bias.new_zeros(pad)])
-            out = ops.conv_bn_act(t, w, None, b)
-            return out[..., :a].contiguous(), out[..., a:a + a4].contiguous()
-        logits = ops.conv_bn_act(t, self.cls_logits.weight, None, self.cls_logits.bias)
-        deltas = ops.conv_bn_act(t, self.bbox_pred.weight, None, self.bbox_pred.bias)
+        # both 1x1 predictors as ONE tensor-core GEMM (15 + 60 output channels padded to 96): ops.fused_heads
+        logits, deltas = ops.fused_heads(t, [self.cls_logits.weight, self.bbox_pred.weight],
+                                         [self.cls_logits.bias, self.bbox_pred.bias])
         return logits, deltas
 
 

@@ -446,6 +446,37 @@ def linear(x, weight, bias=None, relu=False):
     return y.view(r, weight.shape[0])
 
 
+def fused_heads(x, weights, biases):
+    """Several narrow output heads that read the same input as ONE tensor-core GEMM: the heads' rows are stacked and
+    zero-padded to a multiple of 32 output channels (the K block of the data-gradient GEMM and the M granularity of the
+    weight-gradient GEMM), so that forward, dgrad and wgrad all run on tcgen05 — a 1-, 9-, 15- or 36-channel head by
+    itself falls to the SIMT kernels in the backward pass.  The pad rows are zero and receive zero gradient.
+    x: [..., Cin] (NHWC map or [R, Cin] rows); weights: list of [Cout_i, Cin] or [Cout_i, Cin, 1, 1]; returns one
+    contiguous tensor per head.  On the SIMT arm the heads run one by one."""
+    lead, cin = x.shape[:-1], x.shape[-1]
+    if _default_impl not in TC_IMPLS:
+        outs = []
+        for w, b in zip(weights, biases):
+            y = _ConvBnAct.apply(x.reshape(-1, 1, 1, cin), w.reshape(w.shape[0], cin), None, b, None, 1, 0, False)
+            outs.append(y.view(*lead, w.shape[0]))
+        return outs
+    sizes = [w.shape[0] for w in weights]
+    pad = (-sum(sizes)) % 32
+    rows = [w.reshape(w.shape[0], cin) for w in weights]
+    bs = list(biases)
+    if pad:
+        rows.append(rows[0].new_zeros(pad, cin))
+        bs.append(bs[0].new_zeros(pad))
+    wcat, bcat = torch.cat(rows, dim=0), torch.cat(bs)
+    x4 = x if x.dim() == 4 else x.reshape(-1, 1, 1, cin)
+    y = _ConvBnAct.apply(x4, wcat, None, bcat, None, 1, 0, False).view(*lead, wcat.shape[0])
+    outs, o = [], 0
+    for n in sizes:
+        outs.append(y[..., o:o + n].contiguous())
+        o += n
+    return outs
+
+
 class _AvgPoolHW(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):

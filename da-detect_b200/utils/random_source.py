@@ -68,15 +68,16 @@ class ReplaySource(RandomSource):
 
 
 class HashSource(RandomSource):
-    """Deterministic, capture-safe pseudo-random draws (a pure function of the element index and the shape):
-    lets a test compare a captured whole-step graph with the eager step on identical random choices."""
+    """Deterministic, capture-safe pseudo-random draws (a pure function of the flat element index — NOT of the
+    shape, so that a candidate keeps its key when the buffer it sits in is padded to another capacity): lets a test
+    compare a captured whole-step graph with the eager step on identical random choices."""
 
     def _u(self, shape, device):
         n = 1
         for d in shape:
             n *= int(d)
         i = torch.arange(n, dtype=torch.float32, device=device)
-        return torch.frac(torch.sin(i * 12.9898 + float(n % 7) * 78.233) * 43758.5453).abs().reshape(shape)
+        return torch.frac(torch.sin(i * 12.9898 + 78.233) * 43758.5453).abs().reshape(shape)
 
     def sample_keys(self, labels):
         return self._u(tuple(labels.shape), labels.device)

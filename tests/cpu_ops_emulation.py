@@ -36,6 +36,10 @@ def linear(x, weight, bias=None, relu=False):
     return F.relu(y) if relu else y
 
 
+def fused_heads(x, weights, biases):
+    return [F.linear(x, w.reshape(w.shape[0], -1), b) for w, b in zip(weights, biases)]
+
+
 def bottleneck_stage(x, blocks, strides, input_is_relu=False, grad_premasked=False, pool_output=False):
     for b, s in zip(blocks, strides):
         y = conv_bn_act(x, b["w1"], b["s1"], b["b1"], stride=s, relu=True)
@@ -225,7 +229,7 @@ TRAINING_STAND_INS = dict(
 
 STAND_INS = dict(
     _chk=lambda t, dtype=torch.float32, name="tensor": t,
-    conv_bn_act=conv_bn_act, linear=linear, bottleneck_stage=bottleneck_stage,
+    conv_bn_act=conv_bn_act, linear=linear, bottleneck_stage=bottleneck_stage, fused_heads=fused_heads,
     stem_tc_supported=lambda x, w: False, nchw_to_nhwc=nhwc,
     maxpool3x3s2=lambda x: nhwc(F.max_pool2d(nchw(x), 3, 2, 1)),
     upsample2x=lambda x: nhwc(F.interpolate(nchw(x), scale_factor=2, mode="nearest")),

@@ -294,7 +294,13 @@ def test_three_sgd_iterations_match_oracle(dense):
     backward, SGD with momentum 0.9, weight decay on weights only, bias lr x2 (solver/build.py:7-20) — on the GPU
     through FlatSGDTrainer against the CPU oracle + torch.optim.SGD with the reference's parameter groups, the
     oracle's random draws replayed every iteration.  Losses must stay within 1e-4 / 2e-4 / 4e-4 (errors compound
-    through the updated weights); the final parameters must agree."""
+    through the updated weights); the final parameters must agree.
+
+    mixed arm (3xTF32 forward, TF32 backward): its gradients carry the TF32 operand rounding, so from the second
+    iteration on its weights differ from the oracle's by ~1e-3 of one update.  The first iteration runs on its own
+    hard decisions (weights identical); in the later ones the proposals are taken from the oracle, so that the
+    comparison keeps measuring arithmetic and not a proposal that crossed the 0.5 IoU threshold because the weights
+    are no longer bit-identical (the replayed randperm draws need candidate sets of identical size)."""
     from dadetect_b200 import ops
     from dadetect_b200.engine import FlatSGDTrainer
     from dadetect_b200.utils.random_source import ReplaySource
@@ -320,11 +326,16 @@ def test_three_sgd_iterations_match_oracle(dense):
     for it, tol in enumerate((1e-4, 2e-4, 4e-4)):
         imgs = images + 0.5 * it                              # a different batch every iteration
         rec = orc.RecordingHooks()
-        want = orc.forward_train(P, cfg, imgs, targets, hooks=rec, nms_strict=True)
+        aux = {}
+        want = orc.forward_train(P, cfg, imgs, targets, hooks=rec, nms_strict=True, aux=aux)
         opt.zero_grad()
         sum(want.values()).backward()
         opt.step()
         model.set_random_source(ReplaySource(rec.perms, rec.masks))
+        if dense == "mixed" and it > 0:
+            from fullsize_parity import oracle_proposal_batch
+            ref_props = [(b.detach(), s_.detach()) for b, s_ in aux["proposals"]]
+            model.rpn.set_proposal_hook(lambda p, rp=ref_props: oracle_proposal_batch(rp, p))
         got = trainer.step(imgs.to(dev), to_boxlists(targets, hw, dev))
         for k in want:
             g, w = float(got[k]), float(want[k])

@@ -700,7 +700,8 @@ TC_BENCH_CASES = [
 def test_conv_tcgen05_at_bench_shapes(case, arm):
     """Forward (+BN scale/bias, residual, ReLU), data gradient (+addend, ReLU mask) and weight gradient of both
     tensor-core arms at the full-size shapes of the benchmarked step: TF32 within 2e-3 rms of the fp64 result,
-    3xTF32 within 5e-6 rms (fp32 grade; 1e-5 on the weight gradient, whose chains run over up to 25 088 pixels)."""
+    3xTF32 within 5e-6 rms (fp32 grade; 3e-5 on the weight gradient, a sum over up to 262 144 pixels whose fp32
+    partial sums meet through red.add in L2 — measured 1.2e-5 .. 1.5e-5)."""
     n, h, w, cin, cout, k, stride, pad = case
     o = ops()
     impl = o.IMPL_TCGEN05 if arm == "tcgen05" else o.IMPL_TCGEN05_X3
@@ -735,7 +736,7 @@ def test_conv_tcgen05_at_bench_shapes(case, arm):
     del gx, gx_want
     gw = o.conv2d_wgrad_raw(gpre, x, scale, cout, k, k, stride, pad, impl=impl)
     # d(want)/d(wr) already carries the BN scale (it multiplies the conv output)
-    close(gw, gw_want, "wgrad", tol_rms if arm == "tcgen05" else 1e-5)
+    close(gw, gw_want, "wgrad", tol_rms if arm == "tcgen05" else 3e-5)
 
 
 def test_match_and_encode_with_padded_gt_and_device_count():
@@ -758,7 +759,7 @@ def test_match_and_encode_with_padded_gt_and_device_count():
             got, vals = o.match(padded.to(DEV), pred.to(DEV), hi, lo, lq, m_dev=cnt)
             assert torch.equal(got.cpu(), want)
             assert torch.equal(vals.cpu(), iou.max(dim=0)[0])
-        matches = torch.randint(-2, m, (pred.shape[0],), generator=g)
+        matches = torch.randint(-2 if m >= 2 else -1, m, (pred.shape[0],), generator=g)
         want_wrap = orc.box_encode(gt[matches], pred, (10.0, 10.0, 5.0, 5.0))
         got_wrap = o.box_encode(padded.to(DEV), pred.to(DEV), matches.to(DEV), (10.0, 10.0, 5.0, 5.0),
                                 wrap_negative=True, m_dev=cnt)
@@ -801,7 +802,7 @@ def test_adaptive_margin_update_follows_reference_rule():
     m = torch.tensor([0.75], dtype=torch.float32, device=DEV)
     l_dev = o.triplet_margin_loss(a, p, n, m, 64, 48, 1)
     l_host = o.triplet_margin_loss(a, p, n, 0.75, 64, 48, 1)
-    assert float(l_dev) == float(l_host)
+    assert abs(float(l_dev) - float(l_host)) <= 1e-6 * float(l_host)      # (atomic partial sums: order may differ)
 
 
 @pytest.mark.parametrize("impl", ["tcgen05", "tcgen05x3"])
@@ -825,3 +826,22 @@ def test_dgrad_batched_weight_preparation_is_bit_identical(impl):
         b = o.conv2d_dgrad_raw(gy, w, s, (2, 9, 13, cin), k, k, 1, k // 2, impl=code, prepared_ws=ws)
         assert torch.equal(a, b), (cout, cin, k)
     assert o.dgrad_prepare_batch(layers[:2], torch.device(DEV), impl=o.IMPL_SIMT) == [None, None]
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_conv_tcgen05_single_cta_and_forced_pair_modes(mode):
+    """conv_tc_kernel runs as single CTAs or as CTA pairs (tcgen05 cta_group::2, 256-pixel x BN tiles); the library
+    picks pairs when the K loop is long enough.  DD_TC_CTA2=0 forces single CTAs and =2 forces pairs for EVERY shape:
+    the whole dense-tier suite (13 + 13 shapes, both arms, fused stages) must pass unchanged in both."""
+    import subprocess
+    import sys
+    if os.environ.get("DD_TC_CTA2"):
+        pytest.skip("already inside a forced-mode run")
+    env = dict(os.environ, DD_TC_CTA2=mode)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ops.py"), "-m", "gpu", "-q",
+                        "-x", "-p", "no:cacheprovider", "-k",
+                        "test_conv_tcgen05_arm or test_conv_tcgen05_x3_arm_is_fp32_grade or fused_stage or dgrad_batched"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
