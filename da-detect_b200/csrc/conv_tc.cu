@@ -131,6 +131,20 @@ __device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint64_t* b
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast forms (cluster of single-CTA MMAs sharing a B tile): the box lands at the same smem offset in every CTA
+// of the mask and completes bytes on the barrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -270,8 +284,12 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 // D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi; a stage then holds four tiles [A_hi | A_lo | B_hi | B_lo].
 // CTA2 = CTA-pair mode (tcgen05 cta_group::2): two CTAs of a cluster compute a 256 x BN tile; each holds its own 128
 // rows of A and HALF of the B tile (BN/2 columns), the tensor cores of both SMs read both halves.
-template <int BN, bool X3, bool CTA2>
+// PAIR: 0 = single CTAs; 1 = CTA pair with cta_group::2 MMAs (above); 2 = cluster of two single-CTA-MMA CTAs that
+// share the B tile: each loads half of it and TMA-multicasts the half into both (half the B traffic from L2, the
+// TMA -> splitter -> MMA chain stays inside the CTA).
+template <int BN, bool X3, int PAIR>
 struct SmemLayout {
+  static constexpr bool CTA2 = PAIR == 1;
   static constexpr int kABytes = BM * BKB;                       // 16 KB
   static constexpr int kBBytes = (CTA2 ? BN / 2 : BN) * BKB;     // 4 .. 32 KB
   static constexpr int kStageBytes = (X3 ? 2 : 1) * (kABytes + kBBytes);
@@ -351,12 +369,15 @@ enum { EPI_EXTRA = 1, EPI_MASK = 2, EPI_SCALAR = 4 };
 //   split     (3xTF32) leader's barrier, 8 arrivals: the splitter warps of both CTAs (remote arrive for rank 1)
 //   empty     per CTA; the leader's tcgen05.commit is multicast to both
 //   tmem_full per CTA, multicast commit; tmem_empty leader's barrier, 8 arrivals (epilogue warps of both CTAs)
-template <int BN, int EPI, bool X3, bool CTA2>
+template <int BN, int EPI, bool X3, int PAIR>
 __global__ void __launch_bounds__(X3 ? NUM_THREADS_X3 : NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_e,
                const __grid_constant__ CUtensorMap map_m, const TcParams p) {
-  using L = SmemLayout<BN, X3, CTA2>;
+  using L = SmemLayout<BN, X3, PAIR>;
+  constexpr bool CTA2 = PAIR == 1;     // cta_group::2 MMAs issued by the leader
+  constexpr bool MC = PAIR == 2;       // own MMAs, B halves multicast between the two CTAs
+  constexpr bool CL = PAIR != 0;       // launched as a cluster of 2
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + L::kStagingOff;
@@ -374,19 +395,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_iters = p.taps * p.cblocks;
-  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
-  const bool leader = rank == 0;
-  // tile walk: a unit is one CTA (CTA1) or one pair (CTA2)
-  const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int n_units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int m_units = CTA2 ? (p.m_tiles + 1) >> 1 : p.m_tiles;
+  const uint32_t rank = CL ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0 || MC;                 // MC: every CTA issues its own MMAs and owns its barriers
+  // tile walk: a unit is one CTA or one pair
+  const int unit = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_units = CL ? (p.m_tiles + 1) >> 1 : p.m_tiles;
   const int total_tiles = m_units * p.n_tiles;
   // this CTA's 128-pixel tile of unit tile t: (n_tile, mt); mt >= m_tiles (odd count, rank 1) is a phantom tile whose
   // loads are zero-filled and whose stores are clipped away by TMA
   auto tile_of = [&](int t, int& n_tile, int& n0, int& oh0, int& ow0) {
     n_tile = t % p.n_tiles;
     int mt = t / p.n_tiles;
-    if (CTA2) mt = 2 * mt + (int)rank;
+    if (CL) mt = 2 * mt + (int)rank;
     const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
     const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
     n0 = mt * p.tn; oh0 = tile_h * p.th; ow0 = tile_w * p.tw;
@@ -396,7 +417,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (p.tma_store) tma_prefetch_desc(&map_c);
-    for (int s = 0; s < L::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    // MC: a stage is free when the MMAs of BOTH CTAs that read it have retired (the peer multicasts into it)
+    for (int s = 0; s < L::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, MC ? 2 : 1); }
     // consumer-side barriers count WARPS (one elected arrive per warp after __syncwarp): a remote arrive is a DSMEM
     // transaction, and 128 of them per K-iteration made the pair mode a third slower than single CTAs
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, CTA2 ? 8 : 4); }
@@ -414,7 +436,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr int kTmemCols = X3 ? (BN <= 64 ? 256 : 512) : (2 * BN < 32 ? 32 : 2 * BN);
   if (warp == 1) { if (CTA2) tmem_alloc2(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols); }
   tc_fence_before();
-  if (CTA2) cluster_sync_all(); else __syncthreads();       // barriers of both CTAs initialised before any remote use
+  if (CL) cluster_sync_all(); else __syncthreads();         // barriers of both CTAs initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -444,7 +466,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* sa = smem + s * L::kStageBytes;
           uint8_t* sb = sa + kBOff;
           const int kcol = tap * p.Cin + cb * BKE;
-          if constexpr (!CTA2) {
+          if constexpr (MC) {
+            // own A tile; our half of the B tile (rows [rank*BN/2, +BN/2)) goes to both CTAs, the other half comes
+            // from the peer: every CTA's barrier still sees the bytes of one whole stage
+            mbar_expect_tx(full_bar + s, L::kABytes + (X3 ? 2 : 1) * L::kBBytes);
+            tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
+            const int half = (int)rank * (BN / 2);
+            tma_load_2d_mc(&map_b, full_bar + s, sb + half * BKB, kcol, brow + half, (uint16_t)3);
+            if (X3) tma_load_2d_mc(&map_b, full_bar + s, sb + L::kBBytes + half * BKB, kcol, p.b_lo_row + brow + half, (uint16_t)3);
+          } else if constexpr (!CTA2) {
             mbar_expect_tx(full_bar + s, L::kABytes + (X3 ? 2 : 1) * L::kBBytes);
             if (p.stem) tma_load_5d(&map_a, full_bar + s, sa, 0, ow0, oh0 + (tap >> 1), tap & 1, n0);
             else tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
@@ -473,6 +503,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if constexpr (CTA2) umma2_tf32(d, ad, bd, idesc, acc); else umma_tf32(d, ad, bd, idesc, acc);
     };
     auto commit = [&](uint64_t* bar) { if constexpr (CTA2) umma_commit2(bar); else umma_commit(bar); };
+    // release of a smem stage: MC tells both CTAs (each waits for two such arrivals before reloading the stage)
+    auto commit_stage = [&](uint64_t* bar) {
+      if constexpr (MC) umma_commit_mc(bar, (uint16_t)3); else commit(bar);
+    };
     uint32_t it = 0;
     int local = 0;
     if (!leader) {
@@ -511,7 +545,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mma(d, ad, bdl, 1u);
                 mma(d, ad, bd, 1u);
               }
-              commit(empty_bar + s);
+              commit_stage(empty_bar + s);
               if (kit == g1 - 1) commit(tmem_full_bar + pp);                 // partial complete
             }
             __syncwarp();
@@ -540,7 +574,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint64_t bd = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
             mma(tmem_d, ad, bd, (kit | k) ? 1u : 0u);
           }
-          commit(empty_bar + s);                              // frees the smem stage when these MMAs retire
+          commit_stage(empty_bar + s);                        // frees the smem stage when these MMAs retire
           if (kit == k_iters - 1) commit(tmem_full_bar + acc);  // accumulator complete
         }
         __syncwarp();
@@ -775,7 +809,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
-  if (CTA2) cluster_sync_all(); else __syncthreads();   // (pair: the peer may still be arriving on our barriers)
+  if (CL) cluster_sync_all(); else __syncthreads();     // (pair: the peer may still be arriving on our barriers)
   if (warp == 1) {
     tc_fence_after();
     if (CTA2) tmem_dealloc2(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
@@ -1166,71 +1200,73 @@ bool tc_cta2_enabled() {
   return on == 1;
 }
 
-bool tc_cta2_forced() {
-  static int on = -1;
-  if (on < 0) {
+int tc_cta2_forced() {         // 0 = heuristics, 1 = cta_group::2 pairs everywhere, 2 = multicast pairs everywhere
+  static int mode = -1;
+  if (mode < 0) {
     const char* e = getenv("DD_TC_CTA2");
-    on = (e != nullptr && e[0] == '2') ? 1 : 0;
+    mode = (e != nullptr && e[0] == '2') ? 1 : ((e != nullptr && e[0] == '3') ? 2 : 0);
   }
-  return on == 1;
+  return mode;
 }
 
-template <int BN, int EPI, bool X3, bool CTA2>
+template <int BN, int EPI, bool X3, int PAIR>
 int launch_tc4(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
                const CUtensorMap& mm, const TcParams& p, cudaStream_t s) {
-  using L = SmemLayout<BN, X3, CTA2>;
+  using L = SmemLayout<BN, X3, PAIR>;
+  constexpr bool CL = PAIR != 0;
   static bool configured = false;
   if (!configured) {
-    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, EPI, X3, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    DD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, EPI, X3, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  const int m_units = CTA2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int m_units = CL ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const long long total = (long long)m_units * p.n_tiles;
-  const int max_units = CTA2 ? dd::kNumSMs / 2 : dd::kNumSMs;
+  const int max_units = CL ? dd::kNumSMs / 2 : dd::kNumSMs;
   const int units = total < max_units ? (int)total : max_units;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(CTA2 ? 2 * units : units));
+  cfg.gridDim = dim3((unsigned)(CL ? 2 * units : units));
   cfg.blockDim = dim3(X3 ? NUM_THREADS_X3 : NUM_THREADS);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+  attr[0].val.clusterDim.x = CL ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, EPI, X3, CTA2>, ma, mb, mc, me, mm, p));
+  DD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, EPI, X3, PAIR>, ma, mb, mc, me, mm, p));
   DD_LAUNCHED();
   return 0;
 }
 
 template <int BN, int EPI, bool X3>
 int launch_tc3(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
-               const CUtensorMap& mm, const TcParams& p, bool cta2, cudaStream_t s) {
-  if (cta2) return launch_tc4<BN, EPI, X3, true>(ma, mb, mc, me, mm, p, s);
-  return launch_tc4<BN, EPI, X3, false>(ma, mb, mc, me, mm, p, s);
+               const CUtensorMap& mm, const TcParams& p, int pair, cudaStream_t s) {
+  if (pair == 1) return launch_tc4<BN, EPI, X3, 1>(ma, mb, mc, me, mm, p, s);
+  if (pair == 2) return launch_tc4<BN, EPI, X3, 2>(ma, mb, mc, me, mm, p, s);
+  return launch_tc4<BN, EPI, X3, 0>(ma, mb, mc, me, mm, p, s);
 }
 
 template <int BN, int EPI>
 int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
-               const CUtensorMap& mm, const TcParams& p, bool x3, bool cta2, cudaStream_t s) {
+               const CUtensorMap& mm, const TcParams& p, bool x3, int pair, cudaStream_t s) {
   if constexpr (BN <= 128) {
-    if (x3) return launch_tc3<BN, EPI, true>(ma, mb, mc, me, mm, p, cta2, s);
+    if (x3) return launch_tc3<BN, EPI, true>(ma, mb, mc, me, mm, p, pair, s);
   }
-  return launch_tc3<BN, EPI, false>(ma, mb, mc, me, mm, p, cta2, s);
+  return launch_tc3<BN, EPI, false>(ma, mb, mc, me, mm, p, pair, s);
 }
 
 template <int BN>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
-              const CUtensorMap& mm, const TcParams& p, bool x3, bool cta2, cudaStream_t s) {
-  if (!p.tma_store) return launch_tc2<BN, EPI_SCALAR>(ma, mb, mc, me, mm, p, x3, cta2, s);
+              const CUtensorMap& mm, const TcParams& p, bool x3, int pair, cudaStream_t s) {
+  if (!p.tma_store) return launch_tc2<BN, EPI_SCALAR>(ma, mb, mc, me, mm, p, x3, pair, s);
   const int epi = (p.extra ? EPI_EXTRA : 0) | (p.mask ? EPI_MASK : 0);
   switch (epi) {
-    case 0: return launch_tc2<BN, 0>(ma, mb, mc, me, mm, p, x3, cta2, s);
-    case EPI_EXTRA: return launch_tc2<BN, EPI_EXTRA>(ma, mb, mc, me, mm, p, x3, cta2, s);
-    case EPI_MASK: return launch_tc2<BN, EPI_MASK>(ma, mb, mc, me, mm, p, x3, cta2, s);
-    default: return launch_tc2<BN, EPI_EXTRA | EPI_MASK>(ma, mb, mc, me, mm, p, x3, cta2, s);
+    case 0: return launch_tc2<BN, 0>(ma, mb, mc, me, mm, p, x3, pair, s);
+    case EPI_EXTRA: return launch_tc2<BN, EPI_EXTRA>(ma, mb, mc, me, mm, p, x3, pair, s);
+    case EPI_MASK: return launch_tc2<BN, EPI_MASK>(ma, mb, mc, me, mm, p, x3, pair, s);
+    default: return launch_tc2<BN, EPI_EXTRA | EPI_MASK>(ma, mb, mc, me, mm, p, x3, pair, s);
   }
 }
 
@@ -1286,11 +1322,18 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
   // CTA pairs (256-pixel x BN tiles, half the B traffic per output) whenever there are at least two pixel tiles
   // and the K loop is long enough to pay for the pair's cluster barriers (measured per layer, TF32: +5..9 % from 18
   // K-iterations up, -5..25 % on the 2..16-iteration 1x1 layers); DD_TC_CTA2=2 forces pairs everywhere (tests)
-  // The 3xTF32 kernel stays on single CTAs: its stage chain (TMA -> splitter -> MMA) is latency-bound, and the
-  // pair's cross-CTA hops (remote split arrive, cluster-scope wait, multicast commit) lengthen exactly that chain
-  // (measured: RPN 3x3 1.49 ms single, 2.28 ms paired).
-  const bool cta2 = tc_cta2_enabled() && !p.stem && p.m_tiles >= 2 &&
-                    ((!x3 && p.taps * p.cblocks >= 18) || tc_cta2_forced());
+  // The 3xTF32 kernel never pairs its MMAs: its stage chain (TMA -> splitter -> MMA) is latency-bound, and the pair's
+  // cross-CTA hops (remote split arrive, cluster-scope wait, multicast commit) lengthen exactly that chain (measured:
+  // RPN 3x3 1.49 ms single, 2.28 ms paired).  It shares the B tile by TMA multicast instead (PAIR 2).
+  // DD_TC_CTA2: 0 = single CTAs everywhere, 2 = cta_group::2 pairs everywhere, 3 = multicast pairs everywhere (tests).
+  const int k_iters_host = p.taps * p.cblocks;
+  int pair = 0;
+  if (tc_cta2_enabled() && !p.stem && p.m_tiles >= 2) {
+    const int forced = tc_cta2_forced();
+    if (forced) pair = forced;
+    else if (!x3 && k_iters_host >= 18) pair = 1;
+    else if (x3 && k_iters_host >= 18) pair = 2;
+  }
   p.b_lo_row = x3 ? tc_rows_pad(ncols) : 0;
   DD_CHECK_ARG((long long)p.m_tiles * p.n_tiles < (1ll << 31));
   const uintptr_t align_bits = reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.extra) |
@@ -1309,7 +1352,7 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
     const cuuint64_t K = (cuuint64_t)KH * KW * Cin;
     cuuint64_t dims[2] = {K, (cuuint64_t)(x3 ? 2 * tc_rows_pad(ncols) : ncols)};
     cuuint64_t strides[1] = {K * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)(cta2 ? BN / 2 : BN)};    // a CTA of a pair loads half the columns
+    cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)(pair ? BN / 2 : BN)};    // a CTA of a pair loads half the columns
     if (encode_map(&mb, b, 2, dims, strides, box)) return -1;
   }
   if (p.tma_store) {
@@ -1339,9 +1382,9 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
     // read traffic on res2 conv3, 0.192 -> 0.167 ms without it) and changes nothing when both inputs are present.
     p.prefetch_side = 0;
   }
-  if (BN == 256) return launch_tc<256>(ma, mb, mc, me, mm, p, x3, cta2, s);
-  if (BN == 128) return launch_tc<128>(ma, mb, mc, me, mm, p, x3, cta2, s);
-  return launch_tc<64>(ma, mb, mc, me, mm, p, x3, cta2, s);
+  if (BN == 256) return launch_tc<256>(ma, mb, mc, me, mm, p, x3, pair, s);
+  if (BN == 128) return launch_tc<128>(ma, mb, mc, me, mm, p, x3, pair, s);
+  return launch_tc<64>(ma, mb, mc, me, mm, p, x3, pair, s);
 }
 
 
@@ -1450,7 +1493,7 @@ extern "C" int dd_stem_conv7x7s2_forward(const float* x_nchw, const float* w_ohw
     cuuint32_t box[4] = {32, 16, 2, 1};
     if (encode_map(&mc, y, 4, dims, strides, box)) return -1;
   }
-  return launch_tc<64>(ma, mb, mc, ma, ma, p, x3, false, s);
+  return launch_tc<64>(ma, mb, mc, ma, ma, p, x3, 0, s);
 }
 
 namespace {

@@ -829,11 +829,12 @@ def test_dgrad_batched_weight_preparation_is_bit_identical(impl):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("mode", ["0", "2"])
+@pytest.mark.parametrize("mode", ["0", "2", "3"])
 def test_conv_tcgen05_single_cta_and_forced_pair_modes(mode):
-    """conv_tc_kernel runs as single CTAs or as CTA pairs (tcgen05 cta_group::2, 256-pixel x BN tiles); the library
-    picks pairs when the K loop is long enough.  DD_TC_CTA2=0 forces single CTAs and =2 forces pairs for EVERY shape:
-    the whole dense-tier suite (13 + 13 shapes, both arms, fused stages) must pass unchanged in both."""
+    """conv_tc_kernel runs as single CTAs, as CTA pairs with cta_group::2 MMAs (256-pixel x BN tiles) or as multicast
+    pairs (two single-CTA-MMA CTAs sharing the B tile through TMA multicast); the library picks per layer.
+    DD_TC_CTA2=0 forces single CTAs, =2 cta_group::2 pairs and =3 multicast pairs for EVERY shape: the whole
+    dense-tier suite (13 + 13 shapes, both arms, fused stages) must pass unchanged in each."""
     import subprocess
     import sys
     if os.environ.get("DD_TC_CTA2"):
