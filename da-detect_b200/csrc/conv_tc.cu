@@ -223,6 +223,187 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TENSOR MEMORY (M = 128 rows = the 128 lanes, one 32-bit K element per column), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// ---- warp-converged issue forms.  The MMA warp runs its loop with all 32 lanes converged (descriptor arithmetic is
+// warp-uniform, so the compiler keeps it on the uniform datapath) and ONE elected lane issues each tcgen05
+// instruction: `if (lane == 0) { ... }` around plain asm made the compiler wrap every operand of every MMA in an
+// ELECT + R2UR sequence — ~25 SASS instructions per MMA, 300 per K iteration of the 3xTF32 kernel, which made the
+// single issuing warp (not the tensor pipe, not shared memory, not L2) the limiter at ~1470 cycles per K iteration.
+// Shared-memory descriptors are passed as their low word (start address >> 4, plus LBO bit 16 where needed); the
+// high word is the compile-time constant of the layout.
+constexpr uint32_t kDescHiKmajorSw128 = (uint32_t)((1024 >> 4) | (1u << 14) | (2u << 29));   // SBO | version | swizzle
+__device__ __forceinline__ uint32_t desc_lo_kmajor(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void umma_tf32_ss_e(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 ad, bd;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 ad, {%1, %5};\n\t"
+      "mov.b64 bd, {%2, %5};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiKmajorSw128)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_tf32_ss_e(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 ad, bd;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 ad, {%1, %5};\n\t"
+      "mov.b64 bd, {%2, %5};\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::tf32 [%0], ad, bd, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiKmajorSw128)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 bd;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 bd, {%2, %5};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiKmajorSw128)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One K iteration (32 channels = 4 K steps) of the 3xTF32 kernel as ONE asm block: 12 MMAs with the A operand in
+// tensor memory (a_hi: 32 columns, a_lo = a_hi + 32) against the B_hi / B_lo tiles in shared memory, then the two
+// commits (smem stage free; TMEM A slot free).  A single block lets ptxas keep the descriptor arithmetic on the
+// uniform datapath and elect once.  MCAST: the stage commit is multicast to both CTAs of a multicast pair.
+#define DD_X3_KITER_HEAD                                                                                            \
+  "{\n\t"                                                                                                           \
+  ".reg .pred e, p, t;\n\t"                                                                                         \
+  ".reg .b32 ah1, ah2, ah3, al0, al1, al2, al3, x;\n\t"                                                             \
+  ".reg .b64 bh0, bh1, bh2, bh3, bl0, bl1, bl2, bl3;\n\t"                                                           \
+  "elect.sync _|e, 0xffffffff;\n\t"                                                                                 \
+  "setp.ne.b32 p, %5, 0;\n\t"                                                                                       \
+  "setp.eq.b32 t, 0, 0;\n\t"                                                                                        \
+  "add.u32 ah1, %1, 8;\n\tadd.u32 ah2, %1, 16;\n\tadd.u32 ah3, %1, 24;\n\t"                                         \
+  "add.u32 al0, %1, 32;\n\tadd.u32 al1, %1, 40;\n\tadd.u32 al2, %1, 48;\n\tadd.u32 al3, %1, 56;\n\t"                \
+  "mov.b64 bh0, {%2, %6};\n\tadd.u32 x, %2, 2;\n\tmov.b64 bh1, {x, %6};\n\t"                                        \
+  "add.u32 x, %2, 4;\n\tmov.b64 bh2, {x, %6};\n\tadd.u32 x, %2, 6;\n\tmov.b64 bh3, {x, %6};\n\t"                    \
+  "mov.b64 bl0, {%3, %6};\n\tadd.u32 x, %3, 2;\n\tmov.b64 bl1, {x, %6};\n\t"                                        \
+  "add.u32 x, %3, 4;\n\tmov.b64 bl2, {x, %6};\n\tadd.u32 x, %3, 6;\n\tmov.b64 bl3, {x, %6};\n\t"                    \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [al0], bh0, %4, p;\n\t" /* small terms first */                     \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bl0, %4, t;\n\t"                                              \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bh0, %4, t;\n\t"                                              \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [al1], bh1, %4, t;\n\t"                                             \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bl1, %4, t;\n\t"                                             \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah1], bh1, %4, t;\n\t"                                             \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [al2], bh2, %4, t;\n\t"                                             \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bl2, %4, t;\n\t"                                             \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah2], bh2, %4, t;\n\t"                                             \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [al3], bh3, %4, t;\n\t"                                             \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bl3, %4, t;\n\t"                                             \
+  "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [ah3], bh3, %4, t;\n\t"
+#define DD_X3_KITER_TAIL                                                                                            \
+  "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"                              \
+  "}"
+template <bool MCAST>
+__device__ __forceinline__ void umma_x3_kiter(uint32_t d, uint32_t a_hi, uint32_t b_hi, uint32_t b_lo, uint32_t idesc,
+                                              uint32_t accumulate, uint64_t* stage_bar, uint64_t* aslot_bar) {
+  if constexpr (MCAST) {
+    asm volatile(DD_X3_KITER_HEAD
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], %9;\n\t"
+                 DD_X3_KITER_TAIL
+                 ::"r"(d), "r"(a_hi), "r"(b_hi), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiKmajorSw128),
+                   "r"(smem_u32(stage_bar)), "r"(smem_u32(aslot_bar)), "h"((uint16_t)3)
+                 : "memory");
+  } else {
+    asm volatile(DD_X3_KITER_HEAD
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+                 DD_X3_KITER_TAIL
+                 ::"r"(d), "r"(a_hi), "r"(b_hi), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiKmajorSw128),
+                   "r"(smem_u32(stage_bar)), "r"(smem_u32(aslot_bar))
+                 : "memory");
+  }
+}
+
+// The same for the plain TF32 kernel: 4 MMAs (A and B tiles in shared memory) and the stage commit.
+// MODE 0: single CTA; 1: CTA pair (cta_group::2, commit multicast to both); 2: multicast pair (cta_group::1 MMAs,
+// commit multicast to both).
+#define DD_TF32_KITER_BODY(CG)                                                                                      \
+  "{\n\t"                                                                                                           \
+  ".reg .pred e, p, t;\n\t"                                                                                         \
+  ".reg .b32 x;\n\t"                                                                                                \
+  ".reg .b64 a0, a1, a2, a3, b0, b1, b2, b3;\n\t"                                                                   \
+  "elect.sync _|e, 0xffffffff;\n\t"                                                                                 \
+  "setp.ne.b32 p, %4, 0;\n\t"                                                                                       \
+  "setp.eq.b32 t, 0, 0;\n\t"                                                                                        \
+  "mov.b64 a0, {%1, %5};\n\tadd.u32 x, %1, 2;\n\tmov.b64 a1, {x, %5};\n\t"                                          \
+  "add.u32 x, %1, 4;\n\tmov.b64 a2, {x, %5};\n\tadd.u32 x, %1, 6;\n\tmov.b64 a3, {x, %5};\n\t"                      \
+  "mov.b64 b0, {%2, %5};\n\tadd.u32 x, %2, 2;\n\tmov.b64 b1, {x, %5};\n\t"                                          \
+  "add.u32 x, %2, 4;\n\tmov.b64 b2, {x, %5};\n\tadd.u32 x, %2, 6;\n\tmov.b64 b3, {x, %5};\n\t"                      \
+  "@e tcgen05.mma.cta_group::" CG ".kind::tf32 [%0], a0, b0, %3, p;\n\t"                                            \
+  "@e tcgen05.mma.cta_group::" CG ".kind::tf32 [%0], a1, b1, %3, t;\n\t"                                            \
+  "@e tcgen05.mma.cta_group::" CG ".kind::tf32 [%0], a2, b2, %3, t;\n\t"                                            \
+  "@e tcgen05.mma.cta_group::" CG ".kind::tf32 [%0], a3, b3, %3, t;\n\t"
+template <int MODE>
+__device__ __forceinline__ void umma_tf32_kiter(uint32_t d, uint32_t a_d, uint32_t b_d, uint32_t idesc,
+                                                uint32_t accumulate, uint64_t* stage_bar) {
+  if constexpr (MODE == 1) {
+    asm volatile(DD_TF32_KITER_BODY("2")
+                 "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %7;\n\t}"
+                 ::"r"(d), "r"(a_d), "r"(b_d), "r"(idesc), "r"(accumulate), "r"(kDescHiKmajorSw128),
+                   "r"(smem_u32(stage_bar)), "h"((uint16_t)3)
+                 : "memory");
+  } else if constexpr (MODE == 2) {
+    asm volatile(DD_TF32_KITER_BODY("1")
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%6], %7;\n\t}"
+                 ::"r"(d), "r"(a_d), "r"(b_d), "r"(idesc), "r"(accumulate), "r"(kDescHiKmajorSw128),
+                   "r"(smem_u32(stage_bar)), "h"((uint16_t)3)
+                 : "memory");
+  } else {
+    asm volatile(DD_TF32_KITER_BODY("1")
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t}"
+                 ::"r"(d), "r"(a_d), "r"(b_d), "r"(idesc), "r"(accumulate), "r"(kDescHiKmajorSw128),
+                   "r"(smem_u32(stage_bar))
+                 : "memory");
+  }
+}
+
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit2_e(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_e(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -292,7 +473,10 @@ struct SmemLayout {
   static constexpr bool CTA2 = PAIR == 1;
   static constexpr int kABytes = BM * BKB;                       // 16 KB
   static constexpr int kBBytes = (CTA2 ? BN / 2 : BN) * BKB;     // 4 .. 32 KB
-  static constexpr int kStageBytes = (X3 ? 2 : 1) * (kABytes + kBBytes);
+  // 3xTF32: the stage holds the RAW fp32 A tile and the pre-split B_hi / B_lo tiles; the split A operand (hi and lo
+  // parts) lives in tensor memory, written there by the splitter warps and read from there by the MMAs
+  static constexpr int kStageBytes = X3 ? kABytes + 2 * kBBytes : kABytes + kBBytes;
+  static_assert(!(X3 && PAIR == 1), "the 3xTF32 kernel does not pair its MMAs (cta_group::2)");
   static constexpr int kFit = (192 * 1024) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kStagingBytes = BM * 128;                 // one 128-row x 32-column fp32 chunk
@@ -386,14 +570,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty_bar = full_bar + L::kStages;
   uint64_t* tmem_full_bar = empty_bar + L::kStages;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
-  uint64_t* split_bar = tmem_empty_bar + 2;             // [kStages], X3 only: operand tiles split into hi / lo
-  uint64_t* bfull_bar = split_bar + L::kStages;         // [kStages], X3 && CTA2 only: B halves of both CTAs landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull_bar + L::kStages);
-  constexpr int kAOff2 = X3 ? L::kABytes : 0;           // A_lo sits right after A_hi
-  constexpr int kBOff = (X3 ? 2 : 1) * L::kABytes;      // B (hi) tile offset inside a stage
+  uint64_t* split_bar = tmem_empty_bar + 2;             // [2], X3 only: the A operand of a TMEM slot has been written
+  uint64_t* aslot_bar = split_bar + 2;                  // [2], X3 only: the MMAs that read a TMEM A slot have retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aslot_bar + 2);
+  constexpr int kBOff = L::kABytes;                     // B (hi) tile offset inside a stage; B_lo follows it
   constexpr int kBRows = CTA2 ? BN / 2 : BN;            // B rows (output columns) this CTA loads
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: the compiler then KNOWS it is warp-uniform, treats the role branches below as
+  // convergent and keeps the MMA warp's descriptor arithmetic in uniform registers (no ELECT / R2UR per operand)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int k_iters = p.taps * p.cblocks;
   const uint32_t rank = CL ? cluster_ctarank() : 0u;
   const bool leader = rank == 0 || MC;                 // MC: every CTA issues its own MMAs and owns its barriers
@@ -422,7 +607,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // consumer-side barriers count WARPS (one elected arrive per warp after __syncwarp): a remote arrive is a DSMEM
     // transaction, and 128 of them per K-iteration made the pair mode a third slower than single CTAs
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, CTA2 ? 8 : 4); }
-    if (X3) for (int s = 0; s < L::kStages; ++s) { mbar_init(split_bar + s, CTA2 ? 8 : 4); mbar_init(bfull_bar + s, 1); }
+    if (X3) for (int s = 0; s < 2; ++s) { mbar_init(split_bar + s, 4); mbar_init(aslot_bar + s, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // TMEM: 2 x BN columns (two tile accumulators, ping-pong).  3xTF32 mode: [M | P0 | P1], BN columns each.
@@ -432,13 +617,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // finished partial into the running sum M with round-to-nearest fp32 adds (tcgen05.ld / add / tcgen05.st) while
   // the MMA warp fills the other slot.  M never sees a tensor-core accumulation; the last partial of a tile is
   // added on the fly by the epilogue proper.
+  // 3xTF32 keeps the split A operand in tensor memory as well: two slots (ping-pong between the splitter warps and the
+  // MMA warp) of 64 columns — [A_hi: 32 K elements | A_lo: 32 K elements] for the 128 rows of the tile — after the
+  // three accumulator regions.  The MMAs read A from there (tcgen05.mma with a TMEM A operand), so the shared-memory
+  // pipe only carries the raw A tile once (TMA in, splitter out) and the B tiles: 112 KB per K iteration instead of
+  // 192 KB — the kernel was bound by exactly that pipe (ncu: 59 % tensor-active, 1470 cycles per K iteration against
+  // 768 of MMA work; 192 KB / 128 B per cycle = 1536).
   constexpr int kGroup = 8;
-  constexpr int kTmemCols = X3 ? (BN <= 64 ? 256 : 512) : (2 * BN < 32 ? 32 : 2 * BN);
+  constexpr int kTmemCols = X3 ? 512 : (2 * BN < 32 ? 32 : 2 * BN);
+  constexpr int kASlotCols = 64;
+  static_assert(!X3 || 3 * BN + 2 * kASlotCols <= 512, "TMEM budget of the 3xTF32 kernel");
   if (warp == 1) { if (CTA2) tmem_alloc2(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols); }
   tc_fence_before();
   if (CL) cluster_sync_all(); else __syncthreads();         // barriers of both CTAs initialised before any remote use
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // (warp-uniform for the compiler as well)
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -485,13 +678,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (leader) mbar_expect_tx(full_bar + s, 2 * (L::kABytes + L::kBBytes));
             tma2_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
             tma2_load_2d(&map_b, full_bar + s, sb, kcol, brow);
-          } else {
-            // A lands on this CTA's own barrier (its splitter waits there); the B halves on the leader's
-            mbar_expect_tx(full_bar + s, L::kABytes);
-            tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
-            if (leader) mbar_expect_tx(bfull_bar + s, 4 * L::kBBytes);
-            tma2_load_2d(&map_b, bfull_bar + s, sb, kcol, brow);
-            tma2_load_2d(&map_b, bfull_bar + s, sb + L::kBBytes, kcol, p.b_lo_row + brow);
           }
         }
       }
@@ -499,56 +685,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ================================ MMA issuer (CTA pair: the leader only) ================================
     constexpr uint32_t idesc = make_idesc_tf32(CTA2 ? 2 * BM : BM, BN);
-    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
-      if constexpr (CTA2) umma2_tf32(d, ad, bd, idesc, acc); else umma_tf32(d, ad, bd, idesc, acc);
-    };
-    auto commit = [&](uint64_t* bar) { if constexpr (CTA2) umma_commit2(bar); else umma_commit(bar); };
+    // all 32 lanes run this loop converged; one elected lane issues each tcgen05 instruction (see umma_*_e)
+    auto commit = [&](uint64_t* bar) { if constexpr (CTA2) umma_commit2_e(bar); else umma_commit_e(bar); };
     // release of a smem stage: MC tells both CTAs (each waits for two such arrivals before reloading the stage)
     auto commit_stage = [&](uint64_t* bar) {
-      if constexpr (MC) umma_commit_mc(bar, (uint16_t)3); else commit(bar);
+      if constexpr (MC) umma_commit_mc_e(bar, (uint16_t)3); else commit(bar);
     };
+    const uint32_t smem0 = smem_u32(smem);
     uint32_t it = 0;
     int local = 0;
     if (!leader) {
       // the peer's MMA warp only owns its TMEM allocation
     } else if constexpr (X3) {
       uint32_t grp = 0;                                      // partial-slot groups, counted across tiles
+      const uint32_t a_tmem = tmem_base + (uint32_t)(3 * BN);
       for (int t = unit; t < total_tiles; t += n_units) {
         for (int g0 = 0; g0 < k_iters; g0 += kGroup, ++grp) {
           const int pp = grp & 1;
-          // the folding warps (of both CTAs) have drained this slot
-          if (CTA2) mbar_wait_cluster(tmem_empty_bar + pp, ((grp >> 1) & 1) ^ 1);
-          else mbar_wait(tmem_empty_bar + pp, ((grp >> 1) & 1) ^ 1);
+          mbar_wait(tmem_empty_bar + pp, ((grp >> 1) & 1) ^ 1);    // the folding warps have drained this slot
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)((1 + pp) * BN);
           const int g1 = min(g0 + kGroup, k_iters);
           for (int kit = g0; kit < g1; ++kit, ++it) {
             const int s = it % L::kStages;
-            const uint32_t ph = (it / L::kStages) & 1;
-            if (CTA2) {                                      // the splitters of both CTAs are done; the B halves landed
-              mbar_wait_cluster(split_bar + s, ph);
-              mbar_wait(bfull_bar + s, ph);
-            } else {
-              mbar_wait(split_bar + s, ph);                  // the splitter (which waited for TMA) is done
-            }
+            const int slot = it & 1;
+            // the splitter warps (which waited for the stage's TMA bytes, B included) have written this A slot
+            mbar_wait(split_bar + slot, (it >> 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-              const uint32_t b_addr = a_addr + kBOff;
-#pragma unroll
-              for (int k = 0; k < BKE / UMMA_K; ++k) {
-                const uint64_t ad = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
-                const uint64_t bd = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
-                const uint64_t adl = make_kmajor_sw128_desc(a_addr + kAOff2 + k * UMMA_K * 4);
-                const uint64_t bdl = make_kmajor_sw128_desc(b_addr + L::kBBytes + k * UMMA_K * 4);
-                mma(d, adl, bd, (kit > g0 || k > 0) ? 1u : 0u);      // small terms first
-                mma(d, ad, bdl, 1u);
-                mma(d, ad, bd, 1u);
-              }
-              commit_stage(empty_bar + s);
-              if (kit == g1 - 1) commit(tmem_full_bar + pp);                 // partial complete
-            }
-            __syncwarp();
+            const uint32_t b_hi = desc_lo_kmajor(smem0 + s * L::kStageBytes + kBOff);
+            const uint32_t b_lo = desc_lo_kmajor(smem0 + s * L::kStageBytes + kBOff + L::kBBytes);
+            const uint32_t a_hi = a_tmem + (uint32_t)(slot * kASlotCols);      // (A_lo sits 32 columns further)
+            // 12 MMAs (4 K steps x {A_lo B_hi, A_hi B_lo, A_hi B_hi}), then the commits that free the smem stage
+            // (B tiles, raw A tile) and the TMEM A slot
+            umma_x3_kiter<MC>(d, a_hi, b_hi, b_lo, idesc, kit > g0 ? 1u : 0u, empty_bar + s, aslot_bar + slot);
+            if (kit == g1 - 1) commit(tmem_full_bar + pp);                 // partial complete
           }
         }
       }
@@ -565,54 +735,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t ph = (it / L::kStages) & 1;
         mbar_wait(full_bar + s, ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
-          const uint32_t b_addr = a_addr + kBOff;
-#pragma unroll
-          for (int k = 0; k < BKE / UMMA_K; ++k) {
-            const uint64_t ad = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 4);
-            const uint64_t bd = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 4);
-            mma(tmem_d, ad, bd, (kit | k) ? 1u : 0u);
-          }
-          commit_stage(empty_bar + s);                        // frees the smem stage when these MMAs retire
-          if (kit == k_iters - 1) commit(tmem_full_bar + acc);  // accumulator complete
-        }
-        __syncwarp();
+        const uint32_t a_d = desc_lo_kmajor(smem0 + s * L::kStageBytes);
+        const uint32_t b_d = desc_lo_kmajor(smem0 + s * L::kStageBytes + kBOff);
+        // 4 MMAs (K steps of 8) and the commit that frees the smem stage when they retire
+        umma_tf32_kiter<PAIR>(tmem_d, a_d, b_d, idesc, kit ? 1u : 0u, empty_bar + s);
+        if (kit == k_iters - 1) commit(tmem_full_bar + acc);  // accumulator complete
       }
     }
     }
   } else if (X3 && warp >= 6) {
     // ================================ operand splitter (warps 6..9, 3xTF32 mode) ================================
-    // A tile rows are fp32 activations: rewrite each element in place as its TF32-exact high part (low 13 mantissa
-    // bits cleared) and store the TF32-exact part of the remainder next to it.  Both parts are exactly
-    // representable in TF32, so the result does not depend on how the tensor core converts fp32 bit patterns.
-    const int rs = threadIdx.x - 192;                    // 0..127; consecutive threads take consecutive 16-byte
-    uint32_t it = 0;                                     // chunks of the tile (element-wise work: conflict-free)
+    // Each thread owns one row of the A tile (= one TMEM lane): it reads the row's 32 fp32 activations from the landed
+    // (128B-swizzled) tile, splits every element into its TF32-exact high part (low 13 mantissa bits cleared) and the
+    // TF32-exact part of the remainder, and stores both into the TMEM A slot [hi: 32 columns | lo: 32 columns].  Both
+    // parts are exactly representable in TF32, so the result does not depend on how the tensor core converts fp32
+    // bit patterns.  Nothing is written back to shared memory.
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
+    const uint32_t a_tmem = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(3 * BN);
+    uint32_t it = 0;
     for (int t = unit; t < total_tiles; t += n_units) {
       for (int kit = 0; kit < k_iters; ++kit, ++it) {
         const int s = it % L::kStages;
         const uint32_t ph = (it / L::kStages) & 1;
-        mbar_wait(full_bar + s, ph);
-        const uint32_t a_hi = smem_u32(smem + s * L::kStageBytes) + rs * 16;
+        const int slot = it & 1;
+        mbar_wait(full_bar + s, ph);                                  // the stage's bytes have landed
+        mbar_wait(aslot_bar + slot, ((it >> 1) & 1) ^ 1);             // the MMAs of two K-iterations ago have read the slot
+        tc_fence_after();
+        const uint32_t a_row = smem_u32(smem + s * L::kStageBytes) + row_off;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 8; ++j) {                    // quarter-warp phases hit 8 distinct 16-byte bank groups
           float v[4];
-          lds128(a_hi + j * 2048, v);
-          float hi[4], lo[4];
+          lds128(a_row + ((j ^ sw) << 4), v);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            hi[e] = __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u);
-            lo[e] = __uint_as_float(__float_as_uint(v[e] - hi[e]) & 0xFFFFE000u);
+            const uint32_t h = __float_as_uint(v[e]) & 0xFFFFE000u;
+            hi[4 * j + e] = h;
+            lo[4 * j + e] = __float_as_uint(v[e] - __uint_as_float(h)) & 0xFFFFE000u;
           }
-          sts128(a_hi + j * 2048, hi[0], hi[1], hi[2], hi[3]);
-          sts128(a_hi + kAOff2 + j * 2048, lo[0], lo[1], lo[2], lo[3]);
         }
-        fence_async_smem();                               // generic-proxy writes -> visible to the tensor core
+        tmem_st32(a_tmem + (uint32_t)(slot * kASlotCols), hi);
+        tmem_st32(a_tmem + (uint32_t)(slot * kASlotCols + 32), lo);
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          if (CTA2 && !leader) mbar_arrive_remote(split_bar + s, 0);
-          else mbar_arrive(split_bar + s);
-        }
+        if (lane == 0) mbar_arrive(split_bar + slot);
       }
     }
   } else {
@@ -888,7 +1056,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
   uint64_t* split_bar = tmem_empty_bar + 2;                         // [kStages], X3 only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split_bar + L::kStages);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (warp-uniform: see conv_tc_kernel)
   const int total_items = p.taps * p.ci_tiles * p.co_tiles * p.splits;
 
   // item -> (tap, ci tile, co tile, split): consecutive items share the pixel range (L2 reuse of gy / x tiles)
@@ -915,7 +1083,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -958,7 +1126,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
         const uint32_t ph = (it / L::kStages) & 1;
         mbar_wait((X3 ? split_bar : full_bar) + s, ph);
         tc_fence_after();
-        if (lane == 0) {
+        {     // all lanes converged; one elected lane issues (see the note at umma_tf32_ss_e)
           const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
           const uint32_t b_addr = a_addr + kBOff;
 #pragma unroll
@@ -968,17 +1136,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constan
             if (X3) {                                         // small terms first
               const uint64_t adl = make_mnmajor_sw128_desc(a_addr + kALo + k * 1024);
               const uint64_t bdl = make_mnmajor_sw128_desc(b_addr + kBLo + k * 1024);
-              umma_tf32(d, adl, bd, idesc, (kit | k) ? 1u : 0u);
-              umma_tf32(d, ad, bdl, idesc, 1u);
-              umma_tf32(d, ad, bd, idesc, 1u);
+              umma_tf32_e(d, adl, bd, idesc, (kit | k) ? 1u : 0u);
+              umma_tf32_e(d, ad, bdl, idesc, 1u);
+              umma_tf32_e(d, ad, bd, idesc, 1u);
             } else {
-              umma_tf32(d, ad, bd, idesc, (kit | k) ? 1u : 0u);
+              umma_tf32_e(d, ad, bd, idesc, (kit | k) ? 1u : 0u);
             }
           }
-          umma_commit(empty_bar + s);
-          if (kit == k_iters - 1) umma_commit(tmem_full_bar + acc);
+          umma_commit_e(empty_bar + s);
+          if (kit == k_iters - 1) umma_commit_e(tmem_full_bar + acc);
         }
-        __syncwarp();
       }
       ++local;
     }
@@ -1243,7 +1410,9 @@ int launch_tc4(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
 template <int BN, int EPI, bool X3>
 int launch_tc3(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
                const CUtensorMap& mm, const TcParams& p, int pair, cudaStream_t s) {
-  if (pair == 1) return launch_tc4<BN, EPI, X3, 1>(ma, mb, mc, me, mm, p, s);
+  if constexpr (!X3) {
+    if (pair == 1) return launch_tc4<BN, EPI, X3, 1>(ma, mb, mc, me, mm, p, s);
+  }
   if (pair == 2) return launch_tc4<BN, EPI, X3, 2>(ma, mb, mc, me, mm, p, s);
   return launch_tc4<BN, EPI, X3, 0>(ma, mb, mc, me, mm, p, s);
 }
@@ -1330,7 +1499,7 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
   int pair = 0;
   if (tc_cta2_enabled() && !p.stem && p.m_tiles >= 2) {
     const int forced = tc_cta2_forced();
-    if (forced) pair = forced;
+    if (forced) pair = (x3 && forced == 1) ? 0 : forced;
     else if (!x3 && k_iters_host >= 18) pair = 1;
     else if (x3 && k_iters_host >= 18) pair = 2;
   }

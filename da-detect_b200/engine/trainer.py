@@ -17,6 +17,7 @@ Differences from the reference (SURVEY §5 "Distributed communication backend", 
     (`unused_parameter_names`).
 """
 import math
+import os
 from bisect import bisect_right
 
 import torch
@@ -131,6 +132,23 @@ class FlatSGDTrainer(object):
                 p.grad = vg
                 off += pad4(n)
         self.total = total
+        # Gradient exchange in reverse-order segments (world > 1): backward finishes the heads (RPN, box head, DA
+        # heads) first, then res4, then res3; each segment of the flat buffer is all-reduced on a communication
+        # stream as soon as its last weight-gradient kernel has been launched (ops.grad_milestone), overlapping the
+        # exchange with the rest of backward.  Segments: [heads | backbone.body.layer3 | the rest + all biases].
+        offs, o = {}, 0
+        for n, p in self.order:
+            offs[n] = o
+            o += pad4(p.numel())
+        wnames = [n for n, _ in weights]
+        first_head = next((offs[n] for n in wnames if not n.startswith("backbone.")), self.n_weight)
+        l3 = [offs[n] for n in wnames if n.startswith("backbone.body.layer3.")]
+        l3_begin = min(l3) if l3 else first_head
+        self.segments = {"out:body": (first_head, self.n_weight), "in:layer3": (l3_begin, first_head)}
+        self.tail_segments = [(0, l3_begin), (self.n_weight, total)]
+        self.overlap_exchange = os.environ.get("DD_OVERLAP_EXCHANGE", "1") != "0"      # (0: one all_reduce after backward)
+        self.comm_stream = None
+        self._reduced = set()
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_graphs = None          # signature -> captured whole-step CUDA graph (enable_step_graph)
         self.graph_launches = 0          # kernels of ours replayed through step graphs so far
@@ -155,9 +173,49 @@ class FlatSGDTrainer(object):
     def lr(self):
         return self.schedule.lr_at(self.iteration) if self.schedule is not None else self.base_lr
 
+    def _exchange(self, a, b, side):
+        """all_reduce of flat_grad[a:b]; side=True: on the communication stream, ordered after everything launched so
+        far on the current stream (inside a step-graph capture the fork and the join are graph edges)."""
+        if b <= a:
+            return
+        seg = self.flat_grad[a:b]
+        if side and seg.is_cuda:
+            if self.comm_stream is None:
+                self.comm_stream = torch.cuda.Stream(device=seg.device)
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(seg)
+        else:
+            dist.all_reduce(seg)
+
+    def _on_milestone(self, tag):
+        rng = self.segments.get(tag)
+        if rng is not None and tag not in self._reduced:
+            self._reduced.add(tag)
+            self._exchange(rng[0], rng[1], side=True)
+
+    def begin_backward(self):
+        """Arm the overlapped exchange for the backward pass that follows (no-op for one rank)."""
+        self._reduced = set()
+        if self.world > 1 and self.overlap_exchange:
+            ops.set_grad_milestone_callback(self._on_milestone)
+
     def all_reduce(self):
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad)
+        """Finish the gradient exchange: whatever segment was not reduced during backward, then join."""
+        if self.world <= 1:
+            return
+        ops.set_grad_milestone_callback(None)
+        if not self._reduced:
+            dist.all_reduce(self.flat_grad)              # one call over the whole buffer (overlap off / no milestones)
+            return
+        for tag, (a, b) in self.segments.items():
+            if tag not in self._reduced:
+                self._exchange(a, b, side=False)
+        for a, b in self.tail_segments:
+            self._exchange(a, b, side=False)
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._reduced = set()
 
     def optimizer_step(self):
         lr = self.lr()
@@ -264,6 +322,7 @@ class FlatSGDTrainer(object):
         return loss_dict
 
     def _eager_step(self, images, targets, dev_lr=False):
+        self.begin_backward()                 # (the milestone hooks are registered during the forward pass)
         loss_dict = self.model(images, targets)
         losses = sum(loss_dict.values())
         self.zero_grad()
@@ -282,6 +341,7 @@ class FlatSGDTrainer(object):
             if out is not None:
                 return out
         with section("forward"):
+            self.begin_backward()
             loss_dict = self.model(images, targets)
             losses = sum(loss_dict.values())
         with section("backward"):

@@ -184,8 +184,9 @@ class ResNetC4(nn.Module):
         for i, name in enumerate(self.stages):
             # every stage output is a ReLU output consumed only by the next stage, so the mask (x > 0) of the
             # gradient crossing a stage boundary is applied by the consumer's dgrad epilogue
+            x = ops.grad_milestone(x, "in:" + name)          # backward: this stage's weight gradients are complete
             x = getattr(self, name)(x, input_is_relu=i > 0, grad_premasked=i < last)
-        return [x]
+        return [ops.grad_milestone(x, "out:body")]           # backward: every head's weight gradients are complete
 
 
 class ResNetHead(nn.Module):

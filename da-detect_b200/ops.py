@@ -71,6 +71,23 @@ def _wgrad_into(param, gy, x, scale, cout, kh, kw, stride, pad):
     return grad_like_weight(conv2d_wgrad_raw(gy, x, scale, cout, kh, kw, stride, pad), param)
 
 
+_milestone_cb = None
+
+
+def set_grad_milestone_callback(fn):
+    """fn(tag) is called during backward as soon as the gradient of a tensor marked with grad_milestone(x, tag) is
+    complete, i.e. when every kernel of the layers downstream of x has been launched (None = off).  FlatSGDTrainer
+    uses it to start the gradient all-reduce of a finished parameter segment while backward is still running."""
+    global _milestone_cb
+    _milestone_cb = fn
+
+
+def grad_milestone(x, tag):
+    if _milestone_cb is not None and torch.is_tensor(x) and x.requires_grad:
+        x.register_hook(lambda g, t=tag: (_milestone_cb(t), None)[1])
+    return x
+
+
 def tcgen05_available():
     return bool(_lib.load().dd_tcgen05_built())
 

@@ -1,0 +1,152 @@
+"""Multi-GPU (NCCL) tests; each needs >= 2 visible GPUs and is skipped otherwise (`gpurun --gpus 2`).
+
+test_reference_driver_dropin: the model under the REFERENCE's own data-parallel driver — wrapped in
+torch.nn.parallel.DistributedDataParallel(broadcast_buffers=False) exactly as tools/train_net_triplet.py:83-88 does and
+stepped by torch.optim.SGD with the parameter groups of solver/build.py:7-20 — against FlatSGDTrainer (flat buffers,
+segmented overlapped all-reduce, fused SGD; eager and as a whole-step CUDA graph) over three iterations on two ranks
+with different batches: same losses, same parameters.
+"""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import sys
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    import da_frcnn_ref as orc
+    from make_golden import SCENARIOS
+    from dadetect_b200 import ops
+    from dadetect_b200.config import get_cfg_defaults
+    from dadetect_b200.engine import FlatSGDTrainer
+    from dadetect_b200.modeling import build_detection_model
+    from dadetect_b200.structures import BoxList
+    from dadetect_b200.utils.random_source import HashSource
+    from dadetect_b200.utils.synthetic import make_batch, make_state_dict
+    dev = torch.device("cuda", rank)
+    ops.set_default_impl(ops.IMPL_TCGEN05_MIXED)
+    yaml_name, opts, n, H, W, m = SCENARIOS["da_img_ins_cst"]
+    cfg = get_cfg_defaults()
+    cfg.merge_from_file(os.path.join(ROOT, "configs", yaml_name))
+    cfg.merge_from_list(list(opts) + ["SOLVER.BASE_LR", 0.002])
+    S = cfg.SOLVER
+    sd = make_state_dict(orc.param_shapes(cfg))
+
+    def batch(it):
+        images, targets = make_batch(n, H, W, num_classes=cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES, boxes_per_image=m,
+                                     seed=500 + 10 * rank + it)
+        tg = []
+        for t in targets:
+            b = BoxList(t["boxes"].to(dev), (W, H), mode="xyxy")
+            b.add_field("labels", t["labels"].to(dev))
+            b.add_field("is_source", torch.full((len(t["labels"]),), bool(t["is_source"]), dtype=torch.bool, device=dev))
+            tg.append(b)
+        return images.to(dev), tg
+
+    def fresh():
+        model = build_detection_model(cfg).to(dev)
+        model.load_state_dict(sd, strict=False)
+        model.train()
+        model.set_random_source(HashSource())
+        return model
+
+    runs = {}
+    # ---- (A) the reference's driver: DDP + torch.optim.SGD (tools/train_net_triplet.py:83-88, solver/build.py:7-20)
+    model = fresh()
+    params = []
+    for key, value in model.named_parameters():
+        if not value.requires_grad:
+            continue
+        lr, wd = S.BASE_LR, S.WEIGHT_DECAY
+        if "bias" in key:
+            lr, wd = S.BASE_LR * S.BIAS_LR_FACTOR, S.WEIGHT_DECAY_BIAS
+        params += [{"params": [value], "lr": lr, "weight_decay": wd}]
+    optimizer = torch.optim.SGD(params, S.BASE_LR, momentum=S.MOMENTUM)
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[rank], output_device=rank, broadcast_buffers=False)
+    losses = []
+    for it in range(3):
+        images, tg = batch(it)
+        loss_dict = ddp(images, tg)
+        total = sum(loss_dict.values())
+        optimizer.zero_grad()
+        total.backward()
+        optimizer.step()
+        losses.append({k: float(v) for k, v in loss_dict.items()})
+    runs["ddp"] = (losses, {k: v.detach().clone() for k, v in model.named_parameters()})
+    del ddp, optimizer, model
+    # ---- (B) FlatSGDTrainer, eager and as one CUDA graph per step
+    for name, graph in (("flat", False), ("flat_graph", True)):
+        model = fresh()
+        tr = FlatSGDTrainer(model, cfg, world_size=world)
+        if graph:
+            tr.enable_step_graph(True)
+        losses = []
+        for it in range(3):
+            ld = tr.step(*batch(it))
+            losses.append({k: float(v) for k, v in ld.items()})
+        torch.cuda.synchronize()
+        runs[name] = (losses, {k: v.detach().clone() for k, v in model.named_parameters()})
+        if graph:
+            assert tr.graph_launches > 0 and len(tr.step_graphs) == 1
+        ops.set_direct_weight_grad(False)
+        del tr, model
+    report = {}
+    ref_losses, ref_params = runs["ddp"]
+    for name in ("flat", "flat_graph"):
+        losses, params_ = runs[name]
+        worst = 0.0
+        for a, b in zip(ref_losses, losses):
+            assert a.keys() == b.keys()
+            for k in a:
+                worst = max(worst, abs(a[k] - b[k]) / max(abs(a[k]), 0.05))
+        num = den = 0.0
+        for k, p in ref_params.items():
+            if p.requires_grad:
+                num += float((params_[k] - p).double().pow(2).sum())
+                den += float((p - sd[k].to(dev)).double().pow(2).sum())
+        report[name] = (worst, (num / max(den, 1e-30)) ** 0.5)
+    dist.barrier()
+    if rank == 0:
+        q.put(report)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_reference_driver_dropin():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(800)
+        assert p.exitcode == 0
+    report = q.get()
+    print(report)
+    for name, (loss_rel, param_rel) in report.items():
+        # same kernels, same data, same random keys: only the summation order of the exchange / the optimiser differs
+        assert loss_rel < 2e-4, (name, loss_rel)
+        assert param_rel < 2e-3, (name, param_rel)      # relative to how far the parameters moved in three steps

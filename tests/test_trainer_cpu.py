@@ -108,3 +108,95 @@ def test_parameters_outside_the_flat_buffers_are_the_ones_the_reference_never_up
     cfg.merge_from_list(list(fx["opts"]))
     model = build_detection_model(cfg)
     assert sorted(unused_parameter_names(model)) == sorted(fx["params_without_grad"])
+
+
+class _ToyBody(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.layer2 = nn.Linear(6, 6)
+        self.layer3 = nn.Linear(6, 6)
+
+
+class _ToyBackbone(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.body = _ToyBody()
+
+
+class _ToyDetector(nn.Module):
+    """Parameter names shaped like the detector's (backbone.body.layer2/3, heads after the backbone) and the same
+    milestone marks as ResNetC4.forward, so that the trainer's segment bookkeeping is exercised on the CPU."""
+
+    def __init__(self):
+        super().__init__()
+        self.backbone = _ToyBackbone()
+        self.rpn = nn.Linear(6, 4)
+        self.roi_heads = nn.Linear(6, 3)
+
+    def forward(self, x):
+        from dadetect_b200 import ops
+        x = torch.relu(self.backbone.body.layer2(x))
+        x = ops.grad_milestone(x, "in:layer3")
+        x = torch.relu(self.backbone.body.layer3(x))
+        x = ops.grad_milestone(x, "out:body")
+        return self.rpn(x).sum() + self.roi_heads(x).pow(2).sum()
+
+
+def _overlap_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dadetect_b200.config import get_cfg_defaults
+    from dadetect_b200.engine import FlatSGDTrainer
+    torch.manual_seed(0)
+    model = _ToyDetector()
+    tr = FlatSGDTrainer(model, get_cfg_defaults())
+    names = [n for n, _ in tr.order]
+    assert names[:4] == ["backbone.body.layer2.weight", "backbone.body.layer3.weight", "rpn.weight", "roi_heads.weight"]
+    assert tr.segments == {"out:body": (72, 72 + 24 + 20), "in:layer3": (36, 72)}, tr.segments
+    assert tr.tail_segments == [(0, 36), (tr.n_weight, tr.total)]
+    x = torch.randn(5, 6, generator=torch.Generator().manual_seed(100 + rank))
+    results = []
+    for overlap in (True, False):
+        tr.overlap_exchange = overlap
+        seen = []
+        orig = tr._exchange
+        tr._exchange = lambda a, b, side, _o=orig, _s=seen: (_s.append((a, b, side)), _o(a, b, side))[1]
+        tr.begin_backward()
+        loss = model(x)
+        tr.zero_grad()
+        loss.backward()
+        tr.all_reduce()
+        tr._exchange = orig
+        results.append(tr.flat_grad.clone())
+        if overlap:      # heads first, then layer3 (both during backward), then the rest and the biases
+            assert seen == [(72, 116, True), (36, 72, True), (0, 36, False), (tr.n_weight, tr.total, False)], seen
+        else:
+            assert seen == []
+    assert torch.equal(results[0], results[1])
+    # and it is the sum over ranks of the local gradients
+    tr.overlap_exchange = False
+    loss = model(x)
+    tr.zero_grad()
+    loss.backward()
+    local = tr.flat_grad.clone()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    assert torch.allclose(results[0], sum(gathered), atol=1e-6)
+    if rank == 0:
+        out.put("ok")
+    dist.destroy_process_group()
+
+
+def test_overlapped_segment_exchange_world2():
+    """The gradient exchange in reverse-order segments started from backward milestones (heads, then layer3, then
+    the rest + biases) gives exactly the single all_reduce of the whole flat buffer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get() == "ok"
