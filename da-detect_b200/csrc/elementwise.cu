@@ -42,7 +42,15 @@ __global__ void avgpool_fwd_kernel(const float* __restrict__ x, float* __restric
     const long long k = t / C;
     const float* p = x + (size_t)k * HW * C + c;
     float acc = 0.f;
-    for (int i = 0; i < HW; ++i) acc += p[(size_t)i * C];
+    int i = 0;
+    for (; i + 7 <= HW; i += 7) {                 // seven independent loads in flight, added in the original order
+      float v[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) v[j] = __ldg(p + (size_t)(i + j) * C);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) acc += v[j];
+    }
+    for (; i < HW; ++i) acc += __ldg(p + (size_t)i * C);
     y[t] = acc * inv;
   }
 }
