@@ -146,7 +146,11 @@ class FlatSGDTrainer(object):
         l3_begin = min(l3) if l3 else first_head
         self.segments = {"out:body": (first_head, self.n_weight), "in:layer3": (l3_begin, first_head)}
         self.tail_segments = [(0, l3_begin), (self.n_weight, total)]
-        self.overlap_exchange = os.environ.get("DD_OVERLAP_EXCHANGE", "1") != "0"      # (0: one all_reduce after backward)
+        # Off by default: measured on 8 x B200 (profiles/r02_scale_8gpu.txt) the overlapped exchange is SLOWER than one
+        # all_reduce after backward (17.98 vs 17.79 ms/step).  NCCL's NVLS kernels occupy 24 SMs while they run, and the
+        # dense kernels are persistent one-CTA-per-SM grids that need 227 KB of shared memory per SM: every kernel that
+        # overlaps the exchange gets a second wave on the blocked SMs.  DD_OVERLAP_EXCHANGE=1 switches it on.
+        self.overlap_exchange = os.environ.get("DD_OVERLAP_EXCHANGE", "0") == "1"
         self.comm_stream = None
         self._reduced = set()
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)

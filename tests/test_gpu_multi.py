@@ -97,6 +97,7 @@ def _worker(rank, world, port, q):
     for name, graph in (("flat", False), ("flat_graph", True)):
         model = fresh()
         tr = FlatSGDTrainer(model, cfg, world_size=world)
+        tr.overlap_exchange = True           # exercise the segmented, overlapped exchange (off by default)
         if graph:
             tr.enable_step_graph(True)
         losses = []
