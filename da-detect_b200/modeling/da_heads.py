@@ -150,6 +150,104 @@ class DomainAdaptationModule(_Base):
         return losses
 
 
+class DAImgHeadFPN(nn.Module):
+    """One (1x1 conv -> ReLU -> 1x1 conv) image-level domain classifier per pyramid level with the parameter names of
+    da_heads_fpn.py:37-66 (``da_img_conv{1,2}_level{i}``)."""
+
+    def __init__(self, in_channels, levels=5):
+        super().__init__()
+        self.levels = levels
+        for i in range(levels):
+            c1, c2 = Conv2dParams(in_channels, 512, 1, bias=True), Conv2dParams(512, 1, 1, bias=True)
+            for l in (c1, c2):
+                nn.init.normal_(l.weight, std=0.001)
+                nn.init.constant_(l.bias, 0)
+            self.add_module("da_img_conv1_level{}".format(i), c1)
+            self.add_module("da_img_conv2_level{}".format(i), c2)
+
+    def forward(self, feats):
+        outs = []
+        for i, f in enumerate(feats):
+            c1, c2 = getattr(self, "da_img_conv1_level{}".format(i)), getattr(self, "da_img_conv2_level{}".format(i))
+            t = ops.conv_bn_act(f, c1.weight, None, c1.bias, relu=True)
+            outs.append(ops.fused_heads(t, [c2.weight], [c2.bias])[0])
+        return outs
+
+
+class DAInsHeadFPN(nn.Module):
+    """One FC triple (1024-1024-1024-1, ReLU + dropout 0.5) per pooler level (da_heads_fpn.py:146-207,
+    ``da_ins_fc{1,2,3}_level{i}``); every ROI goes through the head of its LevelMapper level."""
+
+    def __init__(self, in_channels, rng, levels=4):
+        super().__init__()
+        self.levels, self.rng = levels, rng
+        for i in range(levels):
+            for j, (cin, cout) in enumerate(((in_channels, 1024), (1024, 1024), (1024, 1)), 1):
+                fc = nn.Linear(cin, cout)
+                nn.init.normal_(fc.weight, std=0.01)
+                nn.init.constant_(fc.bias, 0)
+                self.add_module("da_ins_fc{}_level{}".format(j, i), fc)
+
+    def forward(self, x, roi_levels):
+        """x [K, C]; roi_levels int [K].  Host-driven like the rest of the FPN path (one size read per level)."""
+        out = torch.zeros((x.shape[0], 1), dtype=x.dtype, device=x.device)
+        counts = torch.bincount(roi_levels.to(torch.int64), minlength=self.levels).tolist()
+        for lvl in range(self.levels):
+            if counts[lvl] == 0:                                  # da_heads_fpn.py:194
+                continue
+            idx = torch.nonzero(roi_levels == lvl).squeeze(1)
+            xs = x[idx]
+            for j in (1, 2):
+                fc = getattr(self, "da_ins_fc{}_level{}".format(j, lvl))
+                xs = ops.linear(xs, fc.weight, fc.bias, relu=True)
+                if self.training:
+                    xs = ops.dropout_with_mask(xs, self.rng.dropout_keep(tuple(xs.shape), xs.device))
+            fc3 = getattr(self, "da_ins_fc3_level{}".format(lvl))
+            out = out.index_put((idx,), ops.fused_heads(xs, [fc3.weight], [fc3.bias])[0])
+        return out
+
+
+class DomainAdaptationModuleFPN(nn.Module):
+    """DA heads on an FPN backbone (BASELINE configs[4]).  PARITY UNPINNED: the reference has no runnable FPN + DA
+    combination; this is the intent of da_heads_fpn.py:209-295 with its defects resolved as listed in
+    oracle/fpn_ref.py (per-level image heads, per-level instance heads routed by LevelMapper without the stray
+    `return`, COS_WEIGHT := 1.0, image BCE over the pixels of all levels, layers/consistency_loss.py over the list of
+    levels, DA_*_LOSS_WEIGHT applied as the C4 module does).  Checked against that oracle restatement."""
+
+    def __init__(self, cfg, rng):
+        super().__init__()
+        self.cfg = cfg.clone()
+        D = cfg.MODEL.DA_HEADS
+        self.img_weight, self.ins_weight, self.cst_weight = D.DA_IMG_LOSS_WEIGHT, D.DA_INS_LOSS_WEIGHT, D.DA_CST_LOSS_WEIGHT
+        self.imghead = DAImgHeadFPN(cfg.MODEL.BACKBONE.OUT_CHANNELS, levels=5)
+        self.inshead = DAInsHeadFPN(cfg.MODEL.ROI_BOX_HEAD.MLP_HEAD_DIM, rng, levels=len(cfg.MODEL.ROI_BOX_HEAD.POOLER_SCALES))
+
+    def forward(self, img_features, ins_feas, dom, n_src, targets, roi_levels):
+        if not self.training:
+            return {}
+        D = self.cfg.MODEL.DA_HEADS
+        need_img, need_ins, need_cst = self.img_weight > 0, self.ins_weight > 0, self.cst_weight > 0
+        losses = {}
+        # (same evaluation order as the oracle: instance GRL pass, instance consistency pass, image passes —
+        # the dropout draws of the instance passes are consumed in that order)
+        da_ins = self.inshead(ops.gradient_scalar(ins_feas, -1.0 * D.DA_INS_GRL_WEIGHT), roi_levels)
+        da_ins_c = self.inshead(ops.gradient_scalar(ins_feas, 1.0 * D.DA_INS_GRL_WEIGHT), roi_levels)
+        if need_img:
+            da_img = self.imghead([ops.gradient_scalar(f, -1.0 * D.DA_IMG_GRL_WEIGHT) for f in img_features])
+            n = da_img[0].shape[0]
+            flat = torch.cat([t.reshape(n, -1) for t in da_img], dim=1)
+            losses["loss_da_image"] = self.img_weight * da_img_loss(flat, targets)
+        if need_ins:
+            losses["loss_da_instance"] = self.ins_weight * da_ins_loss(da_ins, dom)
+        if need_cst:
+            da_img_c = self.imghead([ops.gradient_scalar(f, 1.0 * D.DA_IMG_GRL_WEIGHT) for f in img_features])
+            # mean over ROIs x levels of |image-level mean probability - ROI probability| = the mean of the
+            # per-level consistency losses (every level has the same K rows)
+            terms = [ops.consistency_loss(t.reshape(t.shape[0], -1), da_ins_c.reshape(-1), n_src) for t in da_img_c]
+            losses["loss_da_consistency"] = self.cst_weight * (sum(terms) / float(len(terms)))
+        return losses
+
+
 ADV_BCE = float(F.binary_cross_entropy_with_logits(torch.tensor([[0.7, 0.3]]), torch.tensor([[1.0, 0.0]])))
 
 
@@ -237,6 +335,8 @@ class DomainAdaptationModule_triplet(_Base):
 
 def build_da_heads(cfg, rng):
     if cfg.MODEL.DOMAIN_ADAPTATION_ON:
+        if cfg.MODEL.BACKBONE.CONV_BODY.endswith("-FPN"):
+            return DomainAdaptationModuleFPN(cfg, rng)
         return DomainAdaptationModule(cfg, rng)
     return []
 

@@ -87,12 +87,13 @@ class GeneralizedRCNN(nn.Module):
         self.da_heads_triplet = build_da_heads_triplet(cfg, self.rng) if self.triplet_use else False
         self.Aligned = cfg.MODEL.DA_HEADS.ALIGNMENT
         self.size_divisible = cfg.DATALOADER.SIZE_DIVISIBILITY
-        # FPN: multi-level features, host-driven control flow.  The reference ships no working
-        # FPN + DA combination (da_heads.py:368-370 sizes the heads for C4), so none is invented here.
+        # FPN: multi-level features, host-driven control flow.  FPN + DA follows the intent of
+        # da_heads_fpn.py (DomainAdaptationModuleFPN, parity unpinned: the reference's own combination cannot run,
+        # SURVEY §9.9); the triplet module has no FPN counterpart in the reference at all.
         self.fpn = cfg.MODEL.BACKBONE.CONV_BODY.endswith("-FPN")
-        if self.fpn and (self.da_heads or self.da_heads_triplet):
-            raise NotImplementedError("domain-adaptation heads on an FPN backbone: the reference's own combination "
-                                      "is broken (SURVEY §9.9); set MODEL.DOMAIN_ADAPTATION_ON False")
+        if self.fpn and self.da_heads_triplet:
+            raise NotImplementedError("the auxiliary-domain triplet module on an FPN backbone: the reference has no "
+                                      "FPN variant of DomainAdaptationModule_triplet; set MODEL.DA_HEADS.TRIPLET_USE False")
         self.static_shapes = not self.fpn
         self.__dict__["_meta_cache"] = {}
 
@@ -219,7 +220,11 @@ class GeneralizedRCNN(nn.Module):
                     n_src = sum(len(p) for p, t in zip(box.loss_evaluator._proposals, targets)
                                 if is_source_image(t))
                     with section("da_heads_fwd"):
-                        da_losses = self.da_heads(features, box.last_pooled, dom, n_src, targets)
+                        if self.fpn:      # per-level heads; the ROIs' pyramid levels come from the multi-level pooler
+                            da_losses = self.da_heads(features, box.last_pooled, dom, n_src, targets,
+                                                      box.feature_extractor.pooler.last_levels)
+                        else:
+                            da_losses = self.da_heads(features, box.last_pooled, dom, n_src, targets)
                 else:
                     # The reference leaves `detector_losses` unbound here; plain Faster R-CNN
                     # training is the obvious intent.

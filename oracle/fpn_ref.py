@@ -233,3 +233,124 @@ def forward_train_fpn(P, cfg, images, targets, hooks):
     cls_loss, box_loss, _ = orc.fastrcnn_loss(cls_logits, box_reg, samples)
     return dict(loss_classifier=cls_loss, loss_box_reg=box_loss, loss_objectness=obj_loss,
                 loss_rpn_box_reg=rpn_box_loss)
+
+
+# ----------------------------------------------------------------------------------- FPN + DA (BASELINE configs[4])
+# PARITY UNPINNED.  The reference ships no runnable FPN + DA combination: GeneralizedRCNN imports da_heads.py, whose
+# heads are sized for C4 (da_heads.py:368-370), and the FPN variant da_heads_fpn.py cannot even be
+# imported (it imports names loss.py does not define, :12; reads MODEL.DA_HEADS.COS_WEIGHT, :214, which
+# config/defaults.py does not have; its forward signature, :236, is not the one generalized_rcnn.py:126 calls; its
+# DAInsHead.forward returns from inside the level loop, :205; and DALossComputation concatenates the per-level image
+# logits along dim 0, loss.py:82, which fails for maps of different sizes).  What follows restates the INTENT of
+# da_heads_fpn.py with each of those defects resolved in the most conservative way, and says so line by line:
+#   * image head     one (conv 1x1 256->512, ReLU, conv 1x1 512->1) pair PER pyramid level (:37-66), on the GRL'd map
+#   * instance head  one (fc 1024->1024, ReLU, dropout, fc, ReLU, dropout, fc ->1) triple per POOLER level (:146-207),
+#                    every ROI through the head of ITS level (LevelMapper over the sampled proposals, :222-225,254) —
+#                    all four levels, i.e. without the stray `return` of :205
+#   * GRL weights    -DA_IMG_GRL_WEIGHT / -DA_INS_GRL_WEIGHT, consistency branches +1.0 x the same (COS_WEIGHT := 1.0,
+#                    the value da_heads.py:381-382 hard-codes for C4)
+#   * image loss     BCE-with-logits against the image's domain label, mean over ALL pixels of ALL levels (the per-level
+#                    [N, H_l*W_l] logits concatenated along dim 1 instead of dim 0: identical for one level)
+#   * instance loss  BCE-with-logits against the ROI's domain (loss.py:98-100)
+#   * consistency    layers/consistency_loss.py:3-27 as written — it already takes a list of levels: |mean prob of the
+#                    ROI's image at level l - ROI prob|, mean over ROIs x levels
+#   * loss weights   DA_IMG/INS/CST_LOSS_WEIGHT applied and zero-weight terms dropped as da_heads.py:417-436 does.
+def da_img_heads_fpn(pyramid, P, pre="da_heads"):
+    outs = []
+    for i, f in enumerate(pyramid):
+        t = F.relu(F.conv2d(f, P["%s.imghead.da_img_conv1_level%d.weight" % (pre, i)],
+                            P["%s.imghead.da_img_conv1_level%d.bias" % (pre, i)]))
+        outs.append(F.conv2d(t, P["%s.imghead.da_img_conv2_level%d.weight" % (pre, i)],
+                             P["%s.imghead.da_img_conv2_level%d.bias" % (pre, i)]))
+    return outs
+
+
+def da_ins_heads_fpn(x, levels, P, hooks, n_levels, pre="da_heads"):
+    """x [K, 1024]; ROI k goes through the FC triple of levels[k] (dropout draws in level order, only for levels
+    that hold ROIs, like the reference's `if len(idx_in_level) > 0`, :194)."""
+    result = torch.zeros((x.shape[0], 1), dtype=x.dtype)
+    for lvl in range(n_levels):
+        idx = torch.nonzero(levels == lvl).squeeze(1)
+        if idx.numel() == 0:
+            continue
+        xs = x[idx]
+        for j in (1, 2):
+            w, b = P["%s.inshead.da_ins_fc%d_level%d.weight" % (pre, j, lvl)], P["%s.inshead.da_ins_fc%d_level%d.bias" % (pre, j, lvl)]
+            xs = F.relu(F.linear(xs, w, b))
+            xs = xs * hooks.dropout_keep(tuple(xs.shape)) * 2.0                  # F.dropout(p=0.5, training=True)
+        out = F.linear(xs, P["%s.inshead.da_ins_fc3_level%d.weight" % (pre, lvl)], P["%s.inshead.da_ins_fc3_level%d.bias" % (pre, lvl)])
+        result = result.index_put((idx,), out)
+    return result
+
+
+def da_heads_fpn(pyramid, ins_feas, dom, levels, is_source_img, P, cfg, hooks, pre="da_heads"):
+    D = cfg.MODEL.DA_HEADS
+    n_ins_levels = len(cfg.MODEL.ROI_BOX_HEAD.POOLER_SCALES)
+    img_g = [orc.grl(f, -1.0 * D.DA_IMG_GRL_WEIGHT) for f in pyramid]
+    ins_g = orc.grl(ins_feas, -1.0 * D.DA_INS_GRL_WEIGHT)
+    img_c = [orc.grl(f, 1.0 * D.DA_IMG_GRL_WEIGHT) for f in pyramid]
+    ins_c = orc.grl(ins_feas, 1.0 * D.DA_INS_GRL_WEIGHT)
+    da_ins = da_ins_heads_fpn(ins_g, levels, P, hooks, n_ins_levels, pre)
+    da_ins_c = da_ins_heads_fpn(ins_c, levels, P, hooks, n_ins_levels, pre).sigmoid()
+    da_img = da_img_heads_fpn(img_g, P, pre)
+    da_img_c = [t.sigmoid() for t in da_img_heads_fpn(img_c, P, pre)]
+    n = pyramid[0].shape[0]
+    flat = torch.cat([t.permute(0, 2, 3, 1).reshape(n, -1) for t in da_img], dim=1)
+    lab = torch.zeros_like(flat)
+    lab[torch.tensor(is_source_img, dtype=torch.bool), :] = 1
+    l_img = F.binary_cross_entropy_with_logits(flat, lab)
+    l_ins = orc.da_ins_loss(da_ins, dom)
+    # consistency_loss.py:3-27 over the list of levels: [K, L] absolute differences, mean
+    k = da_ins_c.size(0)
+    n_src = int(torch.nonzero(dom).size(0))
+    assert n == 2, "only batch size=2 is supported for consistency loss now, received batch size: {}".format(n)
+    cols = []
+    for t in da_img_c:
+        means = t.reshape(n, -1).mean(1)
+        per_roi = torch.cat([means[0].view(1, 1).repeat(n_src, 1), means[1].view(1, 1).repeat(k - n_src, 1)], dim=0)
+        cols.append(torch.abs(per_roi - da_ins_c))
+    l_cst = torch.cat(cols, dim=1).mean()
+    out = {}
+    if D.DA_IMG_LOSS_WEIGHT > 0:
+        out["loss_da_image"] = D.DA_IMG_LOSS_WEIGHT * l_img
+    if D.DA_INS_LOSS_WEIGHT > 0:
+        out["loss_da_instance"] = D.DA_INS_LOSS_WEIGHT * l_ins
+    if D.DA_CST_LOSS_WEIGHT > 0:
+        out["loss_da_consistency"] = D.DA_CST_LOSS_WEIGHT * l_cst
+    return out
+
+
+def forward_train_fpn_da(P, cfg, images, targets, hooks):
+    """GeneralizedRCNN.forward, training, R-*-FPN WITH the DA heads (the configuration BASELINE configs[4] names):
+    forward_train_fpn's detector losses — RPN labels for source images only, detection losses masked to source ROIs
+    (rpn/loss.py:66-67, box_head/loss.py:84-85,200-219, as on the C4 path) — plus da_heads_fpn on the five pyramid
+    maps and the [K, 1024] MLP features of the sampled ROIs (generalized_rcnn.py:124-128).  Parity unpinned (above)."""
+    n, _, ih, iw = images.shape
+    gt_boxes = [t["boxes"] for t in targets]
+    gt_labels = [t["labels"] for t in targets]
+    is_src = [bool(t["is_source"]) for t in targets]
+    pyramid = fpn_forward(resnet_body_all_stages(images, P, cfg.MODEL.BACKBONE.CONV_BODY), P)
+    heads = [orc.rpn_head(f, P) for f in pyramid]
+    with torch.no_grad():
+        props = rpn_fpn_proposals([f.detach() for f in pyramid], {k: v.detach() for k, v in P.items()}, cfg,
+                                  [(ih, iw)] * n, training=True, nms_strict=True)
+        props = [(torch.cat([b, g]), torch.cat([s, torch.ones(len(g))])) if src else (b, s)
+                 for (b, s), g, src in zip(props, gt_boxes, is_src)]
+    obj_loss, rpn_box_loss = rpn_loss_fpn(pyramid, heads, cfg, gt_boxes, is_src, (ih, iw), hooks)
+    samples = orc.box_head_subsample(props, gt_boxes, gt_labels, is_src, cfg, hooks)
+    B = cfg.MODEL.ROI_BOX_HEAD
+    rois = orc.rois_from(samples)
+    pooled, levels = multilevel_pool(pyramid[:len(B.POOLER_SCALES)], rois, B.POOLER_SCALES, B.POOLER_RESOLUTION,
+                                     B.POOLER_SAMPLING_RATIO)
+    pre = "roi_heads.box.feature_extractor."
+    x = pooled.reshape(pooled.shape[0], -1)
+    x = F.relu(F.linear(x, P[pre + "fc6.weight"], P[pre + "fc6.bias"]))
+    x = F.relu(F.linear(x, P[pre + "fc7.weight"], P[pre + "fc7.bias"]))
+    pp = "roi_heads.box.predictor."
+    cls_logits = F.linear(x, P[pp + "cls_score.weight"], P[pp + "cls_score.bias"])
+    box_reg = F.linear(x, P[pp + "bbox_pred.weight"], P[pp + "bbox_pred.bias"])
+    cls_loss, box_loss, dom = orc.fastrcnn_loss(cls_logits, box_reg, samples)
+    losses = dict(loss_classifier=cls_loss, loss_box_reg=box_loss, loss_objectness=obj_loss,
+                  loss_rpn_box_reg=rpn_box_loss)
+    losses.update(da_heads_fpn(pyramid, x, dom, levels, is_src, P, cfg, hooks))
+    return losses

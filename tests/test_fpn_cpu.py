@@ -47,10 +47,108 @@ def test_cell_anchors_per_level_match_generate_anchors():
         AnchorGenerator((32, 64), (1.0,), (4, 8, 16), 0)
 
 
-def test_fpn_with_da_heads_is_refused():
+def test_fpn_triplet_module_is_refused_and_fpn_da_heads_have_the_reference_names():
+    """The reference has no FPN variant of the triplet module; its FPN DA module (da_heads_fpn.py, not importable) names
+    its parameters da_img_conv{1,2}_level{0..4} (:44-57) and da_ins_fc{1,2,3}_level{0..3} (:164-180)."""
     from dadetect_b200.modeling import build_detection_model
     with pytest.raises(NotImplementedError):
-        build_detection_model(fpn_cfg(["MODEL.DOMAIN_ADAPTATION_ON", True]))
+        build_detection_model(fpn_cfg(["MODEL.DOMAIN_ADAPTATION_ON", True, "MODEL.DA_HEADS.TRIPLET_USE", True]))
+    model = build_detection_model(fpn_cfg(["MODEL.BACKBONE.CONV_BODY", "R-50-FPN", "MODEL.DOMAIN_ADAPTATION_ON", True,
+                                           "MODEL.DA_HEADS.TRIPLET_USE", False]))
+    names = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("da_heads.")}
+    want = {}
+    for i in range(5):
+        want["da_heads.imghead.da_img_conv1_level%d.weight" % i] = (512, 256, 1, 1)
+        want["da_heads.imghead.da_img_conv1_level%d.bias" % i] = (512,)
+        want["da_heads.imghead.da_img_conv2_level%d.weight" % i] = (1, 512, 1, 1)
+        want["da_heads.imghead.da_img_conv2_level%d.bias" % i] = (1,)
+    for i in range(4):
+        for j, (cin, cout) in enumerate(((1024, 1024), (1024, 1024), (1024, 1)), 1):
+            want["da_heads.inshead.da_ins_fc%d_level%d.weight" % (j, i)] = (cout, cin)
+            want["da_heads.inshead.da_ins_fc%d_level%d.bias" % (j, i)] = (cout,)
+    assert names == want
+
+
+@pytest.mark.timeout(900)
+def test_product_fpn_da_training_orchestration_matches_oracle(cpu_ops):
+    """FPN + DA (BASELINE configs[4]; parity unpinned, see oracle/fpn_ref.py): the product's python path — per-level
+    image heads on the GRL'd pyramid, per-level instance heads routed by the pooler's LevelMapper levels, image BCE over
+    all levels, consistency over the list of levels, source-only detection losses — with kernel stand-ins against
+    oracle/fpn_ref.py::forward_train_fpn_da on replayed draws: losses and the gradient of every trainable tensor."""
+    import da_frcnn_ref as orc
+    import fpn_ref
+    from dadetect_b200.modeling import build_detection_model
+    from dadetect_b200.structures import BoxList
+    from dadetect_b200.utils.random_source import ReplaySource
+    from dadetect_b200.utils.synthetic import make_batch, make_state_dict
+    torch.set_num_threads(os.cpu_count())
+    cfg = fpn_cfg(["MODEL.BACKBONE.CONV_BODY", "R-50-FPN", "MODEL.ROI_BOX_HEAD.NUM_CLASSES", 9,
+                   "MODEL.RPN.FPN_POST_NMS_TOP_N_TRAIN", 4000, "MODEL.DOMAIN_ADAPTATION_ON", True,
+                   "MODEL.DA_HEADS.TRIPLET_USE", False])
+    model = build_detection_model(cfg)
+    sd = make_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    sd["rpn.head.cls_logits.weight"] = sd["rpn.head.cls_logits.weight"] * 20.0
+    for k in sd:                                            # sensitive DA losses (std 0.001 heads sit at log 2 otherwise)
+        if ".da_img_conv2_" in k:
+            sd[k] = sd[k] * 100.0
+        if ".da_ins_fc3_" in k:
+            sd[k] = sd[k] * 10.0
+    model.load_state_dict(sd, strict=False)
+    model.train()
+    H, W = 288, 416
+    images, targets = make_batch(2, H, W, num_classes=9, boxes_per_image=4, seed=33)      # [source, target]
+    torch.manual_seed(5)
+    rec = orc.RecordingHooks()
+    frozen = ("backbone.body.stem.", "backbone.body.layer1.")
+    P = {k: v.clone().requires_grad_(v.is_floating_point() and ".bn" not in k and ".downsample.1." not in k
+                                     and not k.startswith(frozen)) for k, v in sd.items()}
+    want = fpn_ref.forward_train_fpn_da(P, cfg, images, targets, rec)
+    assert set(want) == {"loss_classifier", "loss_box_reg", "loss_objectness", "loss_rpn_box_reg", "loss_da_image",
+                         "loss_da_instance", "loss_da_consistency"}
+    sum(want.values()).backward()
+    # The proposals are the oracle's (equal-objectness proposals may come out of the top-k in either order, and the
+    # dropout masks of the instance heads are positional): handed in through the proposal hook.
+    with torch.no_grad():
+        pyramid = fpn_ref.fpn_forward(fpn_ref.resnet_body_all_stages(images, sd, "R-50-FPN"), sd)
+        props = fpn_ref.rpn_fpn_proposals(pyramid, sd, cfg, [(H, W)] * 2, training=True, nms_strict=True)
+    forced = []
+    for (b, s_), t in zip(props, targets):
+        if t["is_source"]:
+            b, s_ = torch.cat([b, t["boxes"]]), torch.cat([s_, torch.ones(len(t["boxes"]))])
+        bl = BoxList(b, (W, H), mode="xyxy")
+        bl.add_field("objectness", s_)
+        forced.append(bl)
+    model.rpn.set_proposal_hook(lambda boxes: forced)
+    replay = ReplaySource(rec.perms, rec.masks)
+    model.set_random_source(replay)
+    tg = []
+    for t in targets:
+        b = BoxList(t["boxes"].clone(), (W, H), mode="xyxy")
+        b.add_field("labels", t["labels"].clone())
+        b.add_field("is_source", torch.full((len(t["labels"]),), bool(t["is_source"]), dtype=torch.bool))
+        tg.append(b)
+    got = model(images, tg)
+    assert set(got) == set(want)
+    assert not replay.perms and not replay.masks
+    for k in want:
+        g, w = float(got[k].detach()), float(want[k].detach())
+        assert abs(g - w) <= 2e-5 * max(1.0, abs(w)), (k, g, w)
+    sum(got.values()).backward()
+    checked = 0
+    for k, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        assert P[k].requires_grad, k
+        if P[k].grad is None:                               # an instance head of a level without ROIs
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, k
+        a, b = p.grad.double(), P[k].grad.double()
+        assert float((a - b).norm()) <= 1e-3 * float(b.norm()) + 1e-9, (k, float((a - b).norm()), float(b.norm()))
+        checked += 1
+    assert checked > 80
+    levels = model.roi_heads.box.feature_extractor.pooler.last_levels
+    assert int((torch.bincount(levels.to(torch.int64), minlength=4) > 0).sum()) >= 2      # several instance heads in use
 
 
 def test_golden_exercises_every_pyramid_level(fx):
