@@ -17,6 +17,7 @@ _SIGS = {
     "dd_last_error": (ctypes.c_char_p, ""),
     "dd_abi_version": (_I, ""),
     "dd_launch_count": (_Q, ""),
+    "dd_set_sm_budget": (_I, "i"),
     "dd_tcgen05_built": (_I, ""),
     "dd_roi_align_forward": (_I, "pppiiiiifiiiip"),
     "dd_roi_align_backward": (_I, "pppiiiiifiiiip"),
@@ -32,6 +33,8 @@ _SIGS = {
     "dd_rpn_topk_decode": (_I, "pppiiiiiiifpppppp"),
     "dd_match": (_I, "pippiffipppp"),
     "dd_box_encode": (_I, "pipppiffffipp"),
+    "dd_rpn_anchor_labels": (_I, "ppipp"),
+    "dd_rpn_sampled_losses": (_I, "pppiiipppppppfpppp"),
     "dd_box_decode": (_I, "ppiiffffpp"),
     "dd_conv2d_forward_workspace_bytes": (_Z, "iiiii"),
     "dd_conv2d_forward": (_I, "ppppppiiiiiiiiiiipp"),

@@ -10,6 +10,7 @@ namespace dd {
 
 extern thread_local char g_err[512];
 extern long long g_launches;
+extern int g_sm_budget;   // SMs the persistent dense kernels may occupy (dd_set_sm_budget)
 
 inline int fail(int code, const char* what, const char* file, int line) {
   snprintf(g_err, sizeof(g_err), "%s (%s:%d): %s", what, file, line,
@@ -39,6 +40,10 @@ inline int fail(int code, const char* what, const char* file, int line) {
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 constexpr int kNumSMs = 148;  // B200
+// CTAs a persistent dense kernel launches at most: all SMs, or fewer while latency-bound few-CTA kernels (top-k, NMS
+// scan, samplers) run beside it on another stream and must keep their SMs (a persistent CTA that cannot become
+// resident runs as a second wave and doubles the kernel's duration).
+inline int sm_budget() { return g_sm_budget > 0 && g_sm_budget < kNumSMs ? g_sm_budget : kNumSMs; }
 
 inline int grid_for(long long work_items, int block, int max_waves = 8) {
   long long b = (work_items + block - 1) / block;

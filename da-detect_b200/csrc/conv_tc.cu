@@ -1388,7 +1388,7 @@ int launch_tc4(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   }
   const int m_units = CL ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const long long total = (long long)m_units * p.n_tiles;
-  const int max_units = CL ? dd::kNumSMs / 2 : dd::kNumSMs;
+  const int max_units = CL ? dd::sm_budget() / 2 : dd::sm_budget();
   const int units = total < max_units ? (int)total : max_units;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(CL ? 2 * units : units));
@@ -1799,14 +1799,15 @@ int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, floa
   // split the pixel range so that the persistent CTAs see whole rounds of work items (items = tiles x splits as
   // close as possible to a multiple of the SM count, 2-4 rounds) and every item still runs >= 8 K-iterations
   const int tiles = co_tiles * p.ci_tiles * p.taps;
+  const int sms = dd::sm_budget();
   int splits = 1;
   {
     const int max_splits = (p.pix_blocks + 7) / 8;
     double best = -1.0;
-    for (int cand = 1; cand <= max_splits && (long long)cand * tiles <= 6ll * dd::kNumSMs; ++cand) {
+    for (int cand = 1; cand <= max_splits && (long long)cand * tiles <= 6ll * sms; ++cand) {
       const long long items = (long long)cand * tiles;
-      const long long rounds = (items + dd::kNumSMs - 1) / dd::kNumSMs;
-      double eff = (double)items / (double)(rounds * dd::kNumSMs);
+      const long long rounds = (items + sms - 1) / sms;
+      double eff = (double)items / (double)(rounds * sms);
       if (rounds < 2) eff *= 0.9;                       // one round: no overlap of reductions with the next item
       if (eff > best + 1e-9) { best = eff; splits = cand; }
     }
@@ -1835,7 +1836,7 @@ int dd_tc_conv2d_wgrad(const float* gy, const float* x, const float* scale, floa
   p.co_tiles = co_tiles; p.splits = splits;
   const long long items = (long long)p.ci_tiles * p.taps * co_tiles * splits;
   DD_CHECK_ARG(items < (1ll << 31));
-  dim3 grid((unsigned)(items < dd::kNumSMs ? items : dd::kNumSMs));
+  dim3 grid((unsigned)(items < sms ? items : sms));
   int rc;
   if (x3) {
     if (BN == 128) rc = launch_wgrad<128, true>(mg, mx, p, grid, s);

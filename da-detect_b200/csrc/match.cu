@@ -40,13 +40,15 @@ __global__ void __launch_bounds__(256) match_pass1(const float4* __restrict__ gt
                                                    const float4* __restrict__ pred, int N, float high, float low,
                                                    int64_t* __restrict__ matches, int32_t* __restrict__ argmax_out,
                                                    float* __restrict__ vals_out, float* __restrict__ gt_best) {
-  extern __shared__ float4 sgt[];          // Mcap boxes, then Mcap areas
+  extern __shared__ float4 sgt[];          // Mcap boxes, then Mcap areas, then Mcap per-CTA maxima
   float* sarea = reinterpret_cast<float*>(sgt + Mcap);
+  int* sbest = reinterpret_cast<int*>(sarea + Mcap);
   const int M = live_rows(Mcap, m_dev);
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
     const float4 g = gt[i];
     sgt[i] = g;
     sarea[i] = area_plus1(g);
+    sbest[i] = 0;
   }
   __syncthreads();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,8 +65,12 @@ __global__ void __launch_bounds__(256) match_pass1(const float4* __restrict__ gt
       float m = v;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(gt_best) + i, __float_as_int(m));
-    }
+      if ((threadIdx.x & 31) == 0) atomicMax(sbest + i, __float_as_int(m));     // per CTA first: 480 CTAs x 8 warps
+    }                                                                            // on M addresses serialise in L2
+  }
+  if (gt_best != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < M; i += blockDim.x) atomicMax(reinterpret_cast<int*>(gt_best) + i, sbest[i]);
   }
   if (live) {
     long long m = arg;
@@ -104,6 +110,21 @@ __global__ void __launch_bounds__(256) match_pass2(const float4* __restrict__ gt
   if (restore) matches[j] = argmax_in[j];
 }
 
+// BoxCoder.encode of one (ground truth, proposal) pair in the reference's operation order (box_coder.py:22-52)
+__device__ __forceinline__ float4 encode_ref_order(const float4 g, const float4 p, float wx, float wy, float ww,
+                                                   float wh) {
+  const float ew = __fadd_rn(__fsub_rn(p.z, p.x), 1.f), eh = __fadd_rn(__fsub_rn(p.w, p.y), 1.f);
+  const float ex = __fadd_rn(p.x, __fmul_rn(0.5f, ew)), ey = __fadd_rn(p.y, __fmul_rn(0.5f, eh));
+  const float gw = __fadd_rn(__fsub_rn(g.z, g.x), 1.f), gh = __fadd_rn(__fsub_rn(g.w, g.y), 1.f);
+  const float gx = __fadd_rn(g.x, __fmul_rn(0.5f, gw)), gy = __fadd_rn(g.y, __fmul_rn(0.5f, gh));
+  float4 t;
+  t.x = __fdiv_rn(__fmul_rn(wx, __fsub_rn(gx, ex)), ew);
+  t.y = __fdiv_rn(__fmul_rn(wy, __fsub_rn(gy, ey)), eh);
+  t.z = __fmul_rn(ww, logf(__fdiv_rn(gw, ew)));
+  t.w = __fmul_rn(wh, logf(__fdiv_rn(gh, eh)));
+  return t;
+}
+
 __global__ void box_encode_kernel(const float4* __restrict__ gt, int Mcap, const int32_t* __restrict__ m_dev,
                                   const float4* __restrict__ pred,
                                   const int64_t* __restrict__ matches, int N, float wx, float wy, float ww, float wh,
@@ -114,17 +135,7 @@ __global__ void box_encode_kernel(const float4* __restrict__ gt, int Mcap, const
   long long m = matches[j];
   if (m < 0) m = wrap_negative ? m + M : 0;
   if (m < 0) m = 0;
-  const float4 g = gt[m], p = pred[j];
-  const float ew = __fadd_rn(__fsub_rn(p.z, p.x), 1.f), eh = __fadd_rn(__fsub_rn(p.w, p.y), 1.f);
-  const float ex = __fadd_rn(p.x, __fmul_rn(0.5f, ew)), ey = __fadd_rn(p.y, __fmul_rn(0.5f, eh));
-  const float gw = __fadd_rn(__fsub_rn(g.z, g.x), 1.f), gh = __fadd_rn(__fsub_rn(g.w, g.y), 1.f);
-  const float gx = __fadd_rn(g.x, __fmul_rn(0.5f, gw)), gy = __fadd_rn(g.y, __fmul_rn(0.5f, gh));
-  float4 t;
-  t.x = __fdiv_rn(__fmul_rn(wx, __fsub_rn(gx, ex)), ew);
-  t.y = __fdiv_rn(__fmul_rn(wy, __fsub_rn(gy, ey)), eh);
-  t.z = __fmul_rn(ww, logf(__fdiv_rn(gw, ew)));
-  t.w = __fmul_rn(wh, logf(__fdiv_rn(gh, eh)));
-  out[j] = t;
+  out[j] = encode_ref_order(gt[m], pred[j], wx, wy, ww, wh);
 }
 
 __global__ void box_decode_kernel(const float* __restrict__ codes, const float4* __restrict__ boxes, int R, int k,
@@ -149,7 +160,97 @@ __global__ void box_decode_kernel(const float* __restrict__ codes, const float4*
   reinterpret_cast<float4*>(out)[t] = o;
 }
 
+
+// RPN anchor labels from the Matcher's result and the visibility mask (rpn/loss.py:57-89): 1 = matched, 0 = below the
+// low threshold, -1 = between the thresholds or straddling the image border (ignored by the sampler).
+__global__ void rpn_anchor_labels_kernel(const int64_t* __restrict__ matches, const uint8_t* __restrict__ vis, int N,
+                                         int32_t* __restrict__ labels) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const long long m = matches[j];
+  int lab = m >= 0 ? 1 : 0;
+  if (m == -2 || !vis[j]) lab = -1;
+  labels[j] = lab;
+}
+
+// RPNLossComputation's loss tail (rpn/loss.py:118-141) over the sampled anchors of all source images, forward and
+// gradient in one launch of one CTA: BCE-with-logits over the sampled anchors and smooth-L1 (beta) over the sampled
+// positives against BoxCoder(1,1,1,1) targets, both divided by the number of sampled anchors.  sel [S,B] / counts [S,2]
+// come from dd_balanced_sample; row s*A + a of logits / deltas belongs to anchor a of source image s (source images
+// come first in a batch).  dlogits / ddeltas (dense, zero-filled by the caller) receive d loss / d input.
+__global__ void __launch_bounds__(256) rpn_sampled_losses_kernel(
+    const float* __restrict__ logits, const float4* __restrict__ deltas, const float4* __restrict__ anchors, int A,
+    int S, int B, const int64_t* __restrict__ sel, const int32_t* __restrict__ counts,
+    const int32_t* __restrict__ labels, const int64_t* __restrict__ matches, const float4* __restrict__ gt_cat,
+    const int32_t* __restrict__ gt_off, const int32_t* __restrict__ src_img, float beta, float* __restrict__ losses,
+    float* __restrict__ dlogits, float4* __restrict__ ddeltas) {
+  __shared__ float red[32];
+  int total = 0;
+  for (int s = 0; s < S; ++s) total += min(max(counts[2 * s + 1], 0), B);
+  const float inv = 1.0f / (float)total;
+  float bce = 0.f, l1 = 0.f;
+  for (int idx = threadIdx.x; idx < S * B; idx += blockDim.x) {
+    const int s = idx / B, r = idx - s * B;
+    if (r >= counts[2 * s + 1]) continue;
+    const int a = (int)sel[idx];
+    const size_t row = (size_t)s * A + a;
+    const int lab = labels[row];
+    const float x = logits[row];
+    const float t = lab == 1 ? 1.f : 0.f;
+    bce += fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+    dlogits[row] = (1.0f / (1.0f + expf(-x)) - t) * inv;
+    if (lab == 1) {
+      long long m = matches[row];
+      if (m < 0) m = 0;
+      const float4 tg = encode_ref_order(gt_cat[gt_off[src_img[s]] + m], anchors[a], 1.f, 1.f, 1.f, 1.f);
+      const float4 d4 = deltas[row];
+      const float dv[4] = {d4.x - tg.x, d4.y - tg.y, d4.z - tg.z, d4.w - tg.w};
+      float gv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float d = dv[c], ad = fabsf(d);
+        if (ad < beta) {
+          l1 += 0.5f * ad * ad / beta;
+          gv[c] = d / beta * inv;
+        } else {
+          l1 += ad - 0.5f * beta;
+          gv[c] = (d > 0.f ? 1.f : -1.f) * inv;
+        }
+      }
+      ddeltas[row] = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    }
+  }
+  bce = dd::block_sum(bce, red);
+  l1 = dd::block_sum(l1, red);
+  if (threadIdx.x == 0) {
+    losses[0] = bce * inv;
+    losses[1] = l1 * inv;
+  }
+}
+
 }  // namespace
+
+extern "C" int dd_rpn_anchor_labels(const int64_t* matches, const uint8_t* visibility, int N, int32_t* labels,
+                                    void* stream) {
+  DD_CHECK_ARG(N > 0);
+  rpn_anchor_labels_kernel<<<(N + 255) / 256, 256, 0, dd::S(stream)>>>(matches, visibility, N, labels);
+  DD_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dd_rpn_sampled_losses(const float* logits, const float* deltas, const float* anchors, int A, int S, int B,
+                                     const int64_t* sel, const int32_t* counts, const int32_t* labels,
+                                     const int64_t* matches, const float* gt_cat, const int32_t* gt_offsets,
+                                     const int32_t* src_img, float beta, float* losses, float* dlogits, float* ddeltas,
+                                     void* stream) {
+  DD_CHECK_ARG(A > 0 && S > 0 && B > 0 && beta > 0.f);
+  rpn_sampled_losses_kernel<<<1, 256, 0, dd::S(stream)>>>(
+      logits, reinterpret_cast<const float4*>(deltas), reinterpret_cast<const float4*>(anchors), A, S, B, sel, counts,
+      labels, matches, reinterpret_cast<const float4*>(gt_cat), gt_offsets, src_img, beta, losses, dlogits,
+      reinterpret_cast<float4*>(ddeltas));
+  DD_LAUNCHED();
+  return 0;
+}
 
 extern "C" int dd_match(const float* gt, int M, const int32_t* m_dev, const float* pred, int N, float high, float low,
                         int allow_low_quality, int64_t* matches, float* matched_vals, float* gt_best, void* stream) {
@@ -160,7 +261,7 @@ extern "C" int dd_match(const float* gt, int M, const int32_t* m_dev, const floa
   DD_CUDA(cudaMallocAsync(&argmax, sizeof(int32_t) * (size_t)N, s));
   if (allow_low_quality) DD_CUDA(cudaMemsetAsync(gt_best, 0, sizeof(float) * M, s));
   const int blocks = (N + 255) / 256;
-  match_pass1<<<blocks, 256, M * 20, s>>>(reinterpret_cast<const float4*>(gt), M, m_dev,
+  match_pass1<<<blocks, 256, M * 24, s>>>(reinterpret_cast<const float4*>(gt), M, m_dev,
                                           reinterpret_cast<const float4*>(pred), N, high, low, matches, argmax,
                                           matched_vals, allow_low_quality ? gt_best : nullptr);
   DD_LAUNCHED();

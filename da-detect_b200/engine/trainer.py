@@ -159,6 +159,7 @@ class FlatSGDTrainer(object):
         self.graph_stream = None
         self.graph_pool = None           # one memory pool shared by all step graphs (their replays never overlap)
         self.max_step_graphs = 16        # signatures kept; the least recently used graph is dropped beyond that
+        self.early_backward = False
 
     def enable_step_graph(self, flag=True):
         """Capture zero_grad + forward + backward + all-reduce + SGD of one iteration into ONE CUDA graph per
@@ -170,6 +171,14 @@ class FlatSGDTrainer(object):
         if flag:
             self.model.enable_static_shapes(True)
             self.model.enable_cuda_graphs(False)
+            self.enable_early_backward(os.environ.get("DD_EARLY_BACKWARD", "1") != "0")
+
+    def enable_early_backward(self, flag=True):
+        """Back-propagate the RPN losses during the forward pass, beside the latency-bound proposal chain
+        (modeling/rpn.py::_forward_static_early).  The gradients are then zeroed BEFORE the forward pass; the loss
+        weights are 1 (`losses = sum(loss_dict.values())`, engine/trainer.py:228-231)."""
+        self.early_backward = bool(flag)
+        self.model.early_backward = self.early_backward
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -327,9 +336,12 @@ class FlatSGDTrainer(object):
 
     def _eager_step(self, images, targets, dev_lr=False):
         self.begin_backward()                 # (the milestone hooks are registered during the forward pass)
+        if self.early_backward:
+            self.zero_grad()
         loss_dict = self.model(images, targets)
         losses = sum(loss_dict.values())
-        self.zero_grad()
+        if not self.early_backward:
+            self.zero_grad()
         losses.backward()
         self.all_reduce()
         if dev_lr:
@@ -346,10 +358,13 @@ class FlatSGDTrainer(object):
                 return out
         with section("forward"):
             self.begin_backward()
+            if self.early_backward:
+                self.zero_grad()
             loss_dict = self.model(images, targets)
             losses = sum(loss_dict.values())
         with section("backward"):
-            self.zero_grad()
+            if not self.early_backward:
+                self.zero_grad()
             losses.backward()
         with section("allreduce+sgd"):
             self.all_reduce()

@@ -9,6 +9,8 @@ the sigmoid of the consistency branch is folded into the loss kernel; the AdvGRL
 consumed on the device (no `.numpy()` / `.cpu()` sync); the AdvGRL "probe" pass of the image
 head is not recomputed because it has the same forward values as the GRL pass.
 """
+import contextlib
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -114,9 +116,40 @@ class _Base(nn.Module):
 class DomainAdaptationModule(_Base):
     """The original DA module (da_heads.py:354-440 + DALossComputation loss.py:28-104)."""
 
-    def forward(self, img_features, pooled_ins, dom, n_src, targets, row_valid=None, seg=None):
+    def early_image_loss(self, feat, targets, seg=None, after=None):
+        """The image-level domain loss with its backward pass run EARLY (see rpn.py::_forward_static_early): it depends
+        on the trunk features only, so its forward AND backward run on their own stream right after the trunk, beside
+        the latency-bound RPN loss / proposal chains.  Returns None when the term is off, else the pending
+        (stream, feat, cut, weighted loss) for forward(..., early_img=...).  after: a CUDA event the pass waits for (the
+        end of the RPN head, so that its dense kernels fill the time of the RPN loss chain instead of delaying the head).
+        Same preconditions as the RPN's early pass: gradients zeroed before the forward pass, unit loss weights."""
+        if not (self.training and self.img_weight > 0):
+            return None
+        D = self.cfg.MODEL.DA_HEADS
+        side = None
+        ctx = contextlib.nullcontext()
+        if feat.is_cuda:
+            if self.__dict__.get("_early_stream") is None:
+                self.__dict__["_early_stream"] = torch.cuda.Stream(device=feat.device)
+            side = self.__dict__["_early_stream"]
+            side.wait_stream(torch.cuda.current_stream())
+            if after is not None:
+                side.wait_event(after)
+            ctx = torch.cuda.stream(side)
+        # its dense kernels leave room for what runs beside them: the proposal chain's one-CTA-per-image kernels and
+        # the 8-CTA cluster of the RPN sampler
+        budget = ops.sm_budget(ops.NUM_SMS - 2 * feat.shape[0] - 8) if feat.is_cuda else contextlib.nullcontext()
+        with ctx, budget:
+            cut = feat.detach().requires_grad_(True)
+            da_img = self.imghead(ops.gradient_scalar(cut, -1.0 * D.DA_IMG_GRL_WEIGHT))
+            loss = self.img_weight * da_img_loss(da_img, targets, seg)
+            torch.autograd.backward([loss])
+            loss = loss.detach()
+        return side, feat, cut, loss
+
+    def forward(self, img_features, pooled_ins, dom, n_src, targets, row_valid=None, seg=None, early_img=None):
         """row_valid / seg: fixed-capacity ROI slots that exist, and the cached per-image domain labels (both
-        optional; supplied by the sync-free training path)."""
+        optional; supplied by the sync-free training path).  early_img: the pending result of early_image_loss()."""
         if not self.training:
             return {}
         D = self.cfg.MODEL.DA_HEADS
@@ -126,7 +159,7 @@ class DomainAdaptationModule(_Base):
         # passes are skipped here.  The instance head's dropout draws are still consumed (RNG-stream parity).
         need_img, need_ins, need_cst = self.img_weight > 0, self.ins_weight > 0, self.cst_weight > 0
         l_img = l_ins = l_cst = None
-        if need_img:
+        if need_img and early_img is None:
             da_img = self.imghead(ops.gradient_scalar(feat, -1.0 * D.DA_IMG_GRL_WEIGHT))
             l_img = da_img_loss(da_img, targets, seg)
         if need_ins:
@@ -142,7 +175,13 @@ class DomainAdaptationModule(_Base):
             self.inshead.skip_draws(pooled_ins, row_valid)
         losses = {}
         if self.img_weight > 0:
-            losses["loss_da_image"] = self.img_weight * l_img
+            if early_img is not None:            # join the early pass: stream, then the autograd graph of `feat`
+                side, feat0, cut, loss = early_img
+                if side is not None:
+                    torch.cuda.current_stream().wait_stream(side)
+                losses["loss_da_image"] = ops.inject_grad(loss, feat0, cut)
+            else:
+                losses["loss_da_image"] = self.img_weight * l_img
         if self.ins_weight > 0:
             losses["loss_da_instance"] = self.ins_weight * l_ins
         if self.cst_weight > 0:

@@ -95,6 +95,10 @@ class GeneralizedRCNN(nn.Module):
             raise NotImplementedError("the auxiliary-domain triplet module on an FPN backbone: the reference has no "
                                       "FPN variant of DomainAdaptationModule_triplet; set MODEL.DA_HEADS.TRIPLET_USE False")
         self.static_shapes = not self.fpn
+        # run the backward pass of the RPN losses during the forward pass, beside the proposal chain (rpn.py); the
+        # caller must zero the gradients BEFORE the forward pass and sum the losses with unit weights: set by
+        # FlatSGDTrainer, off under any other driver
+        self.early_backward = False
         self.__dict__["_meta_cache"] = {}
 
     def enable_static_shapes(self, flag=True):
@@ -115,6 +119,7 @@ class GeneralizedRCNN(nn.Module):
             meta = dict(gt_offsets=torch.tensor(offs, dtype=torch.int32, device=dev),
                         append_gt=torch.tensor([1 if s else 0 for _, s in key], dtype=torch.uint8, device=dev),
                         seg=torch.tensor([1 if s else 0 for _, s in key], dtype=torch.uint8, device=dev),
+                        src_index=torch.tensor([i for i, (_, s) in enumerate(key) if s], dtype=torch.int32, device=dev),
                         max_gt=max([n for n, s in key if s] + [0]))
             self._meta_cache[key] = meta
         meta = dict(meta)
@@ -124,10 +129,24 @@ class GeneralizedRCNN(nn.Module):
             meta["gt_counts"] = torch.cat(counts)
         return meta
 
-    def _forward_static(self, images, targets, feat, logits, deltas):
+    def _forward_static(self, images, targets, feat, head_out):
+        """head_out: the RPN head's (logits, deltas), or None in early-backward mode (rpn.py::_forward_static_early)."""
         meta = self._batch_meta(targets)
         features = [feat]
-        props, proposal_losses = self.rpn.forward_static(images, features, targets, (logits, deltas), meta)
+        early = head_out is None
+        early_img, after_head = [None], None
+        if early and self.da_heads and not self.da_heads_triplet:
+            def after_head(ready):
+                early_img[0] = self.da_heads.early_image_loss(feat, targets, meta["seg"], after=ready)
+        props, proposal_losses, pending = self.rpn.forward_static(images, features, targets, head_out, meta,
+                                                                  early_backward=early, after_head=after_head)
+        losses = self._forward_static_heads(features, targets, props, proposal_losses, meta, early_img[0])
+        if pending is not None:
+            self.rpn.finish_early_backward(losses, pending)
+        return losses
+
+    def _forward_static_heads(self, features, targets, props, proposal_losses, meta, early_img=None):
+        feat = features[0]
         losses = {}
         box = self.roi_heads.box
         B = box.loss_evaluator.batch
@@ -154,7 +173,8 @@ class GeneralizedRCNN(nn.Module):
         losses.update(detector_losses)
         losses.update(proposal_losses)
         if self.da_heads:
-            losses.update(self.da_heads(features, pooled, dom, B, targets, row_valid=row_valid, seg=meta["seg"]))
+            losses.update(self.da_heads(features, pooled, dom, B, targets, row_valid=row_valid, seg=meta["seg"],
+                                        early_img=early_img))
         return losses
 
     def enable_cuda_graphs(self, flag=True):
@@ -183,11 +203,14 @@ class GeneralizedRCNN(nn.Module):
             features = self.backbone(x)
             proposals, proposal_losses = self.rpn(images, features, targets)
         else:
+            static = self.training and self.static_shapes and bool(self.roi_heads)
             with section("trunk_fwd"):
                 x = ops._chk(images.tensors, name="images")        # NCHW; the stem consumes it directly
+                if static and self.early_backward and torch.is_grad_enabled() and not self.segments.enabled:
+                    return self._forward_static(images, targets, self.backbone(x)[0], None)
                 feat, logits, deltas = self.segments.run("trunk", lambda: _Trunk(self.backbone, self.rpn.head), (x,))
-            if self.training and self.static_shapes and self.roi_heads:
-                return self._forward_static(images, targets, feat, logits, deltas)
+            if static:
+                return self._forward_static(images, targets, feat, (logits, deltas))
             features = [feat]
             with section("rpn_proposals_and_loss"):
                 proposals, proposal_losses = self.rpn(images, features, targets, head_out=(logits, deltas))

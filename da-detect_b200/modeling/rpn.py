@@ -262,58 +262,60 @@ class RPNModule(nn.Module):
                                                    gt_counts=meta.get("gt_counts")),
                              sizes=[(int(w), int(h)) for h, w in image_sizes])
 
-    def losses_static(self, anchors, visibility, logits, deltas, targets):
-        """RPNLossComputation (rpn/loss.py:57-143) with the sampler on the device.  Per source image the 256
-        sampled anchors sit in a fixed [256] index vector with a device-side count; rows beyond the count are
-        neutralised (logit +100 against target 1 has exactly zero BCE and zero gradient in fp32)."""
+    def losses_static(self, anchors, visibility, logits, deltas, targets, meta):
+        """RPNLossComputation (rpn/loss.py:57-143) without host reads, as five launches per source image plus two for
+        the batch: Matcher (2), labels, random keys, then ONE sampler launch for all source images (per image the 256
+        sampled anchors sit in a fixed index vector with a device-side count) and ONE fused loss kernel (BCE +
+        smooth-L1 + both gradients)."""
         R = self.cfg.MODEL.RPN
         B = R.BATCH_SIZE_PER_IMAGE
         max_pos = int(B * R.POSITIVE_FRACTION)
         A = anchors.shape[0]
-        obj = logits.reshape(-1)                             # (n, h, w, a) order == permute_and_flatten
-        reg = deltas.reshape(-1, 4)
-        ar = torch.arange(B, device=obj.device)
-        bce_sum = l1_sum = total = None
-        dbg = dict(labels=[], pos=[], neg=[]) if self.keep_debug else None
-        ordinal = 0
-        for i, t in enumerate(targets):                     # labels exist for source images only (:66-67)
-            if not is_source_image(t):
-                continue
-            vis = (visibility[i] if isinstance(visibility, (list, tuple)) else visibility).bool()
+        src = [i for i, t in enumerate(targets) if is_source_image(t)]      # labels exist for source images only (:66-67)
+        if src != list(range(len(src))):
+            raise AssertionError("source images must come first in a batch (rpn/loss.py indexes the objectness of the "
+                                 "first len(labels) images)")
+        labs, ms, keys = [], [], []
+        for i in src:
+            t = targets[i]
+            vis = visibility[i] if isinstance(visibility, (list, tuple)) else visibility
             gt = t.convert("xyxy").bbox
             m_dev = getattr(t, "_gt_count_dev", None)        # GT padded to a capacity (signature-free step graph)
             m, _ = ops.match(gt, anchors, R.FG_IOU_THRESHOLD, R.BG_IOU_THRESHOLD, True, m_dev=m_dev)
-            lab = (m >= 0).to(torch.int32)
-            lab = torch.where((m == BETWEEN_THRESHOLDS) | ~vis, torch.full_like(lab, -1), lab)
-            sel, cnt = ops.balanced_sample(lab.view(1, -1), None, self.rng.sample_keys(lab).view(1, -1), B, max_pos)
-            sel, n_tot = sel[0], cnt[0, 1]
-            valid = ar < n_tot
-            lab_s = lab[sel]
-            rows = sel + ordinal * A
-            x = torch.where(valid, obj[rows], torch.full_like(obj[:1], 100.0))
-            tgt = torch.where(valid, lab_s.to(torch.float32), torch.ones_like(x))
-            bce_i = ops.bce_with_logits_mean(x, tgt) * float(B)
-            posm = (valid & (lab_s == 1)).to(torch.float32).unsqueeze(1)
-            tg = ops.box_encode(gt, anchors[sel], m[sel], (1.0, 1.0, 1.0, 1.0), m_dev=m_dev)
-            l1_i = ops.smooth_l1_sum(reg[rows] * posm, tg * posm, 1.0 / 9, 1.0)
-            bce_sum = bce_i if bce_sum is None else bce_sum + bce_i
-            l1_sum = l1_i if l1_sum is None else l1_sum + l1_i
-            total = n_tot if total is None else total + n_tot
-            if dbg is not None:
-                dbg["labels"].append(lab.to(torch.float32))
-                dbg["pos"].append(rows[valid & (lab_s == 1)])
-                dbg["neg"].append(rows[valid & (lab_s == 0)])
-            ordinal += 1
-        inv = 1.0 / total.to(torch.float32)
-        if dbg is not None:
-            self.last = dict(labels=torch.cat(dbg["labels"]), pos=torch.cat(dbg["pos"]), neg=torch.cat(dbg["neg"]))
-        return bce_sum * inv, l1_sum * inv
+            lab = ops.rpn_anchor_labels(m, vis)
+            labs.append(lab)
+            ms.append(m)
+            keys.append(self.rng.sample_keys(lab))
+        one = len(src) == 1
+        lab = labs[0].view(1, -1) if one else torch.stack(labs)
+        m = ms[0].view(1, -1) if one else torch.stack(ms)
+        key = keys[0].view(1, -1) if one else torch.stack(keys)
+        sel, cnt = ops.balanced_sample(lab, None, key, B, max_pos)
+        src_img = meta.get("src_index")
+        if src_img is None:
+            src_img = torch.tensor(src, dtype=torch.int32, device=anchors.device)
+        obj_loss, box_loss = ops.rpn_sampled_losses(logits, deltas, anchors, sel, cnt, lab, m, meta["gt_cat"],
+                                                    meta["gt_offsets"], src_img, 1.0 / 9)
+        if self.keep_debug:                                  # tests: host reads
+            pos, neg = [], []
+            for s in range(len(src)):
+                sl = sel[s, : int(cnt[s, 1])]
+                ls = lab[s][sl]
+                pos.append(sl[ls == 1] + s * A)
+                neg.append(sl[ls == 0] + s * A)
+            self.last = dict(labels=lab.reshape(-1).to(torch.float32), pos=torch.cat(pos), neg=torch.cat(neg))
+        return obj_loss, box_loss
 
-    def forward_static(self, images, features, targets, head_out, meta):
+    def forward_static(self, images, features, targets, head_out, meta, early_backward=False, after_head=None):
+        """head_out: (logits, deltas) of self.head(features[0]), or None when early_backward is set (the head then runs
+        here, on a detached copy of the features).  Returns (proposals, losses, pending): `pending` is None or the
+        (stream, features, cut) triple finish_early_backward() needs."""
         feat = features[0]
-        logits, deltas = head_out
         n, fh, fw, _ = feat.shape
         anchors, vis = self._anchors_and_visibility(fh, fw, images.image_sizes)
+        if early_backward:
+            return self._forward_static_early(images, feat, targets, meta, anchors, vis, after_head)
+        logits, deltas = head_out
         if self.overlap_loss:
             # The proposal chain (top-k, NMS, gather: one or two CTAs per image, ~1.2 ms) and the RPN loss chain
             # (match, sampler, encode, losses: ~0.45 ms, also a few CTAs) are independent: the loss chain runs on a
@@ -324,15 +326,74 @@ class RPNModule(nn.Module):
                 self._side = torch.cuda.Stream(device=feat.device)
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                obj_loss, box_loss = self.losses_static(anchors, vis, logits, deltas, targets)
+                obj_loss, box_loss = self.losses_static(anchors, vis, logits, deltas, targets, meta)
             props = self.proposals_static(anchors, logits.detach(), deltas.detach(), images.image_sizes, meta)
             main.wait_stream(self._side)
         else:
             props = self.proposals_static(anchors, logits.detach(), deltas.detach(), images.image_sizes, meta)
-            obj_loss, box_loss = self.losses_static(anchors, vis, logits, deltas, targets)
+            obj_loss, box_loss = self.losses_static(anchors, vis, logits, deltas, targets, meta)
         if self.proposal_hook is not None:
             props = self.proposal_hook(props)
-        return props, {"loss_objectness": obj_loss, "loss_rpn_box_reg": box_loss}
+        return props, {"loss_objectness": obj_loss, "loss_rpn_box_reg": box_loss}, None
+
+    def _forward_static_early(self, images, feat, targets, meta, anchors, vis, after_head=None):
+        """The RPN branch with its backward pass run EARLY.  The proposal chain and the box-head sampler that follows it
+        are latency-bound (one CTA per image: ~1.4 ms during which the GPU is otherwise idle), and nothing dense in the
+        forward pass can fill that time — everything after depends on the proposals.  The RPN losses, however, depend
+        on the trunk features only, so their whole backward (the 3x3 conv's data and weight gradients: the largest
+        GEMMs of the step) can run right there: the head is evaluated on `cut = feat.detach()`, the losses are
+        back-propagated on the side stream as soon as they exist (weight gradients accumulate into the zeroed flat
+        buffer, d loss / d feat lands in cut.grad), and finish_early_backward() hands cut.grad to the graph of `feat`.
+        The dense kernels of that pass leave two SMs per image to the one-CTA-per-image kernels of the main stream
+        (ops.sm_budget).  Requires gradients zeroed BEFORE the forward pass and unit loss weights (FlatSGDTrainer).
+        after_head(event): called once the head has been launched, with the event that marks its end."""
+        cuda = feat.is_cuda
+        if cuda:
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=feat.device)
+            side = self._side
+            side.wait_stream(main)
+            on_side = lambda: torch.cuda.stream(side)
+        else:
+            import contextlib
+            main = side = None
+            on_side = contextlib.nullcontext
+        with on_side():
+            cut = feat.detach().requires_grad_(True)
+            logits, deltas = self.head(cut)
+            ready = None
+            if cuda:
+                ready = torch.cuda.Event()
+                ready.record(side)
+        if after_head is not None:          # other early passes (DA image head) start when the RPN head has finished
+            after_head(ready)
+        with on_side():
+            obj_loss, box_loss = self.losses_static(anchors, vis, logits, deltas, targets, meta)
+            if cuda:
+                with ops.sm_budget(ops.NUM_SMS - 2 * feat.shape[0]):
+                    torch.autograd.backward([obj_loss + box_loss])
+            else:
+                torch.autograd.backward([obj_loss + box_loss])
+            obj_loss, box_loss = obj_loss.detach(), box_loss.detach()
+        if cuda:
+            main.wait_event(ready)
+            logits.record_stream(main)
+            deltas.record_stream(main)
+        props = self.proposals_static(anchors, logits.detach(), deltas.detach(), images.image_sizes, meta)
+        if self.proposal_hook is not None:
+            props = self.proposal_hook(props)
+        return props, {"loss_objectness": obj_loss, "loss_rpn_box_reg": box_loss}, (side, feat, cut)
+
+    @staticmethod
+    def finish_early_backward(losses, pending):
+        """Join the early backward pass (stream and autograd graph): after this, back-propagating through
+        losses["loss_objectness"] with a gradient of 1 adds d(RPN losses)/d feat to the gradient of the features."""
+        side, feat, cut = pending
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        losses["loss_objectness"] = ops.inject_grad(losses["loss_objectness"], feat, cut)
+        return losses
 
     # ---- FPN: per-level post-processing + select_over_all_levels (rpn/inference.py:126-181) ----------
     @torch.no_grad()

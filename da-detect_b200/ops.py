@@ -24,6 +24,7 @@ IMPL_TCGEN05_MIXED = 3       # host-level policy: forward products 3xTF32 (fp32-
                              # data- and weight-gradient products plain TF32 (what cuDNN computes by default)
 _default_impl = IMPL_SIMT
 TC_IMPLS = (IMPL_TCGEN05, IMPL_TCGEN05_X3, IMPL_TCGEN05_MIXED)
+NUM_SMS = 148                # B200
 
 
 def fwd_impl(impl=None):
@@ -86,6 +87,44 @@ def grad_milestone(x, tag):
     if _milestone_cb is not None and torch.is_tensor(x) and x.requires_grad:
         x.register_hook(lambda g, t=tag: (_milestone_cb(t), None)[1])
     return x
+
+
+class sm_budget(object):
+    """Context manager: the persistent dense kernels launched inside occupy at most `sms` SMs (baked into the launches
+    of a stream capture).  For dense work that runs beside few-CTA latency-bound kernels on another stream."""
+
+    def __init__(self, sms):
+        self.sms = int(sms)
+
+    def __enter__(self):
+        self.prev = _lib.load().dd_set_sm_budget(self.sms)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().dd_set_sm_budget(self.prev)
+        return False
+
+
+class _InjectGrad(torch.autograd.Function):
+    """value(loss) with the gradient of `holder` handed to `x` in backward: the join of an early backward pass.
+    A loss that depends on `x` only through `cut = x.detach().requires_grad_()` has been back-propagated already
+    (cut.grad is complete); this node re-attaches that gradient to the graph of x.  Exact for an incoming gradient
+    of 1 (losses summed with unit weights, as the reference loop does: engine/trainer.py:228-231)."""
+
+    @staticmethod
+    def forward(ctx, loss, x, holder):
+        ctx.holder = holder
+        return loss.detach().clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        gx = ctx.holder.grad
+        ctx.holder = None
+        return None, gx, None
+
+
+def inject_grad(loss, x, holder):
+    return _InjectGrad.apply(loss, x, holder)
 
 
 def tcgen05_available():
@@ -926,6 +965,49 @@ def box_encode(gt, pred, matches, weights, wrap_negative=False, m_dev=None):
               _ptr(_chk(matches, torch.int64, "matches")), p.shape[0],
               wx, wy, ww, wh, 1 if wrap_negative else 0, _ptr(out), _stream())
     return out
+
+
+def rpn_anchor_labels(matches, visibility):
+    """int32 [N] RPN labels (1 / 0 / -1 = ignored) from the Matcher result and the uint8 visibility mask."""
+    m = _chk(matches, torch.int64, "matches")
+    out = torch.empty(m.shape, dtype=torch.int32, device=m.device)
+    _lib.call("dd_rpn_anchor_labels", _ptr(m), _ptr(_chk(visibility, torch.uint8, "visibility")), m.numel(), _ptr(out),
+              _stream())
+    return out
+
+
+class _RpnSampledLosses(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, deltas, anchors, sel, counts, labels, matches, gt_cat, gt_offsets, src_img, beta):
+        lg = _chk(logits, name="logits")
+        dl = _chk(deltas, name="deltas")
+        s, b = sel.shape
+        a = anchors.shape[0]
+        losses = torch.empty(2, dtype=torch.float32, device=lg.device)
+        g_lg, g_dl = torch.zeros_like(lg), torch.zeros_like(dl)
+        _lib.call("dd_rpn_sampled_losses", _ptr(lg), _ptr(dl), _ptr(_chk(anchors, name="anchors")), a, s, b,
+                  _ptr(_chk(sel, torch.int64, "sel")), _ptr(_chk(counts, torch.int32, "counts")),
+                  _ptr(_chk(labels, torch.int32, "labels")), _ptr(_chk(matches, torch.int64, "matches")),
+                  _ptr(_chk(gt_cat, name="gt")), _ptr(_chk(gt_offsets, torch.int32, "gt_offsets")),
+                  _ptr(_chk(src_img, torch.int32, "src_img")), float(beta), _ptr(losses), _ptr(g_lg), _ptr(g_dl),
+                  _stream())
+        ctx.save_for_backward(g_lg, g_dl)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_obj, g_box):
+        g_lg, g_dl = ctx.saved_tensors
+        return (g_lg * g_obj if ctx.needs_input_grad[0] else None, g_dl * g_box if ctx.needs_input_grad[1] else None,
+                None, None, None, None, None, None, None, None, None)
+
+
+def rpn_sampled_losses(logits, deltas, anchors, sel, counts, labels, matches, gt_cat, gt_offsets, src_img, beta):
+    """(objectness loss, box regression loss) of RPNLossComputation (rpn/loss.py:118-141) over the anchors sampled by
+    balanced_sample for the S source images, forward + gradient in one launch.  logits [n, h, w, a] / deltas
+    [n, h, w, 4a] (source images first); sel int64 [S, B]; counts int32 [S, 2]; labels int32 / matches int64 [S, A];
+    gt_cat [G, 4] with gt_offsets int32 [n + 1]; src_img int32 [S]."""
+    return _RpnSampledLosses.apply(logits, deltas, anchors, sel, counts, labels, matches, gt_cat, gt_offsets, src_img,
+                                   beta)
 
 
 def box_decode(codes, boxes, weights):

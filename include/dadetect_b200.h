@@ -30,6 +30,11 @@ const char* dd_last_error(void);
 int dd_abi_version(void);
 /* number of kernels launched by this library since process start (bench.py's gpu_launches) */
 long long dd_launch_count(void);
+/* Limits the persistent dense kernels (conv / dgrad / wgrad on tcgen05) launched from now on to `sms` CTAs (0 or
+ * >= 148: all SMs); returns the previous limit.  Host-side state read at launch time, so inside a stream capture
+ * it is baked into the captured launches.  Used while few-CTA latency-bound kernels (top-k, NMS scan, samplers)
+ * run beside dense work on another stream. */
+int dd_set_sm_budget(int sms);
 /* 1 when the tcgen05/TMA arm of the dense tier is compiled into this library, else 0 */
 int dd_tcgen05_built(void);
 
@@ -103,6 +108,19 @@ int dd_rpn_topk_decode(const float* logits, const float* deltas, const float* an
  * data/datasets/coco.py:96-97); rows at and beyond *m_dev do not exist for the Matcher. */
 int dd_match(const float* gt, int M, const int32_t* m_dev, const float* pred, int N, float high, float low,
              int allow_low_quality, int64_t* matches, float* matched_vals, float* gt_best, void* stream);
+/* RPN anchor labels (rpn/loss.py:57-89) from dd_match's result and the anchor visibility mask (uint8 [N]):
+ * 1 matched, 0 background, -1 ignored (between the thresholds, or straddling the image border). */
+int dd_rpn_anchor_labels(const int64_t* matches, const uint8_t* visibility, int N, int32_t* labels, void* stream);
+/* RPNLossComputation's loss tail (rpn/loss.py:118-141) over the anchors sampled by dd_balanced_sample for the S source
+ * images of a batch, forward and gradient in one launch: losses[0] = BCE-with-logits / #sampled, losses[1] =
+ * smooth-L1(beta) over the sampled positives against BoxCoder(1,1,1,1) targets / #sampled.  logits [n_img*A],
+ * deltas [n_img*A,4] (rows s*A + a belong to source image s), anchors [A,4], sel int64 [S,B], counts int32 [S,2],
+ * labels int32 [S,A], matches int64 [S,A], gt_cat [G,4] with gt_offsets int32 [n_img+1], src_img int32 [S] (batch
+ * index of each source image).  dlogits / ddeltas: dense gradients, zero-filled by the caller. */
+int dd_rpn_sampled_losses(const float* logits, const float* deltas, const float* anchors, int A, int S, int B,
+                          const int64_t* sel, const int32_t* counts, const int32_t* labels, const int64_t* matches,
+                          const float* gt_cat, const int32_t* gt_offsets, const int32_t* src_img, float beta,
+                          float* losses, float* dlogits, float* ddeltas, void* stream);
 /* BoxCoder.encode (box_coder.py:22-50) of gt[matches[i] clamped at 0] against pred[i];
  * wrap_negative != 0 reproduces the reference's negative-index wrap for target images
  * (box_head/loss.py:47-51) — relative to the live row count (*m_dev when given, else M). */

@@ -218,7 +218,33 @@ def consistency_loss_masked(img_logits, ins_logits, n_src, row_valid=None):
     return (torch.abs(per_roi - ins_logits.sigmoid().reshape(-1)) * v).sum() / v.sum()
 
 
+def rpn_anchor_labels(matches, visibility):
+    lab = (matches >= 0).to(torch.int32)
+    lab[(matches == -2) | ~visibility.bool()] = -1
+    return lab
+
+
+def rpn_sampled_losses(logits, deltas, anchors, sel, counts, labels, matches, gt_cat, gt_offsets, src_img, beta):
+    """torch restatement of rpn/loss.py:118-141 on the sampled anchors (autograd provides the gradients)."""
+    S, B = sel.shape
+    A = anchors.shape[0]
+    obj, reg = logits.reshape(-1), deltas.reshape(-1, 4)
+    total = int(counts[:, 1].sum())
+    bce = l1 = 0.0
+    for s in range(S):
+        sl = sel[s, : int(counts[s, 1])]
+        lab = labels[s][sl]
+        rows = sl + s * A
+        bce = bce + F.binary_cross_entropy_with_logits(obj[rows], (lab == 1).float(), reduction="sum")
+        p = sl[lab == 1]
+        g0 = int(gt_offsets[int(src_img[s])])
+        tg = orc.box_encode(gt_cat[g0 + matches[s][p]], anchors[p], (1.0, 1.0, 1.0, 1.0))
+        l1 = l1 + orc.smooth_l1(reg[p + s * A], tg, beta, size_average=False)
+    return bce / total, l1 / total
+
+
 TRAINING_STAND_INS = dict(
+    rpn_anchor_labels=rpn_anchor_labels, rpn_sampled_losses=rpn_sampled_losses,
     proposals_gather=proposals_gather, balanced_sample=balanced_sample,
     gradient_scalar=lambda x, w: _Grl.apply(x, w), gradient_scalar_dev=lambda x, wdev: _Grl.apply(x, wdev),
     dropout_with_mask=lambda x, keep: x * keep * 2.0, match=match, box_encode=box_encode,

@@ -251,6 +251,40 @@ def test_whole_step_graph_matches_eager_training(name):
 
 
 @pytest.mark.timeout(900)
+@pytest.mark.parametrize("name,dense", [("da_img_ins_cst", "simt"), ("da_img_ins_cst", "mixed"),
+                                        ("triplet_aligned_advgrl", "mixed")])
+def test_early_backward_gives_the_same_gradients(name, dense):
+    """FlatSGDTrainer.enable_early_backward: the RPN losses are back-propagated during the forward pass, on the side
+    stream beside the proposal chain (rpn.py::_forward_static_early).  Same loss dict and the same flat gradient as
+    the plain order (only the order of the adds into the trunk-feature gradient differs)."""
+    from dadetect_b200 import ops
+    from dadetect_b200.engine import FlatSGDTrainer
+    from dadetect_b200.utils.random_source import HashSource
+    cfg, sd, images, targets, hw = scenario(name)
+    dev = torch.device("cuda")
+    ops.set_default_impl(impl_of(dense))
+    try:
+        out = []
+        for early in (False, True):
+            model = build(cfg, sd, dev)
+            model.enable_static_shapes(True)
+            model.set_random_source(HashSource())
+            trainer = FlatSGDTrainer(model, cfg, world_size=1)
+            trainer.enable_early_backward(early)
+            ld = trainer.step(images.to(dev), to_boxlists(targets, hw, dev))
+            torch.cuda.synchronize()
+            out.append(({k: float(v) for k, v in ld.items()}, trainer.flat_grad.clone()))
+        (l0, g0), (l1, g1) = out
+        assert list(l0.keys()) == list(l1.keys())
+        for k in l0:
+            assert abs(l0[k] - l1[k]) <= 1e-6 * max(1.0, abs(l0[k])), (k, l0[k], l1[k])
+        rel = float((g0 - g1).norm() / g0.norm())
+        assert rel < 1e-4, rel      # other split-K partitions under the SM budget, other order of the adds (1.2e-5 seen)
+    finally:
+        ops.set_default_impl(ops.IMPL_SIMT)
+
+
+@pytest.mark.timeout(900)
 @pytest.mark.parametrize("dense", ["simt", "tcgen05x3"])
 def test_eval_mode_matches_real_reference_golden(dense):
     """BASELINE configs[0]: plain R-50-C4 Faster R-CNN (81 classes, DA off), eval mode, 2 synthetic 800x800 images.

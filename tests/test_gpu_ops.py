@@ -127,7 +127,12 @@ def test_nms_batched_ragged_counts_match_single_image():
 
 @pytest.mark.parametrize("n_cap,n,batch,max_pos,p_pos,p_neg,int_keys", [
     (5000, 4321, 256, 64, 0.1, 0.6, False), (122880, 122880, 256, 128, 0.0005, 0.9, False),
-    (600, 600, 256, 128, 0.02, 0.1, False), (300, 150, 256, 64, 0.3, 0.3, True), (64, 64, 16, 4, 0.0, 0.5, True), (301, 301, 64, 16, 0.2, 0.5, True)])
+    (600, 600, 256, 128, 0.02, 0.1, False), (300, 150, 256, 64, 0.3, 0.3, True), (64, 64, 16, 4, 0.0, 0.5, True), (301, 301, 64, 16, 0.2, 0.5, True),
+    # the cluster kernel (n_cap > 8192): massive ties across its eight slices, ragged device-side counts, the largest
+    # supported set, fewer candidates than wanted
+    (122880, 100001, 256, 128, 0.002, 0.5, True), (20000, 20000, 512, 128, 0.5, 0.4, True),
+    (9001, 8999, 256, 128, 0.0, 0.9, False), (131072, 131072, 256, 128, 0.3, 0.3, True),
+    (16384, 9, 256, 128, 0.5, 0.5, True), (40000, 40000, 256, 128, 0.0001, 0.0005, False)])
 def test_balanced_sample_matches_reference_semantics(n_cap, n, batch, max_pos, p_pos, p_neg, int_keys):
     """Device sampler == BalancedPositiveNegativeSampler with `keys` standing for the random permutation:
     min(#pos, max_pos) positives and min(#neg, batch - num_pos) negatives with the smallest keys (ties -> lower
@@ -149,6 +154,73 @@ def test_balanced_sample_matches_reference_semantics(n_cap, n, batch, max_pos, p
         assert cnt[i].tolist() == [num_pos, num_pos + num_neg]
         assert torch.equal(sel[i, : want.numel()], want)
         assert int(sel[i, want.numel():].abs().sum()) == 0
+
+
+def test_balanced_sample_replayed_permutation_at_rpn_size():
+    """Keys = rank in a recorded permutation (how the parity tests replay the oracle's draws), non-candidates 3e7:
+    the cluster kernel picks exactly positive[perm[:k]] / negative[perm[:k]] (balanced_positive_negative_sampler.py:57-63)."""
+    g = torch.Generator().manual_seed(5)
+    n = 122880
+    u = torch.rand(n, generator=g)
+    labels = torch.where(u < 0.003, 1, torch.where(u < 0.7, 0, -1)).to(torch.int32)
+    keys = torch.full((n,), 3.0e7)
+    want = []
+    for cond, k in ((labels >= 1, 128), (labels == 0, None)):
+        idx = torch.nonzero(cond).squeeze(1)
+        perm = torch.randperm(idx.numel(), generator=g)
+        keys[idx[perm]] = torch.arange(idx.numel(), dtype=torch.float32)
+        k = min(idx.numel(), 128) if k else 256 - min(int((labels >= 1).sum()), 128)
+        want.append(idx[perm[:k]])
+    want = torch.sort(torch.cat(want))[0]
+    sel, cnt = ops().balanced_sample(labels.view(1, -1).to(DEV), None, keys.view(1, -1).to(DEV), 256, 128)
+    assert int(cnt[0, 1]) == want.numel() == 256
+    assert torch.equal(sel[0].cpu(), want)
+
+
+def test_rpn_labels_and_fused_sampled_losses():
+    """dd_rpn_anchor_labels + dd_rpn_sampled_losses (the RPN loss tail: BCE + smooth-L1 + both gradients in one launch)
+    against the torch restatement of rpn/loss.py:118-141 used by the CPU suite; two source images + one target image,
+    padded GT capacity."""
+    import cpu_ops_emulation as emu
+    g = torch.Generator().manual_seed(21)
+    A, S, n_img, B, cap = 3000, 2, 3, 256, 16
+    xy = torch.rand(A, 2, generator=g) * 300
+    anchors = torch.cat([xy, xy + 20 + torch.rand(A, 2, generator=g) * 80], dim=1)
+    gt_cat = torch.zeros(n_img * cap, 4)
+    gt_off = torch.arange(0, (n_img + 1) * cap, cap, dtype=torch.int32)
+    live = [5, 9, 3]
+    for i in range(n_img):
+        p = torch.rand(live[i], 2, generator=g) * 280
+        gt_cat[i * cap: i * cap + live[i]] = torch.cat([p, p + 30 + torch.rand(live[i], 2, generator=g) * 60], dim=1)
+    vis = (torch.rand(A, generator=g) < 0.8).to(torch.uint8)
+    o = ops()
+    labs, ms = [], []
+    for s in range(S):
+        m, _ = o.match(gt_cat[s * cap:(s + 1) * cap].to(DEV), anchors.to(DEV), 0.5, 0.3, True,
+                       m_dev=torch.tensor([live[s]], dtype=torch.int32, device=DEV))
+        lab = o.rpn_anchor_labels(m, vis.to(DEV))
+        assert torch.equal(lab.cpu(), emu.rpn_anchor_labels(m.cpu(), vis))
+        labs.append(lab)
+        ms.append(m)
+    lab, m = torch.stack(labs), torch.stack(ms)
+    assert int((lab == 1).sum()) > 10 and int((lab == -1).sum()) > 10
+    keys = torch.rand(S, A, generator=g).to(DEV)
+    sel, cnt = o.balanced_sample(lab, None, keys, B, 128)
+    logits = torch.randn(n_img, 10, 100, 3, generator=g)
+    deltas = torch.randn(n_img, 10, 100, 12, generator=g) * 0.5
+    src = torch.tensor([0, 1], dtype=torch.int32)
+    a = [logits.clone().requires_grad_(True), deltas.clone().requires_grad_(True)]
+    b = [logits.to(DEV).requires_grad_(True), deltas.to(DEV).requires_grad_(True)]
+    want = emu.rpn_sampled_losses(a[0], a[1], anchors, sel.cpu(), cnt.cpu(), lab.cpu(), m.cpu(), gt_cat, gt_off, src, 1 / 9)
+    got = o.rpn_sampled_losses(b[0], b[1], anchors.to(DEV), sel, cnt, lab, m, gt_cat.to(DEV), gt_off.to(DEV),
+                               src.to(DEV), 1 / 9)
+    for w, g_ in zip(want, got):
+        assert abs(float(w) - float(g_)) <= 1e-5 * max(1.0, abs(float(w))), (float(w), float(g_))
+    (want[0] * 0.7 + want[1] * 1.3).backward()
+    (got[0] * 0.7 + got[1] * 1.3).backward()
+    for x, y in zip(a, b):
+        assert float((x.grad - y.grad.cpu()).abs().max()) <= 1e-6 + 1e-5 * float(x.grad.abs().max())
+        assert float(x.grad.abs().sum()) > 0
 
 
 def test_proposals_gather_appends_gt_and_pads():

@@ -29,12 +29,14 @@ def scenario(name):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("name,static", [("da_img_ins_cst", False), ("da_img_ins_cst", True),
-                                         ("triplet_aligned_advgrl", True)])
-def test_training_orchestration_matches_oracle(name, static, cpu_ops):
+@pytest.mark.parametrize("name,static,early", [("da_img_ins_cst", False, False), ("da_img_ins_cst", True, False),
+                                               ("da_img_ins_cst", True, True),
+                                               ("triplet_aligned_advgrl", True, True)])
+def test_training_orchestration_matches_oracle(name, static, early, cpu_ops):
     """static=False: the reference-like host-driven control flow; static=True: the production sync-free path
     (fixed-capacity proposal / ROI buffers with validity masks, device sampler on replayed keys) — its second
-    stream is switched off here, streams being a CUDA notion."""
+    stream is switched off here, streams being a CUDA notion.  early=True: the RPN losses are back-propagated during
+    the forward pass (what FlatSGDTrainer's step graph runs): same loss dict, same total gradients."""
     from dadetect_b200.modeling import build_detection_model
     from dadetect_b200.structures import BoxList
     from dadetect_b200.utils.random_source import ReplaySource
@@ -51,6 +53,7 @@ def test_training_orchestration_matches_oracle(name, static, cpu_ops):
     assert not missing.unexpected_keys and all("cell_anchors" in k for k in missing.missing_keys)
     model.train()
     model.enable_static_shapes(static)
+    model.early_backward = early
     model.rpn.overlap_loss = False
     replay = ReplaySource(rec.perms, rec.masks)
     model.set_random_source(replay)
