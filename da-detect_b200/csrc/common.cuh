@@ -74,6 +74,31 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return v;
 }
 
+// Exclusive scan over the CTA (<= 1024 threads, all participating) of one int per thread: returns this thread's
+// offset, the CTA total in `total`.  `sm32` must hold >= 32 ints.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* sm32, int& total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();
+  if (lane == 31) sm32[wid] = incl;
+  __syncthreads();
+  int w = lane < (int)(blockDim.x >> 5) ? sm32[lane] : 0;
+  int wincl = w;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, wincl, o);
+    if (lane >= o) wincl += t;
+  }
+  total = __shfl_sync(0xffffffffu, wincl, 31);
+  const int base = __shfl_sync(0xffffffffu, wincl - w, wid);
+  return base + incl - v;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 }  // namespace dd

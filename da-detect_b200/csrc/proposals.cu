@@ -3,7 +3,11 @@
 //
 // Reference semantics: rpn/anchor_generator.py:73-111, rpn/inference.py:87-115, box_coder.py:52-95,
 // structures/bounding_box.py:214-225, structures/boxlist_ops.py:37-51, csrc/cuda/nms.cu:13-131.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -223,6 +227,265 @@ __global__ void __launch_bounds__(kTopkThreads) rpn_topk_decode_kernel(
   if (threadIdx.x == 0) valid[img] = out_base;
 }
 
+// ----------------------------------------------------------------------------- top-k + decode, cluster version
+// The one-CTA kernel above walks the 122 880 logits of an image five times through L2 with the memory parallelism of
+// one SM and ranks its compaction 1024 candidates at a time (0.5 ms, on the critical path of the step).  Here a
+// cluster of 8 CTAs owns one image.  Every CTA loads an interleaved eighth of the logits ONCE into shared memory
+// (4096-logit chunks dealt round-robin, so that a region of high scores is spread over all CTAs); the exact k-th
+// largest COMPOSITE key (ordered logit, then lower index first — no ties, so the selection needs no index-ordered
+// ranking) is found by a radix select whose per-pass histograms are summed over the cluster through distributed
+// shared memory; every CTA sorts its own survivors (bitonic, typically k/8 of them) and finds the global rank of
+// each by binary searches in the seven other sorted lists; decode, clip and the min-size filter follow, the ordered
+// compaction of the filter going through a k-bit map gathered from all CTAs.  Output identical to the kernel above.
+constexpr int kTkCl = 8;
+constexpr int kTkIter = 4;                         // float4 loads per thread: 8 CTAs x 1024 threads x 16 = 131 072 logits
+constexpr int kTkStride = 4 * kTkIter + 1;         // odd stride between the chunks of consecutive threads
+
+struct TopkShared {
+  int hist[7][256];          // one histogram per radix pass (never re-used: one cluster barrier per exchange)
+  int ghist[256];
+  int sm32[32];
+  uint32_t digit;
+  int need;
+  int n_local;
+  uint32_t okbits[512];      // bit r: the candidate of global rank r (held by this CTA) passes the min-size filter
+  uint32_t allbits[512];     // the same for all CTAs
+  int okprefix[512];
+};
+
+__device__ __forceinline__ bool decode_clip_box(const float* __restrict__ deltas, const float* __restrict__ anchors,
+                                                size_t delta_row, int idx, float xmax, float ymax, float min_size,
+                                                float4& b) {
+  const float clip = 4.135166556742356f;   // log(1000/16)
+  const float4 d = dd::ldg4(deltas + delta_row * 4);
+  const float4 a = dd::ldg4(anchors + (size_t)idx * 4);
+  const float w = __fadd_rn(__fsub_rn(a.z, a.x), 1.0f), h = __fadd_rn(__fsub_rn(a.w, a.y), 1.0f);
+  const float cx = __fadd_rn(a.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(a.y, __fmul_rn(0.5f, h));
+  const float dw = fminf(d.z, clip), dh = fminf(d.w, clip);
+  const float pcx = __fadd_rn(__fmul_rn(d.x, w), cx), pcy = __fadd_rn(__fmul_rn(d.y, h), cy);
+  const float pw = __fmul_rn(expf(dw), w), phh = __fmul_rn(expf(dh), h);
+  b.x = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+  b.y = __fsub_rn(pcy, __fmul_rn(0.5f, phh));
+  b.z = __fsub_rn(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), 1.0f);
+  b.w = __fsub_rn(__fadd_rn(pcy, __fmul_rn(0.5f, phh)), 1.0f);
+  b.x = fminf(fmaxf(b.x, 0.f), xmax);
+  b.y = fminf(fmaxf(b.y, 0.f), ymax);
+  b.z = fminf(fmaxf(b.z, 0.f), xmax);
+  b.w = fminf(fmaxf(b.w, 0.f), ymax);
+  const float ws = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f), hs = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
+  return ws >= min_size && hs >= min_size;
+}
+
+__global__ void __launch_bounds__(kTopkThreads) rpn_topk_decode_cluster_kernel(
+    const float* __restrict__ logits, const float* __restrict__ deltas, const float* __restrict__ anchors,
+    int num_anchors, int k, int img_w, int img_h, float min_size, float* __restrict__ boxes,
+    float* __restrict__ scores, int32_t* __restrict__ topk_idx, int32_t* __restrict__ valid) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ TopkShared sh;
+  uint32_t* skey = reinterpret_cast<uint32_t*>(dyn);                               // kTopkThreads * kTkStride
+  int* srank = reinterpret_cast<int*>(dyn);                                        // later: rank of list entry p
+  unsigned long long* slist = reinterpret_cast<unsigned long long*>(dyn + kTopkThreads * kTkStride * 4 + 8);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int img = blockIdx.x / kTkCl;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const float* lg = logits + (size_t)img * num_anchors;
+  const bool vec = (num_anchors & 3) == 0 && (reinterpret_cast<uintptr_t>(lg) & 15) == 0;
+
+  for (int i = tid; i < 7 * 256; i += kTopkThreads) (&sh.hist[0][0])[i] = 0;
+  for (int i = tid; i < 512; i += kTopkThreads) sh.okbits[i] = 0u;
+  // ---- the one pass over the logits: this CTA's chunks -> shared memory (ordered keys)
+#pragma unroll
+  for (int j = 0; j < kTkIter; ++j) {
+    const int i0 = 4 * (tid + kTopkThreads * (rank + kTkCl * j));
+    float v[4];
+    if (vec && i0 < num_anchors) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(lg + i0));
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = i0 + e < num_anchors ? lg[i0 + e] : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) skey[tid * kTkStride + j * 4 + e] = float_to_ordered(v[e]);
+  }
+  __syncthreads();
+
+  // ---- radix select of the k-th largest composite key: 4 passes over the ordered logit, 3 over (2^32 - 1 - index)
+  uint32_t pre_hi = 0u, mask_hi = 0u, pre_lo = 0xFF000000u, mask_lo = 0xFF000000u;
+  int need = k;
+  for (int pass = 0; pass < 7; ++pass) {
+    const bool hi = pass < 4;
+    const int shift = hi ? 24 - 8 * pass : 16 - 8 * (pass - 4);
+#pragma unroll
+    for (int j = 0; j < kTkIter; ++j) {
+      const int i0 = 4 * (tid + kTopkThreads * (rank + kTkCl * j));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t key = skey[tid * kTkStride + j * 4 + e];
+        const uint32_t low = 0xFFFFFFFFu - (uint32_t)(i0 + e);
+        const bool in = i0 + e < num_anchors &&
+                        (hi ? (key & mask_hi) == pre_hi : (key == pre_hi && (low & mask_lo) == pre_lo));
+        // objectness logits share their leading bytes: one shared-memory atomic per distinct bin of the warp
+        if (__any_sync(0xffffffffu, in)) {
+          const uint32_t bin = in ? (((hi ? key : low) >> shift) & 0xFF) : 0xFFFFFFFFu;
+          const unsigned peers = __match_any_sync(0xffffffffu, bin);
+          if (in && lane == __ffs(peers) - 1) atomicAdd(&sh.hist[pass][bin], __popc(peers));
+        }
+      }
+    }
+    cluster.sync();
+    if (tid < 256) {
+      int acc = 0;
+#pragma unroll
+      for (int q = 0; q < kTkCl; ++q) acc += cluster.map_shared_rank(&sh, q)->hist[pass][tid];
+      sh.ghist[tid] = acc;
+    }
+    __syncthreads();
+    if (tid < 32) {           // descending walk: lane l owns bins 255 - 8l .. 248 - 8l
+      int b8[8], mine = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { b8[j] = sh.ghist[255 - (lane * 8 + j)]; mine += b8[j]; }
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, incl >= need);
+      const int src = ballot ? __ffs(ballot) - 1 : 31;
+      int acc = incl - mine, pos = lane * 8;
+      if (lane == src) {
+        for (int j = 0; j < 8 && pos < 255; ++j) {          // the serial rule stops at bin 0 without testing it
+          if (acc + b8[j] >= need) break;
+          acc += b8[j];
+          ++pos;
+        }
+      }
+      pos = __shfl_sync(0xffffffffu, pos, src);
+      acc = __shfl_sync(0xffffffffu, acc, src);
+      if (lane == 0) {
+        sh.digit = (uint32_t)(255 - pos);
+        sh.need = need - acc;
+      }
+    }
+    __syncthreads();
+    if (hi) { pre_hi |= sh.digit << shift; mask_hi |= 0xFFu << shift; }
+    else    { pre_lo |= sh.digit << shift; mask_lo |= 0xFFu << shift; }
+    need = sh.need;
+  }
+  const uint32_t kth_hi = pre_hi, kth_lo = pre_lo;           // composite key of the k-th largest candidate
+
+  // ---- survivors of this CTA -> list, sorted descending
+  int mine = 0;
+#pragma unroll
+  for (int j = 0; j < kTkIter; ++j) {
+    const int i0 = 4 * (tid + kTopkThreads * (rank + kTkCl * j));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t key = skey[tid * kTkStride + j * 4 + e];
+      const uint32_t low = 0xFFFFFFFFu - (uint32_t)(i0 + e);
+      mine += i0 + e < num_anchors && (key > kth_hi || (key == kth_hi && low >= kth_lo));
+    }
+  }
+  int n_local;
+  int slot = dd::block_exclusive_scan(mine, sh.sm32, n_local);
+#pragma unroll
+  for (int j = 0; j < kTkIter; ++j) {
+    const int i0 = 4 * (tid + kTopkThreads * (rank + kTkCl * j));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t key = skey[tid * kTkStride + j * 4 + e];
+      const uint32_t low = 0xFFFFFFFFu - (uint32_t)(i0 + e);
+      if (i0 + e < num_anchors && (key > kth_hi || (key == kth_hi && low >= kth_lo)))
+        slist[slot++] = ((unsigned long long)key << 32) | (unsigned long long)low;
+    }
+  }
+  const int n_pow2 = next_pow2(max(n_local, 1));
+  for (int i = n_local + tid; i < n_pow2; i += kTopkThreads) slist[i] = 0ull;
+  if (tid == 0) sh.n_local = n_local;
+  __syncthreads();
+  bitonic_sort_desc(slist, n_pow2);
+  cluster.sync();
+
+  // ---- global rank of every survivor: its local position + the number of larger keys in each other CTA's list
+  const unsigned long long* peer_list[kTkCl];
+  int peer_n[kTkCl];
+#pragma unroll
+  for (int q = 0; q < kTkCl; ++q) {
+    peer_list[q] = cluster.map_shared_rank(slist, q);
+    peer_n[q] = cluster.map_shared_rank(&sh, q)->n_local;
+  }
+  for (int p = tid; p < n_local; p += kTopkThreads) {
+    const unsigned long long x = slist[p];
+    int lo[kTkCl], hi2[kTkCl];
+#pragma unroll
+    for (int q = 0; q < kTkCl; ++q) { lo[q] = 0; hi2[q] = q == rank ? 0 : peer_n[q]; }
+    for (int step = 0; step < 15; ++step) {
+#pragma unroll
+      for (int q = 0; q < kTkCl; ++q) {
+        if (lo[q] < hi2[q]) {
+          const int mid = (lo[q] + hi2[q]) >> 1;
+          if (peer_list[q][mid] > x) lo[q] = mid + 1; else hi2[q] = mid;
+        }
+      }
+    }
+    int r = p;
+#pragma unroll
+    for (int q = 0; q < kTkCl; ++q) r += lo[q];
+    srank[p] = r;
+  }
+  __syncthreads();
+
+  // ---- decode, clip, min-size filter; ordered compaction through the rank bitmap of the whole cluster
+  const float xmax = (float)(img_w - 1), ymax = (float)(img_h - 1);
+  for (int p = tid; p < n_local; p += kTopkThreads) {
+    const int idx = (int)(0xFFFFFFFFu - (uint32_t)(slist[p] & 0xFFFFFFFFull));
+    float4 b;
+    if (decode_clip_box(deltas, anchors, (size_t)img * num_anchors + idx, idx, xmax, ymax, min_size, b)) {
+      const int r = srank[p];
+      atomicOr(&sh.okbits[r >> 5], 1u << (r & 31));
+    }
+  }
+  cluster.sync();
+  if (tid < 512) {
+    uint32_t w = 0u;
+#pragma unroll
+    for (int q = 0; q < kTkCl; ++q) w |= cluster.map_shared_rank(&sh, q)->okbits[tid];
+    sh.allbits[tid] = w;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    int cnt[16], mine16 = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { cnt[j] = __popc(sh.allbits[lane * 16 + j]); mine16 += cnt[j]; }
+    int incl = mine16;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int acc = incl - mine16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { sh.okprefix[lane * 16 + j] = acc; acc += cnt[j]; }
+    if (lane == 31 && rank == 0) valid[img] = acc;
+  }
+  __syncthreads();
+  for (int p = tid; p < n_local; p += kTopkThreads) {
+    const int r = srank[p];
+    const uint32_t w = sh.allbits[r >> 5];
+    if (!((w >> (r & 31)) & 1u)) continue;
+    const int idx = (int)(0xFFFFFFFFu - (uint32_t)(slist[p] & 0xFFFFFFFFull));
+    float4 b;
+    decode_clip_box(deltas, anchors, (size_t)img * num_anchors + idx, idx, xmax, ymax, min_size, b);
+    const size_t o = (size_t)img * k + sh.okprefix[r >> 5] + __popc(w & ((1u << (r & 31)) - 1u));
+    reinterpret_cast<float4*>(boxes)[o] = b;
+    scores[o] = 1.0f / (1.0f + expf(-lg[idx]));
+    topk_idx[o] = idx;
+  }
+  cluster.sync();             // no CTA leaves while another may still read its shared memory
+}
+
 // ----------------------------------------------------------------------------- NMS
 // mask[i][cb] bit j: box (cb*64+j) is suppressed by box i (j > i only).  Upper triangle only.
 // Batched over images (blockIdx.z): image g has n = n_dev ? n_dev[g] : n_cap boxes at boxes + g * n_cap and its own
@@ -434,6 +697,35 @@ extern "C" int dd_rpn_topk_decode(const float* logits, const float* deltas, cons
   (void)workspace;
   const int num_anchors = FH * FW * A;
   DD_CHECK_ARG(N > 0 && num_anchors > 0 && k > 0 && k <= num_anchors && k <= kSortCap);
+  static int cluster_mode = -1;          // DD_TOPK_CLUSTER=0 keeps the one-CTA kernel (A/B runs)
+  if (cluster_mode < 0) {
+    const char* e = getenv("DD_TOPK_CLUSTER");
+    cluster_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (cluster_mode == 1 && num_anchors > 16384 && num_anchors <= kTkCl * kTopkThreads * 4 * kTkIter && k <= kSortCap) {
+    const size_t dyn = (size_t)kTopkThreads * kTkStride * 4 + 8 + (size_t)kSortCap * sizeof(unsigned long long);
+    static bool cl_configured = false;
+    if (!cl_configured) {
+      DD_CUDA(cudaFuncSetAttribute(rpn_topk_decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      cl_configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(N * kTkCl));
+    cfg.blockDim = dim3(kTopkThreads);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = dd::S(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kTkCl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DD_CUDA(cudaLaunchKernelEx(&cfg, rpn_topk_decode_cluster_kernel, logits, deltas, anchors, num_anchors, k, img_w, img_h,
+                               min_size, boxes, scores, topk_idx, valid));
+    DD_LAUNCHED();
+    return 0;
+  }
   const size_t smem = (size_t)host_next_pow2(k) * sizeof(unsigned long long);
   static bool configured = false;
   if (!configured) {

@@ -291,6 +291,55 @@ def test_rpn_topk_decode(fh, fw, k):
         torch.testing.assert_close(boxes[i].cpu(), want, atol=2e-3, rtol=1e-5)
 
 
+@pytest.mark.parametrize("fh,fw,a,k,case", [(64, 128, 15, 12000, "ties"), (64, 128, 15, 12000, "one_region"),
+                                            (41, 37, 15, 6000, "ragged"), (64, 128, 16, 16384, "largest"),
+                                            (64, 128, 15, 12000, "min_size")])
+def test_rpn_topk_decode_cluster_kernel_cases(fh, fw, a, k, case):
+    """The 8-CTA cluster kernel (more than 16 384 anchors per image): heavily tied logits (the lowest indices of the
+    ties at the cut win, and the output is ordered by (score desc, index asc) — what a stable descending sort gives),
+    all high scores inside ONE CTA's share, an anchor count that is not a multiple of 4, the largest supported
+    set, and a min-size filter that removes candidates from the middle of the ranking."""
+    g = torch.Generator().manual_seed(fh + fw + k)
+    n, A = 2, a * fh * fw
+    if case == "ties":
+        logits = torch.randint(-6, 7, (n, A), generator=g).float() * 0.25
+    elif case == "one_region":
+        logits = torch.randn(n, A, generator=g) - 10.0
+        logits[:, 4096:4096 + 3000] += 20.0                       # one 4096-logit chunk holds the whole head of the ranking
+    else:
+        logits = torch.randn(n, A, generator=g) * 3
+    deltas = torch.randn(n, A, 4, generator=g) * 0.5
+    sizes = (32, 64, 128, 256, 512) if a == 15 else (32, 64, 128, 256, 512, 640, 700, 800)
+    ratios = (0.5, 1.0, 2.0) if a == 15 else (0.5, 2.0)
+    anchors = orc.grid_anchors(fh, fw, 16, orc.cell_anchors(16, sizes, ratios))
+    assert anchors.shape[0] == A
+    iw, ih = fw * 16, fh * 16
+    min_size = 40.0 if case == "min_size" else 0.0
+    boxes, scores, idx, valid = ops().rpn_topk_decode(logits.view(n, fh, fw, a).to(DEV),
+                                                      deltas.view(n, fh, fw, 4 * a).to(DEV), anchors.to(DEV), k, iw, ih,
+                                                      min_size)
+    boxes, scores, idx, valid = boxes.cpu(), scores.cpu(), idx.cpu().long(), valid.cpu().tolist()
+    for i in range(n):
+        order = torch.sort(logits[i], descending=True, stable=True)[1][:k]          # ties: lower index first
+        b = orc.clip_boxes(orc.box_decode(deltas[i][order], anchors[order], (1.0, 1.0, 1.0, 1.0)), iw, ih)
+        # the kernel's own boxes decide its filter; the expectation uses them where the torch decode is within rounding
+        keep = ((b[:, 2] - b[:, 0] + 1) >= min_size) & ((b[:, 3] - b[:, 1] + 1) >= min_size)
+        want = order[keep]
+        if case == "min_size":
+            assert 0 < want.numel() < k
+            assert abs(valid[i] - want.numel()) <= 3                # boxes within rounding of the threshold
+            got = set(idx[i, : valid[i]].tolist())
+            assert len(got ^ set(want.tolist())) <= 6
+            pos = {v: j for j, v in enumerate(idx[i, : valid[i]].tolist())}
+            common = [v for v in want.tolist() if v in pos]
+            assert all(pos[x] < pos[y] for x, y in zip(common, common[1:]))          # order preserved
+        else:
+            assert valid[i] == k
+            assert torch.equal(idx[i], want)
+            torch.testing.assert_close(scores[i], logits[i][want].sigmoid(), atol=1e-6, rtol=1e-6)
+            torch.testing.assert_close(boxes[i], b, atol=2e-3, rtol=1e-5)
+
+
 def test_rpn_topk_ties_take_lowest_index_and_min_size_filter():
     fh, fw, a = 4, 4, 3
     logits = torch.zeros(1, fh, fw, a)
