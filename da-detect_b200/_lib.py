@@ -34,6 +34,8 @@ _SIGS = {
     "dd_match": (_I, "pippiffipppp"),
     "dd_box_encode": (_I, "pipppiffffipp"),
     "dd_rpn_anchor_labels": (_I, "ppipp"),
+    "dd_roi_labels": (_I, "ppipipp"),
+    "dd_roi_gather_sampled": (_I, "ppppppppppiiiffffppppppp"),
     "dd_rpn_sampled_losses": (_I, "pppiiipppppppfpppp"),
     "dd_box_decode": (_I, "ppiiffffpp"),
     "dd_conv2d_forward_workspace_bytes": (_Z, "iiiii"),

@@ -228,7 +228,81 @@ __global__ void __launch_bounds__(256) rpn_sampled_losses_kernel(
   }
 }
 
+
+// Box-head proposal labels of one image (box_head/loss.py:55-99): the matched ground-truth class, 0 below the low
+// threshold, -1 (ignored by the sampler) between the thresholds and for buffer rows beyond the image's proposal
+// count; every proposal of a target-domain image is background (:84-85).
+__global__ void roi_labels_kernel(const int64_t* __restrict__ matches, const int64_t* __restrict__ gt_labels,
+                                  int is_source, const int32_t* __restrict__ n_prop, int cap,
+                                  int32_t* __restrict__ labels) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cap) return;
+  const long long m = matches[j];
+  int lab = 0;
+  if (is_source) lab = m >= 0 ? (int)gt_labels[m] : (m == -2 ? -1 : 0);
+  if (j >= *n_prop) lab = -1;
+  labels[j] = lab;
+}
+
+// The sampled ROIs of a batch (box_head/loss.py:100-130 after the sampler): one thread per ROI slot gathers the
+// proposal, its objectness, class label (0 in slots beyond the sampled count) and BoxCoder regression target
+// (negative match indices wrap for target-domain images like the reference's tensor indexing, :47-51).
+__global__ void roi_gather_sampled_kernel(
+    const float4* __restrict__ boxes, const float* __restrict__ objectness, const int64_t* __restrict__ sel,
+    const int32_t* __restrict__ counts, const int32_t* __restrict__ labels, const int64_t* __restrict__ matches,
+    const float4* __restrict__ gt_cat, const int32_t* __restrict__ gt_off, const int32_t* __restrict__ gt_counts,
+    const uint8_t* __restrict__ is_source, int n_img, int cap, int B, float wx, float wy, float ww, float wh,
+    float* __restrict__ rois, int64_t* __restrict__ out_labels, float4* __restrict__ reg_targets,
+    uint8_t* __restrict__ domain, uint8_t* __restrict__ valid, float* __restrict__ out_obj) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_img * B) return;
+  const int img = t / B, r = t - img * B;
+  const int a = (int)sel[t];
+  const size_t row = (size_t)img * cap + a;
+  const float4 bx = boxes[row];
+  const bool ok = r < counts[2 * img + 1];
+  rois[(size_t)t * 5 + 0] = (float)img;
+  rois[(size_t)t * 5 + 1] = bx.x;
+  rois[(size_t)t * 5 + 2] = bx.y;
+  rois[(size_t)t * 5 + 3] = bx.z;
+  rois[(size_t)t * 5 + 4] = bx.w;
+  out_labels[t] = ok ? (int64_t)labels[row] : 0;
+  const int g0 = gt_off[img], mcap = gt_off[img + 1] - g0;
+  const int live = gt_counts ? min(max(gt_counts[img], 0), mcap) : mcap;
+  const int M = max(live, 1);
+  long long m = matches[row];
+  if (m < 0) m = is_source[img] ? 0 : m + M;
+  if (m < 0) m = 0;
+  reg_targets[t] = encode_ref_order(gt_cat[g0 + m], bx, wx, wy, ww, wh);
+  domain[t] = is_source[img];
+  valid[t] = ok ? 1 : 0;
+  out_obj[t] = objectness[row];
+}
+
 }  // namespace
+
+extern "C" int dd_roi_labels(const int64_t* matches, const int64_t* gt_labels, int is_source, const int32_t* n_prop,
+                             int cap, int32_t* labels, void* stream) {
+  DD_CHECK_ARG(cap > 0);
+  roi_labels_kernel<<<(cap + 255) / 256, 256, 0, dd::S(stream)>>>(matches, gt_labels, is_source, n_prop, cap, labels);
+  DD_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dd_roi_gather_sampled(const float* boxes, const float* objectness, const int64_t* sel,
+                                     const int32_t* counts, const int32_t* labels, const int64_t* matches,
+                                     const float* gt_cat, const int32_t* gt_offsets, const int32_t* gt_counts,
+                                     const uint8_t* is_source, int n_img, int cap, int B, float wx, float wy, float ww,
+                                     float wh, float* rois, int64_t* out_labels, float* reg_targets, uint8_t* domain,
+                                     uint8_t* valid, float* out_objectness, void* stream) {
+  DD_CHECK_ARG(n_img > 0 && cap > 0 && B > 0);
+  roi_gather_sampled_kernel<<<(n_img * B + 255) / 256, 256, 0, dd::S(stream)>>>(
+      reinterpret_cast<const float4*>(boxes), objectness, sel, counts, labels, matches,
+      reinterpret_cast<const float4*>(gt_cat), gt_offsets, gt_counts, is_source, n_img, cap, B, wx, wy, ww, wh, rois,
+      out_labels, reinterpret_cast<float4*>(reg_targets), domain, valid, out_objectness);
+  DD_LAUNCHED();
+  return 0;
+}
 
 extern "C" int dd_rpn_anchor_labels(const int64_t* matches, const uint8_t* visibility, int N, int32_t* labels,
                                     void* stream) {

@@ -487,6 +487,25 @@ __global__ void __launch_bounds__(kTopkThreads) rpn_topk_decode_cluster_kernel(
 }
 
 // ----------------------------------------------------------------------------- NMS
+// Reference predicate: inter / (sa + sb - inter) > thresh with an IEEE division (nms.cu:13-24).  The division is only
+// executed inside a +-1e-6 band around the threshold; outside it the comparison inter vs thresh * union decides with
+// a margin ~16x the rounding error of the quotient, so the result is identical.  Disjoint boxes leave after the
+// width test.
+__device__ __forceinline__ bool nms_suppresses(const float4 me, const float my_area, const float4 b, const float thresh) {
+  const float left = fmaxf(me.x, b.x), right = fminf(me.z, b.z);
+  const float top = fmaxf(me.y, b.y), bottom = fminf(me.w, b.w);
+  const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+  const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+  const float inter = __fmul_rn(width, height);
+  const float sb = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+  const float uni = __fsub_rn(__fadd_rn(my_area, sb), inter);
+  const float tu = thresh * uni;
+  if (!(uni > 0.f) || !(thresh > 0.f)) return __fdiv_rn(inter, uni) > thresh;   // degenerate boxes: as written
+  if (inter > tu * 1.000001f) return true;
+  if (inter < tu * 0.999999f) return false;
+  return __fdiv_rn(inter, uni) > thresh;
+}
+
 // mask[i][cb] bit j: box (cb*64+j) is suppressed by box i (j > i only).  Upper triangle only.
 // Batched over images (blockIdx.z): image g has n = n_dev ? n_dev[g] : n_cap boxes at boxes + g * n_cap and its own
 // [n_cap x cb_cap] mask.
@@ -510,23 +529,7 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__
     const int start = (rb == cb) ? threadIdx.x + 1 : 0;
     const float my_area = __fmul_rn(__fadd_rn(__fsub_rn(me.z, me.x), 1.f), __fadd_rn(__fsub_rn(me.w, me.y), 1.f));
     for (int j = start; j < col_size; ++j) {
-      // Reference predicate: inter / (sa + sb - inter) > thresh with an IEEE division (nms.cu:13-24).  The division
-      // is only executed inside a +-1e-6 band around the threshold; outside it the comparison inter vs
-      // thresh * union decides with a margin ~16x the rounding error of the quotient, so the result is identical.
-      const float4 b = cols[j];
-      const float left = fmaxf(me.x, b.x), right = fminf(me.z, b.z);
-      const float top = fmaxf(me.y, b.y), bottom = fminf(me.w, b.w);
-      const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
-      const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
-      const float inter = __fmul_rn(width, height);
-      const float sb = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
-      const float uni = __fsub_rn(__fadd_rn(my_area, sb), inter);
-      const float tu = thresh * uni;
-      bool over;
-      if (!(uni > 0.f) || !(thresh > 0.f)) over = __fdiv_rn(inter, uni) > thresh;   // degenerate boxes: as written
-      else if (inter > tu * 1.000001f) over = true;
-      else if (inter < tu * 0.999999f) over = false;
-      else over = __fdiv_rn(inter, uni) > thresh;
+      const bool over = nms_suppresses(me, my_area, cols[j], thresh);
       if (over) bits |= 1ull << j;
     }
     mask[(size_t)i * cb_cap + cb] = bits;
@@ -598,6 +601,132 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const unsigned l
   if (tid == 0) keep_count[img] = s_nkeep;
 }
 
+// ----------------------------------------------------------------------------- NMS, cluster version (no mask)
+// The two kernels above compute the whole upper triangle of the suppression matrix (72 M IoU tests for 12 000 boxes,
+// on every SM of the GPU) although the greedy scan only ever consults the rows of the boxes it KEEPS, and stops at
+// max_keep.  Here a cluster of 8 CTAs owns one image and the matrix never exists: the column blocks are dealt
+// round-robin to the CTAs (boxes and areas resident in shared memory); per 64-box block every CTA redundantly
+// resolves the block (the diagonal 64 x 64 tests, then the serial find-first-set walk — identical inputs, identical
+// result, nothing to broadcast), and then tests only the boxes just kept against its own later columns, OR-ing the
+// result into its running suppression words.  The only exchange is the suppression word of the next block, read from
+// its owner through distributed shared memory after one cluster barrier per block.
+constexpr int kNmsCl = 8;
+constexpr int kNmsThreads = 1024;
+constexpr int kNmsOwnBlocks = 256 / kNmsCl;          // column blocks per CTA at the largest supported n (16 384)
+
+struct NmsClusterShared {
+  float4 own[kNmsOwnBlocks * 64];
+  float own_area[kNmsOwnBlocks * 64];
+  unsigned long long remv[kNmsOwnBlocks];             // suppression words of the owned column blocks
+  float4 rows[2][64];
+  float rows_area[2][64];
+  unsigned long long diag[64];
+  int kept[64];
+  int cnt, nkeep, done;
+};
+
+__global__ void __launch_bounds__(kNmsThreads) nms_cluster_kernel(const float4* __restrict__ boxes,
+                                                                  const int* __restrict__ n_dev, int n_cap, float thresh,
+                                                                  int max_keep, int64_t* __restrict__ keep_pos,
+                                                                  int keep_stride, int* __restrict__ keep_count) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  NmsClusterShared& sh = *reinterpret_cast<NmsClusterShared*>(dyn);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int q = (int)cluster.block_rank();
+  const int img = blockIdx.x / kNmsCl;
+  const int n = n_dev ? min(n_dev[img], n_cap) : n_cap;
+  const int col_blocks = (n + 63) / 64;
+  boxes += (size_t)img * n_cap;
+  keep_pos += (size_t)img * keep_stride;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint32_t* remv32 = reinterpret_cast<uint32_t*>(sh.remv);
+
+  for (int t = tid; t < kNmsOwnBlocks * 64; t += kNmsThreads) {
+    const int col = ((t >> 6) * kNmsCl + q) * 64 + (t & 63);
+    float4 b = make_float4(0.f, 0.f, -1.f, -1.f);
+    if (col < n) b = boxes[col];
+    sh.own[t] = b;
+    sh.own_area[t] = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+  }
+  if (tid < kNmsOwnBlocks) sh.remv[tid] = 0ull;
+  if (tid == 0) { sh.nkeep = 0; sh.done = 0; }
+  if (tid < 64) {
+    float4 b = make_float4(0.f, 0.f, -1.f, -1.f);
+    if (tid < n) b = boxes[tid];
+    sh.rows[0][tid] = b;
+    sh.rows_area[0][tid] = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+  }
+  __syncthreads();
+  for (int b = 0; b < col_blocks; ++b) {
+    const int buf = b & 1;
+    const int size = min(n - b * 64, 64);
+    if (tid >= 64 && tid < 128 && b + 1 < col_blocks) {           // the next block's boxes
+      const int r = (b + 1) * 64 + tid - 64;
+      float4 bx = make_float4(0.f, 0.f, -1.f, -1.f);
+      if (r < n) bx = boxes[r];
+      sh.rows[buf ^ 1][tid - 64] = bx;
+      sh.rows_area[buf ^ 1][tid - 64] = __fmul_rn(__fadd_rn(__fsub_rn(bx.z, bx.x), 1.f), __fadd_rn(__fsub_rn(bx.w, bx.y), 1.f));
+    }
+    // diagonal tests: 16 threads per row, 4 columns each
+    {
+      const int i = tid >> 4, j0 = (tid & 15) * 4;
+      const float4 me = sh.rows[buf][i];
+      const float my_area = sh.rows_area[buf][i];
+      unsigned long long bits = 0ull;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + e;
+        if (j > i && j < size && i < size && nms_suppresses(me, my_area, sh.rows[buf][j], thresh)) bits |= 1ull << j;
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
+      if ((tid & 15) == 0) sh.diag[i] = bits;
+    }
+    cluster.sync();                        // the owner's suppression word of this block is final
+    if (tid == 0) {
+      unsigned long long cur = cluster.map_shared_rank(&sh, b % kNmsCl)->remv[b / kNmsCl];
+      if (size < 64) cur |= ~0ull << size;
+      int nk = sh.nkeep, cnt = 0;
+      unsigned long long avail = ~cur;
+      while (avail) {
+        if (max_keep > 0 && nk >= max_keep) break;
+        const int i = __ffsll((long long)avail) - 1;
+        sh.kept[cnt++] = i;
+        if (q == 0) keep_pos[nk] = (int64_t)(b * 64 + i);
+        ++nk;
+        cur |= sh.diag[i];
+        avail = ~cur & ~((2ull << i) - 1ull);
+      }
+      sh.cnt = cnt;
+      sh.nkeep = nk;
+      sh.done = (max_keep > 0 && nk >= max_keep) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh.done) break;
+    const int cnt = sh.cnt;
+    if (cnt > 0) {
+      // the boxes just kept against this CTA's later columns: one warp per 32 columns
+      for (int hb = wid; hb < kNmsOwnBlocks * 2; hb += kNmsThreads / 32) {
+        const int cb = (hb >> 1) * kNmsCl + q;                   // warp-uniform
+        if (cb <= b || cb >= col_blocks) continue;
+        const int t = hb * 32 + lane;
+        const float4 c = sh.own[t];
+        const bool live = cb * 64 + (hb & 1) * 32 + lane < n && !((remv32[hb] >> lane) & 1u);
+        bool sup = false;
+        for (int r = 0; r < cnt; ++r) {
+          const int i = sh.kept[r];
+          if (live && !sup) sup = nms_suppresses(sh.rows[buf][i], sh.rows_area[buf][i], c, thresh);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, sup);
+        if (lane == 0 && bal) remv32[hb] |= bal;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && q == 0) keep_count[img] = sh.nkeep;
+  cluster.sync();             // no CTA leaves while another may still read its shared memory
+}
+
 // Sort (score desc, index asc) -> order; gather boxes.  Single CTA, n <= kSortCap.
 __global__ void __launch_bounds__(1024) sort_scores_gather_kernel(const float* __restrict__ scores,
                                                                   const float4* __restrict__ boxes, int n,
@@ -664,6 +793,35 @@ int nms_sorted_impl(const float* boxes_sorted, int images, const int* n_dev, int
                     int64_t* keep, int keep_stride, int* keep_count, unsigned long long* mask, cudaStream_t s) {
   const int cb = (n_cap + 63) / 64;
   DD_CHECK_ARG(cb <= 256 && images > 0 && images <= 65535);
+  static int cluster_mode = -1;          // DD_NMS_CLUSTER=0 keeps the mask + scan kernels (A/B runs)
+  if (cluster_mode < 0) {
+    const char* e = getenv("DD_NMS_CLUSTER");
+    cluster_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (cluster_mode == 1 && n_cap >= 2048) {
+    const size_t dyn = sizeof(NmsClusterShared);
+    static bool configured = false;
+    if (!configured) {
+      DD_CUDA(cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(images * kNmsCl));
+    cfg.blockDim = dim3(kNmsThreads);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kNmsCl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DD_CUDA(cudaLaunchKernelEx(&cfg, nms_cluster_kernel, reinterpret_cast<const float4*>(boxes_sorted), n_dev, n_cap, thresh,
+                               max_keep, keep, keep_stride, keep_count));
+    DD_LAUNCHED();
+    return 0;
+  }
   dim3 grid(cb, cb, images);
   nms_mask_kernel<<<grid, 64, 0, s>>>(reinterpret_cast<const float4*>(boxes_sorted), n_dev, n_cap, thresh, mask, cb);
   DD_LAUNCHED();

@@ -302,7 +302,9 @@ class FlatSGDTrainer(object):
         # Eager warm-up and capture run on ONE dedicated stream, and nothing returned keeps the autograd graph
         # alive: a stale AccumulateGrad node bound to another stream would invalidate the capture.
         if self.graph_stream is None:
-            self.graph_stream = torch.cuda.Stream()
+            # high priority: the step's main stream carries its critical path (proposal chain, box head); the dense
+            # kernels of the early backward passes on the side streams must not queue ahead of it for the SMs
+            self.graph_stream = torch.cuda.Stream(priority=int(os.environ.get("DD_MAIN_PRIORITY", "-1")))
         cur = torch.cuda.current_stream()
         if ent["calls"] == 1:
             # first sight of a signature: one eager step (lazy workspaces, cached constants, kernel attributes)

@@ -138,6 +138,7 @@ class GeneralizedRCNN(nn.Module):
         if early and self.da_heads and not self.da_heads_triplet:
             def after_head(ready):
                 early_img[0] = self.da_heads.early_image_loss(feat, targets, meta["seg"], after=ready)
+                return early_img[0][0] if early_img[0] is not None else None
         props, proposal_losses, pending = self.rpn.forward_static(images, features, targets, head_out, meta,
                                                                   early_backward=early, after_head=after_head)
         losses = self._forward_static_heads(features, targets, props, proposal_losses, meta, early_img[0])

@@ -153,6 +153,7 @@ class FastRCNNLossComputation(object):
         if cfg.MODEL.CLS_AGNOSTIC_BBOX_REG:
             raise NotImplementedError("CLS_AGNOSTIC_BBOX_REG is not used by any DA config")
         self.rng = rng
+        self._static_const = {}
 
     def prepare_targets(self, proposals, targets, sample_for_da=False):
         labels, regs, domains = [], [], []
@@ -210,36 +211,37 @@ class FastRCNNLossComputation(object):
         n_img, cap = boxes.shape[0], boxes.shape[1]
         B = self.batch
         dev = boxes.device
-        ar_cap = torch.arange(cap, device=dev)
-        labs, ms = [], []
-        for i, t in enumerate(targets):
-            gt = t.convert("xyxy").bbox
-            m, _ = ops.match(gt, boxes[i], self.high, self.low, False, m_dev=getattr(t, "_gt_count_dev", None))
-            if is_source_image(t):
-                lab = t.get_field("labels").to(torch.int64)[m.clamp(min=0)]
-                lab = torch.where(m == BELOW_LOW_THRESHOLD, torch.zeros_like(lab), lab)
-                lab = torch.where(m == BETWEEN_THRESHOLDS, torch.full_like(lab, -1), lab)
-            else:                                            # loss.py:84-85: target-domain labels are all 0
-                lab = torch.zeros_like(m)
-            lab = torch.where(ar_cap < nprop[i], lab, torch.full_like(lab, -1))
-            labs.append(lab.to(torch.int32))
+        # per-signature device constants (GT offsets, domain flags): built once, outside any graph capture
+        key = tuple((len(t), bool(is_source_image(t))) for t in targets)
+        const = self._static_const.get(key)
+        if const is None:
+            offs = [0]
+            for n, _ in key:
+                offs.append(offs[-1] + n)
+            const = (torch.tensor(offs, dtype=torch.int32, device=dev),
+                     torch.tensor([1 if s else 0 for _, s in key], dtype=torch.uint8, device=dev))
+            self._static_const[key] = const
+        gt_offsets, src_flags = const
+        gts = [t.convert("xyxy").bbox for t in targets]
+        counts_dev = [getattr(t, "_gt_count_dev", None) for t in targets]
+        lab_all = torch.empty((n_img, cap), dtype=torch.int32, device=dev)
+        ms, keys = [], []
+        for i, t in enumerate(targets):                      # three launches per image: Matcher, labels, random keys
+            m, _ = ops.match(gts[i], boxes[i], self.high, self.low, False, m_dev=counts_dev[i])
+            ops.roi_labels(m, t.get_field("labels"), is_source_image(t), nprop[i:i + 1], out=lab_all[i])
             ms.append(m)
-        lab_all = torch.stack(labs)
-        keys = torch.stack([self.rng.sample_keys(l) for l in labs])
-        sel, cnt = ops.balanced_sample(lab_all, nprop, keys, B, int(B * self.pos_fraction))
-        valid = torch.arange(B, device=dev).unsqueeze(0) < cnt[:, 1:2]
-        rois, labels, regs, doms = [], [], [], []
-        for i, t in enumerate(targets):
-            src = is_source_image(t)
-            bx = boxes[i][sel[i]]
-            rois.append(torch.cat([torch.full((B, 1), float(i), dtype=bx.dtype, device=dev), bx], dim=1))
-            labels.append(torch.where(valid[i], labs[i][sel[i]].to(torch.int64), torch.zeros_like(sel[i])))
-            regs.append(ops.box_encode(t.convert("xyxy").bbox, bx, ms[i][sel[i]], self.weights, wrap_negative=not src,
-                                       m_dev=getattr(t, "_gt_count_dev", None)))
-            doms.append(torch.full((B,), src, dtype=torch.bool, device=dev))
-        st = dict(rois=torch.cat(rois), labels=torch.cat(labels), regression_targets=torch.cat(regs),
-                  domain_labels=torch.cat(doms), valid=valid.reshape(-1), counts=cnt[:, 1], sizes=props.sizes,
-                  objectness=torch.stack([props.objectness[i][sel[i]] for i in range(n_img)]).reshape(-1))
+            keys.append(self.rng.sample_keys(lab_all[i]))
+        one = n_img == 1
+        m_all = ms[0].view(1, -1) if one else torch.stack(ms)
+        key_all = keys[0].view(1, -1) if one else torch.stack(keys)
+        sel, cnt = ops.balanced_sample(lab_all, nprop, key_all, B, int(B * self.pos_fraction))
+        gt_cat = gts[0] if one else torch.cat(gts, dim=0)
+        gt_counts = None
+        if all(c is not None for c in counts_dev):           # GT padded to a capacity: live row counts on the device
+            gt_counts = counts_dev[0] if one else torch.cat(counts_dev)
+        st = ops.roi_gather_sampled(boxes, props.objectness, sel, cnt, lab_all, m_all, gt_cat, gt_offsets, gt_counts,
+                                    src_flags, self.weights)
+        st.update(counts=cnt[:, 1], sizes=props.sizes)
         self._static = st
         self.rng.consume_da_draws(st["counts"])
         return st

@@ -346,7 +346,8 @@ class RPNModule(nn.Module):
         buffer, d loss / d feat lands in cut.grad), and finish_early_backward() hands cut.grad to the graph of `feat`.
         The dense kernels of that pass leave two SMs per image to the one-CTA-per-image kernels of the main stream
         (ops.sm_budget).  Requires gradients zeroed BEFORE the forward pass and unit loss weights (FlatSGDTrainer).
-        after_head(event): called once the head has been launched, with the event that marks its end."""
+        after_head(event): called once the head has been launched, with the event that marks its end; may return the
+        stream its own dense work runs on."""
         cuda = feat.is_cuda
         if cuda:
             main = torch.cuda.current_stream()
@@ -366,10 +367,16 @@ class RPNModule(nn.Module):
             if cuda:
                 ready = torch.cuda.Event()
                 ready.record(side)
+        other = None
         if after_head is not None:          # other early passes (DA image head) start when the RPN head has finished
-            after_head(ready)
+            other = after_head(ready)
         with on_side():
             obj_loss, box_loss = self.losses_static(anchors, vis, logits, deltas, targets, meta)
+            if cuda and other is not None:
+                # two streams of persistent dense kernels beside each other only take turns on the SMs (the second
+                # kernel's CTAs wait for the first's to retire and then run as a late wave): this backward pass
+                # follows the other early pass, which has been running during the loss chain above
+                side.wait_stream(other)
             if cuda:
                 with ops.sm_budget(ops.NUM_SMS - 2 * feat.shape[0]):
                     torch.autograd.backward([obj_loss + box_loss])

@@ -1010,6 +1010,41 @@ def rpn_sampled_losses(logits, deltas, anchors, sel, counts, labels, matches, gt
                                    beta)
 
 
+def roi_labels(matches, gt_labels, is_source, n_prop, out=None):
+    """int32 [cap] box-head labels of one image's proposal buffer (class / 0 / -1 ignored); n_prop: device int32 [1]."""
+    m = _chk(matches, torch.int64, "matches")
+    if out is None:
+        out = torch.empty(m.shape, dtype=torch.int32, device=m.device)
+    _lib.call("dd_roi_labels", _ptr(m), _ptr(_chk(gt_labels, torch.int64, "gt_labels")), 1 if is_source else 0,
+              _ptr(_chk(n_prop, torch.int32, "n_prop")), m.numel(), _ptr(out), _stream())
+    return out
+
+
+def roi_gather_sampled(boxes, objectness, sel, counts, labels, matches, gt_cat, gt_offsets, gt_counts, is_source,
+                       weights):
+    """The sampled ROIs of a batch in one launch -> dict(rois [K,5], labels int64 [K], regression_targets [K,4],
+    domain_labels bool [K], valid bool [K], objectness [K]) with K = images x batch."""
+    n_img, cap = objectness.shape
+    b = sel.shape[1]
+    dev = boxes.device
+    k = n_img * b
+    rois = torch.empty((k, 5), dtype=torch.float32, device=dev)
+    lab = torch.empty((k,), dtype=torch.int64, device=dev)
+    reg = torch.empty((k, 4), dtype=torch.float32, device=dev)
+    dom = torch.empty((k,), dtype=torch.uint8, device=dev)
+    val = torch.empty((k,), dtype=torch.uint8, device=dev)
+    obj = torch.empty((k,), dtype=torch.float32, device=dev)
+    wx, wy, ww, wh = (float(v) for v in weights)
+    _lib.call("dd_roi_gather_sampled", _ptr(_chk(boxes, name="boxes")), _ptr(_chk(objectness, name="objectness")),
+              _ptr(_chk(sel, torch.int64, "sel")), _ptr(_chk(counts, torch.int32, "counts")),
+              _ptr(_chk(labels, torch.int32, "labels")), _ptr(_chk(matches, torch.int64, "matches")),
+              _ptr(_chk(gt_cat, name="gt")), _ptr(_chk(gt_offsets, torch.int32, "gt_offsets")),
+              _ptr(_chk(gt_counts, torch.int32, "gt_counts")), _ptr(_chk(is_source, torch.uint8, "is_source")),
+              n_img, cap, b, wx, wy, ww, wh, _ptr(rois), _ptr(lab), _ptr(reg), _ptr(dom), _ptr(val), _ptr(obj), _stream())
+    return dict(rois=rois, labels=lab, regression_targets=reg, domain_labels=dom.view(torch.bool),
+                valid=val.view(torch.bool), objectness=obj)
+
+
 def box_decode(codes, boxes, weights):
     c = _chk(codes, name="codes")
     b = _chk(boxes, name="boxes")

@@ -121,6 +121,22 @@ int dd_rpn_sampled_losses(const float* logits, const float* deltas, const float*
                           const int64_t* sel, const int32_t* counts, const int32_t* labels, const int64_t* matches,
                           const float* gt_cat, const int32_t* gt_offsets, const int32_t* src_img, float beta,
                           float* losses, float* dlogits, float* ddeltas, void* stream);
+/* Box-head proposal labels of one image (box_head/loss.py:55-99) from dd_match's result (matches int64 [cap]) and
+ * the image's ground-truth classes (int64): class of the match, 0 background, -1 ignored (between the thresholds, or
+ * a buffer row at / beyond *n_prop); is_source == 0: every proposal is background (:84-85). */
+int dd_roi_labels(const int64_t* matches, const int64_t* gt_labels, int is_source, const int32_t* n_prop, int cap,
+                  int32_t* labels, void* stream);
+/* The sampled ROIs of a batch after dd_balanced_sample (box_head/loss.py:100-130): boxes [n_img,cap,4],
+ * objectness [n_img,cap], sel int64 [n_img,B], counts int32 [n_img,2], labels int32 / matches int64 [n_img,cap],
+ * gt_cat [G,4] + gt_offsets int32 [n_img+1] (+ gt_counts int32 [n_img] or NULL: live rows of a padded GT buffer),
+ * is_source uint8 [n_img] -> rois [n_img*B,5] (batch index, box), labels int64 (0 in slots beyond the sampled
+ * count), BoxCoder(wx,wy,ww,wh) regression targets [n_img*B,4] (negative matches wrap for target-domain images,
+ * :47-51), domain / valid uint8 [n_img*B], objectness [n_img*B]. */
+int dd_roi_gather_sampled(const float* boxes, const float* objectness, const int64_t* sel, const int32_t* counts,
+                          const int32_t* labels, const int64_t* matches, const float* gt_cat,
+                          const int32_t* gt_offsets, const int32_t* gt_counts, const uint8_t* is_source, int n_img,
+                          int cap, int B, float wx, float wy, float ww, float wh, float* rois, int64_t* out_labels,
+                          float* reg_targets, uint8_t* domain, uint8_t* valid, float* out_objectness, void* stream);
 /* BoxCoder.encode (box_coder.py:22-50) of gt[matches[i] clamped at 0] against pred[i];
  * wrap_negative != 0 reproduces the reference's negative-index wrap for target images
  * (box_head/loss.py:47-51) — relative to the live row count (*m_dev when given, else M). */

@@ -243,7 +243,47 @@ def rpn_sampled_losses(logits, deltas, anchors, sel, counts, labels, matches, gt
     return bce / total, l1 / total
 
 
+def roi_labels(matches, gt_labels, is_source, n_prop, out=None):
+    m = matches
+    if is_source:
+        lab = gt_labels.to(torch.int64)[m.clamp(min=0)]
+        lab = torch.where(m == -1, torch.zeros_like(lab), lab)
+        lab = torch.where(m == -2, torch.full_like(lab, -1), lab)
+    else:
+        lab = torch.zeros_like(m)
+    lab = torch.where(torch.arange(m.numel()) < int(n_prop), lab, torch.full_like(lab, -1)).to(torch.int32)
+    if out is not None:
+        out.copy_(lab)
+        return out
+    return lab
+
+
+def roi_gather_sampled(boxes, objectness, sel, counts, labels, matches, gt_cat, gt_offsets, gt_counts, is_source,
+                       weights):
+    """torch restatement of the per-image gathers of box_head/loss.py:100-130 (the former Python body of
+    subsample_static)."""
+    n_img, cap = objectness.shape
+    B = sel.shape[1]
+    valid = torch.arange(B).unsqueeze(0) < counts[:, 1:2]
+    rois, labs, regs, doms, objs = [], [], [], [], []
+    for i in range(n_img):
+        src = bool(is_source[i])
+        bx = boxes[i][sel[i]]
+        rois.append(torch.cat([torch.full((B, 1), float(i)), bx], dim=1))
+        labs.append(torch.where(valid[i], labels[i][sel[i]].to(torch.int64), torch.zeros_like(sel[i])))
+        g0, g1 = int(gt_offsets[i]), int(gt_offsets[i + 1])
+        live = g1 - g0 if gt_counts is None else min(int(gt_counts[i]), g1 - g0)
+        m = matches[i][sel[i]]
+        m = torch.where(m < 0, (m + max(live, 1)) if not src else torch.zeros_like(m), m).clamp(min=0)
+        regs.append(orc.box_encode(gt_cat[g0 + m], bx, weights))
+        doms.append(torch.full((B,), src, dtype=torch.bool))
+        objs.append(objectness[i][sel[i]])
+    return dict(rois=torch.cat(rois), labels=torch.cat(labs), regression_targets=torch.cat(regs),
+                domain_labels=torch.cat(doms), valid=valid.reshape(-1), objectness=torch.cat(objs))
+
+
 TRAINING_STAND_INS = dict(
+    roi_labels=roi_labels, roi_gather_sampled=roi_gather_sampled,
     rpn_anchor_labels=rpn_anchor_labels, rpn_sampled_losses=rpn_sampled_losses,
     proposals_gather=proposals_gather, balanced_sample=balanced_sample,
     gradient_scalar=lambda x, w: _Grl.apply(x, w), gradient_scalar_dev=lambda x, wdev: _Grl.apply(x, wdev),

@@ -85,7 +85,8 @@ def test_nms_reference_kats(golden_dir):
     assert got.cpu().tolist() == k["nms53_keep"].tolist()
 
 
-@pytest.mark.parametrize("n,thr", [(1, 0.5), (63, 0.3), (64, 0.5), (65, 0.7), (3000, 0.7), (12000, 0.7)])
+@pytest.mark.parametrize("n,thr", [(1, 0.5), (63, 0.3), (64, 0.5), (65, 0.7), (3000, 0.7), (12000, 0.7), (2048, 0.5),
+                                   (16384, 0.7)])
 def test_nms_matches_oracle_bit_exact(n, thr):
     g = torch.Generator().manual_seed(n)
     boxes = rand_boxes(g, n, 2048, 1024, 8.0)
@@ -221,6 +222,68 @@ def test_rpn_labels_and_fused_sampled_losses():
     for x, y in zip(a, b):
         assert float((x.grad - y.grad.cpu()).abs().max()) <= 1e-6 + 1e-5 * float(x.grad.abs().max())
         assert float(x.grad.abs().sum()) > 0
+
+
+def test_nms_sparse_suppression_stops_at_max_keep():
+    """The benchmark's regime for the cluster kernel: 12 000 boxes spread over the image (few suppressions, 64 kept
+    per block), the scan stops at POST_NMS_TOP_N = 2000 kept (boxlist_ops.py:30-33); two images, ragged counts."""
+    g = torch.Generator().manual_seed(77)
+    cap, counts, thr, post = 12000, [12000, 7001], 0.7, 2000
+    batch = torch.zeros(2, cap, 4)
+    want = []
+    for i, n in enumerate(counts):
+        xy = torch.rand(cap, 2, generator=g) * torch.tensor([1900.0, 900.0])
+        wh = 20 + torch.rand(cap, 2, generator=g) * 300
+        batch[i] = torch.cat([xy, xy + wh], dim=1)
+        scores = torch.arange(n, 0, -1, dtype=torch.float32)
+        want.append(orc.nms(batch[i, :n], scores, thr, strict=True)[:post])
+    keep, cnt = ops().nms_sorted_batched(batch.to(DEV), torch.tensor(counts, dtype=torch.int32, device=DEV), thr, post)
+    for i in range(2):
+        assert int(cnt[i]) == len(want[i]) == post
+        assert torch.equal(keep[i, :post].cpu(), want[i])
+
+
+def test_roi_labels_and_gather_sampled_match_restatement():
+    """dd_roi_labels + dd_roi_gather_sampled (the box head's sampling bookkeeping in two launches) against the torch
+    restatement of box_head/loss.py:55-130 used by the CPU suite: source + target image, padded GT capacity."""
+    import cpu_ops_emulation as emu
+    g = torch.Generator().manual_seed(31)
+    n_img, cap, B, gcap = 2, 500, 64, 8
+    live = [5, 3]
+    nprop = torch.tensor([480, 333], dtype=torch.int32)
+    xy = torch.rand(n_img, cap, 2, generator=g) * 300
+    boxes = torch.cat([xy, xy + 20 + torch.rand(n_img, cap, 2, generator=g) * 80], dim=2)
+    obj = torch.rand(n_img, cap, generator=g)
+    gt_cat = torch.zeros(n_img * gcap, 4)
+    for i in range(n_img):
+        gt_cat[i * gcap: i * gcap + live[i]] = boxes[i, 10: 10 + live[i]] + 3.0
+    gt_off = torch.tensor([0, gcap, 2 * gcap], dtype=torch.int32)
+    gt_counts = torch.tensor(live, dtype=torch.int32)
+    gt_labels = torch.randint(1, 9, (n_img, gcap), generator=g)
+    src = torch.tensor([1, 0], dtype=torch.uint8)
+    o = ops()
+    labs, ms = [], []
+    for i in range(n_img):
+        m, _ = o.match(gt_cat[i * gcap:(i + 1) * gcap].to(DEV), boxes[i].to(DEV), 0.5, 0.3, False,
+                       m_dev=gt_counts[i:i + 1].to(DEV))
+        lab = o.roi_labels(m, gt_labels[i].to(DEV), bool(src[i]), nprop[i:i + 1].to(DEV))
+        assert torch.equal(lab.cpu(), emu.roi_labels(m.cpu(), gt_labels[i], bool(src[i]), nprop[i:i + 1]))
+        labs.append(lab)
+        ms.append(m)
+    lab, m = torch.stack(labs), torch.stack(ms)
+    assert int((lab[0] > 0).sum()) >= 3 and int((lab[0] == -1).sum()) >= cap - 480
+    keys = torch.rand(n_img, cap, generator=g).to(DEV)
+    sel, cnt = o.balanced_sample(lab, nprop.to(DEV), keys, B, 16)
+    w = (10.0, 10.0, 5.0, 5.0)
+    got = o.roi_gather_sampled(boxes.to(DEV), obj.to(DEV), sel, cnt, lab, m, gt_cat.to(DEV), gt_off.to(DEV),
+                               gt_counts.to(DEV), src.to(DEV), w)
+    want = emu.roi_gather_sampled(boxes, obj, sel.cpu(), cnt.cpu(), lab.cpu(), m.cpu(), gt_cat, gt_off, gt_counts, src, w)
+    for k in want:
+        a, b = got[k].cpu(), want[k]
+        if a.dtype.is_floating_point:
+            torch.testing.assert_close(a, b, atol=1e-5, rtol=1e-5)
+        else:
+            assert torch.equal(a, b), k
 
 
 def test_proposals_gather_appends_gt_and_pads():
