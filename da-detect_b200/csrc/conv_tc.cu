@@ -59,6 +59,10 @@ struct TcParams {
   // K loop
   int taps, KW, pad, cblocks;   // taps = KH*KW, cblocks = Cin/32
   int Cin;
+  // 3xTF32, small maps (7x7 ROI maps fill 98 of the 128 rows of a {2, 8, 8} tile): the pixels of all maps are ONE dense
+  // axis like for a 1x1 conv, a filter tap is a constant row offset (kh - pad) * flat_w + (kw - pad) of the TMA load,
+  // and the operand splitter zeroes the rows whose tap falls outside their own flat_h x flat_w map (0 = off)
+  int flat_h, flat_w;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -663,13 +667,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // own A tile; our half of the B tile (rows [rank*BN/2, +BN/2)) goes to both CTAs, the other half comes
             // from the peer: every CTA's barrier still sees the bytes of one whole stage
             mbar_expect_tx(full_bar + s, L::kABytes + (X3 ? 2 : 1) * L::kBBytes);
-            tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
+            if (X3 && p.flat_w) tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + (kh - p.pad) * p.flat_w + kw - p.pad, 0, 0);
+            else tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
             const int half = (int)rank * (BN / 2);
             tma_load_2d_mc(&map_b, full_bar + s, sb + half * BKB, kcol, brow + half, (uint16_t)3);
             if (X3) tma_load_2d_mc(&map_b, full_bar + s, sb + L::kBBytes + half * BKB, kcol, p.b_lo_row + brow + half, (uint16_t)3);
           } else if constexpr (!CTA2) {
             mbar_expect_tx(full_bar + s, L::kABytes + (X3 ? 2 : 1) * L::kBBytes);
             if (p.stem) tma_load_5d(&map_a, full_bar + s, sa, 0, ow0, oh0 + (tap >> 1), tap & 1, n0);
+            else if (X3 && p.flat_w) tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + (kh - p.pad) * p.flat_w + kw - p.pad, 0, 0);
             else tma_load_4d(&map_a, full_bar + s, sa, cb * BKE, ow0 + kw - p.pad, oh0 + kh - p.pad, n0);
             tma_load_2d(&map_b, full_bar + s, sb, kcol, brow);
             if (X3) tma_load_2d(&map_b, full_bar + s, sb + L::kBBytes, kcol, p.b_lo_row + brow);
@@ -756,10 +762,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t a_tmem = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(3 * BN);
     uint32_t it = 0;
     for (int t = unit; t < total_tiles; t += n_units) {
+      // dense-axis 3x3 mode: bit `tap` set = that tap of this row's pixel lies inside the pixel's own map
+      uint32_t tapmask = 0xFFFFFFFFu;
+      if (p.flat_w) {
+        int n_tile, n0, oh0, ow0;
+        tile_of(t, n_tile, n0, oh0, ow0);
+        const int rem = (ow0 + row) % (p.flat_h * p.flat_w);
+        const int oh = rem / p.flat_w, ow = rem - oh * p.flat_w;
+        tapmask = 0u;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          if ((unsigned)(oh + kh - p.pad) < (unsigned)p.flat_h && (unsigned)(ow + kw - p.pad) < (unsigned)p.flat_w)
+            tapmask |= 1u << tap;
+        }
+      }
       for (int kit = 0; kit < k_iters; ++kit, ++it) {
         const int s = it % L::kStages;
         const uint32_t ph = (it / L::kStages) & 1;
         const int slot = it & 1;
+        const uint32_t keep = ((tapmask >> (kit / p.cblocks)) & 1u) ? 0xFFFFFFFFu : 0u;
         mbar_wait(full_bar + s, ph);                                  // the stage's bytes have landed
         mbar_wait(aslot_bar + slot, ((it >> 1) & 1) ^ 1);             // the MMAs of two K-iterations ago have read the slot
         tc_fence_after();
@@ -771,9 +792,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           lds128(a_row + ((j ^ sw) << 4), v);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const uint32_t h = __float_as_uint(v[e]) & 0xFFFFE000u;
+            const uint32_t h = __float_as_uint(v[e]) & 0xFFFFE000u & keep;
             hi[4 * j + e] = h;
-            lo[4 * j + e] = __float_as_uint(v[e] - __uint_as_float(h)) & 0xFFFFE000u;
+            lo[4 * j + e] = __float_as_uint(v[e] - __uint_as_float(h)) & 0xFFFFE000u & keep;
           }
         }
         tmem_st32(a_tmem + (uint32_t)(slot * kASlotCols), hi);
@@ -1469,7 +1490,23 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
                  int pad, int OH, int OW, TcParams p, bool x3, cudaStream_t s) {
   const bool flat = KH == 1 && KW == 1 && pad == 0 && as == 1 && p.os == 1 && OH == AH && OW == AW &&
                     p.out_H == OH && p.out_W == OW;
-  if (flat) {                               // 1x1 stride 1: pixels are one dense axis, no tile padding at all
+  // 3xTF32 3x3 / pad 1 on small maps whose {tn, th, tw} tiles would be poorly filled (7x7 ROI maps: 98 of 128 rows):
+  // the dense pixel axis of the 1x1 case with the taps as row offsets, out-of-map taps zeroed by the operand splitter
+  p.flat_h = p.flat_w = 0;
+  bool flat_taps = false;
+  if (x3 && !flat && KH == 3 && KW == 3 && pad == 1 && as == 1 && p.os == 1 && OH == AH && OW == AW && p.out_H == OH &&
+      p.out_W == OW && !p.stem && OH * OW <= 4096) {
+    const int tw = pow2_ceil(OW < 16 ? OW : 16), th = pow2_ceil(OH < BM / tw ? OH : BM / tw);
+    const double fill = (double)OW / (((OW + tw - 1) / tw) * tw) * (double)OH / (((OH + th - 1) / th) * th);
+    static int flat_mode = -1;             // DD_TC_FLAT3X3=0 keeps the {tn, th, tw} tiles (A/B runs)
+    if (flat_mode < 0) {
+      const char* e = getenv("DD_TC_FLAT3X3");
+      flat_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    flat_taps = flat_mode == 1 && fill < 0.85;
+  }
+  if (flat_taps) { p.flat_h = OH; p.flat_w = OW; }
+  if (flat || flat_taps) {                  // pixels are one dense axis, no tile padding at all
     const long long P = (long long)N * OH * OW;
     DD_CHECK_ARG(P < (1ll << 31));
     N = 1; OH = AH = 1; OW = AW = (int)P;

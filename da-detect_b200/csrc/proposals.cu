@@ -604,26 +604,32 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const unsigned l
 // ----------------------------------------------------------------------------- NMS, cluster version (no mask)
 // The two kernels above compute the whole upper triangle of the suppression matrix (72 M IoU tests for 12 000 boxes,
 // on every SM of the GPU) although the greedy scan only ever consults the rows of the boxes it KEEPS, and stops at
-// max_keep.  Here a cluster of 8 CTAs owns one image and the matrix never exists: the column blocks are dealt
-// round-robin to the CTAs (boxes and areas resident in shared memory); per 64-box block every CTA redundantly
-// resolves the block (the diagonal 64 x 64 tests, then the serial find-first-set walk — identical inputs, identical
-// result, nothing to broadcast), and then tests only the boxes just kept against its own later columns, OR-ing the
-// result into its running suppression words.  The only exchange is the suppression word of the next block, read from
-// its owner through distributed shared memory after one cluster barrier per block.
+// max_keep.  Here a cluster of 8 CTAs owns one image, the matrix never exists and the evaluation is LAZY: when the
+// scan reaches a 64-box block, that block is tested against the boxes kept so far — the kept boxes are dealt
+// round-robin to the CTAs (resident in shared memory), every CTA tests its share against the 64 candidates and the
+// eight partial suppression words meet through distributed shared memory (one cluster barrier per block).  Every CTA
+// then resolves the block redundantly (the diagonal 64 x 64 tests, the serial find-first-set walk: identical inputs,
+// identical result, nothing to broadcast) and appends the newly kept boxes it owns.  Work = (boxes kept so far) x 64
+// per visited block; blocks behind the stopping point cost nothing.
 constexpr int kNmsCl = 8;
 constexpr int kNmsThreads = 1024;
-constexpr int kNmsOwnBlocks = 256 / kNmsCl;          // column blocks per CTA at the largest supported n (16 384)
+constexpr int kNmsLocalCap = 1024;                   // kept boxes per CTA held in shared memory (8192 per image)
 
 struct NmsClusterShared {
-  float4 own[kNmsOwnBlocks * 64];
-  float own_area[kNmsOwnBlocks * 64];
-  unsigned long long remv[kNmsOwnBlocks];             // suppression words of the owned column blocks
-  float4 rows[2][64];
-  float rows_area[2][64];
+  float4 kept_box[kNmsLocalCap];
+  float kept_area[kNmsLocalCap];
+  int kept_idx[kSortCap];                             // position of every kept box (all CTAs hold the full list)
+  float4 cols[2][64];
+  float cols_area[2][64];
   unsigned long long diag[64];
+  uint32_t partial[2][2];                             // this CTA's share of the block's suppression word
   int kept[64];
   int cnt, nkeep, done;
 };
+
+__device__ __forceinline__ float box_area_plus1(const float4 b) {
+  return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+}
 
 __global__ void __launch_bounds__(kNmsThreads) nms_cluster_kernel(const float4* __restrict__ boxes,
                                                                   const int* __restrict__ n_dev, int n_cap, float thresh,
@@ -638,61 +644,77 @@ __global__ void __launch_bounds__(kNmsThreads) nms_cluster_kernel(const float4* 
   const int col_blocks = (n + 63) / 64;
   boxes += (size_t)img * n_cap;
   keep_pos += (size_t)img * keep_stride;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  uint32_t* remv32 = reinterpret_cast<uint32_t*>(sh.remv);
+  const int tid = threadIdx.x, lane = tid & 31;
 
-  for (int t = tid; t < kNmsOwnBlocks * 64; t += kNmsThreads) {
-    const int col = ((t >> 6) * kNmsCl + q) * 64 + (t & 63);
-    float4 b = make_float4(0.f, 0.f, -1.f, -1.f);
-    if (col < n) b = boxes[col];
-    sh.own[t] = b;
-    sh.own_area[t] = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
-  }
-  if (tid < kNmsOwnBlocks) sh.remv[tid] = 0ull;
   if (tid == 0) { sh.nkeep = 0; sh.done = 0; }
   if (tid < 64) {
     float4 b = make_float4(0.f, 0.f, -1.f, -1.f);
     if (tid < n) b = boxes[tid];
-    sh.rows[0][tid] = b;
-    sh.rows_area[0][tid] = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
+    sh.cols[0][tid] = b;
+    sh.cols_area[0][tid] = box_area_plus1(b);
   }
   __syncthreads();
   for (int b = 0; b < col_blocks; ++b) {
     const int buf = b & 1;
     const int size = min(n - b * 64, 64);
+    const int nkeep = sh.nkeep;
+    if (tid < 2) sh.partial[buf][tid] = 0u;
     if (tid >= 64 && tid < 128 && b + 1 < col_blocks) {           // the next block's boxes
       const int r = (b + 1) * 64 + tid - 64;
       float4 bx = make_float4(0.f, 0.f, -1.f, -1.f);
       if (r < n) bx = boxes[r];
-      sh.rows[buf ^ 1][tid - 64] = bx;
-      sh.rows_area[buf ^ 1][tid - 64] = __fmul_rn(__fadd_rn(__fsub_rn(bx.z, bx.x), 1.f), __fadd_rn(__fsub_rn(bx.w, bx.y), 1.f));
+      sh.cols[buf ^ 1][tid - 64] = bx;
+      sh.cols_area[buf ^ 1][tid - 64] = box_area_plus1(bx);
     }
     // diagonal tests: 16 threads per row, 4 columns each
     {
       const int i = tid >> 4, j0 = (tid & 15) * 4;
-      const float4 me = sh.rows[buf][i];
-      const float my_area = sh.rows_area[buf][i];
+      const float4 me = sh.cols[buf][i];
+      const float my_area = sh.cols_area[buf][i];
       unsigned long long bits = 0ull;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = j0 + e;
-        if (j > i && j < size && i < size && nms_suppresses(me, my_area, sh.rows[buf][j], thresh)) bits |= 1ull << j;
+        if (j > i && j < size && i < size && nms_suppresses(me, my_area, sh.cols[buf][j], thresh)) bits |= 1ull << j;
       }
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
       if ((tid & 15) == 0) sh.diag[i] = bits;
     }
-    cluster.sync();                        // the owner's suppression word of this block is final
+    __syncthreads();
+    // this CTA's kept boxes (ordinals q, q + 8, ...) against the 64 candidates: thread = (candidate, row group)
+    {
+      const int c = tid & 63, g = tid >> 6;
+      const int n_local = nkeep > q ? (nkeep - q + kNmsCl - 1) / kNmsCl : 0;
+      const float4 cb = sh.cols[buf][c];
+      bool sup = false;
+      if (c < size) {
+        for (int l = g; l < n_local && !sup; l += kNmsThreads / 64) {
+          float4 kb;
+          float ka;
+          if (l < kNmsLocalCap) { kb = sh.kept_box[l]; ka = sh.kept_area[l]; }
+          else { kb = boxes[sh.kept_idx[l * kNmsCl + q]]; ka = box_area_plus1(kb); }
+          sup = nms_suppresses(kb, ka, cb, thresh);
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, sup);
+      if (lane == 0 && bal) atomicOr(&sh.partial[buf][(tid >> 5) & 1], bal);
+    }
+    cluster.sync();                        // every CTA's partial word of this block is final
     if (tid == 0) {
-      unsigned long long cur = cluster.map_shared_rank(&sh, b % kNmsCl)->remv[b / kNmsCl];
+      unsigned long long cur = 0ull;
+#pragma unroll
+      for (int p = 0; p < kNmsCl; ++p) {
+        const NmsClusterShared* r = cluster.map_shared_rank(&sh, p);
+        cur |= (unsigned long long)r->partial[buf][0] | ((unsigned long long)r->partial[buf][1] << 32);
+      }
       if (size < 64) cur |= ~0ull << size;
-      int nk = sh.nkeep, cnt = 0;
+      int nk = nkeep, cnt = 0;
       unsigned long long avail = ~cur;
       while (avail) {
         if (max_keep > 0 && nk >= max_keep) break;
         const int i = __ffsll((long long)avail) - 1;
         sh.kept[cnt++] = i;
-        if (q == 0) keep_pos[nk] = (int64_t)(b * 64 + i);
         ++nk;
         cur |= sh.diag[i];
         avail = ~cur & ~((2ull << i) - 1ull);
@@ -702,26 +724,17 @@ __global__ void __launch_bounds__(kNmsThreads) nms_cluster_kernel(const float4* 
       sh.done = (max_keep > 0 && nk >= max_keep) ? 1 : 0;
     }
     __syncthreads();
-    if (sh.done) break;
-    const int cnt = sh.cnt;
-    if (cnt > 0) {
-      // the boxes just kept against this CTA's later columns: one warp per 32 columns
-      for (int hb = wid; hb < kNmsOwnBlocks * 2; hb += kNmsThreads / 32) {
-        const int cb = (hb >> 1) * kNmsCl + q;                   // warp-uniform
-        if (cb <= b || cb >= col_blocks) continue;
-        const int t = hb * 32 + lane;
-        const float4 c = sh.own[t];
-        const bool live = cb * 64 + (hb & 1) * 32 + lane < n && !((remv32[hb] >> lane) & 1u);
-        bool sup = false;
-        for (int r = 0; r < cnt; ++r) {
-          const int i = sh.kept[r];
-          if (live && !sup) sup = nms_suppresses(sh.rows[buf][i], sh.rows_area[buf][i], c, thresh);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, sup);
-        if (lane == 0 && bal) remv32[hb] |= bal;
+    if (tid < sh.cnt) {                    // append the boxes just kept
+      const int ordinal = nkeep + tid, i = sh.kept[tid];
+      sh.kept_idx[ordinal] = b * 64 + i;
+      if (q == 0) keep_pos[ordinal] = (int64_t)(b * 64 + i);
+      if (ordinal % kNmsCl == q && ordinal / kNmsCl < kNmsLocalCap) {
+        sh.kept_box[ordinal / kNmsCl] = sh.cols[buf][i];
+        sh.kept_area[ordinal / kNmsCl] = sh.cols_area[buf][i];
       }
     }
     __syncthreads();
+    if (sh.done) break;
   }
   if (tid == 0 && q == 0) keep_count[img] = sh.nkeep;
   cluster.sync();             // no CTA leaves while another may still read its shared memory

@@ -774,6 +774,9 @@ TC_CASES = [
     (2, 16, 24, 128, 60, 1, 1, 0),        # Cout % 32 != 0: the last staged chunk is clipped by the TMA store
     (1, 24, 40, 64, 512, 3, 1, 1),        # several column tiles per pixel tile
     (300, 7, 7, 64, 96, 1, 1, 0),         # 1x1 on ROI maps: flat pixel axis, ragged last tile
+    (41, 7, 7, 64, 128, 3, 1, 1),         # 3x3 on ROI maps (3xTF32: dense pixel axis, taps as row offsets), ragged last tile
+    (3, 5, 9, 64, 64, 3, 1, 1),           # the same on non-square maps
+    (1, 7, 7, 32, 64, 3, 1, 1),           # one map: a single partial tile
 ]
 
 
