@@ -222,6 +222,9 @@ def main():
     except Exception:
         pass
     if world > 1:
+        if os.environ.get("DD_OVERLAP_EXCHANGE", "0") == "1" and int(os.environ.get("DD_EXCHANGE_CTAS", "0")) > 0:
+            # the overlapped exchange leaves DD_EXCHANGE_CTAS SMs to NCCL: keep its kernels within them
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ["DD_EXCHANGE_CTAS"])
         dist.init_process_group("nccl", init_method="env://")
     assert world == args.gpus, "launch with torchrun --nproc-per-node {} for --gpus {}".format(args.gpus, args.gpus)
     warmup = max(3, args.warmup)

@@ -151,6 +151,11 @@ class FlatSGDTrainer(object):
         # dense kernels are persistent one-CTA-per-SM grids that need 227 KB of shared memory per SM: every kernel that
         # overlaps the exchange gets a second wave on the blocked SMs.  DD_OVERLAP_EXCHANGE=1 switches it on.
         self.overlap_exchange = os.environ.get("DD_OVERLAP_EXCHANGE", "0") == "1"
+        # SMs left to the collective's kernels while a segment exchange may be running beside backward: the persistent
+        # dense kernels launched from the first milestone on are limited to the rest (ops.sm_budget), so that none of
+        # their CTAs queues behind NCCL's for an SM.  Pair it with NCCL_MAX_CTAS of the same value (bench.py does).
+        self.exchange_ctas = int(os.environ.get("DD_EXCHANGE_CTAS", "0"))
+        self._budget_prev = None
         self.comm_stream = None
         self._reduced = set()
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -206,6 +211,9 @@ class FlatSGDTrainer(object):
         if rng is not None and tag not in self._reduced:
             self._reduced.add(tag)
             self._exchange(rng[0], rng[1], side=True)
+            if self.exchange_ctas > 0 and self._budget_prev is None and self.flat_grad.is_cuda:
+                from .. import _lib
+                self._budget_prev = _lib.load().dd_set_sm_budget(ops.NUM_SMS - self.exchange_ctas)
 
     def begin_backward(self):
         """Arm the overlapped exchange for the backward pass that follows (no-op for one rank)."""
@@ -218,6 +226,10 @@ class FlatSGDTrainer(object):
         if self.world <= 1:
             return
         ops.set_grad_milestone_callback(None)
+        if self._budget_prev is not None:
+            from .. import _lib
+            _lib.load().dd_set_sm_budget(self._budget_prev)
+            self._budget_prev = None
         if not self._reduced:
             dist.all_reduce(self.flat_grad)              # one call over the whole buffer (overlap off / no milestones)
             return
