@@ -40,6 +40,8 @@ _SIGS = {
     "dd_box_decode": (_I, "ppiiffffpp"),
     "dd_conv2d_forward_workspace_bytes": (_Z, "iiiii"),
     "dd_conv2d_forward": (_I, "ppppppiiiiiiiiiiipp"),
+    "dd_conv2d_forward_prepared": (_I, "ppppppiiiiiiiiiiipp"),
+    "dd_conv2d_forward_prepare_batch": (_I, "ippppppip"),
     "dd_stem_workspace_bytes": (_Z, "iiii"),
     "dd_stem_conv7x7s2_forward": (_I, "pppppiiiiiipp"),
     "dd_conv2d_dgrad_workspace_bytes": (_Z, "iiii"),

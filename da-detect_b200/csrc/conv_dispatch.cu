@@ -11,7 +11,9 @@ int dd_simt_conv2d_wgrad(const float*, const float*, const float*, float*, int, 
                          int, void*, cudaStream_t);
 
 int dd_tc_conv2d_forward(const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
-                         int, int, int, int, int, int, int, bool, float*, cudaStream_t);
+                         int, int, int, int, int, int, int, bool, float*, bool, cudaStream_t);
+int dd_tc_forward_prepare_batch(int, const float* const*, float* const*, const int*, const int*, const int*, const int*,
+                                cudaStream_t);
 int dd_tc_conv2d_dgrad(const float*, const float*, const float*, const float*, const float*, float*, int, int, int,
                        int, int, int, int, int, int, float*, int, bool, cudaStream_t);
 int tc_rows_pad_public(int ncols);
@@ -28,18 +30,44 @@ extern "C" size_t dd_conv2d_forward_workspace_bytes(int Cin, int Cout, int KH, i
   return sizeof(float) * 2 * (size_t)tc_rows_pad_public(Cout) * KH * KW * Cin;
 }
 
-extern "C" int dd_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias,
-                                 const float* residual, float* y, int N, int H, int W, int Cin, int Cout, int KH,
-                                 int KW, int stride, int pad, int act, int impl, void* workspace, void* stream) {
+static int conv2d_forward_impl(const float* x, const float* w, const float* scale, const float* bias,
+                               const float* residual, float* y, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                               int stride, int pad, int act, int impl, void* workspace, bool prepared, void* stream) {
   DD_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0);
   if (is_tc(impl) && dd_tc_supports(0, N, H, W, Cin, Cout, KH, KW, stride, pad)) {
     const bool x3 = impl == DD_IMPL_TCGEN05_X3;
     DD_CHECK_ARG(!x3 || (workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0));
     return dd_tc_conv2d_forward(x, w, scale, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad, act, x3,
-                                (float*)workspace, dd::S(stream));
+                                (float*)workspace, prepared, dd::S(stream));
   }
+  DD_CHECK_ARG(!prepared);
   return dd_simt_conv2d_forward(x, w, scale, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad, act,
                                 dd::S(stream));
+}
+
+extern "C" int dd_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias,
+                                 const float* residual, float* y, int N, int H, int W, int Cin, int Cout, int KH,
+                                 int KW, int stride, int pad, int act, int impl, void* workspace, void* stream) {
+  return conv2d_forward_impl(x, w, scale, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad, act, impl,
+                             workspace, false, stream);
+}
+
+extern "C" int dd_conv2d_forward_prepared(const float* x, const float* w, const float* scale, const float* bias,
+                                          const float* residual, float* y, int N, int H, int W, int Cin, int Cout,
+                                          int KH, int KW, int stride, int pad, int act, int impl, void* workspace,
+                                          void* stream) {
+  DD_CHECK_ARG(impl == DD_IMPL_TCGEN05_X3);
+  return conv2d_forward_impl(x, w, scale, bias, residual, y, N, H, W, Cin, Cout, KH, KW, stride, pad, act, impl,
+                             workspace, true, stream);
+}
+
+extern "C" int dd_conv2d_forward_prepare_batch(int n, const float* const* w, void* const* workspaces, const int* Cin,
+                                               const int* Cout, const int* KH, const int* KW, int impl, void* stream) {
+  DD_CHECK_ARG(n >= 0 && impl == DD_IMPL_TCGEN05_X3);
+  for (int i = 0; i < n; ++i)
+    DD_CHECK_ARG(w[i] != nullptr && workspaces[i] != nullptr && (reinterpret_cast<uintptr_t>(workspaces[i]) & 15) == 0 &&
+                 Cin[i] > 0 && Cout[i] > 0 && KH[i] > 0 && KW[i] > 0);
+  return dd_tc_forward_prepare_batch(n, w, reinterpret_cast<float* const*>(workspaces), Cin, Cout, KH, KW, dd::S(stream));
 }
 
 extern "C" size_t dd_conv2d_dgrad_workspace_bytes(int Cin, int Cout, int KH, int KW) {

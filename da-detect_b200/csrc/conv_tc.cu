@@ -1481,6 +1481,25 @@ __global__ void split_hi_lo_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
+// The same for up to 32 weight matrices in one launch (the forward weights of a whole model, prepared once per step).
+struct SplitBatch {
+  struct Entry { const float* w; float* out; int rows, rows_pad; long long K; long long begin; } e[32];
+  int n;
+  long long total;
+};
+__global__ void split_hi_lo_batch_kernel(const SplitBatch b) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < b.total; t += (long long)gridDim.x * blockDim.x) {
+    int i = 0;
+    while (i + 1 < b.n && t >= b.e[i + 1].begin) ++i;
+    const SplitBatch::Entry& en = b.e[i];
+    const long long u = t - en.begin, plane = (long long)en.rows_pad * en.K;
+    const float v = u / en.K < en.rows ? en.w[u] : 0.f;
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    en.out[u] = hi;
+    en.out[plane + u] = __uint_as_float(__float_as_uint(v - hi) & 0xFFFFE000u);
+  }
+}
+
 // Core: D[pixel, col] = sum_{tap, c} A[n, (oh + kh - pad) * as, (ow + kw - pad) * as, c] * B[col, tap, c]
 //   A: [N, AH, AW, Cin] NHWC fp32 read with pixel stride `as` (as > 1 only for 1x1 taps: the TMA view simply
 //      has doubled strides, nothing is gathered), B: [ncols, taps*Cin] fp32, output rows enumerate (N, OH, OW)
@@ -1751,9 +1770,30 @@ bool dd_tc_supports(int mode, int N, int H, int W, int Cin, int Cout, int KH, in
   return true;
 }
 
+// Split the forward weights of n layers into the hi / lo planes the 3xTF32 kernel consumes (what dd_conv2d_forward does
+// per call) in one launch per 32 layers.  ws[i] must hold dd_conv2d_forward_workspace_bytes(...) bytes.
+int dd_tc_forward_prepare_batch(int n, const float* const* w, float* const* ws, const int* Cin, const int* Cout,
+                                const int* KH, const int* KW, cudaStream_t s) {
+  for (int base = 0; base < n; base += 32) {
+    SplitBatch b = {};
+    b.n = n - base < 32 ? n - base : 32;
+    long long total = 0;
+    for (int i = 0; i < b.n; ++i) {
+      const int j = base + i;
+      b.e[i].w = w[j]; b.e[i].out = ws[j]; b.e[i].rows = Cout[j]; b.e[i].rows_pad = tc_rows_pad(Cout[j]);
+      b.e[i].K = (long long)KH[j] * KW[j] * Cin[j]; b.e[i].begin = total;
+      total += (long long)b.e[i].rows_pad * b.e[i].K;
+    }
+    b.total = total;
+    split_hi_lo_batch_kernel<<<dd::grid_for(total, 256), 256, 0, s>>>(b);
+    DD_LAUNCHED();
+  }
+  return 0;
+}
+
 int dd_tc_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias, const float* residual,
                          float* y, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-                         int act, bool x3, float* ws, cudaStream_t s) {
+                         int act, bool x3, float* ws, bool prepared, cudaStream_t s) {
   const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
   TcParams p = {};
   p.out = y; p.scale = scale; p.bias = bias; p.extra = residual; p.mask = nullptr; p.relu = act == DD_ACT_RELU;
@@ -1763,8 +1803,10 @@ int dd_tc_conv2d_forward(const float* x, const float* w, const float* scale, con
     DD_CHECK_ARG(ws != nullptr);
     const long long K = (long long)KH * KW * Cin;
     const int rp = tc_rows_pad(Cout);
-    split_hi_lo_kernel<<<dd::grid_for((long long)rp * K, 256), 256, 0, s>>>(w, ws, Cout, rp, K);
-    DD_LAUNCHED();
+    if (!prepared) {
+      split_hi_lo_kernel<<<dd::grid_for((long long)rp * K, 256), 256, 0, s>>>(w, ws, Cout, rp, K);
+      DD_LAUNCHED();
+    }
     b = ws;
   }
   // strided 1x1: the TMA view of x addresses every stride-th pixel directly

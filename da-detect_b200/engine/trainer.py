@@ -165,6 +165,10 @@ class FlatSGDTrainer(object):
         self.graph_pool = None           # one memory pool shared by all step graphs (their replays never overlap)
         self.max_step_graphs = 16        # signatures kept; the least recently used graph is dropped beyond that
         self.early_backward = False
+        # the weight operands of the whole step (3xTF32 hi / lo planes, dgrad transposes) prepared by a few batched
+        # launches at the start of the step instead of one small launch in front of every conv (ops.WeightPrepPlan)
+        self.batch_weight_prep = False
+        self._prep_plan = None
 
     def enable_step_graph(self, flag=True):
         """Capture zero_grad + forward + backward + all-reduce + SGD of one iteration into ONE CUDA graph per
@@ -177,6 +181,7 @@ class FlatSGDTrainer(object):
             self.model.enable_static_shapes(True)
             self.model.enable_cuda_graphs(False)
             self.enable_early_backward(os.environ.get("DD_EARLY_BACKWARD", "1") != "0")
+            self.batch_weight_prep = os.environ.get("DD_BATCH_WEIGHT_PREP", "1") != "0"
 
     def enable_early_backward(self, flag=True):
         """Back-propagate the RPN losses during the forward pass, beside the latency-bound proposal chain
@@ -349,6 +354,15 @@ class FlatSGDTrainer(object):
         return loss_dict
 
     def _eager_step(self, images, targets, dev_lr=False):
+        if self.batch_weight_prep and self.flat_param.is_cuda:
+            if self._prep_plan is None:       # first step: record which weights the dense tier prepares
+                stable = [t.untyped_storage().data_ptr() for t in list(self.model.parameters()) + list(self.model.buffers())]
+                self._prep_plan = ops.WeightPrepPlan(stable + [self.flat_param.untyped_storage().data_ptr()])
+            with ops.weight_prep(self._prep_plan):
+                return self._eager_step_body(images, targets, dev_lr)
+        return self._eager_step_body(images, targets, dev_lr)
+
+    def _eager_step_body(self, images, targets, dev_lr=False):
         self.begin_backward()                 # (the milestone hooks are registered during the forward pass)
         if self.early_backward:
             self.zero_grad()

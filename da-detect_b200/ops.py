@@ -187,6 +187,109 @@ def grad_like_weight(g_ohwi, w):
     return g_ohwi.view(co, kh, kw, ci).permute(0, 3, 1, 2)
 
 
+class WeightPrepPlan(object):
+    """Per-step preparation of the dense tier's weight operands, batched.  Every 3xTF32 forward conv splits its weight
+    into hi / lo planes and every tensor-core data gradient builds the flipped, BN-scaled transpose W' of its weight —
+    ~60 + ~80 small launches per training step, each between two large persistent kernels.  A trainer records the
+    (weight, shape) pairs of its first step (`recording`), and from then on prepares ALL of them with a handful of
+    batched launches at the start of the step (run()); the conv calls of that step find their operand in the plan by
+    the weight's address and skip their own preparation.  Only tensors that live in storage the trainer declared stable
+    (parameters, buffers) are recorded, and the plan keeps them alive, so an address can never come to mean another
+    tensor.  Outside `weight_prep(plan)` nothing is looked up: the operands are only valid for the step they were
+    prepared in (the optimiser changes the weights)."""
+
+    def __init__(self, stable_storages):
+        self.stable = set(stable_storages)
+        self.fwd, self.dgrad = {}, {}          # key -> [tensors kept alive..., dims, workspace]
+        self.recording = True
+
+    def is_stable(self, t):
+        return t is None or t.untyped_storage().data_ptr() in self.stable
+
+    def finalize(self):
+        self.recording = False
+
+    def run(self):
+        """Prepare every recorded operand on the current stream."""
+        lib = _lib.load()
+        if self.fwd:
+            ents = list(self.fwd.values())
+            n = len(ents)
+            vp, ip = ctypes.c_void_p * n, ctypes.c_int * n
+            _lib.call("dd_conv2d_forward_prepare_batch", n, vp(*[e["w"].data_ptr() for e in ents]),
+                      vp(*[e["ws"].data_ptr() for e in ents]), ip(*[e["dims"][0] for e in ents]),
+                      ip(*[e["dims"][1] for e in ents]), ip(*[e["dims"][2] for e in ents]),
+                      ip(*[e["dims"][3] for e in ents]), IMPL_TCGEN05_X3, _stream())
+        if self.dgrad:
+            for impl in sorted({e["impl"] for e in self.dgrad.values()}):
+                ents = [e for e in self.dgrad.values() if e["impl"] == impl]
+                n = len(ents)
+                vp, ip = ctypes.c_void_p * n, ctypes.c_int * n
+                _lib.call("dd_conv2d_dgrad_prepare_batch", n, vp(*[e["w"].data_ptr() for e in ents]),
+                          vp(*[None if e["scale"] is None else e["scale"].data_ptr() for e in ents]),
+                          vp(*[e["ws"].data_ptr() for e in ents]), ip(*[e["dims"][0] for e in ents]),
+                          ip(*[e["dims"][1] for e in ents]), ip(*[e["dims"][2] for e in ents]),
+                          ip(*[e["dims"][3] for e in ents]), impl, _stream())
+        del lib
+
+
+_prep_plan = None
+
+
+class weight_prep(object):
+    """Context manager around one training step: `plan` is consulted (and, while it is recording, extended) by the
+    conv calls inside; a finished plan has its operands prepared on entry."""
+
+    def __init__(self, plan):
+        self.plan = plan
+
+    def __enter__(self):
+        global _prep_plan
+        self.prev = _prep_plan
+        _prep_plan = self.plan
+        if self.plan is not None and not self.plan.recording:
+            self.plan.run()
+        return self.plan
+
+    def __exit__(self, *exc):
+        global _prep_plan
+        _prep_plan = self.prev
+        if self.plan is not None and self.plan.recording and exc[0] is None:
+            self.plan.finalize()
+        return False
+
+
+def _prep_fwd(w_ohwi, cin, cout, kh, kw):
+    """The prepared hi / lo planes of a forward weight for this step, or None."""
+    plan = _prep_plan
+    if plan is None:
+        return None
+    key = (w_ohwi.data_ptr(), cin, cout, kh, kw)
+    ent = plan.fwd.get(key)
+    if ent is not None:
+        return None if plan.recording else ent["ws"]
+    if plan.recording and plan.is_stable(w_ohwi):
+        nbytes = _lib.load().dd_conv2d_forward_workspace_bytes(cin, cout, kh, kw, IMPL_TCGEN05_X3)
+        plan.fwd[key] = dict(w=w_ohwi, dims=(cin, cout, kh, kw),
+                             ws=torch.empty(max(int(nbytes) // 4, 4), dtype=torch.float32, device=w_ohwi.device))
+    return None
+
+
+def _prep_dgrad(w_ohwi, scale, cin, cout, kh, kw, impl):
+    """The prepared dgrad weights W' of a layer for this step, or None."""
+    plan = _prep_plan
+    if plan is None or impl == IMPL_SIMT:
+        return None
+    key = (w_ohwi.data_ptr(), 0 if scale is None else scale.data_ptr(), cin, cout, kh, kw, impl)
+    ent = plan.dgrad.get(key)
+    if ent is not None:
+        return None if plan.recording else ent["ws"]
+    if plan.recording and plan.is_stable(w_ohwi):          # (the plan keeps `scale`, a cached derived tensor, alive)
+        plan.dgrad[key] = dict(w=w_ohwi, scale=scale, dims=(cin, cout, kh, kw), impl=impl,
+                               ws=dgrad_workspace(cin, cout, kh, kw, w_ohwi.device))
+    return None
+
+
 # ----------------------------------------------------------------------------------------- raw kernels
 def conv2d_forward_raw(x, w_ohwi, scale, bias, residual, kh, kw, stride, pad, relu, impl=None):
     n, h, wd, cin = x.shape
@@ -195,11 +298,15 @@ def conv2d_forward_raw(x, w_ohwi, scale, bias, residual, kh, kw, stride, pad, re
     ow = (wd + 2 * pad - kw) // stride + 1
     y = torch.empty((n, oh, ow, cout), dtype=torch.float32, device=x.device)
     impl = fwd_impl(impl)
-    ws = None
+    ws, entry = None, "dd_conv2d_forward"
     if impl == IMPL_TCGEN05_X3:
-        nbytes = _lib.load().dd_conv2d_forward_workspace_bytes(cin, cout, kh, kw, impl)
-        ws = torch.empty(max(int(nbytes) // 4, 4), dtype=torch.float32, device=x.device)
-    _lib.call("dd_conv2d_forward", _ptr(x), _ptr(w_ohwi), _ptr(scale), _ptr(bias), _ptr(residual), _ptr(y),
+        ws = _prep_fwd(w_ohwi, cin, cout, kh, kw)          # prepared for this step by the trainer's plan?
+        if ws is not None:
+            entry = "dd_conv2d_forward_prepared"
+        else:
+            nbytes = _lib.load().dd_conv2d_forward_workspace_bytes(cin, cout, kh, kw, impl)
+            ws = torch.empty(max(int(nbytes) // 4, 4), dtype=torch.float32, device=x.device)
+    _lib.call(entry, _ptr(x), _ptr(w_ohwi), _ptr(scale), _ptr(bias), _ptr(residual), _ptr(y),
               n, h, wd, cin, cout, kh, kw, stride, pad, 1 if relu else 0, impl, _ptr(ws), _stream())
     return y
 
@@ -210,6 +317,8 @@ def conv2d_dgrad_raw(gy, w_ohwi, scale, x_shape, kh, kw, stride, pad, addend=Non
     n, h, wd, cin = x_shape
     cout = w_ohwi.shape[0]
     gx = torch.empty(x_shape, dtype=torch.float32, device=gy.device)
+    if prepared_ws is None:
+        prepared_ws = _prep_dgrad(w_ohwi, scale, cin, cout, kh, kw, bwd_impl(impl))
     ws = prepared_ws if prepared_ws is not None else dgrad_workspace(cin, cout, kh, kw, gy.device)
     _lib.call("dd_conv2d_dgrad", _ptr(gy), _ptr(w_ohwi), _ptr(scale), _ptr(addend), _ptr(mask_act), _ptr(gx),
               n, h, wd, cin, cout, kh, kw, stride, pad, bwd_impl(impl), _ptr(ws),
@@ -237,6 +346,9 @@ def dgrad_prepare_batch(layers, device, impl=None):
             dims.append((w.shape[3], w.shape[0], w.shape[1], w.shape[2]))      # OHWI -> (Cin, Cout, KH, KW)
         else:
             dims.append((w.shape[1], w.shape[0], 1, 1))
+    planned = [_prep_dgrad(w, sc, ci, co, kh, kw, impl) for (w, sc), (ci, co, kh, kw) in zip(layers, dims)]
+    if all(p is not None for p in planned):            # prepared for this step by the trainer's plan
+        return planned
     wss = [dgrad_workspace(ci, co, kh, kw, device) for ci, co, kh, kw in dims]
     vp, ip = ctypes.c_void_p * n, ctypes.c_int * n
     _lib.call("dd_conv2d_dgrad_prepare_batch", n, vp(*[w.data_ptr() for w, _ in layers]),

@@ -184,6 +184,14 @@ int dd_balanced_sample(const int* labels, const int* n_dev, const float* keys, i
 int dd_conv2d_forward(const float* x, const float* w, const float* scale, const float* bias,
                       const float* residual, float* y, int N, int H, int W, int Cin, int Cout, int KH, int KW,
                       int stride, int pad, int act, int impl, void* workspace, void* stream);
+/* 3xTF32 arm with the hi / lo weight planes prepared beforehand: dd_conv2d_forward_prepare_batch splits the weights of
+ * n layers (workspaces[i] of dd_conv2d_forward_workspace_bytes bytes each) in one launch per 32 layers — e.g. once per
+ * training step for a whole model — and dd_conv2d_forward_prepared is dd_conv2d_forward minus its per-call split. */
+int dd_conv2d_forward_prepare_batch(int n, const float* const* w, void* const* workspaces, const int* Cin,
+                                    const int* Cout, const int* KH, const int* KW, int impl, void* stream);
+int dd_conv2d_forward_prepared(const float* x, const float* w, const float* scale, const float* bias,
+                               const float* residual, float* y, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                               int stride, int pad, int act, int impl, void* workspace, void* stream);
 /* workspace: dd_conv2d_forward_workspace_bytes(...) bytes (0 unless impl == DD_IMPL_TCGEN05_X3: the hi / lo
  * planes of the weights), 16-byte aligned; may be NULL when 0. */
 size_t dd_conv2d_forward_workspace_bytes(int Cin, int Cout, int KH, int KW, int impl);
