@@ -346,6 +346,8 @@ def main():
                    "parallelism": "dp{}".format(world),
                    "l2": "per-step working set (>4 GB of activations) far exceeds the 126 MB L2; no flush needed",
                    "tflop_per_image": tflop_per_image,
+                   "early_backward": bool(getattr(state["trainer"], "early_backward", False)),
+                   "launches_per_step": launches / max(args.steps, 1),
                    "parity": "losses within 1e-4 of the CPU oracle with the arm's own hard decisions (tests/test_gpu_model.py "
                              "[mixed], tests/test_gpu_fullsize.py at 1024x2048); gradients TF32-grade (1e-2 of the global norm)"},
         "clocks": sampler.summary(),
