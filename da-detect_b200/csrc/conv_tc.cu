@@ -63,6 +63,7 @@ struct TcParams {
   // axis like for a 1x1 conv, a filter tap is a constant row offset (kh - pad) * flat_w + (kw - pad) of the TMA load,
   // and the operand splitter zeroes the rows whose tap falls outside their own flat_h x flat_w map (0 = off)
   int flat_h, flat_w;
+  int onepass;             // 3xTF32 + residual + short K: one-pass epilogue (map_e = the residual's per-warp sub-box)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -472,7 +473,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 // PAIR: 0 = single CTAs; 1 = CTA pair with cta_group::2 MMAs (above); 2 = cluster of two single-CTA-MMA CTAs that
 // share the B tile: each loads half of it and TMA-multicasts the half into both (half the B traffic from L2, the
 // TMA -> splitter -> MMA chain stays inside the CTA).
-template <int BN, bool X3, int PAIR>
+template <int BN, bool X3, int PAIR, bool OP = false>
 struct SmemLayout {
   static constexpr bool CTA2 = PAIR == 1;
   static constexpr int kABytes = BM * BKB;                       // 16 KB
@@ -481,14 +482,20 @@ struct SmemLayout {
   // parts) lives in tensor memory, written there by the splitter warps and read from there by the MMAs
   static constexpr int kStageBytes = X3 ? kABytes + 2 * kBBytes : kABytes + kBBytes;
   static_assert(!(X3 && PAIR == 1), "the 3xTF32 kernel does not pair its MMAs (cta_group::2)");
-  static constexpr int kFit = (192 * 1024) / kStageBytes;
+  // one-pass epilogue (OP): per epilogue warp two 4 KB residual slices landed by TMA and a 1 KB scale / bias table
+  static constexpr int kResBytes = OP ? 4 * 2 * 4096 : 0;
+  static constexpr int kTabBytes = OP ? 4 * 1024 : 0;
+  static constexpr int kFit = (192 * 1024 - kResBytes - kTabBytes) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kStagingBytes = BM * 128;                 // one 128-row x 32-column fp32 chunk
   static constexpr int kStagingOff = kStages * kStageBytes;      // 2 staging buffers (1024-aligned)
-  static constexpr int kRowOff = kStagingOff + 2 * kStagingBytes;  // int32 pixel index per tile row
+  static constexpr int kResOff = kStagingOff + 2 * kStagingBytes;   // (1024-aligned: the slices are 128B-swizzled)
+  static constexpr int kTabOff = kResOff + kResBytes;
+  static constexpr int kRowOff = kTabOff + kTabBytes;            // int32 pixel index per tile row
   static constexpr int kBarOff = kRowOff + BM * 4;
   static constexpr int kTotal = kBarOff + 512 /*barriers*/ + 1024 /*alignment slack*/;
   static_assert(kTotal <= 232448, "shared memory budget");
+  static_assert(kStages >= 2, "at least two pipeline stages");
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -537,7 +544,7 @@ __device__ __forceinline__ void load_scale_bias(const TcParams& p, int col, floa
   }
 }
 
-enum { EPI_EXTRA = 1, EPI_MASK = 2, EPI_SCALAR = 4 };
+enum { EPI_EXTRA = 1, EPI_MASK = 2, EPI_SCALAR = 4, EPI_ONEPASS = 8 };
 
 // ------------------------------------------------------------------------------------------------ kernel
 // Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence t = blockIdx.x + i*gridDim.x.
@@ -562,7 +569,9 @@ __global__ void __launch_bounds__(X3 ? NUM_THREADS_X3 : NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_e,
                const __grid_constant__ CUtensorMap map_m, const TcParams p) {
-  using L = SmemLayout<BN, X3, PAIR>;
+  constexpr bool kOnePass = (EPI & EPI_ONEPASS) != 0;
+  static_assert(!kOnePass || (X3 && (EPI & (EPI_MASK | EPI_SCALAR)) == 0), "one-pass epilogue: 3xTF32, no mask input");
+  using L = SmemLayout<BN, X3, PAIR, kOnePass>;
   constexpr bool CTA2 = PAIR == 1;     // cta_group::2 MMAs issued by the leader
   constexpr bool MC = PAIR == 2;       // own MMAs, B halves multicast between the two CTAs
   constexpr bool CL = PAIR != 0;       // launched as a cluster of 2
@@ -577,6 +586,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* split_bar = tmem_empty_bar + 2;             // [2], X3 only: the A operand of a TMEM slot has been written
   uint64_t* aslot_bar = split_bar + 2;                  // [2], X3 only: the MMAs that read a TMEM A slot have retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aslot_bar + 2);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff + 384);   // one-pass epilogue: [warp][buffer]
   constexpr int kBOff = L::kABytes;                     // B (hi) tile offset inside a stage; B_lo follows it
   constexpr int kBRows = CTA2 ? BN / 2 : BN;            // B rows (output columns) this CTA loads
 
@@ -612,6 +622,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // transaction, and 128 of them per K-iteration made the pair mode a third slower than single CTAs
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, CTA2 ? 8 : 4); }
     if (X3) for (int s = 0; s < 2; ++s) { mbar_init(split_bar + s, 4); mbar_init(aslot_bar + s, 1); }
+    if (kOnePass) for (int s = 0; s < 8; ++s) mbar_init(res_bar + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // TMEM: 2 x BN columns (two tile accumulators, ping-pong).  3xTF32 mode: [M | P0 | P1], BN columns each.
@@ -809,7 +820,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // Each warp owns TMEM lanes / tile rows [32q, 32q+32) end to end (its own staging slices, its own TMA
     // stores), so the chunk loop needs only __syncwarp.  EPI selects the compiled side-input handling.
     constexpr bool kExtra = (EPI & EPI_EXTRA) != 0, kMask = (EPI & EPI_MASK) != 0, kScalar = (EPI & EPI_SCALAR) != 0;
-    constexpr bool kAhead = !X3 && !kScalar && (kExtra != kMask);   // exactly one side input: prefetch it a chunk ahead
+    constexpr bool kAhead = !kScalar && (kExtra != kMask);          // exactly one side input: prefetch it a chunk ahead
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;                 // tile row owned in the TMEM -> smem pass
     const int pc = lane & 7;                             // re-mapped pass: 16-byte column group of the chunk,
@@ -931,6 +942,83 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       };
 
       uint32_t ra[32], rb[32];
+      if constexpr (kOnePass) {
+        // ---- one-pass epilogue (3xTF32 + residual, short K: the memory-bound 1x1 layers of the trunk).  The two-pass
+        // loop below is issue-bound on its four warps (~350 instructions per chunk and lane: transpose through the
+        // staging buffer, address arithmetic of the coalesced side reads; ncu: 6.6 us per tile on res2.conv3 for 3.3
+        // of data movement).  Here the warp's [32 rows x 32 ch] residual sub-box is landed by TMA in the SAME swizzled
+        // row layout as the staging buffer (two slices, loads issued two chunks ahead), the per-channel scale / bias
+        // of the tile sit in a small table read by broadcast, and every lane finishes its own row straight out of the
+        // accumulator registers: tcgen05.ld -> fma, + residual, ReLU -> staging -> TMA store.  Same arithmetic order.
+        const uint32_t my_res = smem_u32(smem + L::kResOff) + quarter * 8192;
+        const uint32_t my_tab = smem_u32(smem + L::kTabOff) + quarter * 1024;         // [BN scale | BN bias]
+        uint64_t* my_bar = res_bar + quarter * 2;
+        auto issue_res = [&](uint32_t c, int ch) {       // chunk counter c (buffer c & 1), chunk ch of this tile
+          if (lane == 0) {
+            mbar_expect_tx(my_bar + (c & 1), 4096);
+            tma_load_4d(&map_e, my_bar + (c & 1), smem + L::kResOff + quarter * 8192 + (c & 1) * 4096,
+                        n_tile * BN + ch * 32, ow0 + sub_w, oh0 + sub_h, n0 + sub_n);
+          }
+        };
+        if (kExtra) {
+          issue_res(chunk_ctr, 0);
+          if (n_chunks > 1) issue_res(chunk_ctr + 1, 1);
+        }
+        {
+          float s4[4], b4[4];
+          if (lane * 4 < BN) {
+            load_scale_bias(p, n_tile * BN + lane * 4, s4, b4);
+            sts128(my_tab + lane * 16, s4[0], s4[1], s4[2], s4[3]);
+            sts128(my_tab + BN * 4 + lane * 16, b4[0], b4[1], b4[2], b4[3]);
+          }
+          __syncwarp();
+        }
+        const int n_groups = (k_iters + kGroup - 1) / kGroup;
+        for (int g = 0; g < n_groups; ++g, ++x3_grp) {
+          const int pp = x3_grp & 1;
+          mbar_wait(tmem_full_bar + pp, (x3_grp >> 1) & 1);
+          tc_fence_after();
+          const uint32_t tp = tm + (uint32_t)((1 + pp) * BN);
+#pragma unroll 1
+          for (int ch = 0; ch < n_chunks; ++ch) {
+            tmem_ld32(tp + (uint32_t)(ch * 32), ra);
+            if (g > 0) {
+              tmem_ld32(tm + (uint32_t)(ch * 32), rb);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
+            }
+            if (g < n_groups - 1) { tmem_st32(tm + (uint32_t)(ch * 32), ra); continue; }
+            if (ch == n_chunks - 1) release_tmem(tmem_empty_bar + pp);     // slot fully read: hand it back
+            const uint32_t stg = my_stage + (chunk_ctr & 1) * L::kStagingBytes;
+            if (lane == 0) tma_store_wait_read<1>();     // the store that last read this staging slice has drained
+            if (kExtra) mbar_wait(my_bar + (chunk_ctr & 1), (chunk_ctr >> 1) & 1);       // the residual slice has landed
+            __syncwarp();
+            const uint32_t res = my_res + (chunk_ctr & 1) * 4096 + st_off;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float s4[4], b4[4], e4[4] = {0.f, 0.f, 0.f, 0.f};
+              lds128(my_tab + (ch * 32 + j * 4) * 4, s4);
+              lds128(my_tab + BN * 4 + (ch * 32 + j * 4) * 4, b4);
+              if (kExtra) lds128(res + ((j ^ st_sw) << 4), e4);
+              float v[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[e] = fmaf(__uint_as_float(ra[4 * j + e]), s4[e], b4[e]);
+                if (kExtra) v[e] += e4[e];
+                v[e] = fmaxf(v[e], lo);
+              }
+              sts128(stg + st_off + ((j ^ st_sw) << 4), v[0], v[1], v[2], v[3]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_4d(&map_c, stg, n_tile * BN + ch * 32, ow0 + sub_w, oh0 + sub_h, n0 + sub_n);
+            if (kExtra && ch + 2 < n_chunks) issue_res(chunk_ctr + 2, ch + 2);       // (every lane has read the slice)
+            ++chunk_ctr;
+          }
+          if (g < n_groups - 1) release_tmem(tmem_empty_bar + pp);
+        }
+        continue;
+      }
       float4 exa[8], mka[8], exb[kAhead ? 8 : 1], mkb[kAhead ? 8 : 1];
       if (kAhead) issue_side(0, exa, mka);             // does not depend on the accumulator: before the wait
       if constexpr (X3) {
@@ -954,8 +1042,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tmem_st32(tm + (uint32_t)(ch * 32), ra);
             }
           } else {
-#pragma unroll 1
-            for (int ch = 0; ch < n_chunks; ++ch) {
+            // the last partial: added on the fly, then the epilogue proper.  The side input (residual) of chunk ch + 1
+            // is requested before chunk ch is processed (two register sets), like in the TF32 loop below: requested
+            // right before its use, every chunk paid the full DRAM latency (res2.conv3: 6.6 us per tile)
+            auto fetch = [&](int ch) {
               tmem_ld32(tp + (uint32_t)(ch * 32), ra);
               if (g > 0) {
                 tmem_ld32(tm + (uint32_t)(ch * 32), rb);
@@ -963,7 +1053,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int j = 0; j < 32; ++j) ra[j] = __float_as_uint(__uint_as_float(ra[j]) + __uint_as_float(rb[j]));
               }
               if (ch == n_chunks - 1) release_tmem(tmem_empty_bar + pp);   // slot fully read: hand it back before the slow part
+            };
+#pragma unroll 1
+            for (int ch = 0; ch < n_chunks; ch += 2) {
+              fetch(ch);
+              if constexpr (kAhead) { if (ch + 1 < n_chunks) issue_side(ch + 1, exb, mkb); }
               process(ra, ch, exa, mka);
+              if (ch + 1 < n_chunks) {
+                fetch(ch + 1);
+                if constexpr (kAhead) {
+                  if (ch + 2 < n_chunks) issue_side(ch + 2, exa, mka);
+                  process(ra, ch + 1, exb, mkb);
+                } else {
+                  process(ra, ch + 1, exa, mka);
+                }
+              }
             }
             continue;
           }
@@ -1400,7 +1504,7 @@ int tc_cta2_forced() {         // 0 = heuristics, 1 = cta_group::2 pairs everywh
 template <int BN, int EPI, bool X3, int PAIR>
 int launch_tc4(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
                const CUtensorMap& mm, const TcParams& p, cudaStream_t s) {
-  using L = SmemLayout<BN, X3, PAIR>;
+  using L = SmemLayout<BN, X3, PAIR, (EPI & EPI_ONEPASS) != 0>;
   constexpr bool CL = PAIR != 0;
   static bool configured = false;
   if (!configured) {
@@ -1444,13 +1548,18 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& 
   if constexpr (BN <= 128) {
     if (x3) return launch_tc3<BN, EPI, true>(ma, mb, mc, me, mm, p, pair, s);
   }
-  return launch_tc3<BN, EPI, false>(ma, mb, mc, me, mm, p, pair, s);
+  if constexpr ((EPI & EPI_ONEPASS) != 0) return dd::fail(-1, "one-pass epilogue needs the 3xTF32 kernel", __FILE__, __LINE__);
+  else return launch_tc3<BN, EPI, false>(ma, mb, mc, me, mm, p, pair, s);
 }
 
 template <int BN>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& me,
               const CUtensorMap& mm, const TcParams& p, bool x3, int pair, cudaStream_t s) {
   if (!p.tma_store) return launch_tc2<BN, EPI_SCALAR>(ma, mb, mc, me, mm, p, x3, pair, s);
+  if constexpr (BN <= 128) {
+    if (p.onepass && p.extra) return launch_tc2<BN, EPI_EXTRA | EPI_ONEPASS>(ma, mb, mc, me, mm, p, x3, pair, s);
+    if (p.onepass) return launch_tc2<BN, EPI_ONEPASS>(ma, mb, mc, me, mm, p, x3, pair, s);
+  }
   const int epi = (p.extra ? EPI_EXTRA : 0) | (p.mask ? EPI_MASK : 0);
   switch (epi) {
     case 0: return launch_tc2<BN, 0>(ma, mb, mc, me, mm, p, x3, pair, s);
@@ -1595,7 +1704,34 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
   }
   CUtensorMap me = ma, mm = ma;
   p.prefetch_side = 0;
-  if (p.tma_store && (p.extra || p.mask)) {
+  p.onepass = 0;
+  {
+    static int onepass_mode = -1;          // DD_TC_ONEPASS=0 keeps the two-pass epilogue everywhere (A/B runs)
+    if (onepass_mode < 0) {
+      const char* e = getenv("DD_TC_ONEPASS");
+      onepass_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    static int onepass_k = -1;             // longest K loop (in 32-channel iterations) that takes the one-pass epilogue
+    if (onepass_k < 0) {
+      const char* e = getenv("DD_TC_ONEPASS_K");
+      onepass_k = e != nullptr ? atoi(e) : 8;
+    }
+    // measured per layer (profiles/r03_layer_bench_x3_onepass.txt): with a residual it pays up to 8 K-iterations, without
+    // one up to 4 — beyond that the pipeline stage the side buffers cost (3 instead of 4 at BN = 128) weighs more
+    const int k_limit = p.extra ? onepass_k : onepass_k / 2;
+    if (onepass_mode == 1 && x3 && p.tma_store && !p.mask && !p.stem && k_iters_host <= k_limit && BN <= 128)
+      p.onepass = 1;
+  }
+  if (p.onepass && p.extra) {
+    cuuint64_t dims[4] = {(cuuint64_t)ncols, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)p.ldc * 4 * p.os, (cuuint64_t)p.out_W * p.ldc * 4 * p.os,
+                             (cuuint64_t)p.out_H * p.out_W * p.ldc * 4};
+    const int bw = p.tw < 32 ? p.tw : 32;
+    const int bh = p.th < 32 / bw ? p.th : 32 / bw;
+    const int bn = 32 / (bw * bh);
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    if (encode_map(&me, p.extra, 4, dims, strides, box)) return -1;
+  } else if (p.tma_store && (p.extra || p.mask)) {
     cuuint64_t dims[4] = {(cuuint64_t)ncols, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)p.ldc * 4 * p.os, (cuuint64_t)p.out_W * p.ldc * 4 * p.os,
                              (cuuint64_t)p.out_H * p.out_W * p.ldc * 4};
