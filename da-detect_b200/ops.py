@@ -61,12 +61,48 @@ def set_direct_weight_grad(flag):
     _direct_wgrad = bool(flag)
 
 
+_wgrad_side = None
+
+
+def set_wgrad_side(main_stream, side_stream, wgrad_sms):
+    """Run the direct-mode weight-gradient kernels launched from `main_stream` on `side_stream`, limited to `wgrad_sms`
+    SMs, while the data-gradient kernels of the fused stages keep the other SMs (None, ... = off).  The weight and data
+    gradient of a layer are independent, and the small layers of res3 / res4 leave most of a 148-SM launch idle (their
+    split-K items are short and end in a burst of reductions): two half-width kernels side by side finish sooner than
+    two full-width ones in a row.  The caller joins with wgrad_side_join() before it reads the gradients."""
+    global _wgrad_side
+    _wgrad_side = None if main_stream is None else dict(main=main_stream, side=side_stream, w=int(wgrad_sms),
+                                                        d=NUM_SMS - int(wgrad_sms), used=False)
+
+
+def wgrad_side_join():
+    cfg = _wgrad_side
+    if cfg is not None and cfg["used"]:
+        cfg["main"].wait_stream(cfg["side"])
+        cfg["used"] = False
+
+
+def _wgrad_side_active():
+    # tensor-core arms only: the SIMT weight-gradient kernels share one split-K scratch buffer per device
+    cfg = _wgrad_side
+    return cfg is not None and bwd_impl() != IMPL_SIMT and torch.cuda.current_stream() == cfg["main"]
+
+
 def _wgrad_into(param, gy, x, scale, cout, kh, kw, stride, pad):
     """Weight gradient of one conv: returned for autograd, or (direct mode) accumulated into param.grad."""
     if _direct_wgrad and param.is_leaf and param.grad is not None:
         g = param.grad
         phys = g.permute(0, 2, 3, 1) if g.dim() == 4 else g
         if phys.is_contiguous() and phys.data_ptr() % 16 == 0:
+            if gy.is_cuda and _wgrad_side_active():
+                cfg = _wgrad_side
+                cfg["side"].wait_stream(cfg["main"])          # gy and x are complete
+                gy.record_stream(cfg["side"])
+                x.record_stream(cfg["side"])
+                with torch.cuda.stream(cfg["side"]), sm_budget(cfg["w"]):
+                    conv2d_wgrad_raw(gy, x, scale, cout, kh, kw, stride, pad, out=phys, accumulate=True)
+                cfg["used"] = True
+                return None
             conv2d_wgrad_raw(gy, x, scale, cout, kh, kw, stride, pad, out=phys, accumulate=True)
             return None
     return grad_like_weight(conv2d_wgrad_raw(gy, x, scale, cout, kh, kw, stride, pad), param)
@@ -454,7 +490,11 @@ class _ConvBnAct(torch.autograd.Function):
         w = weight_ohwi(weight)
         gx = gw = gb = gres = None
         if ctx.needs_input_grad[0]:
-            gx = conv2d_dgrad_raw(g, w, scale, tuple(x.shape), kh, kw, stride, pad)
+            if g.is_cuda and _wgrad_side_active():
+                with sm_budget(_wgrad_side["d"]):
+                    gx = conv2d_dgrad_raw(g, w, scale, tuple(x.shape), kh, kw, stride, pad)
+            else:
+                gx = conv2d_dgrad_raw(g, w, scale, tuple(x.shape), kh, kw, stride, pad)
         if ctx.needs_input_grad[1]:
             gw = _wgrad_into(ctx.weight_ref, g, x, scale, w.shape[0], kh, kw, stride, pad)
         if has_bias and ctx.needs_input_grad[3]:
@@ -526,6 +566,13 @@ class _BottleneckStage(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if g.is_cuda and _wgrad_side_active():             # the data-gradient kernels leave the side stream its SMs
+            with sm_budget(_wgrad_side["d"]):
+                return _BottleneckStage._backward(ctx, g)
+        return _BottleneckStage._backward(ctx, g)
+
+    @staticmethod
+    def _backward(ctx, g):
         strides, has_down, input_is_relu, grad_premasked, pool_output = ctx.meta
         all_saved = ctx.saved_tensors
         acts, tensors = all_saved[:ctx.n_saved], all_saved[ctx.n_saved:]
