@@ -83,9 +83,11 @@ def wgrad_side_join():
 
 
 def _wgrad_side_active():
-    # tensor-core arms only: the SIMT weight-gradient kernels share one split-K scratch buffer per device
+    # TF32 backward arms only (tcgen05, mixed): the SIMT weight-gradient kernels share one split-K scratch buffer per
+    # device, and on the all-3xTF32 arm the weight gradients are twice the work of the data gradients — an even split
+    # of the SMs slows it down (27.4 -> 33.3 ms)
     cfg = _wgrad_side
-    return cfg is not None and bwd_impl() != IMPL_SIMT and torch.cuda.current_stream() == cfg["main"]
+    return cfg is not None and bwd_impl() == IMPL_TCGEN05 and torch.cuda.current_stream() == cfg["main"]
 
 
 def _wgrad_into(param, gy, x, scale, cout, kh, kw, stride, pad):
