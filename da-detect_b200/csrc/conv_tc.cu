@@ -1569,6 +1569,15 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m
   }
 }
 
+bool tc_onepass_enabled() {         // DD_TC_ONEPASS=0 keeps the two-pass epilogue everywhere (A/B runs)
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DD_TC_ONEPASS");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 // 3xTF32 runs tiles of at most 128 columns: TMEM holds the running sum and two partial slots of a tile
 int tc_bn_for(int ncols, bool x3) {
   if (x3) return ncols > 64 ? 128 : 64;
@@ -1706,11 +1715,7 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
   p.prefetch_side = 0;
   p.onepass = 0;
   {
-    static int onepass_mode = -1;          // DD_TC_ONEPASS=0 keeps the two-pass epilogue everywhere (A/B runs)
-    if (onepass_mode < 0) {
-      const char* e = getenv("DD_TC_ONEPASS");
-      onepass_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
-    }
+    const int onepass_mode = tc_onepass_enabled() ? 1 : 0;
     static int onepass_k = -1;             // longest K loop (in 32-channel iterations) that takes the one-pass epilogue
     if (onepass_k < 0) {
       const char* e = getenv("DD_TC_ONEPASS_K");
@@ -1718,8 +1723,10 @@ int tc_conv_core(const float* a, int N, int AH, int AW, int Cin, int as, const f
     }
     // measured per layer (profiles/r03_layer_bench_x3_onepass.txt): with a residual it pays up to 8 K-iterations, without
     // one up to 4 — beyond that the pipeline stage the side buffers cost (3 instead of 4 at BN = 128) weighs more
-    const int k_limit = p.extra ? onepass_k : onepass_k / 2;
-    if (onepass_mode == 1 && x3 && p.tma_store && !p.mask && !p.stem && k_iters_host <= k_limit && BN <= 128)
+    // (64-column tiles keep four stages with the side buffers: up to 8 iterations without a residual as well — the
+    // 64 -> 64 and 256 -> 64 convs of res2)
+    const int k_limit = (p.extra || BN == 64) ? onepass_k : onepass_k / 2;
+    if (onepass_mode == 1 && x3 && p.tma_store && !p.mask && k_iters_host <= k_limit && BN <= 128)
       p.onepass = 1;
   }
   if (p.onepass && p.extra) {
@@ -1831,6 +1838,7 @@ extern "C" int dd_stem_conv7x7s2_forward(const float* x_nchw, const float* w_ohw
   p.tiles_w = (OW + 15) / 16; p.tiles_h = (OH + 7) / 8;
   p.m_tiles = N * p.tiles_h * p.tiles_w; p.n_tiles = 1;
   p.tma_store = 1; p.stem = 1;
+  p.onepass = 0;       // (measured: the one-pass epilogue makes the stem slower, 228 us against 180)
   p.out_H = OH; p.out_W = OW; p.os = 1; p.ldc = Cout; p.Cout = Cout;
   p.taps = 7; p.KW = 1; p.pad = 0; p.cblocks = 1; p.Cin = 32;
   p.b_lo_row = x3 ? 64 : 0;

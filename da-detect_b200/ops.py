@@ -247,28 +247,60 @@ class WeightPrepPlan(object):
     def finalize(self):
         self.recording = False
 
+    EARLY_BYTES = 8 << 20        # forward operands prepared on the step's own stream before anything else runs
+
+    def _split(self, ents):
+        n = len(ents)
+        if n == 0:
+            return
+        vp, ip = ctypes.c_void_p * n, ctypes.c_int * n
+        _lib.call("dd_conv2d_forward_prepare_batch", n, vp(*[e["w"].data_ptr() for e in ents]),
+                  vp(*[e["ws"].data_ptr() for e in ents]), ip(*[e["dims"][0] for e in ents]),
+                  ip(*[e["dims"][1] for e in ents]), ip(*[e["dims"][2] for e in ents]),
+                  ip(*[e["dims"][3] for e in ents]), IMPL_TCGEN05_X3, _stream())
+
     def run(self):
-        """Prepare every recorded operand on the current stream."""
-        lib = _lib.load()
-        if self.fwd:
-            ents = list(self.fwd.values())
-            n = len(ents)
-            vp, ip = ctypes.c_void_p * n, ctypes.c_int * n
-            _lib.call("dd_conv2d_forward_prepare_batch", n, vp(*[e["w"].data_ptr() for e in ents]),
-                      vp(*[e["ws"].data_ptr() for e in ents]), ip(*[e["dims"][0] for e in ents]),
-                      ip(*[e["dims"][1] for e in ents]), ip(*[e["dims"][2] for e in ents]),
-                      ip(*[e["dims"][3] for e in ents]), IMPL_TCGEN05_X3, _stream())
-        if self.dgrad:
+        """Prepare every recorded operand.  The forward operands of the first layers (in the order the step uses them,
+        EARLY_BYTES worth: stem, res2, res3) on the current stream; everything else — 430 MB of split planes for res4,
+        the RPN and the heads, and the data-gradient transposes that only the backward pass reads — on a side stream
+        beside the memory-bound start of the trunk.  A consumer stream waits for the side stream the first time it
+        looks one of those operands up (`_join`)."""
+        main = torch.cuda.current_stream()
+        ents = list(self.fwd.values())                   # insertion order = order of first use
+        early, late, acc = [], [], 0
+        for e in ents:
+            acc += e["ws"].numel() * 4
+            (early if acc <= self.EARLY_BYTES else late).append(e)
+            e["late"] = acc > self.EARLY_BYTES
+        self._split(early)
+        self.joined = set()
+        if not late and not self.dgrad:
+            self.side = None
+            return
+        if getattr(self, "side", None) is None:
+            self.side = torch.cuda.Stream(device=ents[0]["ws"].device if ents else None)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self._split(late)
             for impl in sorted({e["impl"] for e in self.dgrad.values()}):
-                ents = [e for e in self.dgrad.values() if e["impl"] == impl]
-                n = len(ents)
+                ds = [e for e in self.dgrad.values() if e["impl"] == impl]
+                n = len(ds)
                 vp, ip = ctypes.c_void_p * n, ctypes.c_int * n
-                _lib.call("dd_conv2d_dgrad_prepare_batch", n, vp(*[e["w"].data_ptr() for e in ents]),
-                          vp(*[None if e["scale"] is None else e["scale"].data_ptr() for e in ents]),
-                          vp(*[e["ws"].data_ptr() for e in ents]), ip(*[e["dims"][0] for e in ents]),
-                          ip(*[e["dims"][1] for e in ents]), ip(*[e["dims"][2] for e in ents]),
-                          ip(*[e["dims"][3] for e in ents]), impl, _stream())
-        del lib
+                _lib.call("dd_conv2d_dgrad_prepare_batch", n, vp(*[e["w"].data_ptr() for e in ds]),
+                          vp(*[None if e["scale"] is None else e["scale"].data_ptr() for e in ds]),
+                          vp(*[e["ws"].data_ptr() for e in ds]), ip(*[e["dims"][0] for e in ds]),
+                          ip(*[e["dims"][1] for e in ds]), ip(*[e["dims"][2] for e in ds]),
+                          ip(*[e["dims"][3] for e in ds]), impl, _stream())
+
+    def _join(self):
+        """The current stream is about to read an operand prepared on the side stream."""
+        side = getattr(self, "side", None)
+        if side is None:
+            return
+        cur = torch.cuda.current_stream()
+        if cur.cuda_stream not in self.joined:
+            cur.wait_stream(side)
+            self.joined.add(cur.cuda_stream)
 
 
 _prep_plan = None
@@ -305,7 +337,11 @@ def _prep_fwd(w_ohwi, cin, cout, kh, kw):
     key = (w_ohwi.data_ptr(), cin, cout, kh, kw)
     ent = plan.fwd.get(key)
     if ent is not None:
-        return None if plan.recording else ent["ws"]
+        if plan.recording:
+            return None
+        if ent.get("late"):
+            plan._join()
+        return ent["ws"]
     if plan.recording and plan.is_stable(w_ohwi):
         nbytes = _lib.load().dd_conv2d_forward_workspace_bytes(cin, cout, kh, kw, IMPL_TCGEN05_X3)
         plan.fwd[key] = dict(w=w_ohwi, dims=(cin, cout, kh, kw),
@@ -321,7 +357,10 @@ def _prep_dgrad(w_ohwi, scale, cin, cout, kh, kw, impl):
     key = (w_ohwi.data_ptr(), 0 if scale is None else scale.data_ptr(), cin, cout, kh, kw, impl)
     ent = plan.dgrad.get(key)
     if ent is not None:
-        return None if plan.recording else ent["ws"]
+        if plan.recording:
+            return None
+        plan._join()
+        return ent["ws"]
     if plan.recording and plan.is_stable(w_ohwi):          # (the plan keeps `scale`, a cached derived tensor, alive)
         plan.dgrad[key] = dict(w=w_ohwi, scale=scale, dims=(cin, cout, kh, kw), impl=impl,
                                ws=dgrad_workspace(cin, cout, kh, kw, w_ohwi.device))
