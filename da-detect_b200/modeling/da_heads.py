@@ -246,6 +246,30 @@ class DAInsHeadFPN(nn.Module):
         return out
 
 
+def _ins_head_fpn_static(head, x, roi_levels, row_valid):
+    """DAInsHeadFPN on fixed-capacity ROI slots, without host reads: every level head runs on ALL rows and a row keeps
+    the output of the head of its own level (the other products are multiplied by zero, forward and backward).  A
+    replaying random source skips the levels without ROIs like the reference does (da_heads_fpn.py:194) — a host read,
+    test-only — and its recorded masks are scattered into the rows of the level."""
+    out = torch.zeros((x.shape[0], 1), dtype=x.dtype, device=x.device)
+    valid = None if row_valid is None else row_valid.bool()
+    for lvl in range(head.levels):
+        m = roi_levels == lvl
+        if valid is not None:
+            m = m & valid
+        if head.rng.replay and int(m.sum()) == 0:
+            continue
+        xs = x
+        for j in (1, 2):
+            fc = getattr(head, "da_ins_fc{}_level{}".format(j, lvl))
+            xs = ops.linear(xs, fc.weight, fc.bias, relu=True)
+            if head.training:
+                xs = ops.dropout_with_mask(xs, head.rng.dropout_keep(tuple(xs.shape), xs.device, m))
+        fc3 = getattr(head, "da_ins_fc3_level{}".format(lvl))
+        out = out + ops.fused_heads(xs, [fc3.weight], [fc3.bias])[0] * m.to(x.dtype).unsqueeze(1)
+    return out
+
+
 class DomainAdaptationModuleFPN(nn.Module):
     """DA heads on an FPN backbone (BASELINE configs[4]).  PARITY UNPINNED: the reference has no runnable FPN + DA
     combination; this is the intent of da_heads_fpn.py:209-295 with its defects resolved as listed in
@@ -261,28 +285,34 @@ class DomainAdaptationModuleFPN(nn.Module):
         self.imghead = DAImgHeadFPN(cfg.MODEL.BACKBONE.OUT_CHANNELS, levels=5)
         self.inshead = DAInsHeadFPN(cfg.MODEL.ROI_BOX_HEAD.MLP_HEAD_DIM, rng, levels=len(cfg.MODEL.ROI_BOX_HEAD.POOLER_SCALES))
 
-    def forward(self, img_features, ins_feas, dom, n_src, targets, roi_levels):
+    def forward(self, img_features, ins_feas, dom, n_src, targets, roi_levels, row_valid=None, seg=None):
+        """row_valid / seg: the ROI slots that exist and the cached per-image domain labels — given by the sync-free
+        training path (fixed-capacity ROI slots, n_src = slots per image); then no step reads a size on the host."""
         if not self.training:
             return {}
         D = self.cfg.MODEL.DA_HEADS
         need_img, need_ins, need_cst = self.img_weight > 0, self.ins_weight > 0, self.cst_weight > 0
         losses = {}
+        static = row_valid is not None
+        ins = (lambda z: _ins_head_fpn_static(self.inshead, z, roi_levels, row_valid)) if static else \
+              (lambda z: self.inshead(z, roi_levels))
         # (same evaluation order as the oracle: instance GRL pass, instance consistency pass, image passes —
         # the dropout draws of the instance passes are consumed in that order)
-        da_ins = self.inshead(ops.gradient_scalar(ins_feas, -1.0 * D.DA_INS_GRL_WEIGHT), roi_levels)
-        da_ins_c = self.inshead(ops.gradient_scalar(ins_feas, 1.0 * D.DA_INS_GRL_WEIGHT), roi_levels)
+        da_ins = ins(ops.gradient_scalar(ins_feas, -1.0 * D.DA_INS_GRL_WEIGHT))
+        da_ins_c = ins(ops.gradient_scalar(ins_feas, 1.0 * D.DA_INS_GRL_WEIGHT))
         if need_img:
             da_img = self.imghead([ops.gradient_scalar(f, -1.0 * D.DA_IMG_GRL_WEIGHT) for f in img_features])
             n = da_img[0].shape[0]
             flat = torch.cat([t.reshape(n, -1) for t in da_img], dim=1)
-            losses["loss_da_image"] = self.img_weight * da_img_loss(flat, targets)
+            losses["loss_da_image"] = self.img_weight * da_img_loss(flat, targets, seg)
         if need_ins:
-            losses["loss_da_instance"] = self.ins_weight * da_ins_loss(da_ins, dom)
+            losses["loss_da_instance"] = self.ins_weight * da_ins_loss(da_ins, dom, row_valid)
         if need_cst:
             da_img_c = self.imghead([ops.gradient_scalar(f, 1.0 * D.DA_IMG_GRL_WEIGHT) for f in img_features])
             # mean over ROIs x levels of |image-level mean probability - ROI probability| = the mean of the
             # per-level consistency losses (every level has the same K rows)
-            terms = [ops.consistency_loss(t.reshape(t.shape[0], -1), da_ins_c.reshape(-1), n_src) for t in da_img_c]
+            terms = [ops.consistency_loss(t.reshape(t.shape[0], -1), da_ins_c.reshape(-1), n_src, row_valid)
+                     for t in da_img_c]
             losses["loss_da_consistency"] = self.cst_weight * (sum(terms) / float(len(terms)))
         return losses
 

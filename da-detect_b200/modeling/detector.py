@@ -146,6 +146,22 @@ class GeneralizedRCNN(nn.Module):
             self.rpn.finish_early_backward(losses, pending)
         return losses
 
+    def _forward_static_fpn(self, images, targets, features):
+        """FPN training without host reads (enable_static_shapes(True); what FlatSGDTrainer's step graph captures):
+        fixed-capacity proposals over the levels (rpn.py::proposals_fpn_static), fixed ROI slots through the multi-level
+        pooler and the MLP head, per-level DA heads on all slots with level masks."""
+        meta = self._batch_meta(targets)
+        props, proposal_losses = self.rpn.forward_fpn_static(images, features, targets, meta)
+        box = self.roi_heads.box
+        detector_losses, pooled, dom, row_valid = box.forward_static(features, props, targets)
+        losses = {}
+        losses.update(detector_losses)
+        losses.update(proposal_losses)
+        if self.da_heads:
+            losses.update(self.da_heads(features, pooled, dom, box.loss_evaluator.batch, targets,
+                                        box.feature_extractor.pooler.last_levels, row_valid=row_valid, seg=meta["seg"]))
+        return losses
+
     def _forward_static_heads(self, features, targets, props, proposal_losses, meta, early_img=None):
         feat = features[0]
         losses = {}
@@ -202,6 +218,8 @@ class GeneralizedRCNN(nn.Module):
         if self.fpn:
             x = ops._chk(images.tensors, name="images")
             features = self.backbone(x)
+            if self.training and self.static_shapes and self.roi_heads:
+                return self._forward_static_fpn(images, targets, features)
             proposals, proposal_losses = self.rpn(images, features, targets)
         else:
             static = self.training and self.static_shapes and bool(self.roi_heads)

@@ -97,7 +97,16 @@ class FPN2MLPFeatureExtractor(nn.Module):
         self.even_bins = False
 
     def forward(self, feats, proposals):
-        x = self.pooler(feats, proposals)                    # [K, r, r, C]
+        return self._head(self.pooler(feats, proposals))     # [K, r, r, C] -> [K, MLP_HEAD_DIM]
+
+    def forward_rois(self, feats, rois):
+        """The same on a fixed-capacity ROI tensor [K, 5] (sync-free training path)."""
+        p = self.pooler
+        x, p.last_levels = ops.roi_align_levels(list(feats[:len(p.scales)]), rois, p.scales, p.output_size,
+                                                p.sampling_ratio)
+        return self._head(x)
+
+    def _head(self, x):
         k, r, c = x.shape[0], self.resolution, self.channels
         w6 = self.fc6.weight.view(-1, c, r * r).permute(0, 2, 1).reshape(-1, r * r * c)
         x = ops.linear(x.reshape(k, r * r * c), w6, self.fc6.bias, relu=True)
@@ -298,7 +307,10 @@ class ROIBoxHead(nn.Module):
         row_valid uint8 [K]) with K = images x BATCH_SIZE_PER_IMAGE."""
         st = self.loss_evaluator.subsample_static(props, targets)
         segments = self.__dict__.get("segments")
-        if segments is not None:
+        if self.mlp_head:                                     # FPN: multi-level pooling + MLP head on the ROI slots
+            pooled = self.feature_extractor.forward_rois(features, st["rois"])
+            class_logits, box_regression = self.predictor(pooled)
+        elif segments is not None:
             from .detector import _BoxBranch
             pooled, class_logits, box_regression = segments.run(
                 "box", lambda: _BoxBranch(self.feature_extractor, self.predictor), (features[0], st["rois"]))

@@ -448,6 +448,63 @@ class RPNModule(nn.Module):
                     out[i] = bl
         return out
 
+    # ---- FPN, fixed-capacity and sync-free (training): per level top-k / NMS into padded buffers, the batch-wide
+    # select_over_all_levels cut (rpn/inference.py:160-171) as a masked top-k + stable partition on the device
+    @torch.no_grad()
+    def proposals_fpn_static(self, grids, outs, image_sizes, meta):
+        R = self.cfg.MODEL.RPN
+        pre, post, fpn_post = R.PRE_NMS_TOP_N_TRAIN, R.POST_NMS_TOP_N_TRAIN, R.FPN_POST_NMS_TOP_N_TRAIN
+        n = outs[0][0].shape[0]
+        dev = outs[0][0].device
+        no_gt = torch.zeros(n, dtype=torch.uint8, device=dev)
+        bl, sl, vl = [], [], []
+        for (anchors, _), (logits, deltas) in zip(grids, outs):
+            _, fh, fw, a = logits.shape
+            k = min(pre, fh * fw * a)
+            p_l = min(post, k)
+            boxes, scores, _, valid = self._topk_decode(logits, deltas, anchors, k, image_sizes, R.MIN_SIZE)
+            keep, cnt = ops.nms_sorted_batched(boxes, valid, R.NMS_THRESH, p_l)
+            b, s_, c = ops.proposals_gather(boxes, scores, keep, cnt, meta["gt_cat"], meta["gt_offsets"], no_gt, p_l,
+                                            gt_counts=meta.get("gt_counts"))
+            bl.append(b)
+            sl.append(s_)
+            vl.append(torch.arange(p_l, device=dev).unsqueeze(0) < c.unsqueeze(1))
+        allb, alls, valid = torch.cat(bl, dim=1), torch.cat(sl, dim=1), torch.cat(vl, dim=1)     # [N, P, ...]
+        P = alls.shape[1]
+        # ONE top-k over the proposals of the whole batch (the reference's known quirk), then every image keeps its
+        # selected proposals in their concatenated (level-major) order: mask + stable partition, no nonzero
+        masked = torch.where(valid, alls, torch.full_like(alls, float("-inf"))).reshape(-1)
+        top_v, top_i = torch.topk(masked, min(fpn_post, n * P), dim=0, sorted=True)
+        sel = torch.zeros(n * P, dtype=torch.bool, device=dev)
+        sel.scatter_(0, top_i, top_v > float("-inf"))
+        sel = sel.view(n, P)
+        order = torch.sort((~sel).to(torch.uint8), dim=1, stable=True)[1]
+        cap_keep = min(P, fpn_post)
+        boxes, obj, count = ops.proposals_gather(allb, alls, order[:, :cap_keep].contiguous(),
+                                                 sel.sum(dim=1).to(torch.int32), meta["gt_cat"], meta["gt_offsets"],
+                                                 meta["append_gt"], cap_keep + meta["max_gt"],
+                                                 gt_counts=meta.get("gt_counts"))
+        return ProposalBatch(boxes, obj, count, sizes=[(int(w), int(h)) for h, w in image_sizes])
+
+    def forward_fpn_static(self, images, features, targets, meta):
+        outs = [self.head(f) for f in features]              # the same head on every level (rpn.py:39-46)
+        grids = [self._anchors_and_visibility(f.shape[1], f.shape[2], images.image_sizes, level=l)
+                 for l, f in enumerate(features)]
+        props = self.proposals_fpn_static(grids, [(lg.detach(), dl.detach()) for lg, dl in outs], images.image_sizes,
+                                          meta)
+        if self.proposal_hook is not None:
+            props = self.proposal_hook(props)
+        n = outs[0][0].shape[0]
+        obj = torch.cat([lg.reshape(n, -1) for lg, _ in outs], dim=1)
+        reg = torch.cat([dl.reshape(n, -1, 4) for _, dl in outs], dim=1)
+        anchors = torch.cat([g[0] for g in grids], dim=0)
+        if isinstance(grids[0][1], list):                    # images of different sizes: one mask per image
+            vis = [torch.cat([g[1][i] for g in grids], dim=0) for i in range(n)]
+        else:
+            vis = torch.cat([g[1] for g in grids], dim=0)
+        obj_loss, box_loss = self.losses_static(anchors, vis, obj, reg, targets, meta)
+        return props, {"loss_objectness": obj_loss, "loss_rpn_box_reg": box_loss}
+
     def forward_fpn(self, images, features, targets=None):
         outs = [self.head(f) for f in features]              # the same head on every level (rpn.py:39-46)
         grids = [self._anchors_and_visibility(f.shape[1], f.shape[2], images.image_sizes, level=l)

@@ -23,6 +23,18 @@ def _restore_impl():
     ops.set_default_impl(ops.IMPL_SIMT)
 
 
+def proposal_batch(boxlists):
+    """list[BoxList] (with `objectness`) -> the fixed-capacity ProposalBatch of the sync-free path."""
+    from dadetect_b200.modeling.rpn import ProposalBatch
+    cap = max(len(b) for b in boxlists)
+    n = len(boxlists)
+    boxes, obj = torch.zeros(n, cap, 4, device=DEV), torch.zeros(n, cap, device=DEV)
+    for i, b in enumerate(boxlists):
+        boxes[i, : len(b)], obj[i, : len(b)] = b.bbox, b.get_field("objectness")
+    return ProposalBatch(boxes, obj, torch.tensor([len(b) for b in boxlists], dtype=torch.int32, device=DEV),
+                         [b.size for b in boxlists])
+
+
 def nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous()
 
@@ -236,7 +248,8 @@ def test_fpn_training_step_runs_and_reaches_every_trainable_parameter():
 
 
 @pytest.mark.timeout(600)
-def test_fpn_training_proposals_match_oracle():
+@pytest.mark.parametrize("static", [False, True])
+def test_fpn_training_proposals_match_oracle(static):
     """Training-mode RPN over five levels: PRE/POST_NMS_TOP_N_TRAIN per level, then select_over_all_levels' ONE
     top-k over the whole batch (rpn/inference.py:160-171) and the GT boxes appended for source images — against
     oracle/fpn_ref.py (pinned to the real reference by tests/test_fpn_cpu.py) on the fp32 arm."""
@@ -262,9 +275,12 @@ def test_fpn_training_proposals_match_oracle():
         b.add_field("is_source", torch.full((len(t["labels"]),), bool(t["is_source"]), dtype=torch.bool, device=DEV))
         tg.append(b)
     seen = {}
+    model.enable_static_shapes(static)        # True: the device-side select_over_all_levels of the sync-free path
     model.rpn.set_proposal_hook(lambda boxes: seen.setdefault("p", boxes) or boxes)
     with torch.no_grad():
         model(images.to(DEV), tg)
+    if static:
+        seen["p"] = seen["p"].to_boxlists()
     with torch.no_grad():
         pyramid = fpn_ref.fpn_forward(fpn_ref.resnet_body_all_stages(images, sd, "R-50-FPN"), sd)
         want = fpn_ref.rpn_fpn_proposals(pyramid, sd, cfg, [(H, W)] * 2, training=True, nms_strict=True)
@@ -285,8 +301,9 @@ def test_fpn_training_proposals_match_oracle():
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("dense", ["simt", "tcgen05x3", "mixed"])
-def test_fpn_training_step_matches_oracle(dense):
+@pytest.mark.parametrize("dense,static", [("simt", False), ("tcgen05x3", False), ("mixed", False), ("simt", True),
+                                          ("mixed", True)])
+def test_fpn_training_step_matches_oracle(dense, static):
     """Loss-level parity of an FPN training step (BASELINE configs[4] backbone family, plain Faster R-CNN losses over
     five levels: rpn/loss.py:57-143 with concat_box_prediction_layers, box_head/loss.py:165-221, the batch-wide
     proposal cut of rpn/inference.py:160-171) against oracle/fpn_ref.py::forward_train_fpn with its random draws
@@ -331,7 +348,8 @@ def test_fpn_training_step_matches_oracle(dense):
         bl = BoxList(b.to(DEV), (W, H), mode="xyxy")
         bl.add_field("objectness", s_.to(DEV))
         forced.append(bl)
-    model.rpn.set_proposal_hook(lambda boxes: forced)
+    model.enable_static_shapes(static)        # True: the sync-free path FlatSGDTrainer's step graph captures
+    model.rpn.set_proposal_hook((lambda props: proposal_batch(forced)) if static else (lambda boxes: forced))
     replay = ReplaySource(rec.perms, rec.masks)
     model.set_random_source(replay)
     tg = []
@@ -365,8 +383,8 @@ def test_fpn_training_step_matches_oracle(dense):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("dense", ["simt", "mixed"])
-def test_fpn_da_training_step_matches_oracle(dense):
+@pytest.mark.parametrize("dense,static", [("simt", False), ("mixed", False), ("simt", True), ("mixed", True)])
+def test_fpn_da_training_step_matches_oracle(dense, static):
     """FPN + DA heads (BASELINE configs[4]; PARITY UNPINNED — the reference has no runnable combination, the oracle
     restates the intent of da_heads_fpn.py, see oracle/fpn_ref.py): per-level image heads, per-level instance heads
     routed by the pooler's LevelMapper, image BCE over all levels, multi-level consistency — losses within 1e-4 of
@@ -411,7 +429,8 @@ def test_fpn_da_training_step_matches_oracle(dense):
         bl = BoxList(b.to(DEV), (W, H), mode="xyxy")
         bl.add_field("objectness", s_.to(DEV))
         forced.append(bl)
-    model.rpn.set_proposal_hook(lambda boxes: forced)
+    model.enable_static_shapes(static)        # True: the sync-free path FlatSGDTrainer's step graph captures
+    model.rpn.set_proposal_hook((lambda props: proposal_batch(forced)) if static else (lambda boxes: forced))
     replay = ReplaySource(rec.perms, rec.masks)
     model.set_random_source(replay)
     tg = []
@@ -438,4 +457,64 @@ def test_fpn_da_training_step_matches_oracle(dense):
         den += float(b.pow(2).sum())
     assert (num / den) ** 0.5 < tol_global, (num / den) ** 0.5
     levels = model.roi_heads.box.feature_extractor.pooler.last_levels
-    assert int((torch.bincount(levels.to(torch.int64), minlength=4) > 0).sum()) >= 2
+    assert int((torch.bincount(levels.to(torch.int64).clamp(min=0), minlength=4) > 0).sum()) >= 2
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("da", [False, True])
+def test_fpn_whole_step_graph_matches_eager_training(da):
+    """FPN training (BASELINE configs[4] family) through FlatSGDTrainer: four SGD steps replayed from ONE captured CUDA
+    graph (sync-free proposals over five levels, ROI slots through the multi-level pooler, per-level DA heads) == the
+    same steps on the host-driven control flow launched eagerly, on identical hash-based random choices."""
+    from dadetect_b200 import ops
+    from dadetect_b200.engine import FlatSGDTrainer
+    from dadetect_b200.modeling import build_detection_model
+    from dadetect_b200.structures import BoxList
+    from dadetect_b200.utils.random_source import HashSource
+    from dadetect_b200.utils.synthetic import make_batch, make_state_dict
+    ops.set_default_impl(ops.IMPL_SIMT)
+    opts = ["MODEL.BACKBONE.CONV_BODY", "R-50-FPN", "MODEL.ROI_BOX_HEAD.NUM_CLASSES", 9,
+            "MODEL.RPN.FPN_POST_NMS_TOP_N_TRAIN", 600]
+    if da:
+        opts += ["MODEL.DOMAIN_ADAPTATION_ON", True, "MODEL.DA_HEADS.TRIPLET_USE", False]
+    cfg = fpn_cfg(opts)
+    H, W = 192, 256
+    images, targets = make_batch(2, H, W, num_classes=9, boxes_per_image=4, seed=33)
+    if not da:
+        for t in targets:
+            t["is_source"] = True
+    sd = None
+    out = []
+    for graph in (False, True):
+        model = build_detection_model(cfg).to(DEV)
+        if sd is None:
+            sd = make_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+            sd["rpn.head.cls_logits.weight"] = sd["rpn.head.cls_logits.weight"] * 20.0
+        model.load_state_dict(sd, strict=False)
+        model.train()
+        model.set_random_source(HashSource())
+        trainer = FlatSGDTrainer(model, cfg, world_size=1)
+        if graph:
+            trainer.enable_step_graph(True)
+        else:
+            model.enable_static_shapes(True)             # the same sync-free control flow, launched eagerly
+        losses = []
+        for it in range(4):
+            tg = []
+            for t in targets:
+                b = BoxList(t["boxes"].to(DEV), (W, H), mode="xyxy")
+                b.add_field("labels", t["labels"].to(DEV))
+                b.add_field("is_source", torch.full((len(t["labels"]),), bool(t["is_source"]), dtype=torch.bool, device=DEV))
+                tg.append(b)
+            ld = trainer.step(images.to(DEV) + 0.01 * it, tg)
+            losses.append({k: float(v) for k, v in ld.items()})
+        if graph:
+            assert trainer.graph_launches > 0 and len(trainer.step_graphs) == 1
+        out.append((losses, trainer.flat_param.clone()))
+    (l0, p0), (l1, p1) = out
+    for a, b in zip(l0, l1):
+        assert a.keys() == b.keys() and (not da or "loss_da_consistency" in a)
+        for k in a:
+            assert abs(a[k] - b[k]) <= 2e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    rel = float((p0 - p1).norm() / p0.norm())
+    assert rel < 1e-5, rel
