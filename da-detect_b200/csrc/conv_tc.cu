@@ -791,21 +791,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int s = it % L::kStages;
         const uint32_t ph = (it / L::kStages) & 1;
         const int slot = it & 1;
-        const uint32_t keep = ((tapmask >> (kit / p.cblocks)) & 1u) ? 0xFFFFFFFFu : 0u;
         mbar_wait(full_bar + s, ph);                                  // the stage's bytes have landed
         mbar_wait(aslot_bar + slot, ((it >> 1) & 1) ^ 1);             // the MMAs of two K-iterations ago have read the slot
         tc_fence_after();
         const uint32_t a_row = smem_u32(smem + s * L::kStageBytes) + row_off;
         uint32_t hi[32], lo[32];
+        // (the dense-axis 3x3 mode is a separate instance of the loop: this chain is latency-critical, and the tap test
+        // plus 64 extra ANDs per K-iteration cost the RPN conv 8 % when they sat in the common path)
+        const bool zero_row = p.flat_w != 0 && !((tapmask >> (kit / p.cblocks)) & 1u);
+        if (zero_row) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                    // quarter-warp phases hit 8 distinct 16-byte bank groups
-          float v[4];
-          lds128(a_row + ((j ^ sw) << 4), v);
+          for (int j = 0; j < 32; ++j) { hi[j] = 0u; lo[j] = 0u; }
+        } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t h = __float_as_uint(v[e]) & 0xFFFFE000u & keep;
-            hi[4 * j + e] = h;
-            lo[4 * j + e] = __float_as_uint(v[e] - __uint_as_float(h)) & 0xFFFFE000u & keep;
+          for (int j = 0; j < 8; ++j) {                  // quarter-warp phases hit 8 distinct 16-byte bank groups
+            float v[4];
+            lds128(a_row + ((j ^ sw) << 4), v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t h = __float_as_uint(v[e]) & 0xFFFFE000u;
+              hi[4 * j + e] = h;
+              lo[4 * j + e] = __float_as_uint(v[e] - __uint_as_float(h)) & 0xFFFFE000u;
+            }
           }
         }
         tmem_st32(a_tmem + (uint32_t)(slot * kASlotCols), hi);
