@@ -25,6 +25,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -771,57 +773,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int row = q * 32 + lane;
     const uint32_t row_off = (uint32_t)row * 128u, sw = (uint32_t)(row & 7);
     const uint32_t a_tmem = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(3 * BN);
-    uint32_t it = 0;
-    for (int t = unit; t < total_tiles; t += n_units) {
-      // dense-axis 3x3 mode: bit `tap` set = that tap of this row's pixel lies inside the pixel's own map
-      uint32_t tapmask = 0xFFFFFFFFu;
-      if (p.flat_w) {
-        int n_tile, n0, oh0, ow0;
-        tile_of(t, n_tile, n0, oh0, ow0);
-        const int rem = (ow0 + row) % (p.flat_h * p.flat_w);
-        const int oh = rem / p.flat_w, ow = rem - oh * p.flat_w;
-        tapmask = 0u;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int kh = tap / p.KW, kw = tap - kh * p.KW;
-          if ((unsigned)(oh + kh - p.pad) < (unsigned)p.flat_h && (unsigned)(ow + kw - p.pad) < (unsigned)p.flat_w)
-            tapmask |= 1u << tap;
-        }
-      }
-      for (int kit = 0; kit < k_iters; ++kit, ++it) {
-        const int s = it % L::kStages;
-        const uint32_t ph = (it / L::kStages) & 1;
-        const int slot = it & 1;
-        mbar_wait(full_bar + s, ph);                                  // the stage's bytes have landed
-        mbar_wait(aslot_bar + slot, ((it >> 1) & 1) ^ 1);             // the MMAs of two K-iterations ago have read the slot
-        tc_fence_after();
-        const uint32_t a_row = smem_u32(smem + s * L::kStageBytes) + row_off;
-        uint32_t hi[32], lo[32];
-        // (the dense-axis 3x3 mode is a separate instance of the loop: this chain is latency-critical, and the tap test
-        // plus 64 extra ANDs per K-iteration cost the RPN conv 8 % when they sat in the common path)
-        const bool zero_row = p.flat_w != 0 && !((tapmask >> (kit / p.cblocks)) & 1u);
-        if (zero_row) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { hi[j] = 0u; lo[j] = 0u; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {                  // quarter-warp phases hit 8 distinct 16-byte bank groups
-            float v[4];
-            lds128(a_row + ((j ^ sw) << 4), v);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t h = __float_as_uint(v[e]) & 0xFFFFE000u;
-              hi[4 * j + e] = h;
-              lo[4 * j + e] = __float_as_uint(v[e] - __uint_as_float(h)) & 0xFFFFE000u;
-            }
+    // Two instances of the loop (the chain TMA -> splitter -> MMA is latency-critical: the tap test of the dense-axis
+    // 3x3 mode in the common instance cost the RPN conv 2-8 %): FLAT carries the per-row tap mask, the other nothing.
+    auto split_loop = [&](auto flat_tag) {
+      constexpr bool FLAT = decltype(flat_tag)::value;
+      uint32_t it = 0;
+      for (int t = unit; t < total_tiles; t += n_units) {
+        // dense-axis 3x3 mode: bit `tap` set = that tap of this row's pixel lies inside the pixel's own map
+        uint32_t tapmask = 0xFFFFFFFFu;
+        if constexpr (FLAT) {
+          int n_tile, n0, oh0, ow0;
+          tile_of(t, n_tile, n0, oh0, ow0);
+          const int rem = (ow0 + row) % (p.flat_h * p.flat_w);
+          const int oh = rem / p.flat_w, ow = rem - oh * p.flat_w;
+          tapmask = 0u;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+            if ((unsigned)(oh + kh - p.pad) < (unsigned)p.flat_h && (unsigned)(ow + kw - p.pad) < (unsigned)p.flat_w)
+              tapmask |= 1u << tap;
           }
         }
-        tmem_st32(a_tmem + (uint32_t)(slot * kASlotCols), hi);
-        tmem_st32(a_tmem + (uint32_t)(slot * kASlotCols + 32), lo);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(split_bar + slot);
+        for (int kit = 0; kit < k_iters; ++kit, ++it) {
+          const int s = it % L::kStages;
+          const uint32_t ph = (it / L::kStages) & 1;
+          const int slot = it & 1;
+          mbar_wait(full_bar + s, ph);                                  // the stage's bytes have landed
+          mbar_wait(aslot_bar + slot, ((it >> 1) & 1) ^ 1);             // the MMAs of two K-iterations ago have read the slot
+          tc_fence_after();
+          const uint32_t a_row = smem_u32(smem + s * L::kStageBytes) + row_off;
+          uint32_t hi[32], lo[32];
+          bool zero_row = false;
+          if constexpr (FLAT) zero_row = !((tapmask >> (kit / p.cblocks)) & 1u);
+          if (zero_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { hi[j] = 0u; lo[j] = 0u; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {                  // quarter-warp phases hit 8 distinct 16-byte bank groups
+              float v[4];
+              lds128(a_row + ((j ^ sw) << 4), v);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t h = __float_as_uint(v[e]) & 0xFFFFE000u;
+                hi[4 * j + e] = h;
+                lo[4 * j + e] = __float_as_uint(v[e] - __uint_as_float(h)) & 0xFFFFE000u;
+              }
+            }
+          }
+          tmem_st32(a_tmem + (uint32_t)(slot * kASlotCols), hi);
+          tmem_st32(a_tmem + (uint32_t)(slot * kASlotCols + 32), lo);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(split_bar + slot);
+        }
       }
-    }
+    };
+    if (p.flat_w) split_loop(std::true_type{}); else split_loop(std::false_type{});
   } else {
     // ================================ epilogue (warps 2..5) ================================
     // Each warp owns TMEM lanes / tile rows [32q, 32q+32) end to end (its own staging slices, its own TMA
